@@ -1,0 +1,98 @@
+"""Pin the CPU restatement (oracle/mc_path.py) against vectors produced by the UNMODIFIED reference
+(tests/golden/reference_vectors.npz, written by oracle/make_golden.py)."""
+import math
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import mc_path as M
+
+
+def _stats(t):
+    f = t.float().flatten(1)
+    return torch.stack([f.mean(1), f.std(1), f.abs().amax(1)], dim=1).numpy()
+
+
+def test_geometry(golden):
+    assert np.allclose(golden["red_ellipse_mat"], [4, 4, 25, 4, 1.5625], rtol=1e-3)
+    assert np.allclose(golden["red_ellipse_mat_inv"], M.red_ellipse_mat_inv(), rtol=1e-3)
+    d = golden["dirs"]
+    assert d.shape == (5, 512)
+    assert np.allclose(np.linalg.norm(d, axis=1), 1.0, atol=1e-5)
+
+
+def test_kats(golden):
+    for (na, n), p, gap in zip(golden["kat_in"], golden["kat_p"], golden["kat_gap"]):
+        mine = M.lower_confidence_bound(int(na), int(n), 0.001)
+        assert mine == pytest.approx(p, rel=1e-12, abs=1e-15)
+        if 0 < p < 1:
+            assert M.compute_gap(mine) == pytest.approx(gap, rel=1e-12)
+    # SURVEY.md section 8c closed-form values
+    assert M.lower_confidence_bound(100, 100, 0.001) == pytest.approx(0.9332543008, rel=1e-9)
+    assert M.compute_gap(M.lower_confidence_bound(990, 1000, 0.001)) == pytest.approx(1.9780096, rel=1e-6)
+    assert M.lower_confidence_bound(60, 100, 0.001) < 0.5
+
+
+def test_fused_upconv_equivalence(models):
+    """conv_transpose2d with the box-summed 4x4 kernel == nearest x2 + flipped 3x3 conv (borders too)."""
+    g_sd, _ = models
+    x = torch.randn(2, 64, 16, 16, generator=torch.Generator().manual_seed(0)).double()
+    sd = {k: v.double() for k, v in g_sd.items() if k.startswith("synthesis.layer14.")}
+    a = M._upconv(x, sd, 14, literal=True)
+    b = M._upconv(x, sd, 14, literal=False)
+    assert (a - b).abs().max().item() < 1e-11
+
+
+def test_pipeline_against_reference(golden, models):
+    g_sd, f_sd = models
+    w_in = torch.from_numpy(golden["w_in"])
+    wp = M.truncation(w_in, g_sd)
+    assert np.allclose(wp.numpy(), golden["wp"], atol=1e-6)
+    got = {}
+    with torch.no_grad():
+        raw = M.synthesis(wp, g_sd, literal=True, tap=lambda k, t: got.__setitem__(k, _stats(t)))
+        img = M.postprocess(raw)
+        img112 = M.transform(img)
+        blocks = {}
+        emb = M.iresnet50(img112, f_sd, tap=lambda k, t: blocks.__setitem__(k, _stats(t)))
+    ls = np.stack([got[f"layer{i}"] for i in range(M.NUM_LAYERS)])
+    assert np.allclose(ls, golden["layer_stats"], rtol=2e-3, atol=2e-4)
+    sl = slice(0, 1024, 64)
+    assert np.allclose(img[:, :, sl, sl].numpy(), golden["image_sub"], atol=2e-4)
+    assert np.allclose(img112[0].numpy(), golden["img112_0"], atol=5e-4)
+    ref_emb = torch.from_numpy(golden["emb"])
+    cos = F.cosine_similarity(emb, ref_emb).min().item()
+    assert cos > 0.99999, cos
+    assert (emb - ref_emb).abs().max().item() < 2e-2
+
+
+def test_certify_against_reference(golden, models):
+    g_sd, f_sd = models
+    dirs = torch.from_numpy(golden["dirs"])
+    gal = torch.from_numpy(golden["gallery"])
+    z = torch.from_numpy(golden["w_all"][0:1])
+    x = torch.zeros(1, 5)
+    classify = lambda p: M.wrapped_forward(z, p, dirs, gal, g_sd, f_sd)
+    for tag in ("iso", "aniso"):
+        sigma = torch.from_numpy(golden[tag + "_sigma"])
+        torch.manual_seed(1234)
+        pred, gap = M.certify(classify, x, 0, sigma, 4, 12, 0.001, 4, gal.shape[0])
+        assert pred == int(golden[tag + "_pred"])
+        assert gap == pytest.approx(float(golden[tag + "_gap"]), rel=1e-9, abs=1e-12)
+    torch.manual_seed(99)
+    pred, gap = M.certify(classify, x, 3, torch.tensor([0.1]), 4, 12, 0.001, 4, gal.shape[0])
+    assert (pred, gap) == (int(golden["pred_wrong"]), float(golden["gap_wrong"]))
+
+
+def test_count_arr_and_predict():
+    preds = torch.tensor([3, 3, 1, 3, 0, 1])
+    assert M.count_arr(preds, 5).tolist() == [1, 2, 0, 3, 0]
+    probs = torch.zeros(1, 4)
+
+    def classify(p):
+        out = torch.zeros(p.shape[0], 4)
+        out[:, 2] = 1.0
+        return out
+    assert M.predict(classify, torch.zeros(1, 5), torch.tensor([0.1]), 40, 0.001, 16, 4) == 2
