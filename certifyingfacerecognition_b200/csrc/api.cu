@@ -1,0 +1,220 @@
+// C ABI (include/cfr_b200.h): programs (recorded launch lists), immediate ops and the MC sampler.
+#include "../../include/cfr_b200.h"
+#include "conv_igemm.cuh"
+#include "kernels.cuh"
+
+#include <functional>
+#include <memory>
+#include <vector>
+#include <cstring>
+
+using namespace cfr;
+
+struct cfr_program {
+  std::vector<std::function<int(cudaStream_t)>> ops;
+  std::vector<std::unique_ptr<ConvOp>> convs;
+};
+
+struct cfr_sampler {
+  cfr_sampler_desc d;
+  unsigned long long* keys = nullptr;   // [chunk]
+  float* dev_in = nullptr;              // z[512] | x[5] (pad 8) | sigma[5] (pad 8)   (host-entry staging)
+  long long* dev_counts = nullptr;      // [n_gallery]
+  float* pin_in = nullptr;              // pinned mirror of dev_in
+  long long* pin_counts = nullptr;      // pinned [n_gallery]
+};
+
+static inline cudaStream_t S(cfr_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
+
+#define CFR_CUDA(call)                                                        \
+  do {                                                                        \
+    cudaError_t e__ = (call);                                                 \
+    if (e__ != cudaSuccess) {                                                 \
+      set_error("%s: %s", #call, cudaGetErrorString(e__));                    \
+      return 5;                                                               \
+    }                                                                         \
+  } while (0)
+
+extern "C" {
+
+CFR_API const char* cfr_last_error(void) { return last_error(); }
+CFR_API int cfr_version(void) { return 100; }
+CFR_API uint64_t cfr_launch_count(void) { return launch_count(); }
+
+CFR_API int cfr_device_info(int* sm_count, int* cc_major, int* cc_minor) {
+  int dev = 0;
+  CFR_CUDA(cudaGetDevice(&dev));
+  cudaDeviceProp prop;
+  CFR_CUDA(cudaGetDeviceProperties(&prop, dev));
+  if (sm_count) *sm_count = prop.multiProcessorCount;
+  if (cc_major) *cc_major = prop.major;
+  if (cc_minor) *cc_minor = prop.minor;
+  return 0;
+}
+
+CFR_API int cfr_program_create(cfr_program** out) {
+  *out = new cfr_program();
+  return 0;
+}
+CFR_API void cfr_program_destroy(cfr_program* p) { delete p; }
+CFR_API int cfr_program_num_launches(const cfr_program* p) { return static_cast<int>(p->ops.size()); }
+
+CFR_API int cfr_program_run(cfr_program* p, cfr_stream_t stream) {
+  for (auto& op : p->ops) {
+    int r = op(S(stream));
+    if (r != 0) return r;
+  }
+  return 0;
+}
+
+CFR_API int cfr_program_add_conv(cfr_program* p, const cfr_conv_desc* d) {
+  std::unique_ptr<ConvOp> op(new ConvOp());
+  int r = conv_build(*d, op.get());
+  if (r != 0) return r;
+  ConvOp* raw = op.get();
+  p->convs.push_back(std::move(op));
+  p->ops.push_back([raw](cudaStream_t st) { return conv_launch(*raw, st); });
+  return 0;
+}
+
+CFR_API int cfr_program_add_memset(cfr_program* p, void* ptr, int value, size_t bytes) {
+  p->ops.push_back([=](cudaStream_t st) {
+    cudaError_t e = cudaMemsetAsync(ptr, value, bytes, st);
+    if (e != cudaSuccess) { set_error("memset: %s", cudaGetErrorString(e)); return 5; }
+    return 0;
+  });
+  return 0;
+}
+
+CFR_API int cfr_program_add_styles(cfr_program* p, const float* wp2, const float* w_style, const float* b_style, int rows,
+                           int rows_trunc, int b, float* styles) {
+  p->ops.push_back([=](cudaStream_t st) { return launch_styles(wp2, w_style, b_style, rows, rows_trunc, b, styles, st); });
+  return 0;
+}
+
+CFR_API int cfr_program_add_layer0(cfr_program* p, const float* xhat0, const float* styles, int style_stride, int style_off,
+                           int b, void* out_f16) {
+  p->ops.push_back([=](cudaStream_t st) {
+    return launch_layer0(xhat0, styles, style_stride, style_off, b, static_cast<__half*>(out_f16), st);
+  });
+  return 0;
+}
+
+CFR_API int cfr_program_add_blur_act_stats(cfr_program* p, const void* raw_f16, void* y_f16, int n, int h, int w, int c,
+                                   const float* noise, const float* noise_w, const float* bias, float* sum, float* sq,
+                                   int mode) {
+  p->ops.push_back([=](cudaStream_t st) {
+    return launch_blur_act_stats(static_cast<const __half*>(raw_f16), static_cast<__half*>(y_f16), n, h, w, c, noise,
+                                 noise_w, bias, sum, sq, mode, st);
+  });
+  return 0;
+}
+
+CFR_API int cfr_program_add_finalize_stats(cfr_program* p, const float* sum, const float* sq, const float* styles,
+                                   int style_stride, int style_off, int n, int c, float inv_count, float* A, float* B) {
+  p->ops.push_back([=](cudaStream_t st) {
+    return launch_finalize_stats(sum, sq, styles, style_stride, style_off, n, c, inv_count, A, B, st);
+  });
+  return 0;
+}
+
+CFR_API int cfr_program_add_affine(cfr_program* p, const void* y_f16, const float* A, const float* B, int n, int hw, int c,
+                           void* x_f16) {
+  p->ops.push_back([=](cudaStream_t st) {
+    return launch_affine(static_cast<const __half*>(y_f16), A, B, n, hw, c, static_cast<__half*>(x_f16), st);
+  });
+  return 0;
+}
+
+CFR_API int cfr_program_add_torgb_resize(cfr_program* p, const void* x_f16, const float* A, const float* B, int n, int hin,
+                                 int c, const float* w_rgb, const float* b_rgb, int rout, float mean, float stdv,
+                                 void* out_f16_nhwc16, float* out_planar_f32) {
+  p->ops.push_back([=](cudaStream_t st) {
+    return launch_torgb_resize(static_cast<const __half*>(x_f16), A, B, n, hin, c, w_rgb, b_rgb, rout, mean, stdv,
+                               static_cast<__half*>(out_f16_nhwc16), out_planar_f32, st);
+  });
+  return 0;
+}
+
+CFR_API int cfr_noise_project(const float* z, const float* x, const float* sigma, int sigma_len, const float* noise_in,
+                      const float* dir_mat, const float* w_avg, float psi, uint64_t seed, uint64_t sample_offset, int b,
+                      float* noise_out, float* wp2, cfr_stream_t stream) {
+  if (sigma_len != 1 && sigma_len != 5) { set_error("sigma_len must be 1 or 5"); return 2; }
+  return launch_noise_project(z, x, sigma, sigma_len, noise_in, dir_mat, w_avg, psi, seed, sample_offset, b, noise_out,
+                              wp2, S(stream));
+}
+CFR_API int cfr_truncate(const float* w, const float* w_avg, float psi, int b, float* wp2, cfr_stream_t stream) {
+  return launch_truncate(w, w_avg, psi, b, wp2, S(stream));
+}
+CFR_API int cfr_match_vote(const float* emb, int b, const float* gallery, int n, uint64_t* keys, int32_t* pred, int64_t* counts,
+                   cfr_stream_t stream) {
+  return launch_match_vote(emb, b, gallery, n, reinterpret_cast<unsigned long long*>(keys), pred,
+                           reinterpret_cast<long long*>(counts), S(stream));
+}
+
+CFR_API int cfr_sampler_create(const cfr_sampler_desc* d, cfr_sampler** out) {
+  if (d->chunk <= 0 || d->n_gallery <= 0) { set_error("sampler: bad chunk / gallery size"); return 2; }
+  std::unique_ptr<cfr_sampler> s(new cfr_sampler());
+  s->d = *d;
+  CFR_CUDA(cudaMalloc(&s->keys, sizeof(unsigned long long) * d->chunk));
+  CFR_CUDA(cudaMemset(s->keys, 0xFF, sizeof(unsigned long long) * d->chunk));
+  CFR_CUDA(cudaMalloc(&s->dev_in, sizeof(float) * 528));
+  CFR_CUDA(cudaMalloc(&s->dev_counts, sizeof(long long) * d->n_gallery));
+  CFR_CUDA(cudaMallocHost(&s->pin_in, sizeof(float) * 528));
+  CFR_CUDA(cudaMallocHost(&s->pin_counts, sizeof(long long) * d->n_gallery));
+  *out = s.release();
+  return 0;
+}
+CFR_API void cfr_sampler_destroy(cfr_sampler* s) {
+  if (!s) return;
+  cudaFree(s->keys);
+  cudaFree(s->dev_in);
+  cudaFree(s->dev_counts);
+  cudaFreeHost(s->pin_in);
+  cudaFreeHost(s->pin_counts);
+  delete s;
+}
+
+CFR_API int cfr_sample_votes(cfr_sampler* s, const float* z, const float* x, const float* sigma, int sigma_len,
+                     const float* noise_in, int64_t num, uint64_t seed, uint64_t sample_offset, int64_t* counts,
+                     int32_t* pred_out, float* emb_out, float* noise_out, cfr_stream_t stream) {
+  const cfr_sampler_desc& d = s->d;
+  if (sigma_len != 1 && sigma_len != 5) { set_error("sigma_len must be 1 or 5"); return 2; }
+  for (int64_t done = 0; done < num; done += d.chunk) {
+    const int b = static_cast<int>(num - done < d.chunk ? num - done : d.chunk);
+    int r = launch_noise_project(z, x, sigma, sigma_len, noise_in ? noise_in + done * 5 : nullptr, d.dir_mat, d.w_avg,
+                                 d.psi, seed, sample_offset + done, b, noise_out ? noise_out + done * 5 : nullptr,
+                                 d.wp2, S(stream));
+    if (r) return r;
+    if ((r = cfr_program_run(d.synth, stream)) != 0) return r;
+    if ((r = cfr_program_run(d.frm, stream)) != 0) return r;
+    if (emb_out) {
+      CFR_CUDA(cudaMemcpyAsync(emb_out + done * 512, d.emb, sizeof(float) * 512 * b, cudaMemcpyDeviceToDevice, S(stream)));
+    }
+    r = launch_match_vote(d.emb, b, d.gallery, d.n_gallery, s->keys, pred_out ? pred_out + done : nullptr,
+                          reinterpret_cast<long long*>(counts), S(stream));
+    if (r) return r;
+  }
+  return 0;
+}
+
+CFR_API int cfr_sample_votes_host(cfr_sampler* s, const float* z_host, const float* x_host, const float* sigma_host,
+                          int sigma_len, int64_t num, uint64_t seed, uint64_t sample_offset, int64_t* counts_host,
+                          cfr_stream_t stream) {
+  if (sigma_len != 1 && sigma_len != 5) { set_error("sigma_len must be 1 or 5"); return 2; }
+  const int n = s->d.n_gallery;
+  memcpy(s->pin_in, z_host, sizeof(float) * 512);
+  memcpy(s->pin_in + 512, x_host, sizeof(float) * 5);
+  memcpy(s->pin_in + 520, sigma_host, sizeof(float) * sigma_len);
+  CFR_CUDA(cudaMemcpyAsync(s->dev_in, s->pin_in, sizeof(float) * 528, cudaMemcpyHostToDevice, S(stream)));
+  CFR_CUDA(cudaMemsetAsync(s->dev_counts, 0, sizeof(long long) * n, S(stream)));
+  int r = cfr_sample_votes(s, s->dev_in, s->dev_in + 512, s->dev_in + 520, sigma_len, nullptr, num, seed,
+                           sample_offset, reinterpret_cast<int64_t*>(s->dev_counts), nullptr, nullptr, nullptr, stream);
+  if (r) return r;
+  CFR_CUDA(cudaMemcpyAsync(s->pin_counts, s->dev_counts, sizeof(long long) * n, cudaMemcpyDeviceToHost, S(stream)));
+  CFR_CUDA(cudaStreamSynchronize(S(stream)));
+  memcpy(counts_host, s->pin_counts, sizeof(long long) * n);
+  return 0;
+}
+
+}  // extern "C"

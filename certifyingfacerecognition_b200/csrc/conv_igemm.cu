@@ -1,0 +1,476 @@
+// tcgen05/TMEM/TMA implicit-GEMM convolution kernel -- see conv_igemm.cuh for the design.
+#include "conv_igemm.cuh"
+#include "ptx.cuh"
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+
+namespace cfr {
+
+// --------------------------------------------------------------------------------------------
+// device
+// --------------------------------------------------------------------------------------------
+struct TileCoord {
+  int n0, y0, x0, phase, ntile;
+};
+
+__device__ __forceinline__ TileCoord decode_item(const ConvParams& p, int item) {
+  TileCoord t;
+  t.ntile = item % p.numNTiles;
+  int r = item / p.numNTiles;
+  t.phase = r % p.numPhases;
+  int m = r / p.numPhases;
+  int tx = m % p.tilesX;
+  m /= p.tilesX;
+  int ty = m % p.tilesY;
+  int tn = m / p.tilesY;
+  t.x0 = tx * p.TW;
+  t.y0 = ty * p.TH;
+  t.n0 = tn * p.TN;
+  return t;
+}
+
+// Sum v[0..15] over the 32 lanes of a warp, 16 channels at once (transpose-reduce, 16 shuffles).
+// On return lane l (l even) holds in v[0] the warp total of channel ((l>>1)&15) bit-reversed as below.
+__device__ __forceinline__ float warp_reduce16(float (&v)[16], uint32_t lane) {
+#pragma unroll
+  for (int step = 0; step < 4; ++step) {
+    const int off = 16 >> step;      // 16, 8, 4, 2
+    const int cnt = 8 >> step;       // 8, 4, 2, 1
+    const bool upper = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < cnt; ++i) {
+      float send = upper ? v[i] : v[i + cnt];
+      float keep = upper ? v[i + cnt] : v[i];
+      float recv = __shfl_xor_sync(0xffffffffu, send, off);
+      v[i] = keep + recv;
+    }
+  }
+  v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
+  return v[0];
+}
+// channel (0..15) whose total lane `lane` holds after warp_reduce16
+__device__ __forceinline__ int reduce16_channel(uint32_t lane) {
+  return ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+}
+
+__global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __grid_constant__ ConvParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int S = p.numStages;
+  uint8_t* ctrl = smem + static_cast<size_t>(S) * p.stageBytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(ctrl);
+  uint64_t* empty_bar = full_bar + S;
+  uint64_t* tfull_bar = empty_bar + S;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  float* s_sum = reinterpret_cast<float*>(tmem_slot + 4);
+  float* s_sq = s_sum + kStatsMaxC;
+
+  const int warp = threadIdx.x >> 5;
+  const uint32_t lane = lane_id();
+
+  const int totalItems = p.tilesX * p.tilesY * p.tilesN * p.numPhases * p.numNTiles;
+  const int per = (totalItems + gridDim.x - 1) / gridDim.x;
+  const int item0 = blockIdx.x * per;
+  const int item1 = min(totalItems, item0 + per);
+
+  const int chunksTotal = p.ntaps * p.nCB;
+  const int stagesPerTile = (chunksTotal + p.G - 1) / p.G;
+  const uint32_t subBytes = kBM * p.CB * 2;
+  uint32_t tmemCols = 32;
+  while (tmemCols < 2u * p.BN) tmemCols <<= 1;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.tmA);
+    tma_prefetch_desc(&p.tmB);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int i = 0; i < S; ++i) {
+        mbar_init(&full_bar[i], 1);
+        mbar_init(&empty_bar[i], 1);
+      }
+      for (int i = 0; i < 2; ++i) {
+        mbar_init(&tfull_bar[i], 1);
+        mbar_init(&tempty_bar[i], 4);
+      }
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_slot, tmemCols);
+    tmem_relinquish();
+  }
+  if (p.stat_sum != nullptr) {
+    for (int i = threadIdx.x; i < 2 * kStatsMaxC; i += blockDim.x) s_sum[i] = 0.f;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================================================================== TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int item = item0; item < item1; ++item) {
+        const TileCoord t = decode_item(p, item);
+        const int wrow = t.n0 * p.wRowsPerSample + t.phase * p.wRowsPerPhase + t.ntile * p.BN;
+        for (int s = 0; s < stagesPerTile; ++s) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          const int nch = min(p.G, chunksTotal - s * p.G);
+          uint8_t* a_dst = smem + static_cast<size_t>(stage) * p.stageBytes;
+          uint8_t* b_dst = a_dst + kBM * 128;
+          mbar_expect_tx(&full_bar[stage], nch * subBytes + p.BN * 128);
+          for (int g = 0; g < nch; ++g) {
+            const int chunk = s * p.G + g;
+            const int tap = chunk / p.nCB;
+            const int cb = chunk - tap * p.nCB;
+            tma_load_4d(a_dst + g * subBytes, &p.tmA, &full_bar[stage], cb * p.CB,
+                        t.x0 * p.stride + p.tap_dx[t.phase][tap], t.y0 * p.stride + p.tap_dy[t.phase][tap], t.n0);
+          }
+          tma_load_2d(b_dst, &p.tmB, &full_bar[stage], s * 64, wrow);
+          if (++stage == S) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================================== MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_f16(kBM, p.BN);
+      const uint32_t sboA = 8 * p.swizzleA;
+      const int kPerChunk = p.CB / 16;
+      int stage = 0;
+      uint32_t phase = 0;
+      int as = 0;
+      uint32_t aphase = 0;
+      for (int item = item0; item < item1; ++item) {
+        mbar_wait(&tempty_bar[as], aphase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * p.BN;
+        for (int s = 0; s < stagesPerTile; ++s) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const int nch = min(p.G, chunksTotal - s * p.G);
+          const uint32_t a_base = smem_u32(smem + static_cast<size_t>(stage) * p.stageBytes);
+          const uint32_t b_base = a_base + kBM * 128;
+          for (int g = 0; g < nch; ++g) {
+            for (int j = 0; j < kPerChunk; ++j) {
+              const uint64_t adesc = make_smem_desc(a_base + g * subBytes + j * 32, sboA, p.swizzleA);
+              const uint64_t bdesc = make_smem_desc(b_base + (g * kPerChunk + j) * 32, 1024, 128);
+              umma_f16(d_tmem, adesc, bdesc, idesc, (s | g | j) != 0 ? 1u : 0u);
+            }
+          }
+          umma_commit(&empty_bar[stage]);   // frees this smem stage once the MMAs above have read it
+          if (++stage == S) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(&tfull_bar[as]);        // accumulator complete -> epilogue
+        as ^= 1;
+        if (as == 0) aphase ^= 1;
+      }
+    }
+  } else {
+    // ===================================================================== epilogue (warps 2..5)
+    const int q = warp & 3;                      // TMEM lane quarter this warp may read
+    const int row = q * 32 + lane;               // M row == pixel index inside the tile box
+    const int tx = row % p.TW;
+    const int ty = (row / p.TW) % p.TH;
+    const int tn = row / (p.TW * p.TH);
+    const int et = threadIdx.x - 64;             // 0..127
+    int as = 0;
+    uint32_t aphase = 0;
+    int cur_img = -1;
+    const bool do_stats = p.stat_sum != nullptr;
+    for (int item = item0; item < item1; ++item) {
+      const TileCoord t = decode_item(p, item);
+      if (do_stats && cur_img >= 0 && t.n0 != cur_img) {
+        named_bar_sync(1, 128);
+        for (int c = et; c < p.CoutTotal; c += 128) {
+          atomicAdd(&p.stat_sum[cur_img * p.CoutTotal + c], s_sum[c]);
+          atomicAdd(&p.stat_sq[cur_img * p.CoutTotal + c], s_sq[c]);
+          s_sum[c] = 0.f;
+          s_sq[c] = 0.f;
+        }
+        named_bar_sync(1, 128);
+      }
+      cur_img = t.n0;
+      const int gx = t.x0 + tx, gy = t.y0 + ty, n = t.n0 + tn;
+      const bool valid = gx < p.Wout && gy < p.Hout && n < p.N;
+      const int oy = gy * p.oscale + p.ooff_y[t.phase];
+      const int ox = gx * p.oscale + p.ooff_x[t.phase];
+      const size_t pix = (static_cast<size_t>(n) * p.outH + oy) * p.outW + ox;
+      const int cls = (gy == 0 ? 0 : (gy == p.Hout - 1 ? 2 : 1)) * 3 + (gx == 0 ? 0 : (gx == p.Wout - 1 ? 2 : 1));
+      const float* cb_row = nullptr;
+      if (p.cbias != nullptr && valid) {
+        cb_row = p.cbias +
+                 ((static_cast<size_t>(p.cbiasPerSample ? n : 0) * p.numPhases + t.phase) * 9 + cls) * p.CoutTotal;
+      }
+      const float nz = (p.noise != nullptr && valid) ? __ldg(&p.noise[oy * p.outW + ox]) : 0.f;
+
+      mbar_wait(&tfull_bar[as], aphase);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * p.BN;
+      for (int c0 = 0; c0 < p.BN; c0 += 16) {
+        float v[16];
+        tmem_ld16(t_row + c0, v);
+        const int ch0 = t.ntile * p.BN + c0;
+        if (cb_row != nullptr) {
+#pragma unroll
+          for (int i = 0; i < 16; i += 4) {
+            const float4 b4 = __ldg(reinterpret_cast<const float4*>(cb_row + ch0 + i));
+            v[i] += b4.x; v[i + 1] += b4.y; v[i + 2] += b4.z; v[i + 3] += b4.w;
+          }
+        }
+        if (p.bias != nullptr) {
+#pragma unroll
+          for (int i = 0; i < 16; i += 4) {
+            const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + ch0 + i));
+            v[i] += b4.x; v[i + 1] += b4.y; v[i + 2] += b4.z; v[i + 3] += b4.w;
+          }
+        }
+        if (p.noise != nullptr) {
+#pragma unroll
+          for (int i = 0; i < 16; i += 4) {
+            const float4 w4 = __ldg(reinterpret_cast<const float4*>(p.noise_w + ch0 + i));
+            v[i] += nz * w4.x; v[i + 1] += nz * w4.y; v[i + 2] += nz * w4.z; v[i + 3] += nz * w4.w;
+          }
+        }
+        if (p.act == ACT_LRELU) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = v[i] >= 0.f ? v[i] : v[i] * p.slope;
+        } else if (p.act == ACT_PRELU) {
+#pragma unroll
+          for (int i = 0; i < 16; i += 4) {
+            const float4 a4 = __ldg(reinterpret_cast<const float4*>(p.alpha + ch0 + i));
+            v[i] = v[i] >= 0.f ? v[i] : v[i] * a4.x;
+            v[i + 1] = v[i + 1] >= 0.f ? v[i + 1] : v[i + 1] * a4.y;
+            v[i + 2] = v[i + 2] >= 0.f ? v[i + 2] : v[i + 2] * a4.z;
+            v[i + 3] = v[i + 3] >= 0.f ? v[i + 3] : v[i + 3] * a4.w;
+          }
+        }
+        if (p.resid != nullptr && valid) {
+          const uint4* rp = reinterpret_cast<const uint4*>(p.resid + pix * p.residC + ch0);
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const uint4 r4 = __ldg(rp + h);
+            const __half2* h2 = reinterpret_cast<const __half2*>(&r4);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float2 f = __half22float2(h2[i]);
+              v[h * 8 + 2 * i] += f.x;
+              v[h * 8 + 2 * i + 1] += f.y;
+            }
+          }
+        }
+        if (valid) {
+          if (p.out32 != nullptr) {
+            float4* op = reinterpret_cast<float4*>(p.out32 + pix * p.outC + ch0);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) op[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+          } else {
+            uint4 o[2];
+            __half2* h2 = reinterpret_cast<__half2*>(o);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) h2[i] = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+            uint4* op = reinterpret_cast<uint4*>(p.out + pix * p.outC + ch0);
+            op[0] = o[0];
+            op[1] = o[1];
+          }
+        }
+        if (do_stats) {
+          float sq[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            v[i] = valid ? v[i] : 0.f;
+            sq[i] = v[i] * v[i];
+          }
+          const float ssum = warp_reduce16(v, lane);
+          const float ssq = warp_reduce16(sq, lane);
+          if ((lane & 1) == 0) {
+            const int ch = ch0 + reduce16_channel(lane);
+            atomicAdd(&s_sum[ch], ssum);
+            atomicAdd(&s_sq[ch], ssq);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[as]);
+      as ^= 1;
+      if (as == 0) aphase ^= 1;
+    }
+    if (do_stats && cur_img >= 0) {
+      named_bar_sync(1, 128);
+      for (int c = et; c < p.CoutTotal; c += 128) {
+        atomicAdd(&p.stat_sum[cur_img * p.CoutTotal + c], s_sum[c]);
+        atomicAdd(&p.stat_sq[cur_img * p.CoutTotal + c], s_sq[c]);
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, tmemCols);
+  }
+}
+
+// --------------------------------------------------------------------------------------------
+// host
+// --------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+const char* last_error() { return g_err; }
+static unsigned long long g_launches = 0;
+void count_launch(int n) { g_launches += n; }
+unsigned long long launch_count() { return g_launches; }
+
+int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres);
+    if (e == cudaSuccess && qres == cudaDriverEntryPointSuccess) fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  });
+  return fn;
+}
+
+static CUtensorMapSwizzle swz_enum(int bytes) {
+  return bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                      : (bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                     : (bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE));
+}
+
+int conv_build(const ConvSpec& s, ConvOp* op) {
+  EncodeTiledFn enc = get_encode();
+  if (enc == nullptr) {
+    set_error("cuTensorMapEncodeTiled not available (no CUDA driver?)");
+    return 1;
+  }
+  ConvParams& p = op->p;
+  memset(&p, 0, sizeof(p));
+  if (s.TW * s.TH * s.TN != kBM) { set_error("conv: TW*TH*TN must be 128 (got %d*%d*%d)", s.TW, s.TH, s.TN); return 2; }
+  if (s.Cin % 16 != 0 || (s.Cin > 64 && s.Cin % 64 != 0)) { set_error("conv: Cin=%d unsupported", s.Cin); return 2; }
+  if (s.Cout % 16 != 0) { set_error("conv: Cout=%d must be a multiple of 16", s.Cout); return 2; }
+  if (s.ntaps < 1 || s.ntaps > kMaxTaps || s.numPhases < 1 || s.numPhases > kMaxPhases) { set_error("conv: bad taps/phases"); return 2; }
+  if (s.stride != 1 && s.stride != 2) { set_error("conv: stride %d unsupported", s.stride); return 2; }
+  if (s.stat_sum != nullptr && (s.TN != 1 || s.numPhases != 1 || s.Cout > kStatsMaxC)) { set_error("conv: fused stats need TN==1, one phase, Cout<=512"); return 2; }
+
+  p.N = s.N; p.Hout = s.Hout; p.Wout = s.Wout;
+  p.TW = s.TW; p.TH = s.TH; p.TN = s.TN;
+  p.tilesX = (s.Wout + s.TW - 1) / s.TW;
+  p.tilesY = (s.Hout + s.TH - 1) / s.TH;
+  p.tilesN = (s.N + s.TN - 1) / s.TN;
+  p.numPhases = s.numPhases;
+  p.stride = s.stride;
+  p.ntaps = s.ntaps;
+  memcpy(p.tap_dy, s.tap_dy, sizeof(p.tap_dy));
+  memcpy(p.tap_dx, s.tap_dx, sizeof(p.tap_dx));
+  p.CB = s.Cin >= 64 ? 64 : s.Cin;
+  p.nCB = s.Cin / p.CB;
+  p.G = 64 / p.CB;
+  p.swizzleA = p.CB * 2;
+  // N tile: largest of 256/128/.. dividing Cout
+  int bn = s.Cout;
+  if (bn > 256) {
+    bn = 256;
+    while (s.Cout % bn != 0) bn -= 16;
+  }
+  p.BN = bn;
+  p.numNTiles = s.Cout / bn;
+  p.CoutTotal = s.Cout;
+  p.stageBytes = kBM * 128 + bn * 128;
+  const int ctrlBytes = 8 * (2 * 8 + 4) + 16 + 2 * kStatsMaxC * 4;
+  const int budget = 227 * 1024 - 1024 - ctrlBytes;
+  p.numStages = budget / p.stageBytes;
+  if (p.numStages > 8) p.numStages = 8;
+  if (p.numStages < 2) { set_error("conv: not enough shared memory for 2 stages"); return 2; }
+  op->smemBytes = p.numStages * p.stageBytes + ctrlBytes + 1024;
+  p.wRowsPerSample = s.wRowsPerSample;
+  p.wRowsPerPhase = s.wRowsPerPhase;
+  if (s.outIsF32) p.out32 = static_cast<float*>(s.out); else p.out = static_cast<__half*>(s.out);
+  p.outH = s.outH; p.outW = s.outW; p.outC = s.outC; p.oscale = s.oscale;
+  memcpy(p.ooff_y, s.ooff_y, sizeof(p.ooff_y));
+  memcpy(p.ooff_x, s.ooff_x, sizeof(p.ooff_x));
+  p.bias = s.bias; p.cbias = s.cbias; p.cbiasPerSample = s.cbiasPerSample;
+  p.noise = s.noise; p.noise_w = s.noise_w;
+  p.act = s.act; p.slope = s.slope; p.alpha = s.alpha;
+  p.resid = static_cast<const __half*>(s.resid); p.residC = s.residC;
+  p.stat_sum = s.stat_sum; p.stat_sq = s.stat_sq;
+
+  // activations: (C, W, H, N), fp16
+  {
+    cuuint64_t dims[4] = {(cuuint64_t)s.Cin, (cuuint64_t)s.Win, (cuuint64_t)s.Hin, (cuuint64_t)s.N};
+    cuuint64_t strides[3] = {(cuuint64_t)s.Cin * 2, (cuuint64_t)s.Win * s.Cin * 2, (cuuint64_t)s.Hin * s.Win * s.Cin * 2};
+    cuuint32_t box[4] = {(cuuint32_t)p.CB, (cuuint32_t)(s.TW * s.stride), (cuuint32_t)(s.TH * s.stride), (cuuint32_t)s.TN};
+    cuuint32_t estr[4] = {1, (cuuint32_t)s.stride, (cuuint32_t)s.stride, 1};
+    CUresult r = enc(&p.tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(s.in), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, swz_enum(p.swizzleA), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(A) failed: %d (C=%d W=%d H=%d N=%d box=%u,%u,%u,%u)", (int)r, s.Cin, s.Win, s.Hin, s.N, box[0], box[1], box[2], box[3]); return 3; }
+  }
+  // weights: (Kpad, rows), fp16
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)s.Kpad, (cuuint64_t)s.wRows};
+    cuuint64_t strides[1] = {(cuuint64_t)s.Kpad * 2};
+    cuuint32_t box[2] = {64, (cuuint32_t)bn};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(&p.tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(s.w), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(B) failed: %d (K=%d rows=%d bn=%d)", (int)r, s.Kpad, s.wRows, bn); return 3; }
+  }
+  if (s.Kpad % 64 != 0 || s.Kpad < s.ntaps * s.Cin) { set_error("conv: Kpad=%d must be a multiple of 64 and >= taps*Cin", s.Kpad); return 2; }
+
+  const int total = p.tilesX * p.tilesY * p.tilesN * p.numPhases * p.numNTiles;
+  op->grid = total < num_sms() ? total : num_sms();
+  return 0;
+}
+
+int conv_launch(const ConvOp& op, cudaStream_t stream) {
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [] {
+    attr_err = cudaFuncSetAttribute(conv_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  });
+  if (attr_err != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(attr_err)); return 4; }
+  conv_igemm_kernel<<<op.grid, kConvThreads, op.smemBytes, stream>>>(op.p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { set_error("conv launch: %s", cudaGetErrorString(e)); return 4; }
+  count_launch();
+  return 0;
+}
+
+}  // namespace cfr

@@ -1,0 +1,91 @@
+// Implicit-GEMM convolution on the 5th-gen tensor cores (tcgen05.mma, accumulators in TMEM),
+// operands staged by TMA.  One persistent, warp-specialised kernel serves every dense contraction
+// on the certification path:
+//   * StyleGAN ConvBlock 3x3 (stylegan_generator_model.py:738-741) with the fused epilogue
+//     +noise*w_c +b_c -> LeakyReLU(0.2) and per-(n,c) sum / sum-of-squares for InstanceNorm (:559-562,:420-422)
+//   * StyleGAN UpConvBlock (:665-676) as 4 sub-pixel phases x (2x2 taps) on the low-res grid
+//   * iresnet50 3x3 / strided 3x3 / 1x1 convs with folded BN, PReLU and residual add (iresnet.py:46-57)
+//   * the 25088->512 FC (iresnet.py:153) as a 1x1 conv over a 1x1 "image"
+//
+// Layout: activations NHWC fp16; weights [rows = (sample?, phase, Cout)][K = (tap, Cin)] fp16, K-major.
+// GEMM view: M = 128 output pixels (a TW x TH x TN box of the output grid), N = BN output channels,
+// K = taps * Cin walked in 64-element stages.  A tiles come from a 4-D TMA box whose start
+// coordinate is shifted by the tap offset: out-of-bounds rows/cols are zero-filled by TMA, which
+// *is* the conv zero padding; element strides give stride-2 convs.
+#pragma once
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <cstdint>
+
+#include "../../include/cfr_b200.h"
+
+namespace cfr {
+
+constexpr int kConvThreads = 192;   // warp0: TMA producer, warp1: MMA issuer + TMEM owner, warps2-5: epilogue
+constexpr int kBM = 128;
+constexpr int kMaxPhases = 4;
+constexpr int kMaxTaps = 9;
+constexpr int kStatsMaxC = 512;
+
+enum Act : int { ACT_NONE = 0, ACT_LRELU = 1, ACT_PRELU = 2 };
+
+struct ConvParams {
+  CUtensorMap tmA;   // activations: dims (C, W, H, N)
+  CUtensorMap tmB;   // weights: dims (Kpad, rows)
+  // problem
+  int N, Hout, Wout;             // conv output grid (for up-conv phases: the low-res grid)
+  int TW, TH, TN;                // output-grid box per M tile (TW*TH*TN == 128)
+  int tilesX, tilesY, tilesN;    // ceil-div tile counts
+  int numPhases, numNTiles;
+  int stride;                    // 1 or 2 (input coordinate = output coordinate * stride + tap offset)
+  int ntaps;
+  int8_t tap_dy[kMaxPhases][kMaxTaps];
+  int8_t tap_dx[kMaxPhases][kMaxTaps];
+  int CB, nCB, G;                // channel block (<=64), blocks per tap, chunks per 64-wide K stage
+  int BN;                        // output channels per tile (multiple of 16, <= 256)
+  int swizzleA;                  // bytes: 32 / 64 / 128 (= CB*2)
+  int numStages, stageBytes;
+  int wRowsPerSample;            // 0: weights shared by all samples
+  int wRowsPerPhase;
+  // output
+  __half* out;
+  float* out32;                  // if non-null, fp32 output instead of fp16
+  int outH, outW, outC;
+  int oscale;                    // output pixel = grid pixel * oscale + ooff[phase]
+  int8_t ooff_y[kMaxPhases], ooff_x[kMaxPhases];
+  // epilogue
+  const float* bias;             // [Cout] or null
+  const float* cbias;            // [(sample?) x phase x 9 x Cout] border-class bias or null
+  int cbiasPerSample;
+  const float* noise;            // [outH*outW] or null
+  const float* noise_w;          // [Cout]
+  int act;
+  float slope;
+  const float* alpha;            // PReLU [Cout]
+  const __half* resid;           // [N,outH,outW,residC] or null
+  int residC;
+  float* stat_sum;               // [N, Cout] or null (requires TN == 1, numPhases == 1)
+  float* stat_sq;
+  int CoutTotal;
+};
+
+// Host-side op: everything needed to (re)launch one conv.
+struct ConvOp {
+  ConvParams p;
+  int grid;
+  int smemBytes;
+};
+
+// Host-side description == the public C struct (include/cfr_b200.h).
+typedef ::cfr_conv_desc ConvSpec;
+
+int conv_build(const ConvSpec& s, ConvOp* op);
+int conv_launch(const ConvOp& op, cudaStream_t stream);
+void set_error(const char* fmt, ...);
+const char* last_error();
+int num_sms();
+void count_launch(int n = 1);
+unsigned long long launch_count();
+
+}  // namespace cfr

@@ -1,0 +1,466 @@
+// HBM-bound and small kernels of the certification path.  All are coalesced / 128-bit vectorised over the
+// NHWC channel dimension; reductions go registers -> shared -> one global atomic per (block, channel).
+#include "kernels.cuh"
+
+#include <cstdio>
+
+namespace cfr {
+void set_error(const char* fmt, ...);
+void count_launch(int n = 1);
+
+#define CFR_LAUNCH_CHECK(name)                                                   \
+  do {                                                                           \
+    cudaError_t e__ = cudaGetLastError();                                        \
+    if (e__ != cudaSuccess) {                                                    \
+      set_error("%s launch failed: %s", name, cudaGetErrorString(e__));          \
+      return 4;                                                                  \
+    }                                                                            \
+    count_launch();                                                              \
+  } while (0)
+
+// ------------------------------------------------------------------------------------------
+// Philox4x32-10 counter-based RNG (Salmon et al. 2011): counter = (sample index, draw), key = seed.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
+  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(M0, ctr.x), lo0 = M0 * ctr.x;
+    const uint32_t hi1 = __umulhi(M1, ctr.z), lo1 = M1 * ctr.z;
+    ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+    key.x += W0;
+    key.y += W1;
+  }
+  return ctr;
+}
+__device__ __forceinline__ float2 box_muller(uint32_t a, uint32_t b) {
+  const float u1 = (static_cast<float>(a) + 1.0f) * 2.3283064365386963e-10f;   // (0,1]
+  const float u2 = static_cast<float>(b) * 2.3283064365386963e-10f;            // [0,1)
+  const float r = sqrtf(-2.0f * logf(u1));
+  float s, c;
+  sincosf(6.283185307179586f * u2, &s, &c);
+  return make_float2(r * c, r * s);
+}
+
+__global__ void k_noise_project(const float* __restrict__ z, const float* __restrict__ x,
+                                const float* __restrict__ sigma, int sigma_len, const float* __restrict__ noise_in,
+                                const float* __restrict__ dir_mat, const float* __restrict__ w_avg, float psi,
+                                unsigned long long seed, unsigned long long sample_offset, int b,
+                                float* __restrict__ noise_out, float* __restrict__ wp2) {
+  const int s = blockIdx.x;
+  __shared__ float p[5];
+  if (threadIdx.x == 0) {
+    float nz[8];
+    if (noise_in != nullptr) {
+      for (int k = 0; k < 5; ++k) nz[k] = noise_in[s * 5 + k];
+    } else {
+      const unsigned long long idx = sample_offset + s;
+      const uint2 key = make_uint2(static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32));
+      for (int d = 0; d < 2; ++d) {
+        const uint4 r = philox4x32_10(make_uint4(static_cast<uint32_t>(idx), static_cast<uint32_t>(idx >> 32), d, 0), key);
+        const float2 g0 = box_muller(r.x, r.y), g1 = box_muller(r.z, r.w);
+        nz[4 * d] = g0.x; nz[4 * d + 1] = g0.y; nz[4 * d + 2] = g1.x; nz[4 * d + 3] = g1.y;
+      }
+      for (int k = 0; k < 5; ++k) nz[k] *= sigma[sigma_len == 1 ? 0 : k];
+    }
+    for (int k = 0; k < 5; ++k) {
+      if (noise_out != nullptr) noise_out[s * 5 + k] = nz[k];
+      p[k] = x[k] + nz[k];
+    }
+  }
+  __syncthreads();
+  for (int d = threadIdx.x; d < 512; d += blockDim.x) {
+    float pert = 0.f;
+#pragma unroll
+    for (int k = 0; k < 5; ++k) pert += p[k] * dir_mat[k * 512 + d];
+    const float w = z[d] + pert;
+    const float wa = w_avg[d];
+    wp2[(static_cast<size_t>(s) * 2 + 0) * 512 + d] = wa + (w - wa) * psi;
+    wp2[(static_cast<size_t>(s) * 2 + 1) * 512 + d] = wa + (w - wa) * 1.0f;
+  }
+}
+
+int launch_noise_project(const float* z, const float* x, const float* sigma, int sigma_len, const float* noise_in,
+                         const float* dir_mat, const float* w_avg, float psi, unsigned long long seed,
+                         unsigned long long sample_offset, int b, float* noise_out, float* wp2, cudaStream_t st) {
+  if (b <= 0) return 0;
+  k_noise_project<<<b, 128, 0, st>>>(z, x, sigma, sigma_len, noise_in, dir_mat, w_avg, psi, seed, sample_offset, b,
+                                     noise_out, wp2);
+  CFR_LAUNCH_CHECK("noise_project");
+  return 0;
+}
+
+__global__ void k_truncate(const float* __restrict__ w, const float* __restrict__ w_avg, float psi, int b,
+                           float* __restrict__ wp2) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= b * 512) return;
+  const int s = i / 512, d = i % 512;
+  const float wa = w_avg[d], v = w[i];
+  wp2[(static_cast<size_t>(s) * 2 + 0) * 512 + d] = wa + (v - wa) * psi;
+  wp2[(static_cast<size_t>(s) * 2 + 1) * 512 + d] = wa + (v - wa) * 1.0f;
+}
+int launch_truncate(const float* w, const float* w_avg, float psi, int b, float* wp2, cudaStream_t st) {
+  if (b <= 0) return 0;
+  k_truncate<<<(b * 512 + 255) / 256, 256, 0, st>>>(w, w_avg, psi, b, wp2);
+  CFR_LAUNCH_CHECK("truncate");
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// styles[b][row] = <wp2[b][variant(row)], W[row]> / sqrt(512) + bias[row];  one warp per row.
+// ------------------------------------------------------------------------------------------
+__global__ void k_styles(const float* __restrict__ wp2, const float* __restrict__ w_style,
+                         const float* __restrict__ b_style, int rows, int rows_trunc, int b,
+                         float* __restrict__ styles) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  float4 wr[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) wr[k] = __ldg(reinterpret_cast<const float4*>(w_style + static_cast<size_t>(row) * 512) + k * 32 + lane);
+  const int variant = row < rows_trunc ? 0 : 1;
+  const float bias = b_style[row];
+  for (int s = 0; s < b; ++s) {
+    const float4* wp = reinterpret_cast<const float4*>(wp2 + (static_cast<size_t>(s) * 2 + variant) * 512);
+    float acc = 0.f;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float4 v = __ldg(wp + k * 32 + lane);
+      acc += v.x * wr[k].x + v.y * wr[k].y + v.z * wr[k].z + v.w * wr[k].w;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) styles[static_cast<size_t>(s) * rows + row] = acc * 0.044194173824159216f + bias;
+  }
+}
+int launch_styles(const float* wp2, const float* w_style, const float* b_style, int rows, int rows_trunc, int b,
+                  float* styles, cudaStream_t st) {
+  k_styles<<<(rows + 7) / 8, 256, 0, st>>>(wp2, w_style, b_style, rows, rows_trunc, b, styles);
+  CFR_LAUNCH_CHECK("styles");
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+__global__ void k_layer0(const float* __restrict__ xhat0, const float* __restrict__ styles, int style_stride,
+                         int style_off, int b, __half* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;   // over b*16*512
+  if (i >= b * 16 * 512) return;
+  const int c = i % 512, pix = (i / 512) % 16, s = i / (512 * 16);
+  const float s0 = styles[static_cast<size_t>(s) * style_stride + style_off + c];
+  const float s1 = styles[static_cast<size_t>(s) * style_stride + style_off + 512 + c];
+  out[i] = __float2half_rn(xhat0[pix * 512 + c] * (s0 + 1.f) + s1);
+}
+int launch_layer0(const float* xhat0, const float* styles, int style_stride, int style_off, int b, __half* out,
+                  cudaStream_t st) {
+  k_layer0<<<(b * 16 * 512 + 255) / 256, 256, 0, st>>>(xhat0, styles, style_stride, style_off, b, out);
+  CFR_LAUNCH_CHECK("layer0");
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// blur [1,2,1]x[1,2,1]/16 (zero pad) + noise*w + bias + lrelu(0.2) + per-(n,c) sum / sumsq
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void load8(const __half* p, float (&f)[8]) {
+  const uint4 r = __ldg(reinterpret_cast<const uint4*>(p));
+  const __half2* h2 = reinterpret_cast<const __half2*>(&r);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 t = __half22float2(h2[i]);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
+__device__ __forceinline__ void store8(__half* p, const float (&f)[8]) {
+  uint4 o;
+  __half2* h2 = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) h2[i] = __floats2half2_rn(f[2 * i], f[2 * i + 1]);
+  *reinterpret_cast<uint4*>(p) = o;
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(256) k_blur_act_stats(const __half* __restrict__ raw, __half* __restrict__ y, int h,
+                                                        int w, int c, const float* __restrict__ noise,
+                                                        const float* __restrict__ noise_w,
+                                                        const float* __restrict__ bias, float* __restrict__ gsum,
+                                                        float* __restrict__ gsq) {
+  __shared__ float s_sum[512], s_sq[512];
+  const int n = blockIdx.y;
+  const int c8 = c >> 3;
+  const int ppb = 256 / c8;                 // pixels per block step (c8 <= 64)
+  const int cg = threadIdx.x % c8, pl = threadIdx.x / c8;
+  const int ch = cg * 8;
+  for (int i = threadIdx.x; i < c; i += 256) {
+    s_sum[i] = 0.f;
+    s_sq[i] = 0.f;
+  }
+  __syncthreads();
+  float nw[8], bs[8], acc[8], acc2[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    nw[i] = MODE == 0 ? noise_w[ch + i] : 0.f;
+    bs[i] = MODE == 0 ? bias[ch + i] : 0.f;
+    acc[i] = 0.f;
+    acc2[i] = 0.f;
+  }
+  const int hw = h * w;
+  const __half* img = raw + static_cast<size_t>(n) * hw * c;
+  if (pl < ppb) {
+    for (int pix = blockIdx.x * ppb + pl; pix < hw; pix += gridDim.x * ppb) {
+      float v[8];
+      if (MODE == 0) {
+        const int py = pix / w, px = pix - py * w;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = 0.f;
+#pragma unroll
+        for (int dy = -1; dy <= 1; ++dy) {
+          const int yy = py + dy;
+          if (yy < 0 || yy >= h) continue;
+#pragma unroll
+          for (int dx = -1; dx <= 1; ++dx) {
+            const int xx = px + dx;
+            if (xx < 0 || xx >= w) continue;
+            const float k = (dy == 0 ? 2.f : 1.f) * (dx == 0 ? 2.f : 1.f) * 0.0625f;
+            float t[8];
+            load8(img + (static_cast<size_t>(yy) * w + xx) * c + ch, t);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] += k * t[i];
+          }
+        }
+        const float nz = __ldg(&noise[pix]);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          float t = v[i] + nz * nw[i] + bs[i];
+          v[i] = t >= 0.f ? t : 0.2f * t;
+        }
+        store8(y + (static_cast<size_t>(n) * hw + pix) * c + ch, v);
+      } else {
+        load8(img + static_cast<size_t>(pix) * c + ch, v);
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        acc[i] += v[i];
+        acc2[i] += v[i] * v[i];
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      atomicAdd(&s_sum[ch + i], acc[i]);
+      atomicAdd(&s_sq[ch + i], acc2[i]);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < c; i += 256) {
+    atomicAdd(&gsum[n * c + i], s_sum[i]);
+    atomicAdd(&gsq[n * c + i], s_sq[i]);
+  }
+}
+int launch_blur_act_stats(const __half* raw, __half* y, int n, int h, int w, int c, const float* noise,
+                          const float* noise_w, const float* bias, float* sum, float* sq, int mode, cudaStream_t st) {
+  if (c % 8 != 0 || c > 512) { set_error("blur_act_stats: C=%d unsupported", c); return 2; }
+  const int ppb = 256 / (c / 8);
+  int bx = (h * w + ppb - 1) / ppb;
+  const int cap = 16 * 148 / (n > 0 ? n : 1) + 1;       // ~16 blocks per SM in total
+  if (bx > cap) bx = cap;
+  if (bx < 1) bx = 1;
+  dim3 grid(bx, n);
+  if (mode == 0)
+    k_blur_act_stats<0><<<grid, 256, 0, st>>>(raw, y, h, w, c, noise, noise_w, bias, sum, sq);
+  else
+    k_blur_act_stats<1><<<grid, 256, 0, st>>>(raw, y, h, w, c, noise, noise_w, bias, sum, sq);
+  CFR_LAUNCH_CHECK("blur_act_stats");
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+__global__ void k_finalize_stats(const float* __restrict__ sum, const float* __restrict__ sq,
+                                 const float* __restrict__ styles, int style_stride, int style_off, int n, int c,
+                                 float inv_count, float* __restrict__ A, float* __restrict__ B) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * c) return;
+  const int s = i / c, ch = i - s * c;
+  const float mean = sum[i] * inv_count;
+  float var = sq[i] * inv_count - mean * mean;
+  var = var > 0.f ? var : 0.f;
+  const float rstd = 1.0f / sqrtf(var + 1e-8f);
+  const float s0 = styles[static_cast<size_t>(s) * style_stride + style_off + ch];
+  const float s1 = styles[static_cast<size_t>(s) * style_stride + style_off + c + ch];
+  const float a = rstd * (s0 + 1.f);
+  A[i] = a;
+  B[i] = s1 - mean * a;
+}
+int launch_finalize_stats(const float* sum, const float* sq, const float* styles, int style_stride, int style_off,
+                          int n, int c, float inv_count, float* A, float* B, cudaStream_t st) {
+  k_finalize_stats<<<(n * c + 255) / 256, 256, 0, st>>>(sum, sq, styles, style_stride, style_off, n, c, inv_count, A, B);
+  CFR_LAUNCH_CHECK("finalize_stats");
+  return 0;
+}
+
+__global__ void k_affine(const __half* __restrict__ y, const float* __restrict__ A, const float* __restrict__ B,
+                         size_t total8, int hw, int c, __half* __restrict__ x) {
+  const int c8 = c >> 3;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total8;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int cg = static_cast<int>(i % c8);
+    const size_t pix = i / c8;
+    const int n = static_cast<int>(pix / hw);
+    float v[8];
+    load8(y + i * 8, v);
+    const float4* a4 = reinterpret_cast<const float4*>(A + static_cast<size_t>(n) * c + cg * 8);
+    const float4* b4 = reinterpret_cast<const float4*>(B + static_cast<size_t>(n) * c + cg * 8);
+    const float4 a0 = __ldg(a4), a1 = __ldg(a4 + 1), b0 = __ldg(b4), b1 = __ldg(b4 + 1);
+    v[0] = v[0] * a0.x + b0.x; v[1] = v[1] * a0.y + b0.y; v[2] = v[2] * a0.z + b0.z; v[3] = v[3] * a0.w + b0.w;
+    v[4] = v[4] * a1.x + b1.x; v[5] = v[5] * a1.y + b1.y; v[6] = v[6] * a1.z + b1.z; v[7] = v[7] * a1.w + b1.w;
+    store8(x + i * 8, v);
+  }
+}
+int launch_affine(const __half* y, const float* A, const float* B, int n, int hw, int c, __half* x, cudaStream_t st) {
+  const size_t total8 = static_cast<size_t>(n) * hw * c / 8;
+  size_t blocks = (total8 + 255) / 256;
+  if (blocks > 148 * 32) blocks = 148 * 32;
+  k_affine<<<static_cast<unsigned>(blocks), 256, 0, st>>>(y, A, B, total8, hw, c, x);
+  CFR_LAUNCH_CHECK("affine");
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// toRGB (1x1, C->3) + postprocess + bilinear (align_corners=False, no antialias) + normalise.
+// Only the 4 source pixels each output pixel needs are read: 4 x C fp16 per output pixel.
+// ------------------------------------------------------------------------------------------
+__global__ void k_torgb_resize(const __half* __restrict__ x, const float* __restrict__ A, const float* __restrict__ B,
+                               int n, int hin, int c, const float* __restrict__ w_rgb, const float* __restrict__ b_rgb,
+                               int rout, float mean, float stdv, __half* __restrict__ out,
+                               float* __restrict__ out_planar) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * rout * rout) return;
+  const int ox = i % rout, oy = (i / rout) % rout, s = i / (rout * rout);
+  const float scale = static_cast<float>(hin) / static_cast<float>(rout);
+  float sy = scale * (oy + 0.5f) - 0.5f;
+  float sx = scale * (ox + 0.5f) - 0.5f;
+  sy = sy < 0.f ? 0.f : sy;
+  sx = sx < 0.f ? 0.f : sx;
+  const int y0 = static_cast<int>(sy), x0 = static_cast<int>(sx);
+  const int y1 = y0 + (y0 < hin - 1 ? 1 : 0), x1 = x0 + (x0 < hin - 1 ? 1 : 0);
+  const float ly1 = sy - y0, lx1 = sx - x0, ly0 = 1.f - ly1, lx0 = 1.f - lx1;
+  const int ys[2] = {y0, y1}, xs[2] = {x0, x1};
+  float px[2][2][3];
+#pragma unroll
+  for (int a = 0; a < 2; ++a) {
+#pragma unroll
+    for (int bq = 0; bq < 2; ++bq) {
+      float r = 0.f, g = 0.f, bl = 0.f;
+      const __half* src = x + ((static_cast<size_t>(s) * hin + ys[a]) * hin + xs[bq]) * c;
+      for (int cc = 0; cc < c; cc += 8) {
+        float v[8];
+        load8(src + cc, v);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          float t = v[k];
+          if (A != nullptr) t = t * A[s * c + cc + k] + B[s * c + cc + k];
+          r += w_rgb[cc + k] * t;
+          g += w_rgb[c + cc + k] * t;
+          bl += w_rgb[2 * c + cc + k] * t;
+        }
+      }
+      const float rgb[3] = {r + b_rgb[0], g + b_rgb[1], bl + b_rgb[2]};
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        float t = (rgb[k] + 1.0f) / 2.0f + 0.5f / 255.f;
+        px[a][bq][k] = fminf(fmaxf(t, 0.f), 1.f);
+      }
+    }
+  }
+  float res[3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const float v = ly0 * (lx0 * px[0][0][k] + lx1 * px[0][1][k]) + ly1 * (lx0 * px[1][0][k] + lx1 * px[1][1][k]);
+    res[k] = (v - mean) / stdv;
+  }
+  if (out != nullptr) {
+    float o[8] = {res[0], res[1], res[2], 0.f, 0.f, 0.f, 0.f, 0.f};
+    const float zz[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    store8(out + static_cast<size_t>(i) * 16, o);
+    store8(out + static_cast<size_t>(i) * 16 + 8, zz);
+  }
+  if (out_planar != nullptr) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) out_planar[((static_cast<size_t>(s) * 3 + k) * rout + oy) * rout + ox] = res[k];
+  }
+}
+int launch_torgb_resize(const __half* x, const float* A, const float* B, int n, int hin, int c, const float* w_rgb,
+                        const float* b_rgb, int rout, float mean, float stdv, __half* out, float* out_planar,
+                        cudaStream_t st) {
+  const int total = n * rout * rout;
+  k_torgb_resize<<<(total + 127) / 128, 128, 0, st>>>(x, A, B, n, hin, c, w_rgb, b_rgb, rout, mean, stdv, out, out_planar);
+  CFR_LAUNCH_CHECK("torgb_resize");
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// gallery match: key = (float bits of squared distance) << 32 | row  ->  atomicMin == argmin with
+// first-index tie-break (torch.argmax semantics on softmax(-d)).
+// ------------------------------------------------------------------------------------------
+constexpr int kMatchEmb = 8;      // embeddings per block
+constexpr int kMatchRows = 64;    // gallery rows per block
+
+__global__ void __launch_bounds__(256) k_match(const float* __restrict__ emb, int b, const float* __restrict__ gallery,
+                                               int n, unsigned long long* __restrict__ keys) {
+  __shared__ float4 s_emb[kMatchEmb][128];
+  const int e0 = blockIdx.y * kMatchEmb;
+  for (int i = threadIdx.x; i < kMatchEmb * 128; i += 256) {
+    const int e = i / 128, k = i % 128;
+    s_emb[e][k] = (e0 + e < b) ? reinterpret_cast<const float4*>(emb + static_cast<size_t>(e0 + e) * 512)[k]
+                               : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  unsigned long long best[kMatchEmb];
+#pragma unroll
+  for (int e = 0; e < kMatchEmb; ++e) best[e] = ~0ull;
+  const int r_end = min(n, (blockIdx.x + 1) * kMatchRows);
+  for (int r = blockIdx.x * kMatchRows + warp; r < r_end; r += 8) {
+    float4 g[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) g[k] = __ldg(reinterpret_cast<const float4*>(gallery + static_cast<size_t>(r) * 512) + k * 32 + lane);
+#pragma unroll
+    for (int e = 0; e < kMatchEmb; ++e) {
+      float acc = 0.f;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float4 v = s_emb[e][k * 32 + lane];
+        const float dx = v.x - g[k].x, dy = v.y - g[k].y, dz = v.z - g[k].z, dw = v.w - g[k].w;
+        acc += dx * dx + dy * dy + dz * dz + dw * dw;
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+      const unsigned long long key = (static_cast<unsigned long long>(__float_as_uint(acc)) << 32) | static_cast<unsigned>(r);
+      best[e] = key < best[e] ? key : best[e];
+    }
+  }
+  if (lane == 0) {
+#pragma unroll
+    for (int e = 0; e < kMatchEmb; ++e)
+      if (e0 + e < b && best[e] != ~0ull) atomicMin(&keys[e0 + e], best[e]);
+  }
+}
+__global__ void k_vote(unsigned long long* __restrict__ keys, int b, int* __restrict__ pred,
+                       unsigned long long* __restrict__ counts) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= b) return;
+  const int pr = static_cast<int>(keys[i] & 0xffffffffull);
+  keys[i] = ~0ull;                 // re-arm for the next batch
+  if (pred != nullptr) pred[i] = pr;
+  if (counts != nullptr) atomicAdd(&counts[pr], 1ull);
+}
+int launch_match_vote(const float* emb, int b, const float* gallery, int n, unsigned long long* keys, int* pred,
+                      long long* counts, cudaStream_t st) {
+  if (b <= 0) return 0;
+  dim3 grid((n + kMatchRows - 1) / kMatchRows, (b + kMatchEmb - 1) / kMatchEmb);
+  k_match<<<grid, 256, 0, st>>>(emb, b, gallery, n, keys);
+  CFR_LAUNCH_CHECK("match");
+  k_vote<<<(b + 127) / 128, 128, 0, st>>>(keys, b, pred, reinterpret_cast<unsigned long long*>(counts));
+  CFR_LAUNCH_CHECK("vote");
+  return 0;
+}
+
+}  // namespace cfr

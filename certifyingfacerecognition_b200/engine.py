@@ -1,0 +1,444 @@
+"""Host side of the B200 certification engine: packs the reference's weights into the layouts the CUDA
+kernels consume and records the kernel programs (one for StyleGAN synthesis + resize, one for ArcFace).
+
+PyTorch is used for device memory and one-time host-side weight folding only; every launch on the hot
+path is one of our own kernels behind the C ABI (``include/cfr_b200.h``).
+
+Weight dicts use the reference's ``state_dict()`` names:
+  * StyleGAN  -- models/stylegan_generator_model.py
+  * iresnet50 -- models/iresnet.py
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Dict, List, Optional, Tuple
+
+import torch
+
+from . import _lib as L
+
+Tensor = torch.Tensor
+NUM_LAYERS = 18
+PSI, TRUNC_LAYERS = 0.7, 8          # models/model_settings.py:65-66
+
+
+def layer_channels(layer: int) -> int:
+    table = [512, 512, 512, 512, 512, 256, 128, 64, 32, 16]      # stylegan_generator_model.py:23-32
+    return table[layer // 2 + 1] if layer >= 2 else 512
+
+
+def layer_res(layer: int) -> int:
+    return 2 ** (layer // 2 + 2)
+
+
+def tile_for(res: int, n: int = 1 << 30) -> Tuple[int, int, int]:
+    """(TW, TH, TN) box of 128 output-grid pixels per M tile: the power-of-two box wasting the fewest rows on a
+    res x res grid of n images (ties: widest box, i.e. longest contiguous TMA rows)."""
+    best, best_key = None, None
+    for lw in range(8):
+        for lh in range(8 - lw):
+            tw, th = 1 << lw, 1 << lh
+            tn = 128 // (tw * th)
+            if tw > 16 and tw > res:
+                continue
+            cover = (-(-res // tw) * tw) * (-(-res // th) * th) * (-(-n // tn) * tn if n < (1 << 30) else tn)
+            useful = res * res * (n if n < (1 << 30) else tn)
+            key = (useful / cover, tw, th)
+            if best_key is None or key > best_key:
+                best, best_key = (tw, th, tn), key
+    return best
+
+
+def _f16(t: Tensor, dev) -> Tensor:
+    return t.to(device=dev, dtype=torch.float16).contiguous()
+
+
+def _f32(t: Tensor, dev) -> Tensor:
+    return t.to(device=dev, dtype=torch.float32).contiguous()
+
+
+def pack_conv_weight(w: Tensor, cin_pad: Optional[int] = None) -> Tensor:
+    """[Cout,Cin,kh,kw] fp32 -> [Cout, Kpad] with K = (tap=(ky,kx), cin), zero-padded to a multiple of 64."""
+    cout, cin, kh, kw = w.shape
+    cin_pad = cin_pad or cin
+    m = torch.zeros(cout, kh * kw, cin_pad, dtype=torch.float32)
+    m[:, :, :cin] = w.permute(0, 2, 3, 1).reshape(cout, kh * kw, cin)
+    m = m.reshape(cout, kh * kw * cin_pad)
+    kpad = (m.shape[1] + 63) // 64 * 64
+    out = torch.zeros(cout, kpad, dtype=torch.float32)
+    out[:, :m.shape[1]] = m
+    return out
+
+
+TAPS3 = [(dy, dx) for dy in (-1, 0, 1) for dx in (-1, 0, 1)]
+
+# Sub-pixel decomposition of nearest-x2 + 3x3 conv (pad 1): output (2i+a, 2j+b) reads the low-res rows
+# a=0: {i-1: w[0], i: w[1]+w[2]},  a=1: {i: w[0]+w[1], i+1: w[2]}   (same for columns).
+_PHASE_ROWS = {0: [(-1, [0]), (0, [1, 2])], 1: [(0, [0, 1]), (1, [2])]}
+
+
+def upconv_equiv_weight(sd: Dict[str, Tensor], layer: int) -> Tensor:
+    """[Cout,Cin,3,3] (wscale applied) such that UpConvBlock == conv2d(nearest_x2(x), W, pad=1) before the blur.
+    Fused layers (res >= 128, stylegan_generator_model.py:667-672) store [kh,kw,Cin,Cout] and are a
+    conv_transpose of the box-summed kernel == the spatially flipped 3x3 conv on the upsampled grid."""
+    p = f"synthesis.layer{layer}."
+    if layer_res(layer) >= 128:
+        w = sd[p + "weight"].float()
+        scale = math.sqrt(2.0) / math.sqrt(w.shape[2] * 9)
+        return torch.flip(w, dims=[0, 1]).permute(3, 2, 0, 1).contiguous() * scale
+    w = sd[p + "conv.weight"].float()
+    return w * (math.sqrt(2.0) / math.sqrt(w.shape[1] * 9))
+
+
+def pack_upconv_phases(weq: Tensor) -> Tuple[Tensor, List[List[Tuple[int, int]]]]:
+    """-> ([4*Cout, Kpad] rows = (phase, cout), K = (tap, cin)), taps[phase] = [(dy,dx) x4])."""
+    cout, cin = weq.shape[:2]
+    mats, taps = [], []
+    for a in (0, 1):
+        for b in (0, 1):
+            cols, tp = [], []
+            for dy, rs in _PHASE_ROWS[a]:
+                for dx, cs in _PHASE_ROWS[b]:
+                    cols.append(sum(weq[:, :, i, j] for i in rs for j in cs))     # [Cout,Cin]
+                    tp.append((dy, dx))
+            mats.append(torch.stack(cols, dim=1).reshape(cout, 4 * cin))
+            taps.append(tp)
+    m = torch.cat(mats, dim=0)
+    kpad = (m.shape[1] + 63) // 64 * 64
+    out = torch.zeros(m.shape[0], kpad)
+    out[:, :m.shape[1]] = m
+    return out, taps
+
+
+class Program:
+    """Owns a cfr_program handle plus every tensor its launches reference."""
+
+    def __init__(self):
+        self.lib = L.load()
+        h = C.c_void_p()
+        L.check(self.lib.cfr_program_create(C.byref(h)))
+        self.handle = h
+        self.keep: List[Tensor] = []
+
+    def hold(self, t: Tensor) -> Tensor:
+        self.keep.append(t)
+        return t
+
+    def run(self, stream: Optional[int] = None) -> None:
+        if stream is None:
+            stream = torch.cuda.current_stream().cuda_stream
+        L.check(self.lib.cfr_program_run(self.handle, C.c_void_p(stream)))
+
+    @property
+    def num_launches(self) -> int:
+        return self.lib.cfr_program_num_launches(self.handle)
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None):
+                self.lib.cfr_program_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+    # ---- op recorders --------------------------------------------------------------------------
+    def conv(self, *, inp: Tensor, n: int, hin: int, win: int, cin: int, w: Tensor, cout: int, hout: int, wout: int,
+             tile: Tuple[int, int, int], out: Tensor, out_hwc: Tuple[int, int, int], taps, stride: int = 1,
+             oscale: int = 1, ooff=((0, 0),), w_rows_per_sample: int = 0, w_rows_per_phase: int = 0,
+             bias: Optional[Tensor] = None, cbias: Optional[Tensor] = None, cbias_per_sample: bool = False,
+             noise: Optional[Tensor] = None, noise_w: Optional[Tensor] = None, act: int = L.ACT_NONE,
+             slope: float = 0.2, alpha: Optional[Tensor] = None, resid: Optional[Tensor] = None, resid_c: int = 0,
+             stat_sum: Optional[Tensor] = None, stat_sq: Optional[Tensor] = None) -> None:
+        d = L.ConvDesc()
+        d.inp, d.N, d.Hin, d.Win, d.Cin = L.ptr(inp), n, hin, win, cin
+        d.w, d.wRows, d.Kpad = L.ptr(w), w.shape[0], w.shape[1]
+        d.Cout, d.Hout, d.Wout = cout, hout, wout
+        d.TW, d.TH, d.TN = tile
+        d.stride, d.numPhases = stride, len(taps)
+        d.ntaps = len(taps[0])
+        for ph, tp in enumerate(taps):
+            assert len(tp) == d.ntaps
+            for k, (dy, dx) in enumerate(tp):
+                d.tap_dy[ph][k] = dy
+                d.tap_dx[ph][k] = dx
+        d.wRowsPerSample, d.wRowsPerPhase = w_rows_per_sample, w_rows_per_phase
+        d.out, d.outIsF32 = L.ptr(out), int(out.dtype == torch.float32)
+        d.outH, d.outW, d.outC = out_hwc
+        d.oscale = oscale
+        for ph, (oy, ox) in enumerate(ooff):
+            d.ooff_y[ph] = oy
+            d.ooff_x[ph] = ox
+        d.bias, d.cbias, d.cbiasPerSample = L.ptr(bias), L.ptr(cbias), int(cbias_per_sample)
+        d.noise, d.noise_w = L.ptr(noise), L.ptr(noise_w)
+        d.act, d.slope, d.alpha = act, slope, L.ptr(alpha)
+        d.resid, d.residC = L.ptr(resid), resid_c
+        d.stat_sum, d.stat_sq = L.ptr(stat_sum), L.ptr(stat_sq)
+        for t in (inp, w, out, bias, cbias, noise, noise_w, alpha, resid, stat_sum, stat_sq):
+            if t is not None:
+                self.keep.append(t)
+        L.check(self.lib.cfr_program_add_conv(self.handle, C.byref(d)))
+
+    def memset(self, t: Tensor, value: int = 0) -> None:
+        self.keep.append(t)
+        L.check(self.lib.cfr_program_add_memset(self.handle, L.ptr(t), value, t.numel() * t.element_size()))
+
+
+# ------------------------------------------------------------------------------------------------------
+# StyleGAN-FFHQ-1024 synthesis + toRGB + resize  (wp2 [chunk,2,512] -> img [chunk,R,R,16] fp16 NHWC)
+# ------------------------------------------------------------------------------------------------------
+class SynthesisProgram(Program):
+    def __init__(self, g_sd: Dict[str, Tensor], chunk: int, out_res: int = 112, device="cuda",
+                 keep_planar: bool = False, mean: float = 0.5, std: float = 0.5):
+        super().__init__()
+        dev = torch.device(device)
+        self.chunk, self.out_res = chunk, out_res
+        sd = {k: v.detach().float().cpu() for k, v in g_sd.items()}
+        lib, h = self.lib, self.handle
+
+        # ---- inputs / small tensors
+        self.wp2 = self.hold(torch.zeros(chunk, 2, 512, device=dev))
+        self.w_avg = self.hold(_f32(sd["truncation.w_avg"], dev))
+        ws, bs, self.style_off = [], [], []
+        off = 0
+        for l in range(NUM_LAYERS):
+            p = f"synthesis.layer{l}.epilogue.style_mod.dense."
+            ws.append(sd[p + "linear.weight"])
+            bs.append(sd[p + "wscale.bias"])
+            self.style_off.append(off)
+            off += 2 * layer_channels(l)
+        self.style_rows = off
+        rows_trunc = self.style_off[TRUNC_LAYERS]
+        w_style = self.hold(_f32(torch.cat(ws), dev))
+        b_style = self.hold(_f32(torch.cat(bs), dev))
+        self.styles = self.hold(torch.zeros(chunk, off, device=dev))
+        L.check(lib.cfr_program_add_styles(h, L.ptr(self.wp2), L.ptr(w_style), L.ptr(b_style), off, rows_trunc,
+                                           chunk, L.ptr(self.styles)))
+
+        # ---- statistics / affine buffers, zeroed at the start of every run
+        total_c = sum(layer_channels(l) for l in range(NUM_LAYERS))
+        self.stats = self.hold(torch.zeros(2, chunk * total_c, device=dev))
+        self.memset(self.stats)
+        self.A = self.hold(torch.zeros(chunk * 512, device=dev))
+        self.B = self.hold(torch.zeros(chunk * 512, device=dev))
+
+        # ---- activation buffers (NHWC fp16), sized for the largest layer
+        max_elems = chunk * 1024 * 1024 * 16
+        bufs = [self.hold(torch.empty(max_elems, dtype=torch.float16, device=dev)) for _ in range(3)]
+        x, y, raw = bufs
+
+        # ---- layer 0: sample-independent normalised const (FirstConvBlock :581-584 + epilogue :559-564)
+        p0 = "synthesis.layer0.epilogue."
+        c0 = sd["synthesis.layer0.first_layer"][0]                                   # [512,4,4]
+        t = c0 + sd[p0 + "apply_noise.noise"][0] * sd[p0 + "apply_noise.weight"].view(-1, 1, 1) \
+            + sd[p0 + "bias"].view(-1, 1, 1)
+        t = torch.nn.functional.leaky_relu(t, 0.2)
+        t = t - t.mean(dim=[1, 2], keepdim=True)
+        t = t / torch.sqrt((t * t).mean(dim=[1, 2], keepdim=True) + 1e-8)
+        xhat0 = self.hold(_f32(t.permute(1, 2, 0).reshape(16, 512), dev))
+        L.check(lib.cfr_program_add_layer0(h, L.ptr(xhat0), L.ptr(self.styles), off, self.style_off[0], chunk, L.ptr(x)))
+
+        stat_off = chunk * 512          # layer 0 uses no statistics slot
+        for l in range(1, NUM_LAYERS):
+            cin, cout, res = layer_channels(l - 1), layer_channels(l), layer_res(l)
+            pe = f"synthesis.layer{l}.epilogue."
+            noise = self.hold(_f32(sd[pe + "apply_noise.noise"].reshape(-1), dev))
+            noise_w = self.hold(_f32(sd[pe + "apply_noise.weight"], dev))
+            bias = self.hold(_f32(sd[pe + "bias"], dev))
+            ssum = self.stats[0, stat_off:stat_off + chunk * cout]
+            ssq = self.stats[1, stat_off:stat_off + chunk * cout]
+            stat_off += chunk * cout
+            if l % 2 == 1:
+                w = sd[f"synthesis.layer{l}.conv.weight"]
+                wp = self.hold(_f16(pack_conv_weight(w * (math.sqrt(2.0) / math.sqrt(cin * 9))), dev))
+                fused_stats = res >= 16
+                self.conv(inp=x, n=chunk, hin=res, win=res, cin=cin, w=wp, cout=cout, hout=res, wout=res,
+                          tile=tile_for(res), out=y, out_hwc=(res, res, cout), taps=[TAPS3], noise=noise,
+                          noise_w=noise_w, bias=bias, act=L.ACT_LRELU, slope=0.2,
+                          stat_sum=ssum if fused_stats else None, stat_sq=ssq if fused_stats else None)
+                if not fused_stats:
+                    L.check(lib.cfr_program_add_blur_act_stats(h, L.ptr(y), None, chunk, res, res, cout, None, None,
+                                                               None, L.ptr(ssum), L.ptr(ssq), 1))
+            else:
+                lo = res // 2
+                wp, taps = pack_upconv_phases(upconv_equiv_weight(sd, l))
+                wp = self.hold(_f16(wp, dev))
+                self.conv(inp=x, n=chunk, hin=lo, win=lo, cin=cin, w=wp, cout=cout, hout=lo, wout=lo,
+                          tile=tile_for(lo), out=raw, out_hwc=(res, res, cout), taps=taps, oscale=2,
+                          ooff=[(0, 0), (0, 1), (1, 0), (1, 1)], w_rows_per_phase=cout)
+                L.check(lib.cfr_program_add_blur_act_stats(h, L.ptr(raw), L.ptr(y), chunk, res, res, cout, L.ptr(noise),
+                                                           L.ptr(noise_w), L.ptr(bias), L.ptr(ssum), L.ptr(ssq), 0))
+            L.check(lib.cfr_program_add_finalize_stats(h, L.ptr(ssum), L.ptr(ssq), L.ptr(self.styles), off,
+                                                       self.style_off[l], chunk, cout, 1.0 / (res * res),
+                                                       L.ptr(self.A), L.ptr(self.B)))
+            if l < NUM_LAYERS - 1:
+                L.check(lib.cfr_program_add_affine(h, L.ptr(y), L.ptr(self.A), L.ptr(self.B), chunk, res * res, cout,
+                                                   L.ptr(y)))
+                x, y = y, x
+        # ---- toRGB + postprocess + bilinear + normalise; the last layer's IN/AdaIN is applied on load
+        wrgb = sd["synthesis.output8.conv.weight"].reshape(3, 16) * (1.0 / math.sqrt(16))
+        w_rgb = self.hold(_f32(wrgb, dev))
+        b_rgb = self.hold(_f32(sd["synthesis.output8.bias"], dev))
+        self.img = self.hold(torch.zeros(chunk, out_res, out_res, 16, dtype=torch.float16, device=dev))
+        self.img_planar = self.hold(torch.zeros(chunk, 3, out_res, out_res, device=dev)) if keep_planar else None
+        L.check(lib.cfr_program_add_torgb_resize(h, L.ptr(y), L.ptr(self.A), L.ptr(self.B), chunk, 1024, 16,
+                                                 L.ptr(w_rgb), L.ptr(b_rgb), out_res, mean, std, L.ptr(self.img),
+                                                 L.ptr(self.img_planar)))
+        self.last_y = y
+
+
+# ------------------------------------------------------------------------------------------------------
+# ArcFace iresnet50  (img [chunk,112,112,16] fp16 -> emb [chunk,512] fp32)
+# ------------------------------------------------------------------------------------------------------
+def _bn_affine(sd, p, eps=1e-5):
+    s = sd[p + ".weight"] / torch.sqrt(sd[p + ".running_var"] + eps)
+    return s, sd[p + ".bias"] - sd[p + ".running_mean"] * s
+
+
+class ArcFaceProgram(Program):
+    LAYERS = (3, 4, 14, 3)
+    PLANES = (64, 128, 256, 512)
+
+    def __init__(self, f_sd: Dict[str, Tensor], chunk: int, img: Tensor, device="cuda"):
+        super().__init__()
+        dev = torch.device(device)
+        sd = {k: v.detach().float().cpu() for k, v in f_sd.items()}
+        self.chunk = chunk
+        n = chunk
+        max_elems = n * 112 * 112 * 64
+        xs = self.hold(torch.empty(max_elems, dtype=torch.float16, device=dev))     # residual stream
+        xs2 = self.hold(torch.empty(max_elems, dtype=torch.float16, device=dev))
+        hbuf = self.hold(torch.empty(max_elems, dtype=torch.float16, device=dev))    # conv1 output
+        idb = self.hold(torch.empty(max_elems // 4, dtype=torch.float16, device=dev))  # downsample output
+
+        # stem: conv1 3->64 + bn1 + prelu (iresnet.py:142-144); input channels padded 3 -> 16
+        s, t = _bn_affine(sd, "bn1")
+        w = pack_conv_weight(sd["conv1.weight"] * s.view(-1, 1, 1, 1), cin_pad=16)
+        self.conv(inp=img, n=n, hin=112, win=112, cin=16, w=self.hold(_f16(w, dev)), cout=64, hout=112, wout=112,
+                  tile=tile_for(112), out=xs, out_hwc=(112, 112, 64), taps=[TAPS3], bias=self.hold(_f32(t, dev)),
+                  act=L.ACT_PRELU, alpha=self.hold(_f32(sd["prelu.weight"], dev)))
+        res, inplanes = 112, 64
+        for li, (nblocks, planes) in enumerate(zip(self.LAYERS, self.PLANES), start=1):
+            for bi in range(nblocks):
+                p = f"layer{li}.{bi}."
+                stride = 2 if bi == 0 else 1
+                ores = res // stride
+                s1, t1 = _bn_affine(sd, p + "bn1")
+                s2, t2 = _bn_affine(sd, p + "bn2")
+                s3, t3 = _bn_affine(sd, p + "bn3")
+                # conv1: bn1 (pre, scale folded into input channels; shift -> border-class bias), bn2 (post), PReLU
+                w1 = sd[p + "conv1.weight"] * s2.view(-1, 1, 1, 1)
+                tb = torch.einsum("oikl,i->okl", w1, t1).reshape(planes, 9)              # per-tap shift term
+                cb = torch.zeros(9, planes)
+                for rc in range(3):
+                    for cc in range(3):
+                        valid = [k for k, (dy, dx) in enumerate(TAPS3)
+                                 if not (rc == 0 and dy < 0) and not (rc == 2 and dy > 0)
+                                 and not (cc == 0 and dx < 0) and not (cc == 2 and dx > 0)]
+                        cb[rc * 3 + cc] = tb[:, valid].sum(dim=1)
+                w1p = pack_conv_weight(w1 * s1.view(1, -1, 1, 1))
+                self.conv(inp=xs, n=n, hin=res, win=res, cin=inplanes, w=self.hold(_f16(w1p, dev)), cout=planes,
+                          hout=res, wout=res, tile=tile_for(res, n), out=hbuf, out_hwc=(res, res, planes), taps=[TAPS3],
+                          bias=self.hold(_f32(t2, dev)), cbias=self.hold(_f32(cb, dev)), act=L.ACT_PRELU,
+                          alpha=self.hold(_f32(sd[p + "prelu.weight"], dev)))
+                identity = xs
+                if bi == 0:
+                    sdn, tdn = _bn_affine(sd, p + "downsample.1")
+                    wd = pack_conv_weight(sd[p + "downsample.0.weight"] * sdn.view(-1, 1, 1, 1))
+                    self.conv(inp=xs, n=n, hin=res, win=res, cin=inplanes, w=self.hold(_f16(wd, dev)), cout=planes,
+                              hout=ores, wout=ores, tile=tile_for(ores, n), out=idb, out_hwc=(ores, ores, planes),
+                              taps=[[(0, 0)]], stride=stride, bias=self.hold(_f32(tdn, dev)))
+                    identity = idb
+                w2p = pack_conv_weight(sd[p + "conv2.weight"] * s3.view(-1, 1, 1, 1))
+                self.conv(inp=hbuf, n=n, hin=res, win=res, cin=planes, w=self.hold(_f16(w2p, dev)), cout=planes,
+                          hout=ores, wout=ores, tile=tile_for(ores, n), out=xs2, out_hwc=(ores, ores, planes),
+                          taps=[TAPS3], stride=stride, bias=self.hold(_f32(t3, dev)), resid=identity, resid_c=planes)
+                xs, xs2 = xs2, xs
+                res, inplanes = ores, planes
+        # bn2 -> flatten (NCHW order, iresnet.py:149-150) -> fc -> features BN1d, all folded into one GEMM
+        sb, tb2 = _bn_affine(sd, "bn2")
+        sf, tf = _bn_affine(sd, "features")
+        wfc = sd["fc.weight"].view(512, 512, 7, 7)
+        bias = (sd["fc.bias"] + torch.einsum("ochw,c->o", wfc, tb2)) * sf + tf
+        wfold = (wfc * sb.view(1, -1, 1, 1) * sf.view(-1, 1, 1, 1)).permute(0, 2, 3, 1).reshape(512, 49 * 512)
+        self.emb = self.hold(torch.zeros(n, 512, device=dev))
+        self.conv(inp=xs, n=n, hin=1, win=1, cin=49 * 512, w=self.hold(_f16(wfold.contiguous(), dev)), cout=512,
+                  hout=1, wout=1, tile=(1, 1, 128), out=self.emb, out_hwc=(1, 1, 512), taps=[[(0, 0)]],
+                  bias=self.hold(_f32(bias, dev)))
+        self.final_features = xs
+
+
+# ------------------------------------------------------------------------------------------------------
+class Engine:
+    """StyleGAN -> resize -> iresnet50 -> gallery vote, for one GPU."""
+
+    def __init__(self, g_sd, f_sd, dir_mat: Tensor, gallery: Tensor, chunk: int = 32, device="cuda",
+                 keep_planar: bool = False):
+        if not torch.cuda.is_available():
+            raise RuntimeError("certifyingfacerecognition_b200 needs a CUDA device (no CPU fallback)")
+        self.lib = L.load()
+        self.device = torch.device(device)
+        self.chunk = chunk
+        self.synth = SynthesisProgram(g_sd, chunk, 112, device, keep_planar=keep_planar)
+        self.frm = ArcFaceProgram(f_sd, chunk, self.synth.img, device)
+        self.dir_mat = _f32(dir_mat, self.device)
+        self.set_gallery(gallery)
+
+    def set_gallery(self, gallery: Tensor) -> None:
+        self.gallery = _f32(gallery, self.device)
+        d = L.SamplerDesc()
+        d.synth, d.frm, d.chunk = self.synth.handle, self.frm.handle, self.chunk
+        d.wp2, d.emb = L.ptr(self.synth.wp2), L.ptr(self.frm.emb)
+        d.dir_mat, d.w_avg, d.psi = L.ptr(self.dir_mat), L.ptr(self.synth.w_avg), PSI
+        d.gallery, d.n_gallery = L.ptr(self.gallery), self.gallery.shape[0]
+        if getattr(self, "sampler", None):
+            self.lib.cfr_sampler_destroy(self.sampler)
+        h = C.c_void_p()
+        L.check(self.lib.cfr_sampler_create(C.byref(d), C.byref(h)))
+        self.sampler = h
+
+    def __del__(self):
+        try:
+            if getattr(self, "sampler", None):
+                self.lib.cfr_sampler_destroy(self.sampler)
+                self.sampler = None
+        except Exception:
+            pass
+
+    @property
+    def num_classes(self) -> int:
+        return self.gallery.shape[0]
+
+    def _stream(self) -> C.c_void_p:
+        return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    def embed_latents(self, w: Tensor) -> Tensor:
+        """lat2embs (gen_utils.py:108-139): [n,512] W latents -> [n,512] embeddings (device, fp32)."""
+        w = _f32(w, self.device)
+        out = torch.empty(w.shape[0], 512, device=self.device)
+        for i in range(0, w.shape[0], self.chunk):
+            b = min(self.chunk, w.shape[0] - i)
+            L.check(self.lib.cfr_truncate(L.ptr(w[i:i + b]), L.ptr(self.synth.w_avg), PSI, b, L.ptr(self.synth.wp2),
+                                          self._stream()))
+            self.synth.run()
+            self.frm.run()
+            out[i:i + b] = self.frm.emb[:b]
+        return out
+
+    def sample_votes(self, z: Tensor, x: Tensor, sigma: Tensor, num: int, seed: int = 0, sample_offset: int = 0,
+                     noise: Optional[Tensor] = None, counts: Optional[Tensor] = None, want_pred: bool = False,
+                     want_emb: bool = False, want_noise: bool = False):
+        """Smooth._sample_noise body (smooth.py:126-137) on device.  Returns (counts int64 [N], extras dict)."""
+        z = _f32(z.reshape(-1), self.device)
+        x = _f32(x.reshape(-1), self.device)
+        sigma = _f32(sigma.reshape(-1), self.device)
+        if counts is None:
+            counts = torch.zeros(self.num_classes, dtype=torch.int64, device=self.device)
+        noise_d = _f32(noise.reshape(-1, 5), self.device) if noise is not None else None
+        pred = torch.empty(num, dtype=torch.int32, device=self.device) if want_pred else None
+        emb = torch.empty(num, 512, device=self.device) if want_emb else None
+        nz = torch.empty(num, 5, device=self.device) if want_noise else None
+        L.check(self.lib.cfr_sample_votes(self.sampler, L.ptr(z), L.ptr(x), L.ptr(sigma), sigma.numel(),
+                                          L.ptr(noise_d), num, seed, sample_offset, L.ptr(counts), L.ptr(pred),
+                                          L.ptr(emb), L.ptr(nz), self._stream()))
+        return counts, {"pred": pred, "emb": emb, "noise": nz}

@@ -1,0 +1,137 @@
+/* C ABI of libcfr_b200.so -- the B200 (sm_100a) implementation of the Monte-Carlo certification hot path of
+ * juancprzs/certifyingFaceRecognition.
+ *
+ * The reference has no FFI: its seam is the duck-typed Python pair Smooth / base_classifier
+ * (smoothing/smooth.py:21-37,135).  The entry points below are what a binding for that path needs; the
+ * reference symbol each one replaces is cited per function.  INTEGRATION.md shows the ctypes stub.
+ *
+ * Conventions: plain C, every pointer is a DEVICE pointer owned by the caller unless the name ends in
+ * `_host`; every call enqueues on the given cudaStream_t and returns 0 on success (non-zero: see
+ * cfr_last_error()).  No hidden host synchronisation except in the *_host entry points.
+ * Activations are NHWC fp16, accumulation fp32.
+ */
+#ifndef CFR_B200_H
+#define CFR_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define CFR_API __attribute__((visibility("default")))
+#else
+#define CFR_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CUstream_st* cfr_stream_t; /* == cudaStream_t */
+typedef struct cfr_program cfr_program;   /* ordered list of kernel launches with baked-in tensor maps */
+typedef struct cfr_sampler cfr_sampler;   /* the whole Smooth._sample_noise body */
+
+#define CFR_MAX_PHASES 4
+#define CFR_MAX_TAPS 9
+enum { CFR_ACT_NONE = 0, CFR_ACT_LRELU = 1, CFR_ACT_PRELU = 2 };
+
+/* One implicit-GEMM convolution (tcgen05 / TMEM / TMA).  Replaces the F.conv2d / F.conv_transpose2d calls of
+ * stylegan_generator_model.py:667-675,739 and iresnet.py:49,52,55,142,153 together with the element-wise ops
+ * fused into the epilogue (see csrc/conv_igemm.cuh). */
+typedef struct cfr_conv_desc {
+  const void* in; int32_t N, Hin, Win, Cin;   /* NHWC fp16 input; Cin in {16,32} or a multiple of 64 */
+  const void* w; int32_t wRows, Kpad;         /* fp16 [wRows][Kpad], K = (tap, cin), Kpad % 64 == 0 */
+  int32_t Cout;                               /* multiple of 16 */
+  int32_t Hout, Wout;                         /* conv output grid (low-res grid for up-conv phases) */
+  int32_t TW, TH, TN;                         /* M-tile box on the output grid, TW*TH*TN == 128 */
+  int32_t stride, ntaps, numPhases;
+  int8_t tap_dy[CFR_MAX_PHASES][CFR_MAX_TAPS];
+  int8_t tap_dx[CFR_MAX_PHASES][CFR_MAX_TAPS];
+  int32_t wRowsPerSample, wRowsPerPhase;      /* weight row = n*wRowsPerSample + phase*wRowsPerPhase + cout */
+  void* out; int32_t outIsF32, outH, outW, outC, oscale;
+  int8_t ooff_y[CFR_MAX_PHASES], ooff_x[CFR_MAX_PHASES];
+  const float* bias;                          /* [Cout] or NULL */
+  const float* cbias; int32_t cbiasPerSample; /* [(n?) phase][9 border classes][Cout] or NULL */
+  const float* noise; const float* noise_w;   /* [outH*outW], [Cout] or NULL */
+  int32_t act; float slope; const float* alpha;
+  const void* resid; int32_t residC;          /* fp16 [N,outH,outW,residC] or NULL */
+  float* stat_sum; float* stat_sq;            /* [N,Cout] per-(n,c) sum / sum of squares, or NULL */
+} cfr_conv_desc;
+
+CFR_API const char* cfr_last_error(void);
+CFR_API int cfr_version(void);
+CFR_API int cfr_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ---- programs: record once, replay per chunk -------------------------------------------------------- */
+CFR_API int cfr_program_create(cfr_program** out);
+CFR_API void cfr_program_destroy(cfr_program* p);
+CFR_API int cfr_program_run(cfr_program* p, cfr_stream_t stream);
+CFR_API int cfr_program_num_launches(const cfr_program* p);
+
+CFR_API int cfr_program_add_conv(cfr_program* p, const cfr_conv_desc* d);
+CFR_API int cfr_program_add_memset(cfr_program* p, void* ptr, int value, size_t bytes);
+/* StyleModulationLayer dense, stylegan_generator_model.py:503 (all 18 layers): styles[b][rows] */
+CFR_API int cfr_program_add_styles(cfr_program* p, const float* wp2, const float* w_style, const float* b_style,
+                           int rows, int rows_trunc, int b, float* styles);
+/* FirstConvBlock + epilogue, :581-584 */
+CFR_API int cfr_program_add_layer0(cfr_program* p, const float* xhat0, const float* styles, int style_stride,
+                           int style_off, int b, void* out_f16);
+/* BlurLayer :463 + noise/bias/LeakyReLU :560-562 + InstanceNorm sums :420-422.  mode 1 = sums only */
+CFR_API int cfr_program_add_blur_act_stats(cfr_program* p, const void* raw_f16, void* y_f16, int n, int h, int w, int c,
+                                   const float* noise, const float* noise_w, const float* bias, float* sum,
+                                   float* sq, int mode);
+/* InstanceNorm + AdaIN coefficients: x = y*A + B  (:420-422, :505) */
+CFR_API int cfr_program_add_finalize_stats(cfr_program* p, const float* sum, const float* sq, const float* styles,
+                                   int style_stride, int style_off, int n, int c, float inv_count, float* A,
+                                   float* B);
+CFR_API int cfr_program_add_affine(cfr_program* p, const void* y_f16, const float* A, const float* B, int n, int hw, int c,
+                           void* x_f16);
+/* LastConvBlock :759-762 + postprocess (mod_stylegan_generator.py:303-307) + get_transform (gen_utils.py:77-85) */
+CFR_API int cfr_program_add_torgb_resize(cfr_program* p, const void* x_f16, const float* A, const float* B, int n, int hin,
+                                 int c, const float* w_rgb, const float* b_rgb, int rout, float mean, float stdv,
+                                 void* out_f16_nhwc16, float* out_planar_f32);
+
+/* ---- immediate ops ------------------------------------------------------------------------------------ */
+/* L2Certificate.sample_noise (certificate.py:64-67) + WrappedModel.forward latent perturbation
+ * (smoothing_model.py:63-67) + TruncationModule (stylegan_generator_model.py:322-328).
+ * noise_in == NULL: Philox4x32-10 normals, counter = sample_offset + i, key = seed, scaled by sigma[1|5]. */
+CFR_API int cfr_noise_project(const float* z, const float* x, const float* sigma, int sigma_len, const float* noise_in,
+                      const float* dir_mat, const float* w_avg, float psi, uint64_t seed, uint64_t sample_offset,
+                      int b, float* noise_out, float* wp2, cfr_stream_t stream);
+CFR_API int cfr_truncate(const float* w, const float* w_avg, float psi, int b, float* wp2, cfr_stream_t stream);
+/* WrappedModel.compute_probs + .argmax(1) + Smooth._count_arr (smoothing_model.py:56-61, smooth.py:135-146).
+ * keys: b uint64 scratch, all-ones before the first call (re-armed by the call). */
+CFR_API int cfr_match_vote(const float* emb, int b, const float* gallery, int n, uint64_t* keys, int32_t* pred,
+                   int64_t* counts, cfr_stream_t stream);
+
+/* ---- Smooth._sample_noise (smooth.py:109-138) as one call --------------------------------------------- */
+typedef struct cfr_sampler_desc {
+  cfr_program* synth;     /* wp2 -> image at FRM resolution (one chunk) */
+  cfr_program* frm;       /* image -> embeddings */
+  int32_t chunk;          /* samples per program run */
+  float* wp2;             /* [chunk,2,512] program input */
+  const float* emb;       /* [chunk,512] program output */
+  const float* dir_mat;   /* [5,512] */
+  const float* w_avg;     /* [512] */
+  float psi;
+  const float* gallery;   /* [n_gallery,512] */
+  int32_t n_gallery;
+} cfr_sampler_desc;
+CFR_API int cfr_sampler_create(const cfr_sampler_desc* d, cfr_sampler** out);
+CFR_API void cfr_sampler_destroy(cfr_sampler* s);
+/* counts[n_gallery] (int64) is ACCUMULATED into.  noise_in: NULL or [num,5] already-scaled noise.
+ * pred_out / emb_out / noise_out: optional per-sample outputs ([num], [num,512], [num,5]). */
+CFR_API int cfr_sample_votes(cfr_sampler* s, const float* z, const float* x, const float* sigma, int sigma_len,
+                     const float* noise_in, int64_t num, uint64_t seed, uint64_t sample_offset, int64_t* counts,
+                     int32_t* pred_out, float* emb_out, float* noise_out, cfr_stream_t stream);
+/* Same with HOST buffers (z[512], x[5], sigma[sigma_len] in, counts_host[n_gallery] out, overwritten):
+ * H2D copies, the MC loop, the D2H copy of the counts and a stream sync all inside the call. */
+CFR_API int cfr_sample_votes_host(cfr_sampler* s, const float* z_host, const float* x_host, const float* sigma_host,
+                          int sigma_len, int64_t num, uint64_t seed, uint64_t sample_offset, int64_t* counts_host,
+                          cfr_stream_t stream);
+/* kernels launched by this library since load (bench.py reports it as gpu_launches) */
+CFR_API uint64_t cfr_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CFR_B200_H */

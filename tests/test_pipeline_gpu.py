@@ -1,0 +1,110 @@
+"""End-to-end parity of the CUDA path (through the C ABI) against the CPU oracle and against vectors produced by
+the unmodified reference (tests/golden).  Tolerances are BASELINE.json's: embedding cosine >= 0.999, top-1
+agreement >= 99.5 %, vote counts bit-exact wherever predictions agree, certified radius within 1 %."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+N_GALLERY = 5000
+SIGMA = 0.1
+
+
+@pytest.fixture(scope="module")
+def setup(golden, models):
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    from certifyingfacerecognition_b200.engine import Engine
+    from oracle import fixtures
+    g_sd, f_sd = models
+    dirs = torch.from_numpy(golden["dirs"])
+    gal8 = torch.from_numpy(golden["gallery"])
+    eng = Engine(g_sd, f_sd, dirs, gal8, chunk=8, keep_planar=True)
+    # decoys: embeddings of identity 0 pushed along each direction (computed by the engine: the gallery is input data)
+    z = torch.from_numpy(golden["w_all"][0:1])
+    deltas = torch.cat([z + s * 2.0 * SIGMA * dirs[k:k + 1] for k in range(5) for s in (1.0, -1.0)])
+    decoys = eng.embed_latents(deltas).cpu()
+    gallery = fixtures.synthetic_gallery(torch.cat([gal8, decoys]), N_GALLERY)
+    eng.set_gallery(gallery)
+    return eng, g_sd, f_sd, dirs, gallery, z
+
+
+def test_embeddings_match_reference_golden(setup, golden):
+    eng = setup[0]
+    w_in = torch.from_numpy(golden["w_in"])
+    emb = eng.embed_latents(w_in).cpu()
+    ref = torch.from_numpy(golden["emb"])
+    cos = F.cosine_similarity(emb, ref)
+    assert cos.min().item() >= 0.999, cos
+    img = eng.synth.img_planar[0].cpu()
+    assert (img - torch.from_numpy(golden["img112_0"])).abs().mean().item() < 1e-2
+
+
+def test_embeddings_match_oracle(setup):
+    from oracle import mc_path as M
+    from oracle import fixtures
+    eng, g_sd, f_sd = setup[0], setup[1], setup[2]
+    w = torch.from_numpy(fixtures.latents(40)[32:40])
+    ref = M.lat2embs(w, g_sd, f_sd, literal=False)
+    emb = eng.embed_latents(w).cpu()
+    cos = F.cosine_similarity(emb, ref)
+    assert cos.min().item() >= 0.999, cos
+
+
+def test_votes_match_oracle_on_identical_noise(setup):
+    from oracle import mc_path as M
+    eng, g_sd, f_sd, dirs, gallery, z = setup
+    n = 24
+    for sigma in (torch.tensor([SIGMA]), 2.0 * torch.from_numpy(M.red_ellipse_mat_inv()).float()):
+        record = []
+        x = torch.zeros(1, 5)
+        torch.manual_seed(4321)
+        preds_ref = []
+
+        def classify(p):
+            probs = M.wrapped_forward(z, p, dirs, gallery, g_sd, f_sd, literal=False)
+            preds_ref.append(probs.argmax(1))
+            return probs
+        counts_ref = M.sample_noise_counts(classify, x, sigma, n, 8, N_GALLERY, record=record)
+        noise = torch.cat(record).reshape(n, 5)
+        counts, extra = eng.sample_votes(z, x, sigma, n, noise=noise, want_pred=True, want_emb=True)
+        torch.cuda.synchronize()
+        pred = extra["pred"].cpu().long()
+        pref = torch.cat(preds_ref)
+        agree = (pred == pref).float().mean().item()
+        assert agree >= 0.995, (agree, pred, pref)
+        if agree == 1.0:
+            assert np.array_equal(counts.cpu().numpy().astype(np.float64), counts_ref)
+        assert counts.sum().item() == n
+
+
+def test_philox_votes_are_offset_consistent(setup):
+    """Sharding contract: sample i always uses Philox counter i, so splitting [0,n) across calls (ranks) sums to
+    the unsplit result exactly."""
+    eng, _, _, _, _, z = setup
+    x = torch.zeros(1, 5)
+    sigma = torch.tensor([3.0 * SIGMA])
+    full, _ = eng.sample_votes(z, x, sigma, 24, seed=7)
+    part = torch.zeros_like(full)
+    eng.sample_votes(z, x, sigma, 10, seed=7, sample_offset=0, counts=part)
+    eng.sample_votes(z, x, sigma, 14, seed=7, sample_offset=10, counts=part)
+    torch.cuda.synchronize()
+    assert torch.equal(full, part)
+    assert full.sum().item() == 24
+
+
+def test_host_entry_matches_device_entry(setup):
+    import ctypes as C
+    from certifyingfacerecognition_b200 import _lib as L
+    eng, _, _, _, _, z = setup
+    x = np.zeros(5, dtype=np.float32)
+    sigma = np.array([SIGMA], dtype=np.float32)
+    zh = z.numpy().reshape(-1).astype(np.float32)
+    counts = np.zeros(N_GALLERY, dtype=np.int64)
+    L.check(eng.lib.cfr_sample_votes_host(eng.sampler, zh.ctypes.data, x.ctypes.data, sigma.ctypes.data, 1, 16, 11, 0,
+                                          counts.ctypes.data, C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+    dev, _ = eng.sample_votes(z, torch.zeros(1, 5), torch.tensor([SIGMA]), 16, seed=11)
+    torch.cuda.synchronize()
+    assert np.array_equal(counts, dev.cpu().numpy())
