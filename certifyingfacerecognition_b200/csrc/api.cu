@@ -40,6 +40,13 @@ extern "C" {
 CFR_API const char* cfr_last_error(void) { return last_error(); }
 CFR_API int cfr_version(void) { return 100; }
 CFR_API uint64_t cfr_launch_count(void) { return launch_count(); }
+CFR_API int cfr_profile_enable(int on) { profile_enable(on); return 0; }
+CFR_API int cfr_profile_read(double* conv_ms, double* conv_flops, int64_t* conv_launches) {
+  long long l = 0;
+  int r = profile_read(conv_ms, conv_flops, &l);
+  *conv_launches = l;
+  return r;
+}
 
 CFR_API int cfr_device_info(int* sm_count, int* cc_major, int* cc_minor) {
   int dev = 0;

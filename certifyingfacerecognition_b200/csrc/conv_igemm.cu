@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <cstring>
 #include <mutex>
+#include <vector>
 
 namespace cfr {
 
@@ -456,7 +457,48 @@ int conv_build(const ConvSpec& s, ConvOp* op) {
 
   const int total = p.tilesX * p.tilesY * p.tilesN * p.numPhases * p.numNTiles;
   op->grid = total < num_sms() ? total : num_sms();
+  // algorithmic FLOPs of this launch: 2 * (valid output-grid pixels) * phases * taps * Cin * Cout
+  op->flops = 2.0 * s.N * s.Hout * s.Wout * s.numPhases * s.ntaps * static_cast<double>(s.Cin) * s.Cout;
   return 0;
+}
+
+// ---- optional per-launch timing (bench.py roofline): CUDA events around every conv launch -------------
+struct ProfState {
+  bool on = false;
+  std::vector<cudaEvent_t> ev;     // pairs (start, stop)
+  size_t used = 0;
+  double flops = 0.0;
+  long long launches = 0;
+};
+static ProfState g_prof;
+
+void profile_enable(int on) {
+  g_prof.on = on != 0;
+  g_prof.used = 0;
+  g_prof.flops = 0.0;
+  g_prof.launches = 0;
+}
+int profile_read(double* ms, double* flops, long long* launches) {
+  double total = 0.0;
+  for (size_t i = 0; i + 1 < g_prof.used; i += 2) {
+    float t = 0.f;
+    cudaError_t e = cudaEventSynchronize(g_prof.ev[i + 1]);
+    if (e == cudaSuccess) e = cudaEventElapsedTime(&t, g_prof.ev[i], g_prof.ev[i + 1]);
+    if (e != cudaSuccess) { set_error("profile_read: %s", cudaGetErrorString(e)); return 5; }
+    total += t;
+  }
+  *ms = total;
+  *flops = g_prof.flops;
+  *launches = g_prof.launches;
+  return 0;
+}
+static cudaEvent_t prof_event() {
+  if (g_prof.used == g_prof.ev.size()) {
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    g_prof.ev.push_back(e);
+  }
+  return g_prof.ev[g_prof.used++];
 }
 
 int conv_launch(const ConvOp& op, cudaStream_t stream) {
@@ -466,7 +508,17 @@ int conv_launch(const ConvOp& op, cudaStream_t stream) {
     attr_err = cudaFuncSetAttribute(conv_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   });
   if (attr_err != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(attr_err)); return 4; }
+  cudaEvent_t e1 = nullptr;
+  if (g_prof.on) {
+    cudaEventRecord(prof_event(), stream);
+    e1 = prof_event();
+  }
   conv_igemm_kernel<<<op.grid, kConvThreads, op.smemBytes, stream>>>(op.p);
+  if (g_prof.on) {
+    cudaEventRecord(e1, stream);
+    g_prof.flops += op.flops;
+    g_prof.launches += 1;
+  }
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { set_error("conv launch: %s", cudaGetErrorString(e)); return 4; }
   count_launch();

@@ -75,6 +75,7 @@ struct ConvOp {
   ConvParams p;
   int grid;
   int smemBytes;
+  double flops;   // algorithmic (2*MAC, un-padded dims)
 };
 
 // Host-side description == the public C struct (include/cfr_b200.h).
@@ -87,5 +88,7 @@ const char* last_error();
 int num_sms();
 void count_launch(int n = 1);
 unsigned long long launch_count();
+void profile_enable(int on);
+int profile_read(double* ms, double* flops, long long* launches);
 
 }  // namespace cfr

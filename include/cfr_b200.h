@@ -130,6 +130,11 @@ CFR_API int cfr_sample_votes_host(cfr_sampler* s, const float* z_host, const flo
                           cfr_stream_t stream);
 /* kernels launched by this library since load (bench.py reports it as gpu_launches) */
 CFR_API uint64_t cfr_launch_count(void);
+/* Per-launch CUDA-event timing of the implicit-GEMM kernel (bench.py roofline).  enable(1) resets the counters;
+ * read() synchronises on the recorded events and returns summed device time, algorithmic FLOPs (2*MAC on the
+ * un-padded dims) and launch count since enable. */
+CFR_API int cfr_profile_enable(int on);
+CFR_API int cfr_profile_read(double* conv_ms, double* conv_flops, int64_t* conv_launches);
 
 #ifdef __cplusplus
 }
