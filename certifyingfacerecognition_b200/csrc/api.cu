@@ -5,14 +5,27 @@
 
 #include <functional>
 #include <memory>
+#include <string>
 #include <vector>
 #include <cstring>
+#include <cstdio>
 
 using namespace cfr;
 
 struct cfr_program {
   std::vector<std::function<int(cudaStream_t)>> ops;
+  std::vector<std::string> labels;
+  std::vector<double> flops;           // algorithmic FLOPs per op (convs only, else 0)
   std::vector<std::unique_ptr<ConvOp>> convs;
+  std::vector<cudaEvent_t> events;
+  void add(std::function<int(cudaStream_t)> f, std::string label, double fl = 0.0) {
+    ops.push_back(std::move(f));
+    labels.push_back(std::move(label));
+    flops.push_back(fl);
+  }
+  ~cfr_program() {
+    for (auto e : events) cudaEventDestroy(e);
+  }
 };
 
 struct cfr_sampler {
@@ -65,6 +78,31 @@ CFR_API int cfr_program_create(cfr_program** out) {
 }
 CFR_API void cfr_program_destroy(cfr_program* p) { delete p; }
 CFR_API int cfr_program_num_launches(const cfr_program* p) { return static_cast<int>(p->ops.size()); }
+CFR_API const char* cfr_program_op_label(const cfr_program* p, int i) {
+  return (i >= 0 && i < static_cast<int>(p->labels.size())) ? p->labels[i].c_str() : "";
+}
+CFR_API double cfr_program_op_flops(const cfr_program* p, int i) {
+  return (i >= 0 && i < static_cast<int>(p->flops.size())) ? p->flops[i] : 0.0;
+}
+// Run once with a CUDA event between consecutive ops; ms_out[i] = device time of op i.  Synchronises.
+CFR_API int cfr_program_run_timed(cfr_program* p, cfr_stream_t stream, float* ms_out, int n) {
+  const size_t need = p->ops.size() + 1;
+  while (p->events.size() < need) {
+    cudaEvent_t e;
+    CFR_CUDA(cudaEventCreate(&e));
+    p->events.push_back(e);
+  }
+  CFR_CUDA(cudaEventRecord(p->events[0], S(stream)));
+  for (size_t i = 0; i < p->ops.size(); ++i) {
+    int r = p->ops[i](S(stream));
+    if (r != 0) return r;
+    CFR_CUDA(cudaEventRecord(p->events[i + 1], S(stream)));
+  }
+  CFR_CUDA(cudaStreamSynchronize(S(stream)));
+  for (size_t i = 0; i < p->ops.size() && static_cast<int>(i) < n; ++i)
+    CFR_CUDA(cudaEventElapsedTime(&ms_out[i], p->events[i], p->events[i + 1]));
+  return 0;
+}
 
 CFR_API int cfr_program_run(cfr_program* p, cfr_stream_t stream) {
   for (auto& op : p->ops) {
@@ -80,66 +118,69 @@ CFR_API int cfr_program_add_conv(cfr_program* p, const cfr_conv_desc* d) {
   if (r != 0) return r;
   ConvOp* raw = op.get();
   p->convs.push_back(std::move(op));
-  p->ops.push_back([raw](cudaStream_t st) { return conv_launch(*raw, st); });
+  char lab[160];
+  snprintf(lab, sizeof(lab), "conv %dx%d s%d taps%dx%d Cin%d Cout%d grid%dx%d n%d BN%d", d->Hout, d->Wout, d->stride,
+           d->numPhases, d->ntaps, d->Cin, d->Cout, d->Hout, d->Wout, d->N, raw->p.BN);
+  p->add([raw](cudaStream_t st) { return conv_launch(*raw, st); }, lab, raw->flops);
   return 0;
 }
 
 CFR_API int cfr_program_add_memset(cfr_program* p, void* ptr, int value, size_t bytes) {
-  p->ops.push_back([=](cudaStream_t st) {
+  p->add([=](cudaStream_t st) {
     cudaError_t e = cudaMemsetAsync(ptr, value, bytes, st);
     if (e != cudaSuccess) { set_error("memset: %s", cudaGetErrorString(e)); return 5; }
     return 0;
-  });
+  }, "memset");
   return 0;
 }
 
 CFR_API int cfr_program_add_styles(cfr_program* p, const float* wp2, const float* w_style, const float* b_style, int rows,
                            int rows_trunc, int b, float* styles) {
-  p->ops.push_back([=](cudaStream_t st) { return launch_styles(wp2, w_style, b_style, rows, rows_trunc, b, styles, st); });
+  p->add([=](cudaStream_t st) { return launch_styles(wp2, w_style, b_style, rows, rows_trunc, b, styles, st); }, "styles");
   return 0;
 }
 
 CFR_API int cfr_program_add_layer0(cfr_program* p, const float* xhat0, const float* styles, int style_stride, int style_off,
                            int b, void* out_f16) {
-  p->ops.push_back([=](cudaStream_t st) {
+  p->add([=](cudaStream_t st) {
     return launch_layer0(xhat0, styles, style_stride, style_off, b, static_cast<__half*>(out_f16), st);
-  });
+  }, "layer0");
   return 0;
 }
 
 CFR_API int cfr_program_add_blur_act_stats(cfr_program* p, const void* raw_f16, void* y_f16, int n, int h, int w, int c,
                                    const float* noise, const float* noise_w, const float* bias, float* sum, float* sq,
                                    int mode) {
-  p->ops.push_back([=](cudaStream_t st) {
+  p->add([=](cudaStream_t st) {
     return launch_blur_act_stats(static_cast<const __half*>(raw_f16), static_cast<__half*>(y_f16), n, h, w, c, noise,
                                  noise_w, bias, sum, sq, mode, st);
-  });
+  }, "blur_act_stats");
   return 0;
 }
 
 CFR_API int cfr_program_add_finalize_stats(cfr_program* p, const float* sum, const float* sq, const float* styles,
                                    int style_stride, int style_off, int n, int c, float inv_count, float* A, float* B) {
-  p->ops.push_back([=](cudaStream_t st) {
+  p->add([=](cudaStream_t st) {
     return launch_finalize_stats(sum, sq, styles, style_stride, style_off, n, c, inv_count, A, B, st);
-  });
+  }, "finalize_stats");
   return 0;
 }
 
 CFR_API int cfr_program_add_affine(cfr_program* p, const void* y_f16, const float* A, const float* B, int n, int hw, int c,
                            void* x_f16) {
-  p->ops.push_back([=](cudaStream_t st) {
+  p->add([=](cudaStream_t st) {
     return launch_affine(static_cast<const __half*>(y_f16), A, B, n, hw, c, static_cast<__half*>(x_f16), st);
-  });
+  }, "affine");
   return 0;
 }
 
 CFR_API int cfr_program_add_torgb_resize(cfr_program* p, const void* x_f16, const float* A, const float* B, int n, int hin,
                                  int c, const float* w_rgb, const float* b_rgb, int rout, float mean, float stdv,
                                  void* out_f16_nhwc16, float* out_planar_f32) {
-  p->ops.push_back([=](cudaStream_t st) {
+  p->add([=](cudaStream_t st) {
     return launch_torgb_resize(static_cast<const __half*>(x_f16), A, B, n, hin, c, w_rgb, b_rgb, rout, mean, stdv,
                                static_cast<__half*>(out_f16_nhwc16), out_planar_f32, st);
-  });
+  }, "torgb_resize");
   return 0;
 }
 

@@ -66,6 +66,11 @@ CFR_API int cfr_program_create(cfr_program** out);
 CFR_API void cfr_program_destroy(cfr_program* p);
 CFR_API int cfr_program_run(cfr_program* p, cfr_stream_t stream);
 CFR_API int cfr_program_num_launches(const cfr_program* p);
+/* per-op introspection / timing (tools/profile_program.py): label, algorithmic FLOPs, and one timed replay with a
+ * CUDA event between consecutive ops (synchronises) */
+CFR_API const char* cfr_program_op_label(const cfr_program* p, int i);
+CFR_API double cfr_program_op_flops(const cfr_program* p, int i);
+CFR_API int cfr_program_run_timed(cfr_program* p, cfr_stream_t stream, float* ms_out, int n);
 
 CFR_API int cfr_program_add_conv(cfr_program* p, const cfr_conv_desc* d);
 CFR_API int cfr_program_add_memset(cfr_program* p, void* ptr, int value, size_t bytes);
