@@ -1,6 +1,7 @@
 // C ABI (include/cfr_b200.h): programs (recorded launch lists), immediate ops and the MC sampler.
 #include "../../include/cfr_b200.h"
 #include "conv_igemm.cuh"
+#include "conv_halo.cuh"
 #include "kernels.cuh"
 
 #include <functional>
@@ -17,6 +18,7 @@ struct cfr_program {
   std::vector<std::string> labels;
   std::vector<double> flops;           // algorithmic FLOPs per op (convs only, else 0)
   std::vector<std::unique_ptr<ConvOp>> convs;
+  std::vector<std::unique_ptr<HaloOp>> halos;
   std::vector<cudaEvent_t> events;
   void add(std::function<int(cudaStream_t)> f, std::string label, double fl = 0.0) {
     ops.push_back(std::move(f));
@@ -122,6 +124,19 @@ CFR_API int cfr_program_add_conv(cfr_program* p, const cfr_conv_desc* d) {
   snprintf(lab, sizeof(lab), "conv %dx%d s%d taps%dx%d Cin%d Cout%d grid%dx%d n%d BN%d", d->Hout, d->Wout, d->stride,
            d->numPhases, d->ntaps, d->Cin, d->Cout, d->Hout, d->Wout, d->N, raw->p.BN);
   p->add([raw](cudaStream_t st) { return conv_launch(*raw, st); }, lab, raw->flops);
+  return 0;
+}
+
+CFR_API int cfr_program_add_conv_halo(cfr_program* p, const cfr_conv_desc* d, const float* inA, const float* inB) {
+  std::unique_ptr<HaloOp> op(new HaloOp());
+  int r = halo_build(*d, inA, inB, op.get());
+  if (r != 0) return r;
+  HaloOp* raw = op.get();
+  p->halos.push_back(std::move(op));
+  char lab[160];
+  snprintf(lab, sizeof(lab), "halo %dx%d taps%dx%d Cin%d Cout%d n%d TH%d%s", d->Hout, d->Wout, d->numPhases, d->ntaps,
+           d->Cin, d->Cout, d->N, raw->p.TH, inA ? " +affine" : "");
+  p->add([raw](cudaStream_t st) { return halo_launch(*raw, st); }, lab, raw->flops);
   return 0;
 }
 

@@ -1,0 +1,453 @@
+// Halo-resident tcgen05 convolution kernel -- see conv_halo.cuh.
+#include "conv_halo.cuh"
+#include "conv_igemm.cuh"
+#include "ptx.cuh"
+
+#include <cstring>
+#include <mutex>
+
+namespace cfr {
+
+__device__ __forceinline__ float warp_reduce16h(float (&v)[16], uint32_t lane) {
+#pragma unroll
+  for (int step = 0; step < 4; ++step) {
+    const int off = 16 >> step;
+    const int cnt = 8 >> step;
+    const bool upper = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < cnt; ++i) {
+      float send = upper ? v[i] : v[i + cnt];
+      float keep = upper ? v[i + cnt] : v[i];
+      float recv = __shfl_xor_sync(0xffffffffu, send, off);
+      v[i] = keep + recv;
+    }
+  }
+  v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
+  return v[0];
+}
+__device__ __forceinline__ int reduce16_channel_h(uint32_t lane) {
+  return ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+}
+
+struct Band {
+  int n, y0, x0, rows;
+};
+__device__ __forceinline__ Band decode_band(const HaloParams& p, int b) {
+  Band r;
+  const int bx = b % p.bandsX;
+  const int t = b / p.bandsX;
+  const int by = t % p.bandsY;
+  r.n = t / p.bandsY;
+  r.x0 = bx * 128;
+  r.y0 = by * p.TH;
+  r.rows = min(p.TH, p.H - r.y0);
+  return r;
+}
+
+template <int COUT>
+__global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid_constant__ HaloParams p) {
+  constexpr int NCH = COUT / 16;                 // 16-column epilogue chunks
+  constexpr bool REG_STATS = COUT <= 32;         // keep per-thread channel sums in registers across a band
+  constexpr int ACC_COLS = COUT;                 // TMEM columns per accumulator stage
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* halo[2] = {smem, smem + p.haloBytes};
+  uint8_t* wsm = smem + 2 * p.haloBytes;
+  uint8_t* ctrl = wsm + p.wBytes;
+  uint64_t* hfull = reinterpret_cast<uint64_t*>(ctrl);     // [2]
+  uint64_t* hready = hfull + 2;                            // [2] (after the affine transform)
+  uint64_t* hempty = hready + 2;                           // [2]
+  uint64_t* wbar = hempty + 2;                             // [1]
+  uint64_t* tfull = wbar + 1;                              // [16]
+  uint64_t* tempty = tfull + 16;                           // [16]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 16);
+  float* sA = reinterpret_cast<float*>(tmem_slot + 4);     // [64]
+  float* sB = sA + 64;                                     // [64]
+  float* s_sum = sB + 64;                                  // [64]
+  float* s_sq = s_sum + 64;                                // [64]
+
+  const int warp = threadIdx.x >> 5;
+  const uint32_t lane = lane_id();
+  const int AS = p.accStages;
+  const int totalBands = p.N * p.bandsY * p.bandsX;
+  const int per = (totalBands + gridDim.x - 1) / gridDim.x;
+  const int band0 = blockIdx.x * per;
+  const int band1 = min(totalBands, band0 + per);
+  const bool affine = p.inA != nullptr;
+  uint32_t tmemCols = 32;
+  while (tmemCols < static_cast<uint32_t>(AS * ACC_COLS)) tmemCols <<= 1;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.tmX);
+    tma_prefetch_desc(&p.tmW);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int i = 0; i < 2; ++i) {
+        mbar_init(&hfull[i], 1);
+        mbar_init(&hready[i], 1);
+        mbar_init(&hempty[i], 1);
+      }
+      mbar_init(wbar, 1);
+      for (int i = 0; i < 16; ++i) {
+        mbar_init(&tfull[i], 1);
+        mbar_init(&tempty[i], 4);
+      }
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_slot, tmemCols);
+    tmem_relinquish();
+  }
+  if (threadIdx.x < 64) {
+    s_sum[threadIdx.x] = 0.f;
+    s_sq[threadIdx.x] = 0.f;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ================================================================ TMA producer
+    if (lane == 0) {
+      mbar_expect_tx(wbar, p.wRows * p.rowBytes);
+      for (int r0 = 0; r0 < p.wRows; r0 += p.wBoxRows)
+        tma_load_2d(wsm + static_cast<size_t>(r0) * p.rowBytes, &p.tmW, wbar, 0, r0);
+      const uint32_t boxBytes = (p.TH + 2) * kHaloW * p.rowBytes;
+      int bc = 0;
+      for (int b = band0; b < band1; ++b, ++bc) {
+        const Band bd = decode_band(p, b);
+        const int hs = bc & 1;
+        mbar_wait(&hempty[hs], ((bc >> 1) & 1) ^ 1);
+        mbar_expect_tx(&hfull[hs], boxBytes);
+        tma_load_4d(halo[hs], &p.tmX, &hfull[hs], 0, bd.x0 - 1, bd.y0 - 1, bd.n);
+      }
+    }
+  } else if (warp == 1) {
+    // ================================================================ MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_f16(128, COUT);
+      const uint32_t sbo = 8 * p.rowBytes;
+      const int kPer = p.Cin / 16;
+      const uint32_t w_base = smem_u32(wsm);
+      mbar_wait(wbar, 0);
+      int bc = 0;
+      uint32_t tcount = 0;
+      for (int b = band0; b < band1; ++b, ++bc) {
+        const Band bd = decode_band(p, b);
+        const int hs = bc & 1;
+        mbar_wait(affine ? &hready[hs] : &hfull[hs], (bc >> 1) & 1);
+        tc_fence_after();
+        const uint32_t h_base = smem_u32(halo[hs]);
+        for (int r = 0; r < bd.rows; ++r) {
+          for (int ph = 0; ph < p.numPhases; ++ph, ++tcount) {
+            const int as = tcount % AS;
+            mbar_wait(&tempty[as], ((tcount / AS) & 1) ^ 1);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + as * ACC_COLS;
+            for (int tap = 0; tap < p.ntaps; ++tap) {
+              const uint32_t a0 = h_base + ((r + 1 + p.tap_dy[ph][tap]) * kHaloW + 1 + p.tap_dx[ph][tap]) * p.rowBytes;
+              const uint32_t b0 = w_base + ((ph * p.ntaps + tap) * COUT) * p.rowBytes;
+              for (int j = 0; j < kPer; ++j) {
+                umma_f16(d_tmem, make_smem_desc(a0 + j * 32, sbo, p.rowBytes), make_smem_desc(b0 + j * 32, sbo, p.rowBytes),
+                         idesc, (tap | j) != 0 ? 1u : 0u);
+              }
+            }
+            umma_commit(&tfull[as]);
+          }
+        }
+        umma_commit(&hempty[hs]);          // halo stage free once every MMA of this band has read it
+      }
+    }
+  } else if (warp < 6) {
+    // ================================================================ affine-on-load transform (warps 2..5)
+    if (affine) {
+      const int tt = threadIdx.x - 64;     // 0..127
+      const int nch = p.rowBytes >> 4;
+      const int totalChunks = (p.TH + 2) * kHaloW * nch;
+      int bc = 0;
+      int cur_n = -1;
+      for (int b = band0; b < band1; ++b, ++bc) {
+        const Band bd = decode_band(p, b);
+        const int hs = bc & 1;
+        if (bd.n != cur_n) {
+          named_bar_sync(2, 128);
+          if (tt < p.Cin) {
+            sA[tt] = p.inA[bd.n * p.Cin + tt];
+            sB[tt] = p.inB[bd.n * p.Cin + tt];
+          }
+          cur_n = bd.n;
+          named_bar_sync(2, 128);
+        }
+        mbar_wait(&hfull[hs], (bc >> 1) & 1);
+        uint8_t* hb = halo[hs];
+        const uint32_t hb_addr = smem_u32(hb);
+        for (int c = tt; c < totalChunks; c += 128) {
+          const int pix = c / nch;
+          const int row = pix / kHaloW, col = pix - row * kHaloW;
+          const int gy = bd.y0 - 1 + row, gx = bd.x0 - 1 + col;
+          if (gy < 0 || gy >= p.H || gx < 0 || gx >= p.W) continue;      // zero padding stays zero
+          const uint32_t off = static_cast<uint32_t>(c) << 4;
+          const int lc = (c % nch) ^ (((hb_addr + off) >> 7) & (nch - 1));  // logical 8-channel group
+          uint4 v = *reinterpret_cast<uint4*>(hb + off);
+          __half2* h2 = reinterpret_cast<__half2*>(&v);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            float2 f = __half22float2(h2[i]);
+            f.x = f.x * sA[lc * 8 + 2 * i] + sB[lc * 8 + 2 * i];
+            f.y = f.y * sA[lc * 8 + 2 * i + 1] + sB[lc * 8 + 2 * i + 1];
+            h2[i] = __floats2half2_rn(f.x, f.y);
+          }
+          *reinterpret_cast<uint4*>(hb + off) = v;
+        }
+        fence_proxy_async();               // generic-proxy writes -> visible to the tensor core (async proxy)
+        named_bar_sync(2, 128);
+        if (tt == 0) mbar_arrive(&hready[hs]);
+      }
+    }
+  } else {
+    // ================================================================ epilogue (warps 6..13)
+    const int e = warp - 6;
+    const int q = warp & 3;                // TMEM lane quarter
+    const int grp = e >> 2;                // handles tiles with (tcount & 1) == grp
+    const int et = threadIdx.x - 192;      // 0..255
+    const bool do_stats = p.stat_sum != nullptr;
+    float racc[REG_STATS ? COUT : 1], racc2[REG_STATS ? COUT : 1];
+#pragma unroll
+    for (int i = 0; i < (REG_STATS ? COUT : 1); ++i) { racc[i] = 0.f; racc2[i] = 0.f; }
+    uint32_t tcount = 0;
+    int cur_n = -1;
+    for (int b = band0; b < band1; ++b) {
+      const Band bd = decode_band(p, b);
+      if (do_stats && cur_n >= 0 && bd.n != cur_n) {
+        named_bar_sync(1, 256);
+        if (et < COUT) {
+          atomicAdd(&p.stat_sum[cur_n * COUT + et], s_sum[et]);
+          atomicAdd(&p.stat_sq[cur_n * COUT + et], s_sq[et]);
+          s_sum[et] = 0.f;
+          s_sq[et] = 0.f;
+        }
+        named_bar_sync(1, 256);
+      }
+      cur_n = bd.n;
+      const int gx = bd.x0 + q * 32 + static_cast<int>(lane);
+      const bool colok = gx < p.W;
+      for (int r = 0; r < bd.rows; ++r) {
+        const int gy = bd.y0 + r;
+        for (int ph = 0; ph < p.numPhases; ++ph, ++tcount) {
+          if ((tcount & 1) != static_cast<uint32_t>(grp)) continue;
+          const int as = tcount % AS;
+          const int oy = gy * p.oscale + p.ooff_y[ph];
+          const int ox = gx * p.oscale + p.ooff_x[ph];
+          const size_t pix = (static_cast<size_t>(bd.n) * p.outH + oy) * p.outW + ox;
+          const float nz = (p.noise != nullptr && colok) ? __ldg(&p.noise[oy * p.outW + ox]) : 0.f;
+          mbar_wait(&tfull[as], (tcount / AS) & 1);
+          tc_fence_after();
+          const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * ACC_COLS;
+#pragma unroll
+          for (int ci = 0; ci < NCH; ++ci) {
+            float v[16];
+            tmem_ld16(t_row + ci * 16, v);
+            const int ch0 = ci * 16;
+            if (p.bias != nullptr) {
+#pragma unroll
+              for (int i = 0; i < 16; i += 4) {
+                const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + ch0 + i));
+                v[i] += b4.x; v[i + 1] += b4.y; v[i + 2] += b4.z; v[i + 3] += b4.w;
+              }
+            }
+            if (p.noise != nullptr) {
+#pragma unroll
+              for (int i = 0; i < 16; i += 4) {
+                const float4 w4 = __ldg(reinterpret_cast<const float4*>(p.noise_w + ch0 + i));
+                v[i] += nz * w4.x; v[i + 1] += nz * w4.y; v[i + 2] += nz * w4.z; v[i + 3] += nz * w4.w;
+              }
+            }
+            if (p.act == CFR_ACT_LRELU) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) v[i] = v[i] >= 0.f ? v[i] : v[i] * p.slope;
+            }
+            if (colok) {
+              uint4 o[2];
+              __half2* h2 = reinterpret_cast<__half2*>(o);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) h2[i] = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+              uint4* op = reinterpret_cast<uint4*>(p.out + pix * p.outC + ch0);
+              op[0] = o[0];
+              op[1] = o[1];
+            }
+            if (do_stats) {
+              if constexpr (REG_STATS) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                  const float t = colok ? v[i] : 0.f;
+                  racc[ch0 + i] += t;
+                  racc2[ch0 + i] += t * t;
+                }
+              } else {
+                float sq[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                  v[i] = colok ? v[i] : 0.f;
+                  sq[i] = v[i] * v[i];
+                }
+                const float ssum = warp_reduce16h(v, lane);
+                const float ssq = warp_reduce16h(sq, lane);
+                if ((lane & 1) == 0) {
+                  const int ch = ch0 + reduce16_channel_h(lane);
+                  atomicAdd(&s_sum[ch], ssum);
+                  atomicAdd(&s_sq[ch], ssq);
+                }
+              }
+            }
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty[as]);
+        }
+      }
+      if constexpr (REG_STATS) {
+        if (do_stats) {                      // once per band: registers -> shared
+#pragma unroll
+          for (int ci = 0; ci < NCH; ++ci) {
+            float a[16], a2[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              a[i] = racc[ci * 16 + i];
+              a2[i] = racc2[ci * 16 + i];
+              racc[ci * 16 + i] = 0.f;
+              racc2[ci * 16 + i] = 0.f;
+            }
+            const float ssum = warp_reduce16h(a, lane);
+            const float ssq = warp_reduce16h(a2, lane);
+            if ((lane & 1) == 0) {
+              const int ch = ci * 16 + reduce16_channel_h(lane);
+              atomicAdd(&s_sum[ch], ssum);
+              atomicAdd(&s_sq[ch], ssq);
+            }
+          }
+        }
+      }
+    }
+    if (do_stats && cur_n >= 0) {
+      named_bar_sync(1, 256);
+      if (et < COUT) {
+        atomicAdd(&p.stat_sum[cur_n * COUT + et], s_sum[et]);
+        atomicAdd(&p.stat_sq[cur_n * COUT + et], s_sq[et]);
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, tmemCols);
+  }
+}
+
+// --------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+void* get_encode_tiled();
+
+static CUtensorMapSwizzle swz(int bytes) {
+  return bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : (bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+}
+
+int halo_build(const cfr_conv_desc& s, const float* inA, const float* inB, HaloOp* op) {
+  EncodeTiledFn enc = reinterpret_cast<EncodeTiledFn>(get_encode_tiled());
+  if (enc == nullptr) { set_error("cuTensorMapEncodeTiled not available (no CUDA driver?)"); return 1; }
+  HaloParams& p = op->p;
+  memset(&p, 0, sizeof(p));
+  if (!(s.Cin == 16 || s.Cin == 32 || s.Cin == 64) || !(s.Cout == 16 || s.Cout == 32 || s.Cout == 64)) {
+    set_error("halo conv: Cin/Cout must be 16, 32 or 64 (got %d -> %d)", s.Cin, s.Cout);
+    return 2;
+  }
+  if (s.stride != 1 || s.Hout != s.Hin || s.Wout != s.Win || s.outIsF32 || s.cbias || s.resid || s.wRowsPerSample) {
+    set_error("halo conv: unsupported option (stride/out grid/f32/cbias/resid/per-sample weights)");
+    return 2;
+  }
+  if (s.stat_sum != nullptr && s.numPhases != 1) { set_error("halo conv: stats need one phase"); return 2; }
+  p.N = s.N; p.H = s.Hout; p.W = s.Wout; p.Cin = s.Cin; p.Cout = s.Cout;
+  p.numPhases = s.numPhases; p.ntaps = s.ntaps;
+  memcpy(p.tap_dy, s.tap_dy, sizeof(p.tap_dy));
+  memcpy(p.tap_dx, s.tap_dx, sizeof(p.tap_dx));
+  p.rowBytes = s.Cin * 2;
+  p.wRows = s.numPhases * s.ntaps * s.Cout;
+  p.wBytes = (p.wRows * p.rowBytes + 1023) / 1024 * 1024;
+  p.wBoxRows = p.wRows;
+  while (p.wBoxRows > 256 || p.wRows % p.wBoxRows != 0) --p.wBoxRows;
+  const int ctrl = 8 * 40 + 16 + 4 * 64 * 4 + 64;
+  const int budget = 227 * 1024 - 1024 - ctrl - p.wBytes;
+  int th = 16;
+  while (th > 1 && 2 * (((th + 2) * kHaloW * p.rowBytes + 1023) / 1024 * 1024) > budget) --th;
+  if (th > s.Hout) th = s.Hout;
+  if (2 * (((th + 2) * kHaloW * p.rowBytes + 1023) / 1024 * 1024) > budget) { set_error("halo conv: smem budget"); return 2; }
+  p.TH = th;
+  p.haloBytes = ((th + 2) * kHaloW * p.rowBytes + 1023) / 1024 * 1024;
+  p.bandsX = (s.Wout + 127) / 128;
+  p.bandsY = (s.Hout + th - 1) / th;
+  p.accStages = 512 / s.Cout;
+  if (p.accStages > 16) p.accStages = 16;
+  p.inA = inA; p.inB = inB;
+  p.out = static_cast<__half*>(s.out);
+  p.outH = s.outH; p.outW = s.outW; p.outC = s.outC; p.oscale = s.oscale;
+  memcpy(p.ooff_y, s.ooff_y, sizeof(p.ooff_y));
+  memcpy(p.ooff_x, s.ooff_x, sizeof(p.ooff_x));
+  p.bias = s.bias; p.noise = s.noise; p.noise_w = s.noise_w; p.act = s.act; p.slope = s.slope;
+  p.stat_sum = s.stat_sum; p.stat_sq = s.stat_sq;
+  if (s.outC != s.Cout) { set_error("halo conv: outC must equal Cout"); return 2; }
+  {
+    cuuint64_t dims[4] = {(cuuint64_t)s.Cin, (cuuint64_t)s.Win, (cuuint64_t)s.Hin, (cuuint64_t)s.N};
+    cuuint64_t strides[3] = {(cuuint64_t)s.Cin * 2, (cuuint64_t)s.Win * s.Cin * 2, (cuuint64_t)s.Hin * s.Win * s.Cin * 2};
+    cuuint32_t box[4] = {(cuuint32_t)s.Cin, (cuuint32_t)kHaloW, (cuuint32_t)(th + 2), 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = enc(&p.tmX, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(s.in), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, swz(p.rowBytes), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("halo conv: encode(X) failed: %d", (int)r); return 3; }
+  }
+  {
+    if (s.Kpad != s.Cin || s.wRows != p.wRows) { set_error("halo conv: weights must be [phases*taps*Cout][Cin] (got [%d][%d])", s.wRows, s.Kpad); return 2; }
+    cuuint64_t dims[2] = {(cuuint64_t)s.Cin, (cuuint64_t)p.wRows};
+    cuuint64_t strides[1] = {(cuuint64_t)s.Cin * 2};
+    cuuint32_t box[2] = {(cuuint32_t)s.Cin, (cuuint32_t)p.wBoxRows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(&p.tmW, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(s.w), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, swz(p.rowBytes), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("halo conv: encode(W) failed: %d", (int)r); return 3; }
+  }
+  const int total = p.N * p.bandsX * p.bandsY;
+  op->grid = total < num_sms() ? total : num_sms();
+  op->smemBytes = 2 * p.haloBytes + p.wBytes + ctrl + 1024;
+  op->flops = 2.0 * s.N * s.Hout * s.Wout * s.numPhases * s.ntaps * static_cast<double>(s.Cin) * s.Cout;
+  return 0;
+}
+
+int halo_launch(const HaloOp& op, cudaStream_t stream) {
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [] {
+    attr_err = cudaFuncSetAttribute(conv_halo_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (attr_err == cudaSuccess)
+      attr_err = cudaFuncSetAttribute(conv_halo_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (attr_err == cudaSuccess)
+      attr_err = cudaFuncSetAttribute(conv_halo_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  });
+  if (attr_err != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(attr_err)); return 4; }
+  switch (op.p.Cout) {
+    case 16: conv_halo_kernel<16><<<op.grid, kHaloThreads, op.smemBytes, stream>>>(op.p); break;
+    case 32: conv_halo_kernel<32><<<op.grid, kHaloThreads, op.smemBytes, stream>>>(op.p); break;
+    default: conv_halo_kernel<64><<<op.grid, kHaloThreads, op.smemBytes, stream>>>(op.p); break;
+  }
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { set_error("halo conv launch: %s", cudaGetErrorString(e)); return 4; }
+  count_launch();
+  return 0;
+}
+
+}  // namespace cfr

@@ -1,0 +1,58 @@
+// Halo-resident implicit-GEMM convolution for the HBM-bound high-resolution StyleGAN layers (Cin <= 64).
+//
+// conv_igemm.cu re-fetches the activation tile once per filter tap; with 16..64 channels a tap is 128 rows of
+// only 32..128 bytes, so that kernel is TMA-issue / L2 bound on these layers (profiles/ops_r01.tsv).  Here one
+// TMA box brings a (TH+2) x 130 pixel halo band of the NHWC input into shared memory ONCE; every tap of every
+// output row in the band is then just a different start address in the UMMA shared-memory descriptor (the
+// 32/64/128-byte swizzle is a function of absolute smem address bits, so row-shifted starts stay consistent
+// with what TMA wrote).  Weights for all taps/phases stay resident in smem for the CTA's lifetime.
+//
+// Fused on load: the previous layer's InstanceNorm + AdaIN (x = y*A[n,c] + B[n,c], stylegan_generator_model.py
+// :420-422,:505) is applied to the band in shared memory (in-bounds pixels only, so the conv's zero padding
+// stays zero).  Fused in the epilogue: +noise*w_c + b_c, LeakyReLU(0.2), fp16 store, per-(n,c) sum / sumsq.
+#pragma once
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <cstdint>
+
+#include "../../include/cfr_b200.h"
+
+namespace cfr {
+
+constexpr int kHaloThreads = 448;   // warp0 TMA, warp1 MMA, warps2-5 transform, warps6-13 epilogue
+constexpr int kHaloW = 130;         // 128 output columns + 1 halo column each side
+
+struct HaloParams {
+  CUtensorMap tmX;                  // input (C, W, H, N), box {C, 130, TH+2, 1}
+  CUtensorMap tmW;                  // weights (Cin, phases*taps*Cout), box {Cin, wBoxRows}
+  int N, H, W;                      // conv output grid == input grid (stride 1)
+  int Cin, Cout;
+  int TH;                           // output rows per band
+  int bandsX, bandsY;               // per image
+  int numPhases, ntaps;
+  int8_t tap_dy[4][9], tap_dx[4][9];
+  int rowBytes;                     // Cin*2 == swizzle width of the halo band and of the weight rows
+  int haloBytes;                    // (TH+2)*130*rowBytes rounded up to 1024
+  int wBytes, wRows, wBoxRows;
+  int accStages;                    // TMEM accumulator stages (each Cout columns, padded to >=16)
+  // affine on load (may be null)
+  const float* inA; const float* inB;   // [N, Cin]
+  // output
+  __half* out; int outH, outW, outC, oscale;
+  int8_t ooff_y[4], ooff_x[4];
+  const float* bias; const float* noise; const float* noise_w;
+  int act; float slope;
+  float* stat_sum; float* stat_sq;  // [N, Cout] or null
+};
+
+struct HaloOp {
+  HaloParams p;
+  int grid, smemBytes;
+  double flops;
+};
+
+int halo_build(const cfr_conv_desc& s, const float* inA, const float* inB, HaloOp* op);
+int halo_launch(const HaloOp& op, cudaStream_t stream);
+
+}  // namespace cfr

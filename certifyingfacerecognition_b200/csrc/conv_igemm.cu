@@ -368,6 +368,8 @@ static EncodeTiledFn get_encode() {
   return fn;
 }
 
+void* get_encode_tiled() { return reinterpret_cast<void*>(get_encode()); }
+
 static CUtensorMapSwizzle swz_enum(int bytes) {
   return bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
                       : (bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B

@@ -255,19 +255,108 @@ __global__ void __launch_bounds__(256) k_blur_act_stats(const __half* __restrict
     atomicAdd(&gsq[n * c + i], s_sq[i]);
   }
 }
+// Separable [1,2,1]/4 x [1,2,1]/4 blur with a 3-row sliding window in registers: every thread owns 8 channels of one
+// pixel column and walks down a band of kBlurRows rows, so each raw element is loaded ~3x from L1 and ~1x from
+// HBM (the 9-tap form above loads it 9x).  Then +noise*w +bias, LeakyReLU(0.2), fp16 store, per-(n,c) sums.
+constexpr int kBlurRows = 32;
+
+__device__ __forceinline__ void hblur8(const __half* __restrict__ rowp, int px, int w, int c, int ch, bool row_ok,
+                                       float (&h)[8]) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) h[i] = 0.f;
+  if (!row_ok) return;
+  float t[8];
+  load8(rowp + static_cast<size_t>(px) * c + ch, t);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) h[i] = 0.5f * t[i];
+  if (px > 0) {
+    load8(rowp + static_cast<size_t>(px - 1) * c + ch, t);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) h[i] += 0.25f * t[i];
+  }
+  if (px < w - 1) {
+    load8(rowp + static_cast<size_t>(px + 1) * c + ch, t);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) h[i] += 0.25f * t[i];
+  }
+}
+
+__global__ void __launch_bounds__(256) k_blur_rows(const __half* __restrict__ raw, __half* __restrict__ y, int h, int w,
+                                                   int c, const float* __restrict__ noise,
+                                                   const float* __restrict__ noise_w, const float* __restrict__ bias,
+                                                   float* __restrict__ gsum, float* __restrict__ gsq) {
+  __shared__ float s_sum[512], s_sq[512];
+  const int n = blockIdx.z;
+  const int c8 = c >> 3;
+  const int ppb = 256 / c8;
+  const int cg = threadIdx.x % c8, pl = threadIdx.x / c8;
+  const int ch = cg * 8;
+  const int px = blockIdx.x * ppb + pl;
+  const int y0 = blockIdx.y * kBlurRows;
+  for (int i = threadIdx.x; i < c; i += 256) {
+    s_sum[i] = 0.f;
+    s_sq[i] = 0.f;
+  }
+  __syncthreads();
+  if (px < w) {
+    float nw[8], bs[8], acc[8], acc2[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      nw[i] = noise_w[ch + i];
+      bs[i] = bias[ch + i];
+      acc[i] = 0.f;
+      acc2[i] = 0.f;
+    }
+    const __half* img = raw + static_cast<size_t>(n) * h * w * c;
+    float hp[8], hc[8], hn[8];
+    hblur8(img + static_cast<size_t>(y0 - 1) * w * c, px, w, c, ch, y0 - 1 >= 0, hp);
+    hblur8(img + static_cast<size_t>(y0) * w * c, px, w, c, ch, true, hc);
+    const int y1 = min(h, y0 + kBlurRows);
+    for (int yy = y0; yy < y1; ++yy) {
+      hblur8(img + static_cast<size_t>(yy + 1) * w * c, px, w, c, ch, yy + 1 < h, hn);
+      const float nz = __ldg(&noise[yy * w + px]);
+      float v[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float t = 0.25f * hp[i] + 0.5f * hc[i] + 0.25f * hn[i] + nz * nw[i] + bs[i];
+        t = t >= 0.f ? t : 0.2f * t;
+        v[i] = t;
+        acc[i] += t;
+        acc2[i] += t * t;
+        hp[i] = hc[i];
+        hc[i] = hn[i];
+      }
+      store8(y + ((static_cast<size_t>(n) * h + yy) * w + px) * c + ch, v);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      atomicAdd(&s_sum[ch + i], acc[i]);
+      atomicAdd(&s_sq[ch + i], acc2[i]);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < c; i += 256) {
+    atomicAdd(&gsum[n * c + i], s_sum[i]);
+    atomicAdd(&gsq[n * c + i], s_sq[i]);
+  }
+}
+
 int launch_blur_act_stats(const __half* raw, __half* y, int n, int h, int w, int c, const float* noise,
                           const float* noise_w, const float* bias, float* sum, float* sq, int mode, cudaStream_t st) {
   if (c % 8 != 0 || c > 512) { set_error("blur_act_stats: C=%d unsupported", c); return 2; }
   const int ppb = 256 / (c / 8);
+  if (mode == 0) {
+    dim3 grid((w + ppb - 1) / ppb, (h + kBlurRows - 1) / kBlurRows, n);
+    k_blur_rows<<<grid, 256, 0, st>>>(raw, y, h, w, c, noise, noise_w, bias, sum, sq);
+    CFR_LAUNCH_CHECK("blur_rows");
+    return 0;
+  }
   int bx = (h * w + ppb - 1) / ppb;
   const int cap = 16 * 148 / (n > 0 ? n : 1) + 1;       // ~16 blocks per SM in total
   if (bx > cap) bx = cap;
   if (bx < 1) bx = 1;
   dim3 grid(bx, n);
-  if (mode == 0)
-    k_blur_act_stats<0><<<grid, 256, 0, st>>>(raw, y, h, w, c, noise, noise_w, bias, sum, sq);
-  else
-    k_blur_act_stats<1><<<grid, 256, 0, st>>>(raw, y, h, w, c, noise, noise_w, bias, sum, sq);
+  k_blur_act_stats<1><<<grid, 256, 0, st>>>(raw, y, h, w, c, noise, noise_w, bias, sum, sq);
   CFR_LAUNCH_CHECK("blur_act_stats");
   return 0;
 }

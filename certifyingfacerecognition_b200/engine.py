@@ -111,6 +111,26 @@ def pack_upconv_phases(weq: Tensor) -> Tuple[Tensor, List[List[Tuple[int, int]]]
     return out, taps
 
 
+def pack_halo_weight(w: Tensor) -> Tensor:
+    """[Cout,Cin,3,3] -> [9*Cout, Cin], rows = (tap=(ky,kx), cout): the halo kernel's per-tap B tiles."""
+    cout, cin = w.shape[:2]
+    return w.permute(2, 3, 0, 1).reshape(9 * cout, cin).contiguous()
+
+
+def pack_halo_upconv(weq: Tensor) -> Tuple[Tensor, List[List[Tuple[int, int]]]]:
+    """[Cout,Cin,3,3] -> ([4*4*Cout, Cin] rows = (phase, tap, cout), taps[phase])."""
+    mats, taps = [], []
+    for a in (0, 1):
+        for b in (0, 1):
+            tp = []
+            for dy, rs in _PHASE_ROWS[a]:
+                for dx, cs in _PHASE_ROWS[b]:
+                    mats.append(sum(weq[:, :, i, j] for i in rs for j in cs))
+                    tp.append((dy, dx))
+            taps.append(tp)
+    return torch.cat(mats, dim=0).contiguous(), taps
+
+
 class Program:
     """Owns a cfr_program handle plus every tensor its launches reference."""
 
@@ -149,7 +169,8 @@ class Program:
              bias: Optional[Tensor] = None, cbias: Optional[Tensor] = None, cbias_per_sample: bool = False,
              noise: Optional[Tensor] = None, noise_w: Optional[Tensor] = None, act: int = L.ACT_NONE,
              slope: float = 0.2, alpha: Optional[Tensor] = None, resid: Optional[Tensor] = None, resid_c: int = 0,
-             stat_sum: Optional[Tensor] = None, stat_sq: Optional[Tensor] = None) -> None:
+             stat_sum: Optional[Tensor] = None, stat_sq: Optional[Tensor] = None, halo: bool = False,
+             in_affine: Optional[Tuple[Tensor, Tensor]] = None) -> None:
         d = L.ConvDesc()
         d.inp, d.N, d.Hin, d.Win, d.Cin = L.ptr(inp), n, hin, win, cin
         d.w, d.wRows, d.Kpad = L.ptr(w), w.shape[0], w.shape[1]
@@ -177,7 +198,15 @@ class Program:
         for t in (inp, w, out, bias, cbias, noise, noise_w, alpha, resid, stat_sum, stat_sq):
             if t is not None:
                 self.keep.append(t)
-        L.check(self.lib.cfr_program_add_conv(self.handle, C.byref(d)))
+        if halo:
+            a, b = in_affine if in_affine is not None else (None, None)
+            for t in (a, b):
+                if t is not None:
+                    self.keep.append(t)
+            L.check(self.lib.cfr_program_add_conv_halo(self.handle, C.byref(d), L.ptr(a), L.ptr(b)))
+        else:
+            assert in_affine is None, "affine-on-load is a halo-kernel feature"
+            L.check(self.lib.cfr_program_add_conv(self.handle, C.byref(d)))
 
     def memset(self, t: Tensor, value: int = 0) -> None:
         self.keep.append(t)
@@ -189,7 +218,7 @@ class Program:
 # ------------------------------------------------------------------------------------------------------
 class SynthesisProgram(Program):
     def __init__(self, g_sd: Dict[str, Tensor], chunk: int, out_res: int = 112, device="cuda",
-                 keep_planar: bool = False, mean: float = 0.5, std: float = 0.5):
+                 keep_planar: bool = False, mean: float = 0.5, std: float = 0.5, halo: bool = True):
         super().__init__()
         dev = torch.device(device)
         self.chunk, self.out_res = chunk, out_res
@@ -219,8 +248,8 @@ class SynthesisProgram(Program):
         total_c = sum(layer_channels(l) for l in range(NUM_LAYERS))
         self.stats = self.hold(torch.zeros(2, chunk * total_c, device=dev))
         self.memset(self.stats)
-        self.A = self.hold(torch.zeros(chunk * 512, device=dev))
-        self.B = self.hold(torch.zeros(chunk * 512, device=dev))
+        self.AB = [(self.hold(torch.zeros(chunk * 512, device=dev)), self.hold(torch.zeros(chunk * 512, device=dev)))
+                   for _ in range(2)]
 
         # ---- activation buffers (NHWC fp16), sized for the largest layer
         max_elems = chunk * 1024 * 1024 * 16
@@ -239,6 +268,8 @@ class SynthesisProgram(Program):
         L.check(lib.cfr_program_add_layer0(h, L.ptr(xhat0), L.ptr(self.styles), off, self.style_off[0], chunk, L.ptr(x)))
 
         stat_off = chunk * 512          # layer 0 uses no statistics slot
+        pending = None                  # (A, B) of the previous layer when its IN/AdaIN has not been applied yet
+        use_halo = lambda l: halo and layer_channels(l - 1) <= 64 and layer_channels(l) <= 64
         for l in range(1, NUM_LAYERS):
             cin, cout, res = layer_channels(l - 1), layer_channels(l), layer_res(l)
             pe = f"synthesis.layer{l}.epilogue."
@@ -248,32 +279,42 @@ class SynthesisProgram(Program):
             ssum = self.stats[0, stat_off:stat_off + chunk * cout]
             ssq = self.stats[1, stat_off:stat_off + chunk * cout]
             stat_off += chunk * cout
+            hk = use_halo(l)
+            assert pending is None or hk
             if l % 2 == 1:
-                w = sd[f"synthesis.layer{l}.conv.weight"]
-                wp = self.hold(_f16(pack_conv_weight(w * (math.sqrt(2.0) / math.sqrt(cin * 9))), dev))
+                w = sd[f"synthesis.layer{l}.conv.weight"] * (math.sqrt(2.0) / math.sqrt(cin * 9))
                 fused_stats = res >= 16
+                wp = self.hold(_f16(pack_halo_weight(w) if hk else pack_conv_weight(w), dev))
                 self.conv(inp=x, n=chunk, hin=res, win=res, cin=cin, w=wp, cout=cout, hout=res, wout=res,
                           tile=tile_for(res), out=y, out_hwc=(res, res, cout), taps=[TAPS3], noise=noise,
                           noise_w=noise_w, bias=bias, act=L.ACT_LRELU, slope=0.2,
-                          stat_sum=ssum if fused_stats else None, stat_sq=ssq if fused_stats else None)
+                          stat_sum=ssum if fused_stats else None, stat_sq=ssq if fused_stats else None,
+                          halo=hk, in_affine=pending)
                 if not fused_stats:
                     L.check(lib.cfr_program_add_blur_act_stats(h, L.ptr(y), None, chunk, res, res, cout, None, None,
                                                                None, L.ptr(ssum), L.ptr(ssq), 1))
             else:
                 lo = res // 2
-                wp, taps = pack_upconv_phases(upconv_equiv_weight(sd, l))
+                weq = upconv_equiv_weight(sd, l)
+                wp, taps = pack_halo_upconv(weq) if hk else pack_upconv_phases(weq)
                 wp = self.hold(_f16(wp, dev))
                 self.conv(inp=x, n=chunk, hin=lo, win=lo, cin=cin, w=wp, cout=cout, hout=lo, wout=lo,
                           tile=tile_for(lo), out=raw, out_hwc=(res, res, cout), taps=taps, oscale=2,
-                          ooff=[(0, 0), (0, 1), (1, 0), (1, 1)], w_rows_per_phase=cout)
+                          ooff=[(0, 0), (0, 1), (1, 0), (1, 1)], w_rows_per_phase=0 if hk else cout,
+                          halo=hk, in_affine=pending)
                 L.check(lib.cfr_program_add_blur_act_stats(h, L.ptr(raw), L.ptr(y), chunk, res, res, cout, L.ptr(noise),
                                                            L.ptr(noise_w), L.ptr(bias), L.ptr(ssum), L.ptr(ssq), 0))
+            # A/B double-buffered by layer parity: the consumer of layer l reads them while layer l+1's are written
+            A, B = self.AB[l % 2]
             L.check(lib.cfr_program_add_finalize_stats(h, L.ptr(ssum), L.ptr(ssq), L.ptr(self.styles), off,
                                                        self.style_off[l], chunk, cout, 1.0 / (res * res),
-                                                       L.ptr(self.A), L.ptr(self.B)))
+                                                       L.ptr(A), L.ptr(B)))
+            if l < NUM_LAYERS - 1 and not use_halo(l + 1):
+                L.check(lib.cfr_program_add_affine(h, L.ptr(y), L.ptr(A), L.ptr(B), chunk, res * res, cout, L.ptr(y)))
+                pending = None
+            else:
+                pending = (A, B)            # applied on load by the consumer (halo conv / toRGB)
             if l < NUM_LAYERS - 1:
-                L.check(lib.cfr_program_add_affine(h, L.ptr(y), L.ptr(self.A), L.ptr(self.B), chunk, res * res, cout,
-                                                   L.ptr(y)))
                 x, y = y, x
         # ---- toRGB + postprocess + bilinear + normalise; the last layer's IN/AdaIN is applied on load
         wrgb = sd["synthesis.output8.conv.weight"].reshape(3, 16) * (1.0 / math.sqrt(16))
@@ -281,7 +322,7 @@ class SynthesisProgram(Program):
         b_rgb = self.hold(_f32(sd["synthesis.output8.bias"], dev))
         self.img = self.hold(torch.zeros(chunk, out_res, out_res, 16, dtype=torch.float16, device=dev))
         self.img_planar = self.hold(torch.zeros(chunk, 3, out_res, out_res, device=dev)) if keep_planar else None
-        L.check(lib.cfr_program_add_torgb_resize(h, L.ptr(y), L.ptr(self.A), L.ptr(self.B), chunk, 1024, 16,
+        L.check(lib.cfr_program_add_torgb_resize(h, L.ptr(y), L.ptr(pending[0]), L.ptr(pending[1]), chunk, 1024, 16,
                                                  L.ptr(w_rgb), L.ptr(b_rgb), out_res, mean, std, L.ptr(self.img),
                                                  L.ptr(self.img_planar)))
         self.last_y = y

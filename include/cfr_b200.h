@@ -73,6 +73,11 @@ CFR_API double cfr_program_op_flops(const cfr_program* p, int i);
 CFR_API int cfr_program_run_timed(cfr_program* p, cfr_stream_t stream, float* ms_out, int n);
 
 CFR_API int cfr_program_add_conv(cfr_program* p, const cfr_conv_desc* d);
+/* Same contract as add_conv for the HBM-bound high-resolution layers (Cin, Cout in {16,32,64}, stride 1): the
+ * input band + halo is staged in shared memory once and shared by all taps; weights are [phase*tap*Cout][Cin]
+ * (Kpad == Cin).  inA/inB (may be NULL): per-(n, cin) affine x = y*A + B applied on load -- the previous layer's
+ * InstanceNorm + AdaIN (stylegan_generator_model.py:420-422,:505) -- with the conv's zero padding left at zero. */
+CFR_API int cfr_program_add_conv_halo(cfr_program* p, const cfr_conv_desc* d, const float* inA, const float* inB);
 CFR_API int cfr_program_add_memset(cfr_program* p, void* ptr, int value, size_t bytes);
 /* StyleModulationLayer dense, stylegan_generator_model.py:503 (all 18 layers): styles[b][rows] */
 CFR_API int cfr_program_add_styles(cfr_program* p, const float* wp2, const float* w_style, const float* b_style,
