@@ -54,9 +54,9 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
   uint8_t* halo[2] = {smem, smem + p.haloBytes};
   uint8_t* wsm = smem + 2 * p.haloBytes;
   uint8_t* ctrl = wsm + p.wBytes;
-  uint64_t* hfull = reinterpret_cast<uint64_t*>(ctrl);     // [2]
-  uint64_t* hready = hfull + 2;                            // [2] (after the affine transform)
-  uint64_t* hempty = hready + 2;                           // [2]
+  uint64_t* hready = reinterpret_cast<uint64_t*>(ctrl);    // [2] band loaded (+ affine applied)
+  uint64_t* hspare = hready + 2;                           // [2] (unused)
+  uint64_t* hempty = hspare + 2;                           // [2]
   uint64_t* wbar = hempty + 2;                             // [1]
   uint64_t* tfull = wbar + 1;                              // [16]
   uint64_t* tempty = tfull + 16;                           // [16]
@@ -78,13 +78,12 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
   while (tmemCols < static_cast<uint32_t>(AS * ACC_COLS)) tmemCols <<= 1;
 
   if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&p.tmX);
     tma_prefetch_desc(&p.tmW);
   }
   if (warp == 1) {
     if (lane == 0) {
       for (int i = 0; i < 2; ++i) {
-        mbar_init(&hfull[i], 1);
+        mbar_init(&hspare[i], 1);
         mbar_init(&hready[i], 1);
         mbar_init(&hempty[i], 1);
       }
@@ -114,15 +113,6 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
       mbar_expect_tx(wbar, p.wRows * p.rowBytes);
       for (int r0 = 0; r0 < p.wRows; r0 += p.wBoxRows)
         tma_load_2d(wsm + static_cast<size_t>(r0) * p.rowBytes, &p.tmW, wbar, 0, r0);
-      const uint32_t boxBytes = (p.TH + 2) * kHaloW * p.rowBytes;
-      int bc = 0;
-      for (int b = band0; b < band1; ++b, ++bc) {
-        const Band bd = decode_band(p, b);
-        const int hs = bc & 1;
-        mbar_wait(&hempty[hs], ((bc >> 1) & 1) ^ 1);
-        mbar_expect_tx(&hfull[hs], boxBytes);
-        tma_load_4d(halo[hs], &p.tmX, &hfull[hs], 0, bd.x0 - 1, bd.y0 - 1, bd.n);
-      }
     }
   } else if (warp == 1) {
     // ================================================================ MMA issuer
@@ -137,7 +127,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
       for (int b = band0; b < band1; ++b, ++bc) {
         const Band bd = decode_band(p, b);
         const int hs = bc & 1;
-        mbar_wait(affine ? &hready[hs] : &hfull[hs], (bc >> 1) & 1);
+        mbar_wait(&hready[hs], (bc >> 1) & 1);
         tc_fence_after();
         const uint32_t h_base = smem_u32(halo[hs]);
         for (int r = 0; r < bd.rows; ++r) {
@@ -160,36 +150,67 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
         umma_commit(&hempty[hs]);          // halo stage free once every MMA of this band has read it
       }
     }
-  } else if (warp < 6) {
-    // ================================================================ affine-on-load transform (warps 2..5)
-    if (affine) {
-      const int tt = threadIdx.x - 64;     // 0..127
-      const int nch = p.rowBytes >> 4;
-      const int totalChunks = (p.TH + 2) * kHaloW * nch;
-      int bc = 0;
-      int cur_n = -1;
-      for (int b = band0; b < band1; ++b, ++bc) {
-        const Band bd = decode_band(p, b);
-        const int hs = bc & 1;
+  } else if (warp < 2 + kLoaderWarps) {
+    // ================================================================ band loader + affine-on-load (warps 2..9)
+    // cp.async 16-byte chunks straight into the swizzled operand layout (TMA boxes with 32..128-byte rows are
+    // row-rate bound: profiles/ncu_r01_halo_tma.txt), zero-filling out-of-image pixels == the conv padding.
+    constexpr int LT = kLoaderWarps * 32;
+    const int tt = threadIdx.x - 64;
+    const int nchLog = p.rowBytes == 32 ? 1 : (p.rowBytes == 64 ? 2 : 3);
+    const int nch = 1 << nchLog;
+    const int totalChunks = (p.TH + 2) * kHaloW * nch;
+    const size_t imgStride = static_cast<size_t>(p.H) * p.W * p.Cin;
+
+    auto issue = [&](const Band& bd, int hs) {
+      const uint32_t hb_addr = smem_u32(halo[hs]);
+      const __half* img = p.in + static_cast<size_t>(bd.n) * imgStride;
+      for (int c = tt; c < totalChunks; c += LT) {
+        const int pix = c >> nchLog;
+        const int row = pix / kHaloW, col = pix - row * kHaloW;
+        const int gy = bd.y0 - 1 + row, gx = bd.x0 - 1 + col;
+        const bool ok = gy >= 0 && gy < p.H && gx >= 0 && gx < p.W;
+        const uint32_t lin = hb_addr + (static_cast<uint32_t>(c) << 4);
+        const uint32_t dst = lin ^ (((lin >> 7) & (nch - 1)) << 4);
+        const __half* src = ok ? img + (static_cast<size_t>(gy) * p.W + gx) * p.Cin + ((c & (nch - 1)) << 3) : p.in;
+        cp_async16(dst, src, ok ? 16u : 0u);
+      }
+      cp_async_commit();
+    };
+
+    int bc = 0;
+    int cur_n = -1;
+    if (band0 < band1) issue(decode_band(p, band0), 0);
+    for (int b = band0; b < band1; ++b, ++bc) {
+      const Band bd = decode_band(p, b);
+      const int hs = bc & 1;
+      if (b + 1 < band1) {
+        const int nbc = bc + 1;
+        mbar_wait(&hempty[nbc & 1], ((nbc >> 1) & 1) ^ 1);      // the MMAs of the band two back are done with it
+        issue(decode_band(p, b + 1), nbc & 1);
+        cp_async_wait<1>();
+      } else {
+        cp_async_wait<0>();
+      }
+      if (affine) {
         if (bd.n != cur_n) {
-          named_bar_sync(2, 128);
+          named_bar_sync(2, LT);
           if (tt < p.Cin) {
             sA[tt] = p.inA[bd.n * p.Cin + tt];
             sB[tt] = p.inB[bd.n * p.Cin + tt];
           }
           cur_n = bd.n;
-          named_bar_sync(2, 128);
+          named_bar_sync(2, LT);
         }
-        mbar_wait(&hfull[hs], (bc >> 1) & 1);
+        const uint32_t hb_addr = smem_u32(halo[hs]);
         uint8_t* hb = halo[hs];
-        const uint32_t hb_addr = smem_u32(hb);
-        for (int c = tt; c < totalChunks; c += 128) {
-          const int pix = c / nch;
+        for (int c = tt; c < totalChunks; c += LT) {        // same chunks this thread copied: no barrier needed
+          const int pix = c >> nchLog;
           const int row = pix / kHaloW, col = pix - row * kHaloW;
           const int gy = bd.y0 - 1 + row, gx = bd.x0 - 1 + col;
           if (gy < 0 || gy >= p.H || gx < 0 || gx >= p.W) continue;      // zero padding stays zero
-          const uint32_t off = static_cast<uint32_t>(c) << 4;
-          const int lc = (c % nch) ^ (((hb_addr + off) >> 7) & (nch - 1));  // logical 8-channel group
+          const uint32_t lin = hb_addr + (static_cast<uint32_t>(c) << 4);
+          const uint32_t off = (lin ^ (((lin >> 7) & (nch - 1)) << 4)) - hb_addr;
+          const int lc = c & (nch - 1);
           uint4 v = *reinterpret_cast<uint4*>(hb + off);
           __half2* h2 = reinterpret_cast<__half2*>(&v);
 #pragma unroll
@@ -201,17 +222,17 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
           }
           *reinterpret_cast<uint4*>(hb + off) = v;
         }
-        fence_proxy_async();               // generic-proxy writes -> visible to the tensor core (async proxy)
-        named_bar_sync(2, 128);
-        if (tt == 0) mbar_arrive(&hready[hs]);
       }
+      fence_proxy_async();                 // generic-proxy writes -> visible to the tensor core (async proxy)
+      named_bar_sync(2, LT);
+      if (tt == 0) mbar_arrive(&hready[hs]);
     }
   } else {
-    // ================================================================ epilogue (warps 6..13)
-    const int e = warp - 6;
+    // ================================================================ epilogue (last 8 warps)
+    const int e = warp - (2 + kLoaderWarps);
     const int q = warp & 3;                // TMEM lane quarter
     const int grp = e >> 2;                // handles tiles with (tcount & 1) == grp
-    const int et = threadIdx.x - 192;      // 0..255
+    const int et = threadIdx.x - (2 + kLoaderWarps) * 32;      // 0..255
     const bool do_stats = p.stat_sum != nullptr;
     float racc[REG_STATS ? COUT : 1], racc2[REG_STATS ? COUT : 1];
 #pragma unroll
@@ -400,16 +421,7 @@ int halo_build(const cfr_conv_desc& s, const float* inA, const float* inB, HaloO
   p.bias = s.bias; p.noise = s.noise; p.noise_w = s.noise_w; p.act = s.act; p.slope = s.slope;
   p.stat_sum = s.stat_sum; p.stat_sq = s.stat_sq;
   if (s.outC != s.Cout) { set_error("halo conv: outC must equal Cout"); return 2; }
-  {
-    cuuint64_t dims[4] = {(cuuint64_t)s.Cin, (cuuint64_t)s.Win, (cuuint64_t)s.Hin, (cuuint64_t)s.N};
-    cuuint64_t strides[3] = {(cuuint64_t)s.Cin * 2, (cuuint64_t)s.Win * s.Cin * 2, (cuuint64_t)s.Hin * s.Win * s.Cin * 2};
-    cuuint32_t box[4] = {(cuuint32_t)s.Cin, (cuuint32_t)kHaloW, (cuuint32_t)(th + 2), 1};
-    cuuint32_t estr[4] = {1, 1, 1, 1};
-    CUresult r = enc(&p.tmX, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(s.in), dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, swz(p.rowBytes), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) { set_error("halo conv: encode(X) failed: %d", (int)r); return 3; }
-  }
+  p.in = static_cast<const __half*>(s.in);
   {
     if (s.Kpad != s.Cin || s.wRows != p.wRows) { set_error("halo conv: weights must be [phases*taps*Cout][Cin] (got [%d][%d])", s.wRows, s.Kpad); return 2; }
     cuuint64_t dims[2] = {(cuuint64_t)s.Cin, (cuuint64_t)p.wRows};

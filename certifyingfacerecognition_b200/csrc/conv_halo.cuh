@@ -20,11 +20,12 @@
 
 namespace cfr {
 
-constexpr int kHaloThreads = 448;   // warp0 TMA, warp1 MMA, warps2-5 transform, warps6-13 epilogue
+constexpr int kLoaderWarps = 8;
+constexpr int kHaloThreads = (2 + kLoaderWarps + 8) * 32;   // warp0 weights TMA, warp1 MMA, 8 loader/transform, 8 epilogue
 constexpr int kHaloW = 130;         // 128 output columns + 1 halo column each side
 
 struct HaloParams {
-  CUtensorMap tmX;                  // input (C, W, H, N), box {C, 130, TH+2, 1}
+  const __half* in;                 // NHWC fp16 input [N,H,W,Cin]
   CUtensorMap tmW;                  // weights (Cin, phases*taps*Cout), box {Cin, wBoxRows}
   int N, H, W;                      // conv output grid == input grid (stride 1)
   int Cin, Cout;

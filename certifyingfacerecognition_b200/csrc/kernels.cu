@@ -281,7 +281,7 @@ __device__ __forceinline__ void hblur8(const __half* __restrict__ rowp, int px, 
   }
 }
 
-__global__ void __launch_bounds__(256) k_blur_rows(const __half* __restrict__ raw, __half* __restrict__ y, int h, int w,
+__global__ void __launch_bounds__(256, 4) k_blur_rows(const __half* __restrict__ raw, __half* __restrict__ y, int h, int w,
                                                    int c, const float* __restrict__ noise,
                                                    const float* __restrict__ noise_w, const float* __restrict__ bias,
                                                    float* __restrict__ gsum, float* __restrict__ gsq) {

@@ -345,7 +345,7 @@ def test_halo_conv_matches_torch(E, n, cin, cout, h, w, affine):
     assert torch.allclose(ssq, 2 * (ref * ref).sum(dim=[2, 3]), rtol=1e-3, atol=5e-2)
 
 
-@pytest.mark.parametrize("n,cin,cout,lo_h,lo_w", [(2, 64, 32, 12, 128), (1, 32, 16, 20, 256), (2, 64, 64, 5, 96)])
+@pytest.mark.parametrize("n,cin,cout,lo_h,lo_w", [(2, 64, 32, 12, 128), (1, 32, 16, 20, 256), (2, 64, 32, 5, 96)])
 def test_halo_upconv_matches_torch(E, n, cin, cout, lo_h, lo_w):
     g = torch.Generator().manual_seed(cin + lo_h)
     yprev = torch.randn(n, cin, lo_h, lo_w, generator=g).cuda().half().float()
