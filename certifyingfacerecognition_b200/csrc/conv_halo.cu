@@ -118,33 +118,54 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
     // ================================================================ MMA issuer
     if (lane == 0) {
       const uint32_t idesc = make_idesc_f16(128, COUT);
-      const uint32_t sbo = 8 * p.rowBytes;
+      const uint32_t dhi = smem_desc_hi(8 * p.rowBytes, p.rowBytes);
       const int kPer = p.Cin / 16;
-      const uint32_t w_base = smem_u32(wsm);
+      const uint32_t rb16 = p.rowBytes >> 4;                 // row pitch in 16-byte units
+      const uint32_t w_lo = smem_desc_lo(smem_u32(wsm));
+      const uint32_t w_tap = COUT * rb16;                    // B tile pitch per (phase, tap)
+      // per-(phase, tap) A offsets inside the halo band, in 16-byte units (registers: loops fully unrolled)
+      uint32_t toff[4][9];
+#pragma unroll
+      for (int ph = 0; ph < 4; ++ph)
+#pragma unroll
+        for (int t = 0; t < 9; ++t)
+          toff[ph][t] = (ph < p.numPhases && t < p.ntaps)
+                            ? ((1 + p.tap_dy[ph][t]) * kHaloW + 1 + p.tap_dx[ph][t]) * rb16 : 0u;
+      const uint32_t row_step = kHaloW * rb16;
       mbar_wait(wbar, 0);
       int bc = 0;
       uint32_t tcount = 0;
+      uint32_t as = 0, aphase = 0;
       for (int b = band0; b < band1; ++b, ++bc) {
         const Band bd = decode_band(p, b);
         const int hs = bc & 1;
         mbar_wait(&hready[hs], (bc >> 1) & 1);
         tc_fence_after();
-        const uint32_t h_base = smem_u32(halo[hs]);
-        for (int r = 0; r < bd.rows; ++r) {
-          for (int ph = 0; ph < p.numPhases; ++ph, ++tcount) {
-            const int as = tcount % AS;
-            mbar_wait(&tempty[as], ((tcount / AS) & 1) ^ 1);
-            tc_fence_after();
-            const uint32_t d_tmem = tmem_base + as * ACC_COLS;
-            for (int tap = 0; tap < p.ntaps; ++tap) {
-              const uint32_t a0 = h_base + ((r + 1 + p.tap_dy[ph][tap]) * kHaloW + 1 + p.tap_dx[ph][tap]) * p.rowBytes;
-              const uint32_t b0 = w_base + ((ph * p.ntaps + tap) * COUT) * p.rowBytes;
-              for (int j = 0; j < kPer; ++j) {
-                umma_f16(d_tmem, make_smem_desc(a0 + j * 32, sbo, p.rowBytes), make_smem_desc(b0 + j * 32, sbo, p.rowBytes),
-                         idesc, (tap | j) != 0 ? 1u : 0u);
+        uint32_t a_row = smem_desc_lo(smem_u32(halo[hs]));
+        for (int r = 0; r < bd.rows; ++r, a_row += row_step) {
+#pragma unroll
+          for (int ph = 0; ph < 4; ++ph) {
+            if (ph < p.numPhases) {
+              mbar_wait(&tempty[as], aphase ^ 1);
+              tc_fence_after();
+              const uint32_t d_tmem = tmem_base + as * ACC_COLS;
+              uint32_t b_lo = w_lo + ph * p.ntaps * w_tap;
+#pragma unroll
+              for (int t = 0; t < 9; ++t) {
+                if (t < p.ntaps) {
+                  const uint32_t a_lo = a_row + toff[ph][t];
+                  for (int j = 0; j < kPer; ++j)
+                    umma_f16_lohi(d_tmem, a_lo + 2 * j, dhi, b_lo + 2 * j, dhi, idesc, (t | j) != 0 ? 1u : 0u);
+                  b_lo += w_tap;
+                }
+              }
+              umma_commit(&tfull[as]);
+              ++tcount;
+              if (++as == static_cast<uint32_t>(AS)) {
+                as = 0;
+                aphase ^= 1;
               }
             }
-            umma_commit(&tfull[as]);
           }
         }
         umma_commit(&hempty[hs]);          // halo stage free once every MMA of this band has read it

@@ -145,8 +145,12 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
     // ===================================================================== MMA issuer
     if (lane == 0) {
       const uint32_t idesc = make_idesc_f16(kBM, p.BN);
-      const uint32_t sboA = 8 * p.swizzleA;
-      const int kPerChunk = p.CB / 16;
+      const uint32_t a_hi = smem_desc_hi(8 * p.swizzleA, p.swizzleA);
+      const uint32_t b_hi = smem_desc_hi(1024, 128);
+      const int kPer = p.CB / 16;
+      const uint32_t sub16 = subBytes >> 4;
+      const uint32_t smem_lo = smem_desc_lo(smem_u32(smem));
+      const uint32_t stage16 = static_cast<uint32_t>(p.stageBytes) >> 4;
       int stage = 0;
       uint32_t phase = 0;
       int as = 0;
@@ -155,17 +159,30 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
         mbar_wait(&tempty_bar[as], aphase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * p.BN;
+        uint32_t acc = 0;
+        int remaining = chunksTotal;
         for (int s = 0; s < stagesPerTile; ++s) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const int nch = min(p.G, chunksTotal - s * p.G);
-          const uint32_t a_base = smem_u32(smem + static_cast<size_t>(stage) * p.stageBytes);
-          const uint32_t b_base = a_base + kBM * 128;
-          for (int g = 0; g < nch; ++g) {
-            for (int j = 0; j < kPerChunk; ++j) {
-              const uint64_t adesc = make_smem_desc(a_base + g * subBytes + j * 32, sboA, p.swizzleA);
-              const uint64_t bdesc = make_smem_desc(b_base + (g * kPerChunk + j) * 32, 1024, 128);
-              umma_f16(d_tmem, adesc, bdesc, idesc, (s | g | j) != 0 ? 1u : 0u);
+          const int nk = (remaining < p.G ? remaining : p.G) * kPer;     // K=16 steps in this stage
+          remaining -= p.G;
+          const uint32_t a0 = smem_lo + stage * stage16;
+          const uint32_t b0 = a0 + (kBM * 128 >> 4);
+          if (kPer == 4) {                 // one 64-channel chunk per stage: 4 K-steps inside the 128B swizzle row
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              umma_f16_lohi(d_tmem, a0 + 2 * j, a_hi, b0 + 2 * j, b_hi, idesc, acc);
+              acc = 1;
+            }
+          } else {
+            uint32_t a_lo = a0;
+            for (int k = 0, j = 0; k < nk; ++k) {
+              umma_f16_lohi(d_tmem, a_lo + 2 * j, a_hi, b0 + 2 * k, b_hi, idesc, acc);
+              acc = 1;
+              if (++j == kPer) {
+                j = 0;
+                a_lo += sub16;
+              }
             }
           }
           umma_commit(&empty_bar[stage]);   // frees this smem stage once the MMAs above have read it

@@ -142,6 +142,26 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t 
   d |= layout << 61;
   return d;
 }
+// Split form for hot issue loops: the high word (SBO, version, layout) is loop-invariant, the low word is
+// (address >> 4) | LBO<<16 and can be advanced with plain integer adds (16-byte units).
+__device__ __forceinline__ uint32_t smem_desc_hi(uint32_t sbo_bytes, uint32_t swizzle_bytes) {
+  return static_cast<uint32_t>(make_smem_desc(0, sbo_bytes, swizzle_bytes) >> 32);
+}
+__device__ __forceinline__ uint32_t smem_desc_lo(uint32_t smem_addr) {
+  return ((smem_addr & 0x3FFFF) >> 4) | (1u << 16);
+}
+__device__ __forceinline__ void umma_f16_lohi(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                              uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}\n" ::"r"(d_tmem),
+      "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
 // Instruction descriptor: fp16 x fp16 -> fp32, both operands K-major, M x N tile.
 __host__ __device__ __forceinline__ uint32_t make_idesc_f16(uint32_t M, uint32_t N) {
   uint32_t d = 0;
