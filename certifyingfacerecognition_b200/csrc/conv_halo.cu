@@ -77,10 +77,10 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
   uint32_t tmemCols = 32;
   while (tmemCols < static_cast<uint32_t>(AS * ACC_COLS)) tmemCols <<= 1;
 
-  if (warp == 0 && lane == 0) {
+  if (warp == kHaloProducerWarp && lane == 0) {
     tma_prefetch_desc(&p.tmW);
   }
-  if (warp == 1) {
+  if (warp == kHaloMmaWarp) {
     if (lane == 0) {
       for (int i = 0; i < 2; ++i) {
         mbar_init(&hspare[i], 1);
@@ -107,14 +107,14 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 0) {
-    // ================================================================ TMA producer
+  if (warp == kHaloProducerWarp) {
+    // ================================================================ TMA producer (weights only)
     if (lane == 0) {
       mbar_expect_tx(wbar, p.wRows * p.rowBytes);
       for (int r0 = 0; r0 < p.wRows; r0 += p.wBoxRows)
         tma_load_2d(wsm + static_cast<size_t>(r0) * p.rowBytes, &p.tmW, wbar, 0, r0);
     }
-  } else if (warp == 1) {
+  } else if (warp == kHaloMmaWarp) {
     // ================================================================ MMA issuer
     if (lane == 0) {
       const uint32_t idesc = make_idesc_f16(128, COUT);
@@ -171,12 +171,12 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
         umma_commit(&hempty[hs]);          // halo stage free once every MMA of this band has read it
       }
     }
-  } else if (warp < 2 + kLoaderWarps) {
-    // ================================================================ band loader + affine-on-load (warps 2..9)
+  } else if (warp >= 8) {
+    // ================================================================ band loader + affine-on-load (warps 8..15)
     // cp.async 16-byte chunks straight into the swizzled operand layout (TMA boxes with 32..128-byte rows are
     // row-rate bound: profiles/ncu_r01_halo_tma.txt), zero-filling out-of-image pixels == the conv padding.
     constexpr int LT = kLoaderWarps * 32;
-    const int tt = threadIdx.x - 64;
+    const int tt = threadIdx.x - 256;
     const int nchLog = p.rowBytes == 32 ? 1 : (p.rowBytes == 64 ? 2 : 3);
     const int nch = 1 << nchLog;
     const int totalChunks = (p.TH + 2) * kHaloW * nch;
@@ -249,11 +249,10 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
       if (tt == 0) mbar_arrive(&hready[hs]);
     }
   } else {
-    // ================================================================ epilogue (last 8 warps)
-    const int e = warp - (2 + kLoaderWarps);
+    // ================================================================ epilogue (warps 0..7)
     const int q = warp & 3;                // TMEM lane quarter
-    const int grp = e >> 2;                // handles tiles with (tcount & 1) == grp
-    const int et = threadIdx.x - (2 + kLoaderWarps) * 32;      // 0..255
+    const int grp = warp >> 2;             // handles tiles with (tcount & 1) == grp
+    const int et = threadIdx.x;            // 0..255
     const bool do_stats = p.stat_sum != nullptr;
     float racc[REG_STATS ? COUT : 1], racc2[REG_STATS ? COUT : 1];
 #pragma unroll
@@ -383,7 +382,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) {
+  if (warp == kHaloMmaWarp) {
     tc_fence_after();
     tmem_dealloc(tmem_base, tmemCols);
   }

@@ -13,6 +13,11 @@ namespace cfr {
 // --------------------------------------------------------------------------------------------
 // device
 // --------------------------------------------------------------------------------------------
+// Warp roles.  The single MMA-issuing thread lives in the HIGHEST warp: the SM sub-partition arbiter favours
+// higher warp ids, and a starved issuer stalls the whole pipeline (profiles/ncu_r01_notes.md).
+constexpr int kProducerWarp = 4;
+constexpr int kMmaWarp = 5;
+
 struct TileCoord {
   int n0, y0, x0, phase, ntile;
 };
@@ -84,11 +89,11 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
   uint32_t tmemCols = 32;
   while (tmemCols < 2u * p.BN) tmemCols <<= 1;
 
-  if (warp == 0 && lane == 0) {
+  if (warp == kProducerWarp && lane == 0) {
     tma_prefetch_desc(&p.tmA);
     tma_prefetch_desc(&p.tmB);
   }
-  if (warp == 1) {
+  if (warp == kMmaWarp) {
     if (lane == 0) {
       for (int i = 0; i < S; ++i) {
         mbar_init(&full_bar[i], 1);
@@ -112,7 +117,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 0) {
+  if (warp == kProducerWarp) {
     // ===================================================================== TMA producer
     if (lane == 0) {
       int stage = 0;
@@ -141,7 +146,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == kMmaWarp) {
     // ===================================================================== MMA issuer
     if (lane == 0) {
       const uint32_t idesc = make_idesc_f16(kBM, p.BN);
@@ -197,13 +202,13 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
       }
     }
   } else {
-    // ===================================================================== epilogue (warps 2..5)
+    // ===================================================================== epilogue (warps 0..3)
     const int q = warp & 3;                      // TMEM lane quarter this warp may read
     const int row = q * 32 + lane;               // M row == pixel index inside the tile box
     const int tx = row % p.TW;
     const int ty = (row / p.TW) % p.TH;
     const int tn = row / (p.TW * p.TH);
-    const int et = threadIdx.x - 64;             // 0..127
+    const int et = threadIdx.x;                  // 0..127
     int as = 0;
     uint32_t aphase = 0;
     int cur_img = -1;
@@ -337,7 +342,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) {
+  if (warp == kMmaWarp) {
     tc_fence_after();
     tmem_dealloc(tmem_base, tmemCols);
   }

@@ -22,7 +22,7 @@
 
 namespace cfr {
 
-constexpr int kConvThreads = 192;   // warp0: TMA producer, warp1: MMA issuer + TMEM owner, warps2-5: epilogue
+constexpr int kConvThreads = 192;   // warps0-3: epilogue, warp4: TMA producer, warp5: MMA issuer + TMEM owner
 constexpr int kBM = 128;
 constexpr int kMaxPhases = 4;
 constexpr int kMaxTaps = 9;
