@@ -116,60 +116,67 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
     }
   } else if (warp == kHaloMmaWarp) {
     // ================================================================ MMA issuer
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc_f16(128, COUT);
-      const uint32_t dhi = smem_desc_hi(8 * p.rowBytes, p.rowBytes);
-      const int kPer = p.Cin / 16;
-      const uint32_t rb16 = p.rowBytes >> 4;                 // row pitch in 16-byte units
-      const uint32_t w_lo = smem_desc_lo(smem_u32(wsm));
-      const uint32_t w_tap = COUT * rb16;                    // B tile pitch per (phase, tap)
-      // per-(phase, tap) A offsets inside the halo band, in 16-byte units (registers: loops fully unrolled)
-      uint32_t toff[4][9];
+    // The whole warp runs the loop (so every descriptor word stays in uniform registers); one elected lane
+    // issues tcgen05.mma / commit.  With N = 16..64 an MMA takes only 8..32 tensor cycles, so the issue loop
+    // itself must cost a handful of instructions per MMA (profiles/ncu_r01_notes.md).
+    const bool leader = elect_one();
+    const uint32_t idesc = make_idesc_f16(128, COUT);
+    const uint32_t dhi = smem_desc_hi(8 * p.rowBytes, p.rowBytes);
+    const int kPer = p.Cin / 16;
+    const uint32_t rb16 = p.rowBytes >> 4;                 // row pitch in 16-byte units
+    const uint32_t w_lo = smem_desc_lo(smem_u32(wsm));
+    const uint32_t w_tap = COUT * rb16;                    // B tile pitch per (phase, tap)
+    uint32_t toff[4][9];                                   // A offsets of every (phase, tap), 16-byte units
 #pragma unroll
-      for (int ph = 0; ph < 4; ++ph)
+    for (int ph = 0; ph < 4; ++ph)
 #pragma unroll
-        for (int t = 0; t < 9; ++t)
-          toff[ph][t] = (ph < p.numPhases && t < p.ntaps)
-                            ? ((1 + p.tap_dy[ph][t]) * kHaloW + 1 + p.tap_dx[ph][t]) * rb16 : 0u;
-      const uint32_t row_step = kHaloW * rb16;
-      mbar_wait(wbar, 0);
-      int bc = 0;
-      uint32_t tcount = 0;
-      uint32_t as = 0, aphase = 0;
-      for (int b = band0; b < band1; ++b, ++bc) {
-        const Band bd = decode_band(p, b);
-        const int hs = bc & 1;
-        mbar_wait(&hready[hs], (bc >> 1) & 1);
-        tc_fence_after();
-        uint32_t a_row = smem_desc_lo(smem_u32(halo[hs]));
-        for (int r = 0; r < bd.rows; ++r, a_row += row_step) {
+      for (int t = 0; t < 9; ++t)
+        toff[ph][t] = (ph < p.numPhases && t < p.ntaps)
+                          ? ((1 + p.tap_dy[ph][t]) * kHaloW + 1 + p.tap_dx[ph][t]) * rb16 : 0u;
+    const uint32_t row_step = kHaloW * rb16;
+    mbar_wait(wbar, 0);
+    int bc = 0;
+    uint32_t as = 0, aphase = 0;
+    for (int b = band0; b < band1; ++b, ++bc) {
+      const Band bd = decode_band(p, b);
+      const int hs = bc & 1;
+      mbar_wait(&hready[hs], (bc >> 1) & 1);
+      tc_fence_after();
+      uint32_t a_row = smem_desc_lo(smem_u32(halo[hs]));
+      for (int r = 0; r < bd.rows; ++r, a_row += row_step) {
 #pragma unroll
-          for (int ph = 0; ph < 4; ++ph) {
-            if (ph < p.numPhases) {
-              mbar_wait(&tempty[as], aphase ^ 1);
-              tc_fence_after();
-              const uint32_t d_tmem = tmem_base + as * ACC_COLS;
-              uint32_t b_lo = w_lo + ph * p.ntaps * w_tap;
+        for (int ph = 0; ph < 4; ++ph) {
+          if (ph < p.numPhases) {
+            mbar_wait(&tempty[as], aphase ^ 1);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + as * ACC_COLS;
+            uint32_t b_lo = w_lo + ph * p.ntaps * w_tap;
 #pragma unroll
-              for (int t = 0; t < 9; ++t) {
-                if (t < p.ntaps) {
-                  const uint32_t a_lo = a_row + toff[ph][t];
-                  for (int j = 0; j < kPer; ++j)
-                    umma_f16_lohi(d_tmem, a_lo + 2 * j, dhi, b_lo + 2 * j, dhi, idesc, (t | j) != 0 ? 1u : 0u);
-                  b_lo += w_tap;
+            for (int t = 0; t < 9; ++t) {
+              if (t < p.ntaps) {
+                const uint32_t a_lo = a_row + toff[ph][t];
+                if (leader) {
+                  umma_f16_lohi(d_tmem, a_lo, dhi, b_lo, dhi, idesc, t != 0 ? 1u : 0u);
+                  if (kPer > 1) umma_f16_lohi(d_tmem, a_lo + 2, dhi, b_lo + 2, dhi, idesc, 1u);
+                  if (kPer > 2) {
+                    umma_f16_lohi(d_tmem, a_lo + 4, dhi, b_lo + 4, dhi, idesc, 1u);
+                    umma_f16_lohi(d_tmem, a_lo + 6, dhi, b_lo + 6, dhi, idesc, 1u);
+                  }
                 }
+                b_lo += w_tap;
               }
-              umma_commit(&tfull[as]);
-              ++tcount;
-              if (++as == static_cast<uint32_t>(AS)) {
-                as = 0;
-                aphase ^= 1;
-              }
+            }
+            if (leader) umma_commit(&tfull[as]);
+            __syncwarp();
+            if (++as == static_cast<uint32_t>(AS)) {
+              as = 0;
+              aphase ^= 1;
             }
           }
         }
-        umma_commit(&hempty[hs]);          // halo stage free once every MMA of this band has read it
       }
+      if (leader) umma_commit(&hempty[hs]);          // halo stage free once every MMA of this band has read it
+      __syncwarp();
     }
   } else if (warp >= 8) {
     // ================================================================ band loader + affine-on-load (warps 8..15)

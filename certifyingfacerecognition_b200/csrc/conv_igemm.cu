@@ -119,71 +119,77 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
 
   if (warp == kProducerWarp) {
     // ===================================================================== TMA producer
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int item = item0; item < item1; ++item) {
-        const TileCoord t = decode_item(p, item);
-        const int wrow = t.n0 * p.wRowsPerSample + t.phase * p.wRowsPerPhase + t.ntile * p.BN;
-        for (int s = 0; s < stagesPerTile; ++s) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);
-          const int nch = min(p.G, chunksTotal - s * p.G);
-          uint8_t* a_dst = smem + static_cast<size_t>(stage) * p.stageBytes;
-          uint8_t* b_dst = a_dst + kBM * 128;
+    // (whole warp runs the loop so coordinates / descriptors stay in uniform registers; one elected lane issues)
+    const bool leader = elect_one();
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int item = item0; item < item1; ++item) {
+      const TileCoord t = decode_item(p, item);
+      const int wrow = t.n0 * p.wRowsPerSample + t.phase * p.wRowsPerPhase + t.ntile * p.BN;
+      const int xb = t.x0 * p.stride, yb = t.y0 * p.stride;
+      int chunk = 0;
+      for (int s = 0; s < stagesPerTile; ++s) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        const int nch = min(p.G, chunksTotal - chunk);
+        uint8_t* a_dst = smem + static_cast<size_t>(stage) * p.stageBytes;
+        if (leader) {
           mbar_expect_tx(&full_bar[stage], nch * subBytes + p.BN * 128);
           for (int g = 0; g < nch; ++g) {
-            const int chunk = s * p.G + g;
-            const int tap = chunk / p.nCB;
-            const int cb = chunk - tap * p.nCB;
-            tma_load_4d(a_dst + g * subBytes, &p.tmA, &full_bar[stage], cb * p.CB,
-                        t.x0 * p.stride + p.tap_dx[t.phase][tap], t.y0 * p.stride + p.tap_dy[t.phase][tap], t.n0);
+            const int c = chunk + g;
+            const int tap = c / p.nCB;
+            const int cb = c - tap * p.nCB;
+            tma_load_4d(a_dst + g * subBytes, &p.tmA, &full_bar[stage], cb * p.CB, xb + p.tap_dx[t.phase][tap],
+                        yb + p.tap_dy[t.phase][tap], t.n0);
           }
-          tma_load_2d(b_dst, &p.tmB, &full_bar[stage], s * 64, wrow);
-          if (++stage == S) {
-            stage = 0;
-            phase ^= 1;
-          }
+          tma_load_2d(a_dst + kBM * 128, &p.tmB, &full_bar[stage], s * 64, wrow);
+        }
+        __syncwarp();
+        chunk += nch;
+        if (++stage == S) {
+          stage = 0;
+          phase ^= 1;
         }
       }
     }
   } else if (warp == kMmaWarp) {
     // ===================================================================== MMA issuer
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc_f16(kBM, p.BN);
-      const uint32_t a_hi = smem_desc_hi(8 * p.swizzleA, p.swizzleA);
-      const uint32_t b_hi = smem_desc_hi(1024, 128);
-      const int kPer = p.CB / 16;
-      const uint32_t sub16 = subBytes >> 4;
-      const uint32_t smem_lo = smem_desc_lo(smem_u32(smem));
-      const uint32_t stage16 = static_cast<uint32_t>(p.stageBytes) >> 4;
-      int stage = 0;
-      uint32_t phase = 0;
-      int as = 0;
-      uint32_t aphase = 0;
-      for (int item = item0; item < item1; ++item) {
-        mbar_wait(&tempty_bar[as], aphase ^ 1);
+    const bool leader = elect_one();
+    const uint32_t idesc = make_idesc_f16(kBM, p.BN);
+    const uint32_t a_hi = smem_desc_hi(8 * p.swizzleA, p.swizzleA);
+    const uint32_t b_hi = smem_desc_hi(1024, 128);
+    const int kPer = p.CB / 16;
+    const uint32_t sub16 = subBytes >> 4;
+    const uint32_t smem_lo = smem_desc_lo(smem_u32(smem));
+    const uint32_t stage16 = static_cast<uint32_t>(p.stageBytes) >> 4;
+    int stage = 0;
+    uint32_t phase = 0;
+    int as = 0;
+    uint32_t aphase = 0;
+    for (int item = item0; item < item1; ++item) {
+      mbar_wait(&tempty_bar[as], aphase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + as * p.BN;
+      uint32_t acc = 0;
+      int remaining = chunksTotal;
+      for (int s = 0; s < stagesPerTile; ++s) {
+        mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + as * p.BN;
-        uint32_t acc = 0;
-        int remaining = chunksTotal;
-        for (int s = 0; s < stagesPerTile; ++s) {
-          mbar_wait(&full_bar[stage], phase);
-          tc_fence_after();
-          const int nk = (remaining < p.G ? remaining : p.G) * kPer;     // K=16 steps in this stage
-          remaining -= p.G;
-          const uint32_t a0 = smem_lo + stage * stage16;
-          const uint32_t b0 = a0 + (kBM * 128 >> 4);
+        const int nk = (remaining < p.G ? remaining : p.G) * kPer;     // K=16 steps in this stage
+        remaining -= p.G;
+        const uint32_t a0 = smem_lo + stage * stage16;
+        const uint32_t b0 = a0 + (kBM * 128 >> 4);
+        if (leader) {
           if (kPer == 4) {                 // one 64-channel chunk per stage: 4 K-steps inside the 128B swizzle row
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              umma_f16_lohi(d_tmem, a0 + 2 * j, a_hi, b0 + 2 * j, b_hi, idesc, acc);
-              acc = 1;
-            }
+            umma_f16_lohi(d_tmem, a0, a_hi, b0, b_hi, idesc, acc);
+            umma_f16_lohi(d_tmem, a0 + 2, a_hi, b0 + 2, b_hi, idesc, 1u);
+            umma_f16_lohi(d_tmem, a0 + 4, a_hi, b0 + 4, b_hi, idesc, 1u);
+            umma_f16_lohi(d_tmem, a0 + 6, a_hi, b0 + 6, b_hi, idesc, 1u);
           } else {
             uint32_t a_lo = a0;
+            uint32_t accl = acc;
             for (int k = 0, j = 0; k < nk; ++k) {
-              umma_f16_lohi(d_tmem, a_lo + 2 * j, a_hi, b0 + 2 * k, b_hi, idesc, acc);
-              acc = 1;
+              umma_f16_lohi(d_tmem, a_lo + 2 * j, a_hi, b0 + 2 * k, b_hi, idesc, accl);
+              accl = 1;
               if (++j == kPer) {
                 j = 0;
                 a_lo += sub16;
@@ -191,15 +197,18 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
             }
           }
           umma_commit(&empty_bar[stage]);   // frees this smem stage once the MMAs above have read it
-          if (++stage == S) {
-            stage = 0;
-            phase ^= 1;
-          }
         }
-        umma_commit(&tfull_bar[as]);        // accumulator complete -> epilogue
-        as ^= 1;
-        if (as == 0) aphase ^= 1;
+        acc = 1;
+        __syncwarp();
+        if (++stage == S) {
+          stage = 0;
+          phase ^= 1;
+        }
       }
+      if (leader) umma_commit(&tfull_bar[as]);        // accumulator complete -> epilogue
+      __syncwarp();
+      as ^= 1;
+      if (as == 0) aphase ^= 1;
     }
   } else {
     // ===================================================================== epilogue (warps 0..3)
