@@ -188,25 +188,37 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
     const int nch = 1 << nchLog;
     const int totalChunks = (p.TH + 2) * kHaloW * nch;
     const size_t imgStride = static_cast<size_t>(p.H) * p.W * p.Cin;
+    const int lc = tt & (nch - 1);            // this thread's 8-channel group (LT % nch == 0: constant)
+    const int pstep = LT >> nchLog;           // pixels advanced per iteration (<= 128 < kHaloW)
+    const int pix0 = tt >> nchLog;
+    const int row0 = pix0 / kHaloW, col0 = pix0 - row0 * kHaloW;
 
     auto issue = [&](const Band& bd, int hs) {
       const uint32_t hb_addr = smem_u32(halo[hs]);
-      const __half* img = p.in + static_cast<size_t>(bd.n) * imgStride;
+      const __half* img = p.in + static_cast<size_t>(bd.n) * imgStride + lc * 8;
+      int row = row0, col = col0;
       for (int c = tt; c < totalChunks; c += LT) {
-        const int pix = c >> nchLog;
-        const int row = pix / kHaloW, col = pix - row * kHaloW;
         const int gy = bd.y0 - 1 + row, gx = bd.x0 - 1 + col;
-        const bool ok = gy >= 0 && gy < p.H && gx >= 0 && gx < p.W;
+        const bool ok = static_cast<unsigned>(gy) < static_cast<unsigned>(p.H) &&
+                        static_cast<unsigned>(gx) < static_cast<unsigned>(p.W);
         const uint32_t lin = hb_addr + (static_cast<uint32_t>(c) << 4);
         const uint32_t dst = lin ^ (((lin >> 7) & (nch - 1)) << 4);
-        const __half* src = ok ? img + (static_cast<size_t>(gy) * p.W + gx) * p.Cin + ((c & (nch - 1)) << 3) : p.in;
+        const __half* src = ok ? img + (static_cast<size_t>(gy) * p.W + gx) * p.Cin : p.in;
         cp_async16(dst, src, ok ? 16u : 0u);
+        col += pstep;
+        if (col >= kHaloW) {
+          col -= kHaloW;
+          ++row;
+        }
       }
       cp_async_commit();
     };
 
     int bc = 0;
     int cur_n = -1;
+    float ca[8], cb[8];                       // this thread's A/B for the current image
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { ca[i] = 1.f; cb[i] = 0.f; }
     if (band0 < band1) issue(decode_band(p, band0), 0);
     for (int b = band0; b < band1; ++b, ++bc) {
       const Band bd = decode_band(p, b);
@@ -221,31 +233,35 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
       }
       if (affine) {
         if (bd.n != cur_n) {
-          named_bar_sync(2, LT);
-          if (tt < p.Cin) {
-            sA[tt] = p.inA[bd.n * p.Cin + tt];
-            sB[tt] = p.inB[bd.n * p.Cin + tt];
-          }
           cur_n = bd.n;
-          named_bar_sync(2, LT);
+          const float4* ap = reinterpret_cast<const float4*>(p.inA + bd.n * p.Cin + lc * 8);
+          const float4* bp = reinterpret_cast<const float4*>(p.inB + bd.n * p.Cin + lc * 8);
+          const float4 a0 = __ldg(ap), a1 = __ldg(ap + 1), b0 = __ldg(bp), b1 = __ldg(bp + 1);
+          ca[0] = a0.x; ca[1] = a0.y; ca[2] = a0.z; ca[3] = a0.w; ca[4] = a1.x; ca[5] = a1.y; ca[6] = a1.z; ca[7] = a1.w;
+          cb[0] = b0.x; cb[1] = b0.y; cb[2] = b0.z; cb[3] = b0.w; cb[4] = b1.x; cb[5] = b1.y; cb[6] = b1.z; cb[7] = b1.w;
         }
         const uint32_t hb_addr = smem_u32(halo[hs]);
         uint8_t* hb = halo[hs];
+        int row = row0, col = col0;
         for (int c = tt; c < totalChunks; c += LT) {        // same chunks this thread copied: no barrier needed
-          const int pix = c >> nchLog;
-          const int row = pix / kHaloW, col = pix - row * kHaloW;
           const int gy = bd.y0 - 1 + row, gx = bd.x0 - 1 + col;
-          if (gy < 0 || gy >= p.H || gx < 0 || gx >= p.W) continue;      // zero padding stays zero
+          const bool ok = static_cast<unsigned>(gy) < static_cast<unsigned>(p.H) &&
+                          static_cast<unsigned>(gx) < static_cast<unsigned>(p.W);
+          col += pstep;
+          if (col >= kHaloW) {
+            col -= kHaloW;
+            ++row;
+          }
+          if (!ok) continue;                                   // zero padding stays zero
           const uint32_t lin = hb_addr + (static_cast<uint32_t>(c) << 4);
           const uint32_t off = (lin ^ (((lin >> 7) & (nch - 1)) << 4)) - hb_addr;
-          const int lc = c & (nch - 1);
           uint4 v = *reinterpret_cast<uint4*>(hb + off);
           __half2* h2 = reinterpret_cast<__half2*>(&v);
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             float2 f = __half22float2(h2[i]);
-            f.x = f.x * sA[lc * 8 + 2 * i] + sB[lc * 8 + 2 * i];
-            f.y = f.y * sA[lc * 8 + 2 * i + 1] + sB[lc * 8 + 2 * i + 1];
+            f.x = fmaf(f.x, ca[2 * i], cb[2 * i]);
+            f.y = fmaf(f.y, ca[2 * i + 1], cb[2 * i + 1]);
             h2[i] = __floats2half2_rn(f.x, f.y);
           }
           *reinterpret_cast<uint4*>(hb + off) = v;
@@ -257,14 +273,27 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
     }
   } else {
     // ================================================================ epilogue (warps 0..7)
+    constexpr bool HOIST = COUT == 16;     // per-channel noise gain / bias live in registers
     const int q = warp & 3;                // TMEM lane quarter
     const int grp = warp >> 2;             // handles tiles with (tcount & 1) == grp
     const int et = threadIdx.x;            // 0..255
     const bool do_stats = p.stat_sum != nullptr;
+    const bool has_noise = p.noise != nullptr, has_bias = p.bias != nullptr;
+    const bool lrelu = p.act == CFR_ACT_LRELU;
+    const float slope = p.slope;
     float racc[REG_STATS ? COUT : 1], racc2[REG_STATS ? COUT : 1];
 #pragma unroll
     for (int i = 0; i < (REG_STATS ? COUT : 1); ++i) { racc[i] = 0.f; racc2[i] = 0.f; }
+    float hnw[HOIST ? COUT : 1], hbs[HOIST ? COUT : 1];
+    if constexpr (HOIST) {
+#pragma unroll
+      for (int i = 0; i < COUT; ++i) {
+        hnw[i] = has_noise ? p.noise_w[i] : 0.f;
+        hbs[i] = has_bias ? p.bias[i] : 0.f;
+      }
+    }
     uint32_t tcount = 0;
+    uint32_t as = 0, aphase = 0;
     int cur_n = -1;
     for (int b = band0; b < band1; ++b) {
       const Band bd = decode_band(p, b);
@@ -284,44 +313,54 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
       for (int r = 0; r < bd.rows; ++r) {
         const int gy = bd.y0 + r;
         for (int ph = 0; ph < p.numPhases; ++ph, ++tcount) {
+          const uint32_t my_as = as, my_ph = aphase;
+          if (++as == static_cast<uint32_t>(AS)) {
+            as = 0;
+            aphase ^= 1;
+          }
           if ((tcount & 1) != static_cast<uint32_t>(grp)) continue;
-          const int as = tcount % AS;
           const int oy = gy * p.oscale + p.ooff_y[ph];
           const int ox = gx * p.oscale + p.ooff_x[ph];
           const size_t pix = (static_cast<size_t>(bd.n) * p.outH + oy) * p.outW + ox;
-          const float nz = (p.noise != nullptr && colok) ? __ldg(&p.noise[oy * p.outW + ox]) : 0.f;
-          mbar_wait(&tfull[as], (tcount / AS) & 1);
+          const float nz = (has_noise && colok) ? __ldg(&p.noise[oy * p.outW + ox]) : 0.f;
+          mbar_wait(&tfull[my_as], my_ph);
           tc_fence_after();
-          const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * ACC_COLS;
+          const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + my_as * ACC_COLS;
 #pragma unroll
           for (int ci = 0; ci < NCH; ++ci) {
             float v[16];
             tmem_ld16(t_row + ci * 16, v);
             const int ch0 = ci * 16;
-            if (p.bias != nullptr) {
+            if constexpr (HOIST) {
 #pragma unroll
-              for (int i = 0; i < 16; i += 4) {
-                const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + ch0 + i));
-                v[i] += b4.x; v[i + 1] += b4.y; v[i + 2] += b4.z; v[i + 3] += b4.w;
+              for (int i = 0; i < 16; ++i) v[i] = fmaf(nz, hnw[i], v[i]) + hbs[i];
+            } else {
+              if (has_bias) {
+#pragma unroll
+                for (int i = 0; i < 16; i += 4) {
+                  const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + ch0 + i));
+                  v[i] += b4.x; v[i + 1] += b4.y; v[i + 2] += b4.z; v[i + 3] += b4.w;
+                }
+              }
+              if (has_noise) {
+#pragma unroll
+                for (int i = 0; i < 16; i += 4) {
+                  const float4 w4 = __ldg(reinterpret_cast<const float4*>(p.noise_w + ch0 + i));
+                  v[i] = fmaf(nz, w4.x, v[i]); v[i + 1] = fmaf(nz, w4.y, v[i + 1]);
+                  v[i + 2] = fmaf(nz, w4.z, v[i + 2]); v[i + 3] = fmaf(nz, w4.w, v[i + 3]);
+                }
               }
             }
-            if (p.noise != nullptr) {
+            if (lrelu) {
 #pragma unroll
-              for (int i = 0; i < 16; i += 4) {
-                const float4 w4 = __ldg(reinterpret_cast<const float4*>(p.noise_w + ch0 + i));
-                v[i] += nz * w4.x; v[i + 1] += nz * w4.y; v[i + 2] += nz * w4.z; v[i + 3] += nz * w4.w;
-              }
-            }
-            if (p.act == CFR_ACT_LRELU) {
-#pragma unroll
-              for (int i = 0; i < 16; ++i) v[i] = v[i] >= 0.f ? v[i] : v[i] * p.slope;
+              for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], v[i] * slope);      // slope < 1
             }
             if (colok) {
               uint4 o[2];
               __half2* h2 = reinterpret_cast<__half2*>(o);
 #pragma unroll
               for (int i = 0; i < 8; ++i) h2[i] = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
-              uint4* op = reinterpret_cast<uint4*>(p.out + pix * p.outC + ch0);
+              uint4* op = reinterpret_cast<uint4*>(p.out + pix * COUT + ch0);
               op[0] = o[0];
               op[1] = o[1];
             }
@@ -331,7 +370,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
                 for (int i = 0; i < 16; ++i) {
                   const float t = colok ? v[i] : 0.f;
                   racc[ch0 + i] += t;
-                  racc2[ch0 + i] += t * t;
+                  racc2[ch0 + i] = fmaf(t, t, racc2[ch0 + i]);
                 }
               } else {
                 float sq[16];
@@ -352,7 +391,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
           }
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&tempty[as]);
+          if (lane == 0) mbar_arrive(&tempty[my_as]);
         }
       }
       if constexpr (REG_STATS) {
