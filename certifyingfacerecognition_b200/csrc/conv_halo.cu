@@ -77,15 +77,15 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
   uint32_t tmemCols = 32;
   while (tmemCols < static_cast<uint32_t>(AS * ACC_COLS)) tmemCols <<= 1;
 
-  if (warp == kHaloProducerWarp && lane == 0) {
+  if (warp == kHaloMmaWarp0 && lane == 0) {
     tma_prefetch_desc(&p.tmW);
   }
-  if (warp == kHaloMmaWarp) {
+  if (warp == kHaloMmaWarp0) {
     if (lane == 0) {
       for (int i = 0; i < 2; ++i) {
         mbar_init(&hspare[i], 1);
         mbar_init(&hready[i], 1);
-        mbar_init(&hempty[i], 1);
+        mbar_init(&hempty[i], kMmaWarps);
       }
       mbar_init(wbar, 1);
       for (int i = 0; i < 16; ++i) {
@@ -107,18 +107,11 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == kHaloProducerWarp) {
-    // ================================================================ TMA producer (weights only)
-    if (lane == 0) {
-      mbar_expect_tx(wbar, p.wRows * p.rowBytes);
-      for (int r0 = 0; r0 < p.wRows; r0 += p.wBoxRows)
-        tma_load_2d(wsm + static_cast<size_t>(r0) * p.rowBytes, &p.tmW, wbar, 0, r0);
-    }
-  } else if (warp == kHaloMmaWarp) {
-    // ================================================================ MMA issuer
-    // The whole warp runs the loop (so every descriptor word stays in uniform registers); one elected lane
-    // issues tcgen05.mma / commit.  With N = 16..64 an MMA takes only 8..32 tensor cycles, so the issue loop
-    // itself must cost a handful of instructions per MMA (profiles/ncu_r01_notes.md).
+  if (warp >= kHaloMmaWarp0) {
+    // ================================================================ MMA issuers (kMmaWarps warps, alternate tiles)
+    // The whole warp runs the loop (so descriptor words stay warp-uniform); one elected lane issues
+    // tcgen05.mma / commit.  Warp m issues the tiles with (tile index mod kMmaWarps) == m.
+    const uint32_t mw = warp - kHaloMmaWarp0;
     const bool leader = elect_one();
     const uint32_t idesc = make_idesc_f16(128, COUT);
     const uint32_t dhi = smem_desc_hi(8 * p.rowBytes, p.rowBytes);
@@ -134,9 +127,15 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
         toff[ph][t] = (ph < p.numPhases && t < p.ntaps)
                           ? ((1 + p.tap_dy[ph][t]) * kHaloW + 1 + p.tap_dx[ph][t]) * rb16 : 0u;
     const uint32_t row_step = kHaloW * rb16;
+    if (mw == 0 && leader) {              // weights for every (phase, tap): resident for the CTA's lifetime
+      mbar_expect_tx(wbar, p.wRows * p.rowBytes);
+      for (int r0 = 0; r0 < p.wRows; r0 += p.wBoxRows)
+        tma_load_2d(wsm + static_cast<size_t>(r0) * p.rowBytes, &p.tmW, wbar, 0, r0);
+    }
+    __syncwarp();
     mbar_wait(wbar, 0);
     int bc = 0;
-    uint32_t as = 0, aphase = 0;
+    uint32_t as = 0, aphase = 0, tsel = 0;
     for (int b = band0; b < band1; ++b, ++bc) {
       const Band bd = decode_band(p, b);
       const int hs = bc & 1;
@@ -147,6 +146,9 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
 #pragma unroll
         for (int ph = 0; ph < 4; ++ph) {
           if (ph < p.numPhases) {
+            const bool mine = tsel == mw;
+            tsel = (tsel + 1) & (kMmaWarps - 1);
+            if (mine) {
             mbar_wait(&tempty[as], aphase ^ 1);
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + as * ACC_COLS;
@@ -168,6 +170,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
             }
             if (leader) umma_commit(&tfull[as]);
             __syncwarp();
+            }
             if (++as == static_cast<uint32_t>(AS)) {
               as = 0;
               aphase ^= 1;
@@ -428,7 +431,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
 
   tc_fence_before();
   __syncthreads();
-  if (warp == kHaloMmaWarp) {
+  if (warp == kHaloMmaWarp0) {
     tc_fence_after();
     tmem_dealloc(tmem_base, tmemCols);
   }

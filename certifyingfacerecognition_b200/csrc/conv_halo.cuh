@@ -21,9 +21,10 @@
 namespace cfr {
 
 constexpr int kLoaderWarps = 8;
-constexpr int kHaloThreads = (8 + kLoaderWarps + 2) * 32;   // warps0-7 epilogue, 8-15 loader/transform, 16 weights TMA, 17 MMA
-constexpr int kHaloProducerWarp = 8 + kLoaderWarps;
-constexpr int kHaloMmaWarp = 9 + kLoaderWarps;        // highest warp id: the arbiter favours it (see conv_igemm.cu)
+constexpr int kMmaWarps = 4;          // tcgen05.mma issue is per-thread serial (~30 SASS instr per MMA incl. R2UR moves);
+                                      // with N = 16..64 the MMAs are tiny, so several warps issue alternate tiles
+constexpr int kHaloMmaWarp0 = 8 + kLoaderWarps;      // warps 0-7 epilogue, 8-15 loader/transform, 16-19 MMA issuers
+constexpr int kHaloThreads = (8 + kLoaderWarps + kMmaWarps) * 32;
 constexpr int kHaloW = 130;         // 128 output columns + 1 halo column each side
 
 struct HaloParams {
