@@ -51,13 +51,12 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
   constexpr int ACC_COLS = COUT;                 // TMEM columns per accumulator stage
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* halo[2] = {smem, smem + p.haloBytes};
-  uint8_t* wsm = smem + 2 * p.haloBytes;
+  const int NS = p.haloStages;                                   // 2 or 3 halo band buffers
+  uint8_t* wsm = smem + NS * p.haloBytes;
   uint8_t* ctrl = wsm + p.wBytes;
-  uint64_t* hready = reinterpret_cast<uint64_t*>(ctrl);    // [2] band loaded (+ affine applied)
-  uint64_t* hspare = hready + 2;                           // [2] (unused)
-  uint64_t* hempty = hspare + 2;                           // [2]
-  uint64_t* wbar = hempty + 2;                             // [1]
+  uint64_t* hready = reinterpret_cast<uint64_t*>(ctrl);    // [3] band loaded (+ affine applied)
+  uint64_t* hempty = hready + 3;                           // [3]
+  uint64_t* wbar = hempty + 3;                             // [1]
   uint64_t* tfull = wbar + 1;                              // [16]
   uint64_t* tempty = tfull + 16;                           // [16]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 16);
@@ -82,8 +81,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
   }
   if (warp == kHaloMmaWarp0) {
     if (lane == 0) {
-      for (int i = 0; i < 2; ++i) {
-        mbar_init(&hspare[i], 1);
+      for (int i = 0; i < 3; ++i) {
         mbar_init(&hready[i], 1);
         mbar_init(&hempty[i], kMmaWarps);
       }
@@ -134,14 +132,14 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
     }
     __syncwarp();
     mbar_wait(wbar, 0);
-    int bc = 0;
+    int hs = 0;
+    uint32_t hphase = 0;
     uint32_t as = 0, aphase = 0, tsel = 0;
-    for (int b = band0; b < band1; ++b, ++bc) {
+    for (int b = band0; b < band1; ++b) {
       const Band bd = decode_band(p, b);
-      const int hs = bc & 1;
-      mbar_wait(&hready[hs], (bc >> 1) & 1);
+      mbar_wait(&hready[hs], hphase);
       tc_fence_after();
-      uint32_t a_row = smem_desc_lo(smem_u32(halo[hs]));
+      uint32_t a_row = smem_desc_lo(smem_u32(smem + hs * p.haloBytes));
       for (int r = 0; r < bd.rows; ++r, a_row += row_step) {
 #pragma unroll
         for (int ph = 0; ph < 4; ++ph) {
@@ -180,6 +178,10 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
       }
       if (leader) umma_commit(&hempty[hs]);          // halo stage free once every MMA of this band has read it
       __syncwarp();
+      if (++hs == NS) {
+        hs = 0;
+        hphase ^= 1;
+      }
     }
   } else if (warp >= 8) {
     // ================================================================ band loader + affine-on-load (warps 8..15)
@@ -197,7 +199,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
     const int row0 = pix0 / kHaloW, col0 = pix0 - row0 * kHaloW;
 
     auto issue = [&](const Band& bd, int hs) {
-      const uint32_t hb_addr = smem_u32(halo[hs]);
+      const uint32_t hb_addr = smem_u32(smem + hs * p.haloBytes);
       const __half* img = p.in + static_cast<size_t>(bd.n) * imgStride + lc * 8;
       int row = row0, col = col0;
       for (int c = tt; c < totalChunks; c += LT) {
@@ -217,23 +219,18 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
       cp_async_commit();
     };
 
-    int bc = 0;
     int cur_n = -1;
     float ca[8], cb[8];                       // this thread's A/B for the current image
 #pragma unroll
     for (int i = 0; i < 8; ++i) { ca[i] = 1.f; cb[i] = 0.f; }
-    if (band0 < band1) issue(decode_band(p, band0), 0);
-    for (int b = band0; b < band1; ++b, ++bc) {
+    // prefetch distance NS-1: band b+NS-1 is requested right after band b has been handed to the MMA warps
+    for (int i = 0; i < NS - 1; ++i)
+      if (band0 + i < band1) issue(decode_band(p, band0 + i), i);
+    int hs = 0;                               // stage of band b
+    for (int b = band0; b < band1; ++b) {
       const Band bd = decode_band(p, b);
-      const int hs = bc & 1;
-      if (b + 1 < band1) {
-        const int nbc = bc + 1;
-        mbar_wait(&hempty[nbc & 1], ((nbc >> 1) & 1) ^ 1);      // the MMAs of the band two back are done with it
-        issue(decode_band(p, b + 1), nbc & 1);
-        cp_async_wait<1>();
-      } else {
-        cp_async_wait<0>();
-      }
+      const int ahead = min(NS - 1, band1 - b) - 1;      // younger groups still allowed in flight
+      if (ahead >= 1) cp_async_wait<1>(); else cp_async_wait<0>();
       if (affine) {
         if (bd.n != cur_n) {
           cur_n = bd.n;
@@ -243,8 +240,8 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
           ca[0] = a0.x; ca[1] = a0.y; ca[2] = a0.z; ca[3] = a0.w; ca[4] = a1.x; ca[5] = a1.y; ca[6] = a1.z; ca[7] = a1.w;
           cb[0] = b0.x; cb[1] = b0.y; cb[2] = b0.z; cb[3] = b0.w; cb[4] = b1.x; cb[5] = b1.y; cb[6] = b1.z; cb[7] = b1.w;
         }
-        const uint32_t hb_addr = smem_u32(halo[hs]);
-        uint8_t* hb = halo[hs];
+        uint8_t* hb = smem + hs * p.haloBytes;
+        const uint32_t hb_addr = smem_u32(hb);
         int row = row0, col = col0;
         for (int c = tt; c < totalChunks; c += LT) {        // same chunks this thread copied: no barrier needed
           const int gy = bd.y0 - 1 + row, gx = bd.x0 - 1 + col;
@@ -273,6 +270,15 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
       fence_proxy_async();                 // generic-proxy writes -> visible to the tensor core (async proxy)
       named_bar_sync(2, LT);
       if (tt == 0) mbar_arrive(&hready[hs]);
+      if (b + NS - 1 < band1) {
+        // band j = (b - band0) + NS - 1 goes into stage j % NS, whose previous tenant was band j - NS: wait for
+        // that band's MMAs (the (j/NS - 1)-th completion of hempty[stage]) before overwriting it.
+        const int j = (b - band0) + NS - 1;
+        const int js = j % NS, jt = j / NS;
+        if (jt >= 1) mbar_wait(&hempty[js], (jt & 1) ^ 1);
+        issue(decode_band(p, b + NS - 1), js);
+      }
+      if (++hs == NS) hs = 0;
     }
   } else {
     // ================================================================ epilogue (warps 0..7)
@@ -472,12 +478,21 @@ int halo_build(const cfr_conv_desc& s, const float* inA, const float* inB, HaloO
   while (p.wBoxRows > 256 || p.wRows % p.wBoxRows != 0) --p.wBoxRows;
   const int ctrl = 8 * 40 + 16 + 4 * 64 * 4 + 64;
   const int budget = 227 * 1024 - 1024 - ctrl - p.wBytes;
-  int th = 16;
-  while (th > 1 && 2 * (((th + 2) * kHaloW * p.rowBytes + 1023) / 1024 * 1024) > budget) --th;
+  auto halo_bytes = [&](int th) { return ((th + 2) * kHaloW * p.rowBytes + 1023) / 1024 * 1024; };
+  // three band buffers (prefetch distance 2) with the tallest band that fits, but at least 4 rows per band;
+  // otherwise fall back to two buffers
+  int ns = 3, th = 16;
+  while (th > 1 && ns * halo_bytes(th) > budget) --th;
+  if (th < 4) {
+    ns = 2;
+    th = 16;
+    while (th > 1 && ns * halo_bytes(th) > budget) --th;
+  }
   if (th > s.Hout) th = s.Hout;
-  if (2 * (((th + 2) * kHaloW * p.rowBytes + 1023) / 1024 * 1024) > budget) { set_error("halo conv: smem budget"); return 2; }
+  if (ns * halo_bytes(th) > budget) { set_error("halo conv: smem budget"); return 2; }
   p.TH = th;
-  p.haloBytes = ((th + 2) * kHaloW * p.rowBytes + 1023) / 1024 * 1024;
+  p.haloStages = ns;
+  p.haloBytes = halo_bytes(th);
   p.bandsX = (s.Wout + 127) / 128;
   p.bandsY = (s.Hout + th - 1) / th;
   p.accStages = 512 / s.Cout;
@@ -504,7 +519,7 @@ int halo_build(const cfr_conv_desc& s, const float* inA, const float* inB, HaloO
   }
   const int total = p.N * p.bandsX * p.bandsY;
   op->grid = total < num_sms() ? total : num_sms();
-  op->smemBytes = 2 * p.haloBytes + p.wBytes + ctrl + 1024;
+  op->smemBytes = p.haloStages * p.haloBytes + p.wBytes + ctrl + 1024;
   op->flops = 2.0 * s.N * s.Hout * s.Wout * s.numPhases * s.ntaps * static_cast<double>(s.Cin) * s.Cout;
   return 0;
 }

@@ -38,6 +38,7 @@ struct HaloParams {
   int8_t tap_dy[4][9], tap_dx[4][9];
   int rowBytes;                     // Cin*2 == swizzle width of the halo band and of the weight rows
   int haloBytes;                    // (TH+2)*130*rowBytes rounded up to 1024
+  int haloStages;                   // band buffers in the ring (2 or 3)
   int wBytes, wRows, wBoxRows;
   int accStages;                    // TMEM accumulator stages (each Cout columns, padded to >=16)
   // affine on load (may be null)
