@@ -375,11 +375,12 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
             }
             if (do_stats) {
               if constexpr (REG_STATS) {
+                if (colok) {
 #pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                  const float t = colok ? v[i] : 0.f;
-                  racc[ch0 + i] += t;
-                  racc2[ch0 + i] = fmaf(t, t, racc2[ch0 + i]);
+                  for (int i = 0; i < 16; ++i) {
+                    racc[ch0 + i] += v[i];
+                    racc2[ch0 + i] = fmaf(v[i], v[i], racc2[ch0 + i]);
+                  }
                 }
               } else {
                 float sq[16];

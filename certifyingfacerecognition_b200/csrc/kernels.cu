@@ -260,31 +260,37 @@ __global__ void __launch_bounds__(256) k_blur_act_stats(const __half* __restrict
 // HBM (the 9-tap form above loads it 9x).  Then +noise*w +bias, LeakyReLU(0.2), fp16 store, per-(n,c) sums.
 constexpr int kBlurRows = 32;
 
-__device__ __forceinline__ void hblur8(const __half* __restrict__ rowp, int px, int w, int c, int ch, bool row_ok,
-                                       float (&h)[8]) {
-#pragma unroll
-  for (int i = 0; i < 8; ++i) h[i] = 0.f;
-  if (!row_ok) return;
-  float t[8];
-  load8(rowp + static_cast<size_t>(px) * c + ch, t);
-#pragma unroll
-  for (int i = 0; i < 8; ++i) h[i] = 0.5f * t[i];
-  if (px > 0) {
-    load8(rowp + static_cast<size_t>(px - 1) * c + ch, t);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) h[i] += 0.25f * t[i];
+struct Raw3 {
+  uint4 l, c, r;
+};
+__device__ __forceinline__ Raw3 load_raw3(const __half* __restrict__ rowp, int px, int w, int c, int ch, bool row_ok) {
+  Raw3 o;
+  const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+  o.l = z; o.c = z; o.r = z;
+  if (row_ok) {
+    const __half* pc = rowp + static_cast<size_t>(px) * c + ch;
+    o.c = __ldg(reinterpret_cast<const uint4*>(pc));
+    if (px > 0) o.l = __ldg(reinterpret_cast<const uint4*>(pc - c));
+    if (px < w - 1) o.r = __ldg(reinterpret_cast<const uint4*>(pc + c));
   }
-  if (px < w - 1) {
-    load8(rowp + static_cast<size_t>(px + 1) * c + ch, t);
+  return o;
+}
+__device__ __forceinline__ void hblur8(const Raw3& t, float (&h)[8]) {
+  const __half2* l2 = reinterpret_cast<const __half2*>(&t.l);
+  const __half2* c2 = reinterpret_cast<const __half2*>(&t.c);
+  const __half2* r2 = reinterpret_cast<const __half2*>(&t.r);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) h[i] += 0.25f * t[i];
+  for (int i = 0; i < 4; ++i) {
+    const float2 a = __half22float2(l2[i]), b = __half22float2(c2[i]), d = __half22float2(r2[i]);
+    h[2 * i] = 0.25f * (a.x + d.x) + 0.5f * b.x;
+    h[2 * i + 1] = 0.25f * (a.y + d.y) + 0.5f * b.y;
   }
 }
 
-__global__ void __launch_bounds__(256, 4) k_blur_rows(const __half* __restrict__ raw, __half* __restrict__ y, int h, int w,
-                                                   int c, const float* __restrict__ noise,
-                                                   const float* __restrict__ noise_w, const float* __restrict__ bias,
-                                                   float* __restrict__ gsum, float* __restrict__ gsq) {
+__global__ void __launch_bounds__(256, 3) k_blur_rows(const __half* __restrict__ raw, __half* __restrict__ y, int h, int w,
+                                                      int c, const float* __restrict__ noise,
+                                                      const float* __restrict__ noise_w, const float* __restrict__ bias,
+                                                      float* __restrict__ gsum, float* __restrict__ gsq) {
   __shared__ float s_sum[512], s_sq[512];
   const int n = blockIdx.z;
   const int c8 = c >> 3;
@@ -308,21 +314,31 @@ __global__ void __launch_bounds__(256, 4) k_blur_rows(const __half* __restrict__
       acc2[i] = 0.f;
     }
     const __half* img = raw + static_cast<size_t>(n) * h * w * c;
+    const size_t rstride = static_cast<size_t>(w) * c;
     float hp[8], hc[8], hn[8];
-    hblur8(img + static_cast<size_t>(y0 - 1) * w * c, px, w, c, ch, y0 - 1 >= 0, hp);
-    hblur8(img + static_cast<size_t>(y0) * w * c, px, w, c, ch, true, hc);
+    hblur8(load_raw3(img + (y0 - 1) * static_cast<long long>(rstride), px, w, c, ch, y0 - 1 >= 0), hp);
+    hblur8(load_raw3(img + y0 * rstride, px, w, c, ch, true), hc);
     const int y1 = min(h, y0 + kBlurRows);
+    // software pipeline: the three loads of row yy+2 are in flight while row yy is blurred, activated and stored
+    Raw3 nxt = load_raw3(img + (y0 + 1) * rstride, px, w, c, ch, y0 + 1 < h);
+    float nz = __ldg(&noise[y0 * w + px]);
     for (int yy = y0; yy < y1; ++yy) {
-      hblur8(img + static_cast<size_t>(yy + 1) * w * c, px, w, c, ch, yy + 1 < h, hn);
-      const float nz = __ldg(&noise[yy * w + px]);
+      const Raw3 cur = nxt;
+      const float nzc = nz;
+      if (yy + 1 < y1) {
+        nxt = load_raw3(img + (yy + 2) * rstride, px, w, c, ch, yy + 2 < h);
+        nz = __ldg(&noise[(yy + 1) * w + px]);
+      }
+      hblur8(cur, hn);
       float v[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        float t = 0.25f * hp[i] + 0.5f * hc[i] + 0.25f * hn[i] + nz * nw[i] + bs[i];
-        t = t >= 0.f ? t : 0.2f * t;
+        float t = 0.25f * (hp[i] + hn[i]) + 0.5f * hc[i];
+        t = fmaf(nzc, nw[i], t) + bs[i];
+        t = fmaxf(t, 0.2f * t);
         v[i] = t;
         acc[i] += t;
-        acc2[i] += t * t;
+        acc2[i] = fmaf(t, t, acc2[i]);
         hp[i] = hc[i];
         hc[i] = hn[i];
       }
