@@ -1,0 +1,59 @@
+"""N > 1 path on CPU (gloo, world_size 2): MC samples of one identity are split across ranks by global sample
+index, the int64 counts are summed by one all-reduce, and the result equals the single-rank tally exactly."""
+import os
+import socket
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from certifyingfacerecognition_b200.smoothing import L2Certificate, Smooth
+
+
+class FakeFused:
+    """Stands in for WrappedModel.sample_votes: the vote of sample i is a pure function of (seed, i)."""
+    supports_fused_votes = True
+
+    def __init__(self, n=16):
+        self.n = n
+
+    def eval(self):
+        return self
+
+    def sample_votes(self, z, x, sigma, num, seed=0, sample_offset=0):
+        idx = torch.arange(sample_offset, sample_offset + num, dtype=torch.int64)
+        votes = (idx * 2654435761 + seed * 40503) % 7 % self.n
+        return torch.bincount(votes, minlength=self.n).to(torch.int64)
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    s = Smooth(FakeFused(), 16, torch.tensor([0.1]), L2Certificate(1, device="cpu"), seed=5,
+               process_group=dist.group.WORLD)
+    c1 = s._sample_noise(None, None, 101, 10, device=torch.device("cpu"))
+    c2 = s._sample_noise(None, None, 1000, 10, device=torch.device("cpu"))
+    pred = s.certify(None, None, torch.tensor([int(c2.argmax())]), 101, 1000, 0.001, 10, device=torch.device("cpu"))
+    if rank == 0:
+        np.savez(out, c1=c1, c2=c2, pred=np.array(pred, dtype=np.float64))
+    dist.destroy_process_group()
+
+
+def test_sample_sharding_two_ranks_equals_single_rank(tmp_path):
+    out = str(tmp_path / "r.npz")
+    mp.start_processes(_worker, args=(2, _free_port(), out), nprocs=2, join=True, start_method="fork")
+    got = np.load(out)
+    ref = Smooth(FakeFused(), 16, torch.tensor([0.1]), L2Certificate(1, device="cpu"), seed=5)
+    c1 = ref._sample_noise(None, None, 101, 10, device=torch.device("cpu"))
+    c2 = ref._sample_noise(None, None, 1000, 10, device=torch.device("cpu"))
+    assert np.array_equal(got["c1"], c1) and c1.sum() == 101
+    assert np.array_equal(got["c2"], c2) and c2.sum() == 1000
+    pred = ref.certify(None, None, torch.tensor([int(c2.argmax())]), 101, 1000, 0.001, 10, device=torch.device("cpu"))
+    assert np.allclose(got["pred"], np.array(pred, dtype=np.float64))

@@ -1,0 +1,161 @@
+"""Host-side logic (no GPU): the Smooth mirror on a duck-typed base classifier, Clopper-Pearson KATs, weight packing,
+tile selection, geometry setup, CLI surface."""
+import math
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from certifyingfacerecognition_b200 import engine as E
+from certifyingfacerecognition_b200.smoothing import L2Certificate, Smooth
+from certifyingfacerecognition_b200.smoothing.smooth import lower_confidence_bound
+from oracle import mc_path as M
+
+CPU = torch.device("cpu")
+
+
+class FakeClassifier:
+    """Votes class 1 when the first perturbation coefficient is > thr, else class 0."""
+
+    def __init__(self, n=4, thr=0.0):
+        self.n, self.thr = n, thr
+
+    def eval(self):
+        return self
+
+    def __call__(self, z, p):
+        out = torch.zeros(p.shape[0], self.n)
+        hit = (p[:, 0, 0, 0] > self.thr).long()
+        out[torch.arange(p.shape[0]), hit] = 1.0
+        return out
+
+
+def test_kats_match_oracle_and_survey_values(golden):
+    for (na, n), p in zip(golden["kat_in"], golden["kat_p"]):
+        assert lower_confidence_bound(int(na), int(n), 0.001) == pytest.approx(float(p), rel=1e-12, abs=1e-15)
+        assert lower_confidence_bound(int(na), int(n), 0.001) == M.lower_confidence_bound(int(na), int(n), 0.001)
+    assert lower_confidence_bound(100, 100, 0.001) == pytest.approx(0.9332543008, rel=1e-9)
+
+
+def test_generic_loop_certify_predict_abstain():
+    cert = L2Certificate(1, device=CPU)
+    x = torch.zeros(1, 5)
+    z = torch.zeros(1, 512)
+    # threshold far above the noise: always class 0 -> certified with the closed-form gap
+    s = Smooth(FakeClassifier(thr=10.0), 4, torch.tensor([0.1]), cert)
+    pred, gap = s.certify(z, x, torch.tensor([0]), 20, 100, 0.001, 32, device=CPU)
+    assert pred == 0 and gap == pytest.approx(M.compute_gap(M.lower_confidence_bound(100, 100, 0.001)))
+    assert s.samples_classified == 120
+    # wrong label -> early exit after n0 samples (smooth.py:66-68)
+    s = Smooth(FakeClassifier(thr=10.0), 4, torch.tensor([0.1]), cert)
+    assert s.certify(z, x, torch.tensor([2]), 20, 100, 0.001, 32, device=CPU) == (0, 0.0)
+    assert s.samples_classified == 20
+    # 50/50 votes -> abstain in certify (pABar < 0.5) and in predict (binomial test)
+    torch.manual_seed(0)
+    s = Smooth(FakeClassifier(thr=0.0), 4, torch.tensor([0.1]), cert)
+    counts = s._sample_noise(z, x, 1000, 100, device=CPU)
+    assert counts.dtype == np.float64 and counts.sum() == 1000 and 400 < counts[0] < 600
+    label = int(counts.argmax())
+    res = s.certify(z, x, torch.tensor([label]), 1000, 1000, 0.001, 100, device=CPU)
+    assert res[1] == 0.0
+    assert s.predict(z, x, 200, 0.001, 50, device=CPU) == Smooth.ABSTAIN
+    s = Smooth(FakeClassifier(thr=10.0), 4, torch.tensor([0.1]), cert)
+    assert s.predict(z, x, 64, 0.001, 64, device=CPU) == 0
+
+
+def test_count_arr_matches_reference_semantics():
+    s = Smooth(FakeClassifier(), 5, torch.tensor([0.1]), L2Certificate(1, device=CPU))
+    assert s._count_arr(torch.tensor([3, 3, 1, 3, 0, 1]), CPU, 5).tolist() == [1, 2, 0, 3, 0]
+
+
+def test_anisotropic_sigma_broadcast():
+    cert = L2Certificate(1, device=CPU)
+    sigma = 0.1 * torch.tensor(M.red_ellipse_mat_inv(), dtype=torch.float32)
+    torch.manual_seed(1)
+    noise = cert.sample_noise(torch.zeros(4000, 1, 1, 5), sigma)
+    assert noise.shape == (4000, 1, 1, 5)
+    assert torch.allclose(noise.reshape(-1, 5).std(0), sigma, rtol=0.1)
+
+
+def test_pack_conv_weight_is_tap_major_k():
+    w = torch.arange(2 * 3 * 3 * 3, dtype=torch.float32).reshape(2, 3, 3, 3)
+    p = E.pack_conv_weight(w, cin_pad=16)
+    assert p.shape == (2, 192)
+    for tap, (ky, kx) in enumerate([(a, b) for a in range(3) for b in range(3)]):
+        assert torch.equal(p[:, tap * 16:tap * 16 + 3], w[:, :, ky, kx])
+        assert (p[:, tap * 16 + 3:(tap + 1) * 16] == 0).all()
+    assert (p[:, 144:] == 0).all()
+
+
+@pytest.mark.parametrize("packer", ["igemm", "halo"])
+def test_upconv_phase_decomposition_is_exact(packer):
+    """4 sub-pixel phases x (2x2 taps) on the low-res grid == nearest-x2 upsample + 3x3 conv (pad 1), borders included."""
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(2, 16, 5, 7, generator=g).double()
+    w = torch.randn(32, 16, 3, 3, generator=g).double()
+    ref = F.conv2d(F.interpolate(x, scale_factor=2, mode="nearest"), w, padding=1)
+    if packer == "igemm":
+        wp, taps = E.pack_upconv_phases(w.float())
+        wp = wp.double()[:, :4 * 16].reshape(4, 32, 4, 16)            # [phase][cout][tap][cin]
+    else:
+        wp, taps = E.pack_halo_upconv(w.float())
+        wp = wp.double().reshape(4, 4, 32, 16).permute(0, 2, 1, 3)    # [phase][tap][cout][cin] -> [phase][cout][tap][cin]
+    out = torch.zeros_like(ref)
+    xp = F.pad(x, (1, 1, 1, 1))
+    for ph, (a, b) in enumerate([(0, 0), (0, 1), (1, 0), (1, 1)]):
+        acc = 0
+        for t, (dy, dx) in enumerate(taps[ph]):
+            patch = xp[:, :, 1 + dy:1 + dy + 5, 1 + dx:1 + dx + 7]
+            acc = acc + torch.einsum("oc,bchw->bohw", wp[ph, :, t], patch)
+        out[:, :, a::2, b::2] = acc
+    assert (out - ref).abs().max().item() < 1e-5
+
+
+def test_fused_upconv_equivalent_weight(models):
+    g_sd, _ = models
+    sd = {k: v.double() for k, v in g_sd.items() if k.startswith("synthesis.layer14.")}
+    x = torch.randn(1, 64, 6, 6, generator=torch.Generator().manual_seed(1)).double()
+    ref = M._upconv(x, sd, 14, literal=True)           # conv_transpose2d form, then blur
+    weq = E.upconv_equiv_weight({k: v.float() for k, v in sd.items()}, 14).double()
+    got = M._blur(F.conv2d(F.interpolate(x, scale_factor=2, mode="nearest"), weq, padding=1))
+    assert (got - ref).abs().max().item() < 1e-6         # weq is built in fp32 by the engine
+
+
+def test_tile_for_covers_128_rows():
+    for res in (1, 4, 7, 8, 14, 16, 28, 56, 112, 128, 1024):
+        for n in (1, 8, 50, 250):
+            tw, th, tn = E.tile_for(res, n)
+            assert tw * th * tn == 128
+    assert E.tile_for(14, 32) == (2, 2, 32)
+    assert E.tile_for(112, 50) == (16, 8, 1)
+
+
+def test_geometry_setup(tmp_path, monkeypatch):
+    from certifyingfacerecognition_b200.attack_utils import gen_utils, proj_utils
+    rs = np.random.RandomState(0)
+    os.makedirs(tmp_path / "boundaries")
+    for attr in proj_utils.ATTRS:
+        v = rs.randn(1, 512)
+        np.save(tmp_path / "boundaries" / f"stylegan_ffhq_{attr}_w_boundary.npy", v / np.linalg.norm(v))
+    monkeypatch.chdir(tmp_path)
+    proj, ell, dirs, red, files = proj_utils.get_projection_matrices("ffhq", "stylegan")
+    assert dirs.shape == (512, 5) and len(files) == 5
+    assert np.allclose(red, [4, 4, 25, 4, 1.5625], rtol=2e-3)            # 1/eps^2
+    assert np.allclose(proj @ proj, proj, atol=1e-8) and np.allclose(proj @ dirs, dirs, atol=1e-8)
+    mats = gen_utils.get_all_matrices(device=torch.device("cpu"))
+    assert len(mats) == 7 and mats[3].shape == (512, 5)
+    assert torch.allclose(mats[6], torch.tensor([0.25, 0.25, 0.04, 0.25, 0.64]), rtol=2e-3)
+
+
+def test_cli_surface_matches_reference():
+    import certify
+    p = certify.build_parser()
+    a = p.parse_args(["--face-recog-model", "insightface", "--outfile", "o.tsv", "--sigma", "0.1"])
+    assert (a.skip, a.max, a.batch_sz, a.N0, a.N, a.alpha, a.load_n_embs, a.anisotropic_sigma) == \
+        (1, -1, 100, 100, 100000, 0.001, 1_000_000, False)
+    with pytest.raises(SystemExit):
+        p.parse_args(["--face-recog-model", "vgg", "--outfile", "o", "--sigma", "1"])
+    row = "{}\t{}\t{}\t{}\t{:.3}\t{:.3}\t{}".format(3, 3, 3, 1, 1.9780096, 0.19780096, "0:00:01.5")
+    assert row == "3\t3\t3\t1\t1.98\t0.198\t0:00:01.5"
