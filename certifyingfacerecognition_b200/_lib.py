@@ -75,7 +75,7 @@ SIGNATURES = {
     "cfr_sample_votes_host": (_I, [_P, _P, _P, _P, _I, _I64, _U64, _U64, _P, _P]),
     "cfr_launch_count": (_U64, []),
     "cfr_profile_enable": (_I, [_I]),
-    "cfr_profile_read": (_I, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(_I64)]),
+    "cfr_profile_read": (_I, [_I, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(_I64)]),
 }
 
 _lib = None

@@ -56,10 +56,10 @@ CFR_API const char* cfr_last_error(void) { return last_error(); }
 CFR_API int cfr_version(void) { return 100; }
 CFR_API uint64_t cfr_launch_count(void) { return launch_count(); }
 CFR_API int cfr_profile_enable(int on) { profile_enable(on); return 0; }
-CFR_API int cfr_profile_read(double* conv_ms, double* conv_flops, int64_t* conv_launches) {
+CFR_API int cfr_profile_read(int kind, double* ms, double* work, int64_t* launches) {
   long long l = 0;
-  int r = profile_read(conv_ms, conv_flops, &l);
-  *conv_launches = l;
+  int r = profile_read(kind, ms, work, &l);
+  *launches = l;
   return r;
 }
 

@@ -522,6 +522,8 @@ int halo_build(const cfr_conv_desc& s, const float* inA, const float* inB, HaloO
   op->grid = total < num_sms() ? total : num_sms();
   op->smemBytes = p.haloStages * p.haloBytes + p.wBytes + ctrl + 1024;
   op->flops = 2.0 * s.N * s.Hout * s.Wout * s.numPhases * s.ntaps * static_cast<double>(s.Cin) * s.Cout;
+  // algorithmic HBM bytes: every input element read once, every output element written once (fp16)
+  op->bytes = 2.0 * s.N * (static_cast<double>(s.Hin) * s.Win * s.Cin + static_cast<double>(s.outH) * s.outW * s.Cout);
   return 0;
 }
 
@@ -536,10 +538,19 @@ int halo_launch(const HaloOp& op, cudaStream_t stream) {
       attr_err = cudaFuncSetAttribute(conv_halo_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   });
   if (attr_err != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(attr_err)); return 4; }
+  cudaEvent_t e1 = nullptr;
+  if (profile_on()) {
+    cudaEventRecord(profile_event(1), stream);
+    e1 = profile_event(1);
+  }
   switch (op.p.Cout) {
     case 16: conv_halo_kernel<16><<<op.grid, kHaloThreads, op.smemBytes, stream>>>(op.p); break;
     case 32: conv_halo_kernel<32><<<op.grid, kHaloThreads, op.smemBytes, stream>>>(op.p); break;
     default: conv_halo_kernel<64><<<op.grid, kHaloThreads, op.smemBytes, stream>>>(op.p); break;
+  }
+  if (profile_on()) {
+    cudaEventRecord(e1, stream);
+    profile_account(1, op.bytes);
   }
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { set_error("halo conv launch: %s", cudaGetErrorString(e)); return 4; }

@@ -55,6 +55,7 @@ struct HaloOp {
   HaloParams p;
   int grid, smemBytes;
   double flops;
+  double bytes;   // algorithmic HBM traffic per launch
 };
 
 int halo_build(const cfr_conv_desc& s, const float* inA, const float* inB, HaloOp* op);

@@ -496,42 +496,52 @@ int conv_build(const ConvSpec& s, ConvOp* op) {
 }
 
 // ---- optional per-launch timing (bench.py roofline): CUDA events around every conv launch -------------
+// kind 0: conv_igemm_kernel (work = algorithmic FLOPs), kind 1: conv_halo_kernel (work = algorithmic bytes)
 struct ProfState {
-  bool on = false;
   std::vector<cudaEvent_t> ev;     // pairs (start, stop)
   size_t used = 0;
-  double flops = 0.0;
+  double work = 0.0;
   long long launches = 0;
 };
-static ProfState g_prof;
+static bool g_prof_on = false;
+static ProfState g_prof[2];
 
 void profile_enable(int on) {
-  g_prof.on = on != 0;
-  g_prof.used = 0;
-  g_prof.flops = 0.0;
-  g_prof.launches = 0;
+  g_prof_on = on != 0;
+  for (auto& p : g_prof) {
+    p.used = 0;
+    p.work = 0.0;
+    p.launches = 0;
+  }
 }
-int profile_read(double* ms, double* flops, long long* launches) {
+int profile_read(int kind, double* ms, double* work, long long* launches) {
+  ProfState& p = g_prof[kind & 1];
   double total = 0.0;
-  for (size_t i = 0; i + 1 < g_prof.used; i += 2) {
+  for (size_t i = 0; i + 1 < p.used; i += 2) {
     float t = 0.f;
-    cudaError_t e = cudaEventSynchronize(g_prof.ev[i + 1]);
-    if (e == cudaSuccess) e = cudaEventElapsedTime(&t, g_prof.ev[i], g_prof.ev[i + 1]);
+    cudaError_t e = cudaEventSynchronize(p.ev[i + 1]);
+    if (e == cudaSuccess) e = cudaEventElapsedTime(&t, p.ev[i], p.ev[i + 1]);
     if (e != cudaSuccess) { set_error("profile_read: %s", cudaGetErrorString(e)); return 5; }
     total += t;
   }
   *ms = total;
-  *flops = g_prof.flops;
-  *launches = g_prof.launches;
+  *work = p.work;
+  *launches = p.launches;
   return 0;
 }
-static cudaEvent_t prof_event() {
-  if (g_prof.used == g_prof.ev.size()) {
+bool profile_on() { return g_prof_on; }
+cudaEvent_t profile_event(int kind) {
+  ProfState& p = g_prof[kind & 1];
+  if (p.used == p.ev.size()) {
     cudaEvent_t e;
     cudaEventCreate(&e);
-    g_prof.ev.push_back(e);
+    p.ev.push_back(e);
   }
-  return g_prof.ev[g_prof.used++];
+  return p.ev[p.used++];
+}
+void profile_account(int kind, double work) {
+  g_prof[kind & 1].work += work;
+  g_prof[kind & 1].launches += 1;
 }
 
 int conv_launch(const ConvOp& op, cudaStream_t stream) {
@@ -542,15 +552,14 @@ int conv_launch(const ConvOp& op, cudaStream_t stream) {
   });
   if (attr_err != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(attr_err)); return 4; }
   cudaEvent_t e1 = nullptr;
-  if (g_prof.on) {
-    cudaEventRecord(prof_event(), stream);
-    e1 = prof_event();
+  if (profile_on()) {
+    cudaEventRecord(profile_event(0), stream);
+    e1 = profile_event(0);
   }
   conv_igemm_kernel<<<op.grid, kConvThreads, op.smemBytes, stream>>>(op.p);
-  if (g_prof.on) {
+  if (profile_on()) {
     cudaEventRecord(e1, stream);
-    g_prof.flops += op.flops;
-    g_prof.launches += 1;
+    profile_account(0, op.flops);
   }
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { set_error("conv launch: %s", cudaGetErrorString(e)); return 4; }

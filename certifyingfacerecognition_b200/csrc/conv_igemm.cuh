@@ -89,6 +89,9 @@ int num_sms();
 void count_launch(int n = 1);
 unsigned long long launch_count();
 void profile_enable(int on);
-int profile_read(double* ms, double* flops, long long* launches);
+int profile_read(int kind, double* ms, double* work, long long* launches);
+bool profile_on();
+cudaEvent_t profile_event(int kind);
+void profile_account(int kind, double work);
 
 }  // namespace cfr

@@ -140,11 +140,12 @@ CFR_API int cfr_sample_votes_host(cfr_sampler* s, const float* z_host, const flo
                           cfr_stream_t stream);
 /* kernels launched by this library since load (bench.py reports it as gpu_launches) */
 CFR_API uint64_t cfr_launch_count(void);
-/* Per-launch CUDA-event timing of the implicit-GEMM kernel (bench.py roofline).  enable(1) resets the counters;
- * read() synchronises on the recorded events and returns summed device time, algorithmic FLOPs (2*MAC on the
- * un-padded dims) and launch count since enable. */
+/* Per-launch CUDA-event timing of the two tcgen05 conv kernels (bench.py roofline).  enable(1) resets the
+ * counters; read() synchronises on the recorded events and returns, since enable: summed device time, summed
+ * algorithmic work and launch count.  kind 0 = conv_igemm_kernel (work = FLOPs, 2*MAC on un-padded dims),
+ * kind 1 = conv_halo_kernel (work = bytes: input read once + output written once). */
 CFR_API int cfr_profile_enable(int on);
-CFR_API int cfr_profile_read(double* conv_ms, double* conv_flops, int64_t* conv_launches);
+CFR_API int cfr_profile_read(int kind, double* ms, double* work, int64_t* launches);
 
 #ifdef __cplusplus
 }
