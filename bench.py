@@ -127,7 +127,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=250, help="MC samples per step (BASELINE config 2: 250)")
-    ap.add_argument("--chunk", type=int, default=50, help="samples per GAN+FRM program run")
+    ap.add_argument("--chunk", type=int, default=125, help="samples per GAN+FRM program run")
     ap.add_argument("--shard", default="identities", choices=["identities", "samples"])
     ap.add_argument("--cpu-sample", type=int, default=4, help="MC samples per CPU-baseline step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
