@@ -129,13 +129,39 @@ CFR_API int cfr_program_add_conv(cfr_program* p, const cfr_conv_desc* d) {
 
 CFR_API int cfr_program_add_conv_halo(cfr_program* p, const cfr_conv_desc* d, const float* inA, const float* inB) {
   std::unique_ptr<HaloOp> op(new HaloOp());
-  int r = halo_build(*d, inA, inB, op.get());
+  int r = halo_build(*d, inA, inB, nullptr, op.get());
   if (r != 0) return r;
   HaloOp* raw = op.get();
   p->halos.push_back(std::move(op));
   char lab[160];
   snprintf(lab, sizeof(lab), "halo %dx%d taps%dx%d Cin%d Cout%d n%d TH%d%s", d->Hout, d->Wout, d->numPhases, d->ntaps,
            d->Cin, d->Cout, d->N, raw->p.TH, inA ? " +affine" : "");
+  p->add([raw](cudaStream_t st) { return halo_launch(*raw, st); }, lab, raw->flops);
+  return 0;
+}
+
+CFR_API int cfr_program_add_conv_halo_folded(cfr_program* p, const cfr_conv_desc* d, const float* base_w, const float* inA,
+                                             const float* inB, int center_tap, void* w_main_f16, void* w_aux_f16) {
+  std::unique_ptr<HaloOp> op(new HaloOp());
+  cfr_conv_desc dd = *d;
+  dd.w = w_main_f16;
+  const int pt = d->numPhases * d->ntaps;
+  dd.wRows = d->N * pt * d->Cout;
+  dd.Kpad = d->Cin;
+  int r = halo_build(dd, nullptr, nullptr, w_aux_f16, op.get());
+  if (r != 0) return r;
+  HaloOp* raw = op.get();
+  p->halos.push_back(std::move(op));
+  const int n = d->N, cout = d->Cout, cin = d->Cin;
+  const float* bias = d->bias;
+  const float* noise_w = d->noise_w;
+  p->add([=](cudaStream_t st) {
+    return launch_fold_weights(base_w, inA, inB, bias, noise_w, center_tap, n, pt, cout, cin,
+                               static_cast<__half*>(w_main_f16), static_cast<__half*>(w_aux_f16), st);
+  }, "fold_weights");
+  char lab[160];
+  snprintf(lab, sizeof(lab), "halo-folded %dx%d taps%dx%d Cin%d Cout%d n%d TH%d", d->Hout, d->Wout, d->numPhases,
+           d->ntaps, d->Cin, d->Cout, d->N, raw->p.TH);
   p->add([raw](cudaStream_t st) { return halo_launch(*raw, st); }, lab, raw->flops);
   return 0;
 }

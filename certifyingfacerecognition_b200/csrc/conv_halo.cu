@@ -44,7 +44,10 @@ __device__ __forceinline__ Band decode_band(const HaloParams& p, int b) {
   return r;
 }
 
-template <int COUT>
+// FOLD: the previous layer's IN+AdaIN scale is folded into per-sample weights, and its shift, this layer's bias and
+// noise ride on an auxiliary 16-channel band {noise, inside-image indicator, 0..} consumed by one extra MMA per tap,
+// so neither the loaders nor the epilogue touch them.
+template <int COUT, bool FOLD>
 __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid_constant__ HaloParams p) {
   constexpr int NCH = COUT / 16;                 // 16-column epilogue chunks
   constexpr bool REG_STATS = COUT <= 32;         // keep per-thread channel sums in registers across a band
@@ -52,12 +55,15 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int NS = p.haloStages;                                   // 2 or 3 halo band buffers
-  uint8_t* wsm = smem + NS * p.haloBytes;
-  uint8_t* ctrl = wsm + p.wBytes;
+  uint8_t* aux = smem + NS * p.haloBytes;                        // [NS] aux bands (FOLD only; auxBytes == 0 otherwise)
+  uint8_t* wsm = aux + NS * p.auxBytes;
+  uint8_t* wasm = wsm + p.wBytes;                                // aux weight tiles (FOLD only)
+  uint8_t* ctrl = wasm + p.wAuxBytes;
   uint64_t* hready = reinterpret_cast<uint64_t*>(ctrl);    // [3] band loaded (+ affine applied)
   uint64_t* hempty = hready + 3;                           // [3]
   uint64_t* wbar = hempty + 3;                             // [1]
-  uint64_t* tfull = wbar + 1;                              // [16]
+  uint64_t* wdrain = wbar + 1;                             // [1] all MMAs reading the current weights are done
+  uint64_t* tfull = wdrain + 1;                            // [16]
   uint64_t* tempty = tfull + 16;                           // [16]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 16);
   float* sA = reinterpret_cast<float*>(tmem_slot + 4);     // [64]
@@ -78,6 +84,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
 
   if (warp == kHaloMmaWarp0 && lane == 0) {
     tma_prefetch_desc(&p.tmW);
+    if (FOLD) tma_prefetch_desc(&p.tmWa);
   }
   if (warp == kHaloMmaWarp0) {
     if (lane == 0) {
@@ -86,6 +93,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
         mbar_init(&hempty[i], kMmaWarps);
       }
       mbar_init(wbar, 1);
+      mbar_init(wdrain, kMmaWarps);
       for (int i = 0; i < 16; ++i) {
         mbar_init(&tfull[i], 1);
         mbar_init(&tempty[i], 4);
@@ -99,6 +107,11 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
   if (threadIdx.x < 64) {
     s_sum[threadIdx.x] = 0.f;
     s_sq[threadIdx.x] = 0.f;
+  }
+  if constexpr (FOLD) {                      // aux rows are {noise, indicator, 0 x14}: zero everything once
+    const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+    for (int i = threadIdx.x; i < (NS * p.auxBytes) >> 4; i += kHaloThreads) reinterpret_cast<uint4*>(aux)[i] = z;
+    fence_proxy_async();
   }
   tc_fence_before();
   __syncthreads();
@@ -125,22 +138,54 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
         toff[ph][t] = (ph < p.numPhases && t < p.ntaps)
                           ? ((1 + p.tap_dy[ph][t]) * kHaloW + 1 + p.tap_dx[ph][t]) * rb16 : 0u;
     const uint32_t row_step = kHaloW * rb16;
-    if (mw == 0 && leader) {              // weights for every (phase, tap): resident for the CTA's lifetime
-      mbar_expect_tx(wbar, p.wRows * p.rowBytes);
-      for (int r0 = 0; r0 < p.wRows; r0 += p.wBoxRows)
-        tma_load_2d(wsm + static_cast<size_t>(r0) * p.rowBytes, &p.tmW, wbar, 0, r0);
+    const uint32_t dhi_aux = smem_desc_hi(256, 32);        // aux operands: 32-byte rows, SWIZZLE_32B
+    const uint32_t wa_lo = smem_desc_lo(smem_u32(wasm));
+    const uint32_t aux_row_step = kHaloW * 2;
+    uint32_t atoff[4][9];                                  // aux-band offsets (32-byte rows)
+#pragma unroll
+    for (int ph = 0; ph < 4; ++ph)
+#pragma unroll
+      for (int t = 0; t < 9; ++t)
+        atoff[ph][t] = (FOLD && ph < p.numPhases && t < p.ntaps)
+                           ? ((1 + p.tap_dy[ph][t]) * kHaloW + 1 + p.tap_dx[ph][t]) * 2u : 0u;
+    auto load_weights = [&](int n) {      // every (phase, tap) tile; FOLD: the per-sample set of image n
+      const int row_base = FOLD ? n * p.wRows : 0;
+      mbar_expect_tx(wbar, p.wRows * p.rowBytes + (FOLD ? p.wRows * 32 : 0));
+      for (int r0 = 0; r0 < p.wRows; r0 += p.wBoxRows) {
+        tma_load_2d(wsm + static_cast<size_t>(r0) * p.rowBytes, &p.tmW, wbar, 0, row_base + r0);
+        if (FOLD) tma_load_2d(wasm + static_cast<size_t>(r0) * 32, &p.tmWa, wbar, 0, row_base + r0);
+      }
+    };
+    uint32_t wphase = 0, dphase = 0;
+    int cur_n = -1;
+    if (!FOLD) {
+      if (mw == 0 && leader) load_weights(0);
+      __syncwarp();
+      mbar_wait(wbar, 0);
     }
-    __syncwarp();
-    mbar_wait(wbar, 0);
     int hs = 0;
     uint32_t hphase = 0;
     uint32_t as = 0, aphase = 0, tsel = 0;
     for (int b = band0; b < band1; ++b) {
       const Band bd = decode_band(p, b);
+      if (FOLD && bd.n != cur_n) {
+        if (cur_n >= 0) {                  // drain: every MMA that reads the old weights must have completed
+          if (leader) umma_commit(wdrain);
+          __syncwarp();
+          mbar_wait(wdrain, dphase);
+          dphase ^= 1;
+        }
+        if (mw == 0 && leader) load_weights(bd.n);
+        __syncwarp();
+        mbar_wait(wbar, wphase);
+        wphase ^= 1;
+        cur_n = bd.n;
+      }
       mbar_wait(&hready[hs], hphase);
       tc_fence_after();
       uint32_t a_row = smem_desc_lo(smem_u32(smem + hs * p.haloBytes));
-      for (int r = 0; r < bd.rows; ++r, a_row += row_step) {
+      uint32_t x_row = smem_desc_lo(smem_u32(aux + hs * p.auxBytes));
+      for (int r = 0; r < bd.rows; ++r, a_row += row_step, x_row += aux_row_step) {
 #pragma unroll
         for (int ph = 0; ph < 4; ++ph) {
           if (ph < p.numPhases) {
@@ -164,6 +209,16 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
                   }
                 }
                 b_lo += w_tap;
+              }
+            }
+            if constexpr (FOLD) {
+              uint32_t ba_lo = wa_lo + ph * p.ntaps * (COUT * 2);
+#pragma unroll
+              for (int t = 0; t < 9; ++t) {
+                if (t < p.ntaps) {
+                  if (leader) umma_f16_lohi(d_tmem, x_row + atoff[ph][t], dhi_aux, ba_lo, dhi_aux, idesc, 1u);
+                  ba_lo += COUT * 2;
+                }
               }
             }
             if (leader) umma_commit(&tfull[as]);
@@ -217,6 +272,23 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
         }
       }
       cp_async_commit();
+      if constexpr (FOLD) {                 // aux band: first 16-byte chunk of every pixel row = {noise, inside?, 0..}
+        const uint32_t xb_addr = smem_u32(aux + hs * p.auxBytes);
+        const int npix = (p.TH + 2) * kHaloW;
+        for (int px = tt; px < npix; px += LT) {
+          const int row = px / kHaloW, col = px - row * kHaloW;
+          const int gy = bd.y0 - 1 + row, gx = bd.x0 - 1 + col;
+          const bool ok = static_cast<unsigned>(gy) < static_cast<unsigned>(p.H) &&
+                          static_cast<unsigned>(gx) < static_cast<unsigned>(p.W);
+          const float nzv = (ok && p.noise != nullptr) ? __ldg(&p.noise[gy * p.W + gx]) : 0.f;
+          const __half2 h = __floats2half2_rn(nzv, ok ? 1.f : 0.f);
+          const uint32_t lin = xb_addr + (static_cast<uint32_t>(px) << 5);
+          const uint32_t dst = lin ^ (((lin >> 7) & 1u) << 4);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %2, %2};" ::"r"(dst), "r"(*reinterpret_cast<const uint32_t*>(&h)),
+                       "r"(0u)
+                       : "memory");
+        }
+      }
     };
 
     int cur_n = -1;
@@ -231,7 +303,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
       const Band bd = decode_band(p, b);
       const int ahead = min(NS - 1, band1 - b) - 1;      // younger groups still allowed in flight
       if (ahead >= 1) cp_async_wait<1>(); else cp_async_wait<0>();
-      if (affine) {
+      if (!FOLD && affine) {
         if (bd.n != cur_n) {
           cur_n = bd.n;
           const float4* ap = reinterpret_cast<const float4*>(p.inA + bd.n * p.Cin + lc * 8);
@@ -282,12 +354,12 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
     }
   } else {
     // ================================================================ epilogue (warps 0..7)
-    constexpr bool HOIST = COUT == 16;     // per-channel noise gain / bias live in registers
+    constexpr bool HOIST = COUT == 16 && !FOLD;     // per-channel noise gain / bias live in registers
     const int q = warp & 3;                // TMEM lane quarter
     const int grp = warp >> 2;             // handles tiles with (tcount & 1) == grp
     const int et = threadIdx.x;            // 0..255
     const bool do_stats = p.stat_sum != nullptr;
-    const bool has_noise = p.noise != nullptr, has_bias = p.bias != nullptr;
+    const bool has_noise = !FOLD && p.noise != nullptr, has_bias = !FOLD && p.bias != nullptr;
     const bool lrelu = p.act == CFR_ACT_LRELU;
     const float slope = p.slope;
     float racc[REG_STATS ? COUT : 1], racc2[REG_STATS ? COUT : 1];
@@ -343,7 +415,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
             if constexpr (HOIST) {
 #pragma unroll
               for (int i = 0; i < 16; ++i) v[i] = fmaf(nz, hnw[i], v[i]) + hbs[i];
-            } else {
+            } else if constexpr (!FOLD) {
               if (has_bias) {
 #pragma unroll
                 for (int i = 0; i < 16; i += 4) {
@@ -454,7 +526,44 @@ static CUtensorMapSwizzle swz(int bytes) {
   return bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : (bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
 }
 
-int halo_build(const cfr_conv_desc& s, const float* inA, const float* inB, HaloOp* op) {
+// ---------------------------------------------------------------------------------------------------------
+// Per-sample weight folding (FOLD variant).  For image n and (phase,tap) pt:
+//   w_main[n][pt][co][ci] = fp16( W[pt][co][ci] * A[n][ci] )                       -- IN+AdaIN scale of the input
+//   w_aux [n][pt][co][0]  = noise_w[co]            if pt == center_tap else 0        -- x aux channel 0 (noise image)
+//   w_aux [n][pt][co][1]  = sum_ci W[pt][co][ci]*B[n][ci]  (+ bias[co] at the center tap)  -- x aux channel 1 (inside?)
+// so that  conv_W(A*y + B, zero padded) + noise*w + bias  ==  conv_wmain(y) + conv_waux({noise, inside}).
+// ---------------------------------------------------------------------------------------------------------
+__global__ void k_fold_weights(const float* __restrict__ base_w, const float* __restrict__ inA,
+                               const float* __restrict__ inB, const float* __restrict__ bias,
+                               const float* __restrict__ noise_w, int center_tap, int pt_count, int cout, int cin,
+                               __half* __restrict__ w_main, __half* __restrict__ w_aux) {
+  const int n = blockIdx.y, pt = blockIdx.x;
+  const int co = threadIdx.x / cin, ci = threadIdx.x % cin;          // cin in {16, 32}: a group never straddles a warp
+  const size_t widx = (static_cast<size_t>(pt) * cout + co) * cin + ci;
+  const float w = base_w[widx];
+  const float a = inA != nullptr ? inA[n * cin + ci] : 1.f;
+  const float b = inB != nullptr ? inB[n * cin + ci] : 0.f;
+  w_main[(static_cast<size_t>(n) * pt_count) * cout * cin + widx] = __float2half_rn(w * a);
+  float sh = w * b;
+  for (int o = cin >> 1; o > 0; o >>= 1) sh += __shfl_xor_sync(0xffffffffu, sh, o);
+  if (ci < 16) {
+    float v = 0.f;
+    if (ci == 0 && pt == center_tap && noise_w != nullptr) v = noise_w[co];
+    if (ci == 1) v = sh + ((pt == center_tap && bias != nullptr) ? bias[co] : 0.f);
+    w_aux[((static_cast<size_t>(n) * pt_count + pt) * cout + co) * 16 + ci] = __float2half_rn(v);
+  }
+}
+int launch_fold_weights(const float* base_w, const float* inA, const float* inB, const float* bias, const float* noise_w,
+                        int center_tap, int n, int pt, int cout, int cin, __half* w_main, __half* w_aux, cudaStream_t st) {
+  if (cout * cin > 1024 || (cin != 16 && cin != 32)) { set_error("fold_weights: Cout*Cin=%d unsupported", cout * cin); return 2; }
+  k_fold_weights<<<dim3(pt, n), cout * cin, 0, st>>>(base_w, inA, inB, bias, noise_w, center_tap, pt, cout, cin, w_main, w_aux);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { set_error("fold_weights launch: %s", cudaGetErrorString(e)); return 4; }
+  count_launch();
+  return 0;
+}
+
+int halo_build(const cfr_conv_desc& s, const float* inA, const float* inB, const void* w_aux, HaloOp* op) {
   EncodeTiledFn enc = reinterpret_cast<EncodeTiledFn>(get_encode_tiled());
   if (enc == nullptr) { set_error("cuTensorMapEncodeTiled not available (no CUDA driver?)"); return 1; }
   HaloParams& p = op->p;
@@ -472,14 +581,18 @@ int halo_build(const cfr_conv_desc& s, const float* inA, const float* inB, HaloO
   p.numPhases = s.numPhases; p.ntaps = s.ntaps;
   memcpy(p.tap_dy, s.tap_dy, sizeof(p.tap_dy));
   memcpy(p.tap_dx, s.tap_dx, sizeof(p.tap_dx));
+  p.fold = w_aux != nullptr;
+  if (p.fold && s.Cin > 32) { set_error("halo conv: folded variant needs Cin <= 32"); return 2; }
   p.rowBytes = s.Cin * 2;
   p.wRows = s.numPhases * s.ntaps * s.Cout;
+  p.wAuxBytes = p.fold ? (p.wRows * 32 + 1023) / 1024 * 1024 : 0;
   p.wBytes = (p.wRows * p.rowBytes + 1023) / 1024 * 1024;
   p.wBoxRows = p.wRows;
   while (p.wBoxRows > 256 || p.wRows % p.wBoxRows != 0) --p.wBoxRows;
-  const int ctrl = 8 * 40 + 16 + 4 * 64 * 4 + 64;
-  const int budget = 227 * 1024 - 1024 - ctrl - p.wBytes;
-  auto halo_bytes = [&](int th) { return ((th + 2) * kHaloW * p.rowBytes + 1023) / 1024 * 1024; };
+  const int ctrl = 8 * 44 + 16 + 4 * 64 * 4 + 64;
+  const int budget = 227 * 1024 - 1024 - ctrl - p.wBytes - p.wAuxBytes;
+  auto aux_bytes = [&](int th) { return p.fold ? ((th + 2) * kHaloW * 32 + 1023) / 1024 * 1024 : 0; };
+  auto halo_bytes = [&](int th) { return ((th + 2) * kHaloW * p.rowBytes + 1023) / 1024 * 1024 + aux_bytes(th); };
   // three band buffers (prefetch distance 2) with the tallest band that fits, but at least 4 rows per band;
   // otherwise fall back to two buffers
   int ns = 3, th = 16;
@@ -493,7 +606,8 @@ int halo_build(const cfr_conv_desc& s, const float* inA, const float* inB, HaloO
   if (ns * halo_bytes(th) > budget) { set_error("halo conv: smem budget"); return 2; }
   p.TH = th;
   p.haloStages = ns;
-  p.haloBytes = halo_bytes(th);
+  p.auxBytes = aux_bytes(th);
+  p.haloBytes = halo_bytes(th) - p.auxBytes;
   p.bandsX = (s.Wout + 127) / 128;
   p.bandsY = (s.Hout + th - 1) / th;
   p.accStages = 512 / s.Cout;
@@ -508,8 +622,9 @@ int halo_build(const cfr_conv_desc& s, const float* inA, const float* inB, HaloO
   if (s.outC != s.Cout) { set_error("halo conv: outC must equal Cout"); return 2; }
   p.in = static_cast<const __half*>(s.in);
   {
-    if (s.Kpad != s.Cin || s.wRows != p.wRows) { set_error("halo conv: weights must be [phases*taps*Cout][Cin] (got [%d][%d])", s.wRows, s.Kpad); return 2; }
-    cuuint64_t dims[2] = {(cuuint64_t)s.Cin, (cuuint64_t)p.wRows};
+    const int totalRows = p.fold ? s.N * p.wRows : p.wRows;
+    if (s.Kpad != s.Cin || s.wRows != totalRows) { set_error("halo conv: weights must be [(n x) phases*taps*Cout][Cin] (got [%d][%d], want %d rows)", s.wRows, s.Kpad, totalRows); return 2; }
+    cuuint64_t dims[2] = {(cuuint64_t)s.Cin, (cuuint64_t)totalRows};
     cuuint64_t strides[1] = {(cuuint64_t)s.Cin * 2};
     cuuint32_t box[2] = {(cuuint32_t)s.Cin, (cuuint32_t)p.wBoxRows};
     cuuint32_t estr[2] = {1, 1};
@@ -517,10 +632,19 @@ int halo_build(const cfr_conv_desc& s, const float* inA, const float* inB, HaloO
                      CU_TENSOR_MAP_INTERLEAVE_NONE, swz(p.rowBytes), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("halo conv: encode(W) failed: %d", (int)r); return 3; }
+    if (p.fold) {
+      cuuint64_t adims[2] = {16, (cuuint64_t)totalRows};
+      cuuint64_t astr[1] = {32};
+      cuuint32_t abox[2] = {16, (cuuint32_t)p.wBoxRows};
+      r = enc(&p.tmWa, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(w_aux), adims, astr, abox, estr,
+              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) { set_error("halo conv: encode(Waux) failed: %d", (int)r); return 3; }
+    }
   }
   const int total = p.N * p.bandsX * p.bandsY;
   op->grid = total < num_sms() ? total : num_sms();
-  op->smemBytes = p.haloStages * p.haloBytes + p.wBytes + ctrl + 1024;
+  op->smemBytes = p.haloStages * (p.haloBytes + p.auxBytes) + p.wBytes + p.wAuxBytes + ctrl + 1024;
   op->flops = 2.0 * s.N * s.Hout * s.Wout * s.numPhases * s.ntaps * static_cast<double>(s.Cin) * s.Cout;
   // algorithmic HBM bytes: every input element read once, every output element written once (fp16)
   op->bytes = 2.0 * s.N * (static_cast<double>(s.Hin) * s.Win * s.Cin + static_cast<double>(s.outH) * s.outW * s.Cout);
@@ -531,11 +655,12 @@ int halo_launch(const HaloOp& op, cudaStream_t stream) {
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(conv_halo_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (attr_err == cudaSuccess)
-      attr_err = cudaFuncSetAttribute(conv_halo_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (attr_err == cudaSuccess)
-      attr_err = cudaFuncSetAttribute(conv_halo_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    const void* fns[] = {(const void*)conv_halo_kernel<16, false>, (const void*)conv_halo_kernel<32, false>,
+                         (const void*)conv_halo_kernel<64, false>, (const void*)conv_halo_kernel<16, true>,
+                         (const void*)conv_halo_kernel<32, true>};
+    for (const void* f : fns)
+      if (attr_err == cudaSuccess)
+        attr_err = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   });
   if (attr_err != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(attr_err)); return 4; }
   cudaEvent_t e1 = nullptr;
@@ -544,9 +669,15 @@ int halo_launch(const HaloOp& op, cudaStream_t stream) {
     e1 = profile_event(1);
   }
   switch (op.p.Cout) {
-    case 16: conv_halo_kernel<16><<<op.grid, kHaloThreads, op.smemBytes, stream>>>(op.p); break;
-    case 32: conv_halo_kernel<32><<<op.grid, kHaloThreads, op.smemBytes, stream>>>(op.p); break;
-    default: conv_halo_kernel<64><<<op.grid, kHaloThreads, op.smemBytes, stream>>>(op.p); break;
+    case 16:
+      if (op.p.fold) conv_halo_kernel<16, true><<<op.grid, kHaloThreads, op.smemBytes, stream>>>(op.p);
+      else conv_halo_kernel<16, false><<<op.grid, kHaloThreads, op.smemBytes, stream>>>(op.p);
+      break;
+    case 32:
+      if (op.p.fold) conv_halo_kernel<32, true><<<op.grid, kHaloThreads, op.smemBytes, stream>>>(op.p);
+      else conv_halo_kernel<32, false><<<op.grid, kHaloThreads, op.smemBytes, stream>>>(op.p);
+      break;
+    default: conv_halo_kernel<64, false><<<op.grid, kHaloThreads, op.smemBytes, stream>>>(op.p); break;
   }
   if (profile_on()) {
     cudaEventRecord(e1, stream);

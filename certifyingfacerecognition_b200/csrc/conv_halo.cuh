@@ -29,7 +29,10 @@ constexpr int kHaloW = 130;         // 128 output columns + 1 halo column each s
 
 struct HaloParams {
   const __half* in;                 // NHWC fp16 input [N,H,W,Cin]
-  CUtensorMap tmW;                  // weights (Cin, phases*taps*Cout), box {Cin, wBoxRows}
+  CUtensorMap tmW;                  // weights (Cin, [n *] phases*taps*Cout), box {Cin, wBoxRows}
+  CUtensorMap tmWa;                 // FOLD: aux weight tiles (16, n*phases*taps*Cout), box {16, wBoxRows}
+  int fold;                         // per-sample folded weights + aux band
+  int auxBytes, wAuxBytes;          // aux band bytes per stage / aux weight bytes (0 unless fold)
   int N, H, W;                      // conv output grid == input grid (stride 1)
   int Cin, Cout;
   int TH;                           // output rows per band
@@ -58,7 +61,10 @@ struct HaloOp {
   double bytes;   // algorithmic HBM traffic per launch
 };
 
-int halo_build(const cfr_conv_desc& s, const float* inA, const float* inB, HaloOp* op);
+int halo_build(const cfr_conv_desc& s, const float* inA, const float* inB, const void* w_aux, HaloOp* op);
+// per-sample weight folding for the FOLD variant (see conv_halo.cu)
+int launch_fold_weights(const float* base_w, const float* inA, const float* inB, const float* bias, const float* noise_w,
+                        int center_tap, int n, int pt, int cout, int cin, __half* w_main, __half* w_aux, cudaStream_t st);
 int halo_launch(const HaloOp& op, cudaStream_t stream);
 
 }  // namespace cfr

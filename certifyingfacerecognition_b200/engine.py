@@ -170,7 +170,10 @@ class Program:
              noise: Optional[Tensor] = None, noise_w: Optional[Tensor] = None, act: int = L.ACT_NONE,
              slope: float = 0.2, alpha: Optional[Tensor] = None, resid: Optional[Tensor] = None, resid_c: int = 0,
              stat_sum: Optional[Tensor] = None, stat_sq: Optional[Tensor] = None, halo: bool = False,
-             in_affine: Optional[Tuple[Tensor, Tensor]] = None) -> None:
+             in_affine: Optional[Tuple[Tensor, Tensor]] = None, fold_center_tap: Optional[int] = None) -> None:
+        """Record one convolution.  ``halo``: use the halo-resident kernel (Cin, Cout <= 64); ``in_affine`` (A, B):
+        apply x = y*A + B on load; ``fold_center_tap`` (halo, Cin <= 32): fold A into per-sample weights and carry
+        B / bias / noise on the auxiliary band -- ``w`` is then the fp32 base weight [phases*taps*Cout, Cin]."""
         d = L.ConvDesc()
         d.inp, d.N, d.Hin, d.Win, d.Cin = L.ptr(inp), n, hin, win, cin
         d.w, d.wRows, d.Kpad = L.ptr(w), w.shape[0], w.shape[1]
@@ -203,7 +206,15 @@ class Program:
             for t in (a, b):
                 if t is not None:
                     self.keep.append(t)
-            L.check(self.lib.cfr_program_add_conv_halo(self.handle, C.byref(d), L.ptr(a), L.ptr(b)))
+            if fold_center_tap is not None:
+                assert w.dtype == torch.float32
+                rows = n * w.shape[0]
+                w_main = self.hold(torch.zeros(rows, cin, dtype=torch.float16, device=w.device))
+                w_aux = self.hold(torch.zeros(rows, 16, dtype=torch.float16, device=w.device))
+                L.check(self.lib.cfr_program_add_conv_halo_folded(self.handle, C.byref(d), L.ptr(w), L.ptr(a), L.ptr(b),
+                                                                  fold_center_tap, L.ptr(w_main), L.ptr(w_aux)))
+            else:
+                L.check(self.lib.cfr_program_add_conv_halo(self.handle, C.byref(d), L.ptr(a), L.ptr(b)))
         else:
             assert in_affine is None, "affine-on-load is a halo-kernel feature"
             L.check(self.lib.cfr_program_add_conv(self.handle, C.byref(d)))
@@ -218,7 +229,8 @@ class Program:
 # ------------------------------------------------------------------------------------------------------
 class SynthesisProgram(Program):
     def __init__(self, g_sd: Dict[str, Tensor], chunk: int, out_res: int = 112, device="cuda",
-                 keep_planar: bool = False, mean: float = 0.5, std: float = 0.5, halo: bool = True):
+                 keep_planar: bool = False, mean: float = 0.5, std: float = 0.5, halo: bool = True,
+                 fold_small: bool = True):
         super().__init__()
         dev = torch.device(device)
         self.chunk, self.out_res = chunk, out_res
@@ -280,16 +292,20 @@ class SynthesisProgram(Program):
             ssq = self.stats[1, stat_off:stat_off + chunk * cout]
             stat_off += chunk * cout
             hk = use_halo(l)
+            fold = hk and fold_small and cin <= 32
             assert pending is None or hk
             if l % 2 == 1:
                 w = sd[f"synthesis.layer{l}.conv.weight"] * (math.sqrt(2.0) / math.sqrt(cin * 9))
                 fused_stats = res >= 16
-                wp = self.hold(_f16(pack_halo_weight(w) if hk else pack_conv_weight(w), dev))
+                if fold:
+                    wp = self.hold(_f32(pack_halo_weight(w), dev))
+                else:
+                    wp = self.hold(_f16(pack_halo_weight(w) if hk else pack_conv_weight(w), dev))
                 self.conv(inp=x, n=chunk, hin=res, win=res, cin=cin, w=wp, cout=cout, hout=res, wout=res,
                           tile=tile_for(res), out=y, out_hwc=(res, res, cout), taps=[TAPS3], noise=noise,
                           noise_w=noise_w, bias=bias, act=L.ACT_LRELU, slope=0.2,
                           stat_sum=ssum if fused_stats else None, stat_sq=ssq if fused_stats else None,
-                          halo=hk, in_affine=pending)
+                          halo=hk, in_affine=pending, fold_center_tap=4 if fold else None)
                 if not fused_stats:
                     L.check(lib.cfr_program_add_blur_act_stats(h, L.ptr(y), None, chunk, res, res, cout, None, None,
                                                                None, L.ptr(ssum), L.ptr(ssq), 1))
@@ -297,11 +313,11 @@ class SynthesisProgram(Program):
                 lo = res // 2
                 weq = upconv_equiv_weight(sd, l)
                 wp, taps = pack_halo_upconv(weq) if hk else pack_upconv_phases(weq)
-                wp = self.hold(_f16(wp, dev))
+                wp = self.hold(_f32(wp, dev) if fold else _f16(wp, dev))
                 self.conv(inp=x, n=chunk, hin=lo, win=lo, cin=cin, w=wp, cout=cout, hout=lo, wout=lo,
                           tile=tile_for(lo), out=raw, out_hwc=(res, res, cout), taps=taps, oscale=2,
                           ooff=[(0, 0), (0, 1), (1, 0), (1, 1)], w_rows_per_phase=0 if hk else cout,
-                          halo=hk, in_affine=pending)
+                          halo=hk, in_affine=pending, fold_center_tap=-1 if fold else None)
                 L.check(lib.cfr_program_add_blur_act_stats(h, L.ptr(raw), L.ptr(y), chunk, res, res, cout, L.ptr(noise),
                                                            L.ptr(noise_w), L.ptr(bias), L.ptr(ssum), L.ptr(ssq), 0))
             # A/B double-buffered by layer parity: the consumer of layer l reads them while layer l+1's are written

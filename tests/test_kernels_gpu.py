@@ -314,10 +314,11 @@ def test_match_vote_bit_exact(E):
 # ------------------------------------------------------------------------------------------------------------
 # halo-resident conv kernel (high-resolution StyleGAN layers)
 # ------------------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("n,cin,cout,h,w,affine", [(2, 16, 16, 40, 256, True), (1, 32, 32, 24, 128, True),
-                                                    (2, 64, 64, 16, 200, True), (3, 16, 16, 8, 64, False),
-                                                    (1, 64, 64, 9, 130, False)])
-def test_halo_conv_matches_torch(E, n, cin, cout, h, w, affine):
+@pytest.mark.parametrize("n,cin,cout,h,w,affine,fold", [
+    (2, 16, 16, 40, 256, True, False), (1, 32, 32, 24, 128, True, False), (2, 64, 64, 16, 200, True, False),
+    (3, 16, 16, 8, 64, False, False), (1, 64, 64, 9, 130, False, False),
+    (3, 16, 16, 40, 256, True, True), (2, 32, 32, 24, 200, True, True), (2, 16, 16, 8, 64, False, True)])
+def test_halo_conv_matches_torch(E, n, cin, cout, h, w, affine, fold):
     g = torch.Generator().manual_seed(cin * 7 + h)
     yprev = torch.randn(n, cin, h, w, generator=g).cuda().half().float()
     wt = (torch.randn(cout, cin, 3, 3, generator=g) / math.sqrt(cin * 9)).cuda().half().float()
@@ -331,22 +332,28 @@ def test_halo_conv_matches_torch(E, n, cin, cout, h, w, affine):
     out = torch.full((n * h * w * cout,), float("nan"), dtype=torch.float16, device="cuda")
     ssum, ssq = torch.zeros(n, cout, device="cuda"), torch.zeros(n, cout, device="cuda")
     prog = E.Program()
-    prog.conv(inp=_nhwc16(yprev), n=n, hin=h, win=w, cin=cin, w=E.pack_halo_weight(wt.cpu()).cuda().half(), cout=cout,
+    wpk = E.pack_halo_weight(wt.cpu()).cuda()
+    prog.conv(inp=_nhwc16(yprev), n=n, hin=h, win=w, cin=cin, w=wpk.float().contiguous() if fold else wpk.half(), cout=cout,
               hout=h, wout=w, tile=(16, 8, 1), out=out, out_hwc=(h, w, cout), taps=[E.TAPS3], bias=bias,
               noise=noise.reshape(-1).contiguous(), noise_w=nw, act=E.L.ACT_LRELU, slope=0.2, stat_sum=ssum, stat_sq=ssq,
-              halo=True, in_affine=(A.contiguous(), B.contiguous()) if affine else None)
+              halo=True, in_affine=(A.contiguous(), B.contiguous()) if affine else None,
+              fold_center_tap=4 if fold else None)
     prog.run()
     prog.run()          # replays must be idempotent for the output (stats accumulate)
     _sync()
     got = _from_nhwc(out, n, h, w, cout)
     assert torch.isfinite(got).all()
-    assert (got - ref).abs().max().item() < 2e-2 * max(1.0, ref.abs().max().item())
-    assert torch.allclose(ssum, 2 * ref.sum(dim=[2, 3]), rtol=1e-3, atol=5e-2)
-    assert torch.allclose(ssq, 2 * (ref * ref).sum(dim=[2, 3]), rtol=1e-3, atol=5e-2)
+    # folded variant: scale rounded into fp16 weights, shift / bias / noise through fp16 aux operands -> looser bound
+    tol = (4e-2 if fold else 2e-2) * max(1.0, ref.abs().max().item())
+    assert (got - ref).abs().max().item() < tol
+    assert (got - ref).abs().mean().item() < 2e-3 * max(1.0, ref.abs().max().item())
+    assert torch.allclose(ssum, 2 * ref.sum(dim=[2, 3]), rtol=2e-3, atol=0.5 if fold else 5e-2)
+    assert torch.allclose(ssq, 2 * (ref * ref).sum(dim=[2, 3]), rtol=2e-3, atol=0.5 if fold else 5e-2)
 
 
-@pytest.mark.parametrize("n,cin,cout,lo_h,lo_w", [(2, 64, 32, 12, 128), (1, 32, 16, 20, 256), (2, 64, 32, 5, 96)])
-def test_halo_upconv_matches_torch(E, n, cin, cout, lo_h, lo_w):
+@pytest.mark.parametrize("n,cin,cout,lo_h,lo_w,fold", [(2, 64, 32, 12, 128, False), (1, 32, 16, 20, 256, False),
+                                                        (2, 64, 32, 5, 96, False), (3, 32, 16, 20, 256, True)])
+def test_halo_upconv_matches_torch(E, n, cin, cout, lo_h, lo_w, fold):
     g = torch.Generator().manual_seed(cin + lo_h)
     yprev = torch.randn(n, cin, lo_h, lo_w, generator=g).cuda().half().float()
     weq = torch.randn(cout, cin, 3, 3, generator=g) / math.sqrt(cin * 9)
@@ -358,9 +365,10 @@ def test_halo_upconv_matches_torch(E, n, cin, cout, lo_h, lo_w):
     H, W = 2 * lo_h, 2 * lo_w
     out = torch.full((n * H * W * cout,), float("nan"), dtype=torch.float16, device="cuda")
     prog = E.Program()
-    prog.conv(inp=_nhwc16(yprev), n=n, hin=lo_h, win=lo_w, cin=cin, w=wp.cuda().half(), cout=cout, hout=lo_h, wout=lo_w,
-              tile=(16, 8, 1), out=out, out_hwc=(H, W, cout), taps=taps, oscale=2,
-              ooff=[(0, 0), (0, 1), (1, 0), (1, 1)], halo=True, in_affine=(A.contiguous(), B.contiguous()))
+    prog.conv(inp=_nhwc16(yprev), n=n, hin=lo_h, win=lo_w, cin=cin, w=wp.cuda().float().contiguous() if fold else wp.cuda().half(),
+              cout=cout, hout=lo_h, wout=lo_w, tile=(16, 8, 1), out=out, out_hwc=(H, W, cout), taps=taps, oscale=2,
+              ooff=[(0, 0), (0, 1), (1, 0), (1, 1)], halo=True, in_affine=(A.contiguous(), B.contiguous()),
+              fold_center_tap=-1 if fold else None)
     prog.run()
     _sync()
     got = _from_nhwc(out, n, H, W, cout)
