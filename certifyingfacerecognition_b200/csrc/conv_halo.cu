@@ -281,11 +281,12 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
           const bool ok = static_cast<unsigned>(gy) < static_cast<unsigned>(p.H) &&
                           static_cast<unsigned>(gx) < static_cast<unsigned>(p.W);
           const float nzv = (ok && p.noise != nullptr) ? __ldg(&p.noise[gy * p.W + gx]) : 0.f;
-          const __half2 h = __floats2half2_rn(nzv, ok ? 1.f : 0.f);
+          const __half2 h01 = __floats2half2_rn(nzv, ok ? 1.f : 0.f);      // {noise, inside}
+          const __half2 h23 = __floats2half2_rn(ok ? 1.f : 0.f, 0.f);       // {inside (for the fp16 residual of the shift), 0}
           const uint32_t lin = xb_addr + (static_cast<uint32_t>(px) << 5);
           const uint32_t dst = lin ^ (((lin >> 7) & 1u) << 4);
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %2, %2};" ::"r"(dst), "r"(*reinterpret_cast<const uint32_t*>(&h)),
-                       "r"(0u)
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %3};" ::"r"(dst), "r"(*reinterpret_cast<const uint32_t*>(&h01)),
+                       "r"(*reinterpret_cast<const uint32_t*>(&h23)), "r"(0u)
                        : "memory");
         }
       }
@@ -531,6 +532,7 @@ static CUtensorMapSwizzle swz(int bytes) {
 //   w_main[n][pt][co][ci] = fp16( W[pt][co][ci] * A[n][ci] )                       -- IN+AdaIN scale of the input
 //   w_aux [n][pt][co][0]  = noise_w[co]            if pt == center_tap else 0        -- x aux channel 0 (noise image)
 //   w_aux [n][pt][co][1]  = sum_ci W[pt][co][ci]*B[n][ci]  (+ bias[co] at the center tap)  -- x aux channel 1 (inside?)
+//   w_aux [n][pt][co][2]  = fp16 rounding residual of the previous entry                     -- x aux channel 2 (inside?)
 // so that  conv_W(A*y + B, zero padded) + noise*w + bias  ==  conv_wmain(y) + conv_waux({noise, inside}).
 // ---------------------------------------------------------------------------------------------------------
 __global__ void k_fold_weights(const float* __restrict__ base_w, const float* __restrict__ inA,
@@ -548,8 +550,10 @@ __global__ void k_fold_weights(const float* __restrict__ base_w, const float* __
   for (int o = cin >> 1; o > 0; o >>= 1) sh += __shfl_xor_sync(0xffffffffu, sh, o);
   if (ci < 16) {
     float v = 0.f;
+    const float shift = sh + ((pt == center_tap && bias != nullptr) ? bias[co] : 0.f);
     if (ci == 0 && pt == center_tap && noise_w != nullptr) v = noise_w[co];
-    if (ci == 1) v = sh + ((pt == center_tap && bias != nullptr) ? bias[co] : 0.f);
+    if (ci == 1) v = shift;
+    if (ci == 2) v = shift - __half2float(__float2half_rn(shift));      // fp16 residual: shift is carried to ~2^-22
     w_aux[((static_cast<size_t>(n) * pt_count + pt) * cout + co) * 16 + ci] = __float2half_rn(v);
   }
 }

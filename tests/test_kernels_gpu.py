@@ -347,8 +347,10 @@ def test_halo_conv_matches_torch(E, n, cin, cout, h, w, affine, fold):
     tol = (4e-2 if fold else 2e-2) * max(1.0, ref.abs().max().item())
     assert (got - ref).abs().max().item() < tol
     assert (got - ref).abs().mean().item() < 2e-3 * max(1.0, ref.abs().max().item())
-    assert torch.allclose(ssum, 2 * ref.sum(dim=[2, 3]), rtol=2e-3, atol=0.5 if fold else 5e-2)
-    assert torch.allclose(ssq, 2 * (ref * ref).sum(dim=[2, 3]), rtol=2e-3, atol=0.5 if fold else 5e-2)
+    # sums over 2*h*w pixels: allow a per-pixel systematic 1e-4 for the folded variant (fp16 noise gain / weights)
+    atol = 1e-4 * 2 * h * w if fold else 5e-2
+    assert torch.allclose(ssum, 2 * ref.sum(dim=[2, 3]), rtol=2e-3, atol=atol)
+    assert torch.allclose(ssq, 2 * (ref * ref).sum(dim=[2, 3]), rtol=2e-3, atol=4 * atol)
 
 
 @pytest.mark.parametrize("n,cin,cout,lo_h,lo_w,fold", [(2, 64, 32, 12, 128, False), (1, 32, 16, 20, 256, False),
