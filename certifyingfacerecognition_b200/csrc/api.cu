@@ -190,7 +190,7 @@ CFR_API int cfr_program_add_layer0(cfr_program* p, const float* xhat0, const flo
 }
 
 CFR_API int cfr_program_add_blur_act_stats(cfr_program* p, const void* raw_f16, void* y_f16, int n, int h, int w, int c,
-                                   const float* noise, const float* noise_w, const float* bias, float* sum, float* sq,
+                                   const float* noise, const float* noise_w, const float* bias, int64_t* sum, int64_t* sq,
                                    int mode) {
   p->add([=](cudaStream_t st) {
     return launch_blur_act_stats(static_cast<const __half*>(raw_f16), static_cast<__half*>(y_f16), n, h, w, c, noise,
@@ -199,7 +199,7 @@ CFR_API int cfr_program_add_blur_act_stats(cfr_program* p, const void* raw_f16, 
   return 0;
 }
 
-CFR_API int cfr_program_add_finalize_stats(cfr_program* p, const float* sum, const float* sq, const float* styles,
+CFR_API int cfr_program_add_finalize_stats(cfr_program* p, const int64_t* sum, const int64_t* sq, const float* styles,
                                    int style_stride, int style_off, int n, int c, float inv_count, float* A, float* B) {
   p->add([=](cudaStream_t st) {
     return launch_finalize_stats(sum, sq, styles, style_stride, style_off, n, c, inv_count, A, B, st);

@@ -68,8 +68,8 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 16);
   float* sA = reinterpret_cast<float*>(tmem_slot + 4);     // [64]
   float* sB = sA + 64;                                     // [64]
-  float* s_sum = sB + 64;                                  // [64]
-  float* s_sq = s_sum + 64;                                // [64]
+  stat_t* s_sum = reinterpret_cast<stat_t*>(sB + 64);      // [64]
+  stat_t* s_sq = s_sum + 64;                               // [64]
 
   const int warp = threadIdx.x >> 5;
   const uint32_t lane = lane_id();
@@ -105,8 +105,8 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
     tmem_relinquish();
   }
   if (threadIdx.x < 64) {
-    s_sum[threadIdx.x] = 0.f;
-    s_sq[threadIdx.x] = 0.f;
+    s_sum[threadIdx.x] = 0ull;
+    s_sq[threadIdx.x] = 0ull;
   }
   if constexpr (FOLD) {                      // aux rows are {noise, indicator, 0 x14}: zero everything once
     const uint4 z = make_uint4(0u, 0u, 0u, 0u);
@@ -384,8 +384,8 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
         if (et < COUT) {
           atomicAdd(&p.stat_sum[cur_n * COUT + et], s_sum[et]);
           atomicAdd(&p.stat_sq[cur_n * COUT + et], s_sq[et]);
-          s_sum[et] = 0.f;
-          s_sq[et] = 0.f;
+          s_sum[et] = 0ull;
+          s_sq[et] = 0ull;
         }
         named_bar_sync(1, 256);
       }
@@ -466,8 +466,8 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
                 const float ssq = warp_reduce16h(sq, lane);
                 if ((lane & 1) == 0) {
                   const int ch = ch0 + reduce16_channel_h(lane);
-                  atomicAdd(&s_sum[ch], ssum);
-                  atomicAdd(&s_sq[ch], ssq);
+                  atomicAdd(&s_sum[ch], stat_fx(ssum));
+                  atomicAdd(&s_sq[ch], stat_fx(ssq));
                 }
               }
             }
@@ -493,8 +493,8 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
             const float ssq = warp_reduce16h(a2, lane);
             if ((lane & 1) == 0) {
               const int ch = ci * 16 + reduce16_channel_h(lane);
-              atomicAdd(&s_sum[ch], ssum);
-              atomicAdd(&s_sq[ch], ssq);
+              atomicAdd(&s_sum[ch], stat_fx(ssum));
+              atomicAdd(&s_sq[ch], stat_fx(ssq));
             }
           }
         }
@@ -593,7 +593,7 @@ int halo_build(const cfr_conv_desc& s, const float* inA, const float* inB, const
   p.wBytes = (p.wRows * p.rowBytes + 1023) / 1024 * 1024;
   p.wBoxRows = p.wRows;
   while (p.wBoxRows > 256 || p.wRows % p.wBoxRows != 0) --p.wBoxRows;
-  const int ctrl = 8 * 44 + 16 + 4 * 64 * 4 + 64;
+  const int ctrl = 8 * 44 + 16 + 2 * 64 * 4 + 2 * 64 * 8 + 64;
   const int budget = 227 * 1024 - 1024 - ctrl - p.wBytes - p.wAuxBytes;
   auto aux_bytes = [&](int th) { return p.fold ? ((th + 2) * kHaloW * 32 + 1023) / 1024 * 1024 : 0; };
   auto halo_bytes = [&](int th) { return ((th + 2) * kHaloW * p.rowBytes + 1023) / 1024 * 1024 + aux_bytes(th); };
@@ -622,7 +622,7 @@ int halo_build(const cfr_conv_desc& s, const float* inA, const float* inB, const
   memcpy(p.ooff_y, s.ooff_y, sizeof(p.ooff_y));
   memcpy(p.ooff_x, s.ooff_x, sizeof(p.ooff_x));
   p.bias = s.bias; p.noise = s.noise; p.noise_w = s.noise_w; p.act = s.act; p.slope = s.slope;
-  p.stat_sum = s.stat_sum; p.stat_sq = s.stat_sq;
+  p.stat_sum = reinterpret_cast<unsigned long long*>(s.stat_sum); p.stat_sq = reinterpret_cast<unsigned long long*>(s.stat_sq);
   if (s.outC != s.Cout) { set_error("halo conv: outC must equal Cout"); return 2; }
   p.in = static_cast<const __half*>(s.in);
   {

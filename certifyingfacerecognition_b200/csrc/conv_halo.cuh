@@ -51,7 +51,7 @@ struct HaloParams {
   int8_t ooff_y[4], ooff_x[4];
   const float* bias; const float* noise; const float* noise_w;
   int act; float slope;
-  float* stat_sum; float* stat_sq;  // [N, Cout] or null
+  unsigned long long* stat_sum; unsigned long long* stat_sq;  // [N, Cout] Q43.20 fixed point, or null
 };
 
 struct HaloOp {

@@ -72,8 +72,8 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
   uint64_t* tfull_bar = empty_bar + S;
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
-  float* s_sum = reinterpret_cast<float*>(tmem_slot + 4);
-  float* s_sq = s_sum + kStatsMaxC;
+  stat_t* s_sum = reinterpret_cast<stat_t*>(tmem_slot + 4);
+  stat_t* s_sq = s_sum + kStatsMaxC;
 
   const int warp = threadIdx.x >> 5;
   const uint32_t lane = lane_id();
@@ -110,7 +110,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
     tmem_relinquish();
   }
   if (p.stat_sum != nullptr) {
-    for (int i = threadIdx.x; i < 2 * kStatsMaxC; i += blockDim.x) s_sum[i] = 0.f;
+    for (int i = threadIdx.x; i < 2 * kStatsMaxC; i += blockDim.x) s_sum[i] = 0ull;
   }
   tc_fence_before();
   __syncthreads();
@@ -229,8 +229,8 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
         for (int c = et; c < p.CoutTotal; c += 128) {
           atomicAdd(&p.stat_sum[cur_img * p.CoutTotal + c], s_sum[c]);
           atomicAdd(&p.stat_sq[cur_img * p.CoutTotal + c], s_sq[c]);
-          s_sum[c] = 0.f;
-          s_sq[c] = 0.f;
+          s_sum[c] = 0ull;
+          s_sq[c] = 0ull;
         }
         named_bar_sync(1, 128);
       }
@@ -329,8 +329,8 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
           const float ssq = warp_reduce16(sq, lane);
           if ((lane & 1) == 0) {
             const int ch = ch0 + reduce16_channel(lane);
-            atomicAdd(&s_sum[ch], ssum);
-            atomicAdd(&s_sq[ch], ssq);
+            atomicAdd(&s_sum[ch], stat_fx(ssum));
+            atomicAdd(&s_sq[ch], stat_fx(ssq));
           }
         }
       }
@@ -446,7 +446,7 @@ int conv_build(const ConvSpec& s, ConvOp* op) {
   p.numNTiles = s.Cout / bn;
   p.CoutTotal = s.Cout;
   p.stageBytes = kBM * 128 + bn * 128;
-  const int ctrlBytes = 8 * (2 * 8 + 4) + 16 + 2 * kStatsMaxC * 4;
+  const int ctrlBytes = 8 * (2 * 8 + 4) + 16 + 2 * kStatsMaxC * 8;
   const int budget = 227 * 1024 - 1024 - ctrlBytes;
   p.numStages = budget / p.stageBytes;
   if (p.numStages > 8) p.numStages = 8;
@@ -462,7 +462,7 @@ int conv_build(const ConvSpec& s, ConvOp* op) {
   p.noise = s.noise; p.noise_w = s.noise_w;
   p.act = s.act; p.slope = s.slope; p.alpha = s.alpha;
   p.resid = static_cast<const __half*>(s.resid); p.residC = s.residC;
-  p.stat_sum = s.stat_sum; p.stat_sq = s.stat_sq;
+  p.stat_sum = reinterpret_cast<stat_t*>(s.stat_sum); p.stat_sq = reinterpret_cast<stat_t*>(s.stat_sq);
 
   // activations: (C, W, H, N), fp16
   {

@@ -65,8 +65,8 @@ struct ConvParams {
   const float* alpha;            // PReLU [Cout]
   const __half* resid;           // [N,outH,outW,residC] or null
   int residC;
-  float* stat_sum;               // [N, Cout] or null (requires TN == 1, numPhases == 1)
-  float* stat_sq;
+  unsigned long long* stat_sum;  // [N, Cout] Q43.20 fixed point, or null (requires TN == 1, numPhases == 1)
+  unsigned long long* stat_sq;
   int CoutTotal;
 };
 

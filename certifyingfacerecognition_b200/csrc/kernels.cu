@@ -1,6 +1,7 @@
 // HBM-bound and small kernels of the certification path.  All are coalesced / 128-bit vectorised over the
 // NHWC channel dimension; reductions go registers -> shared -> one global atomic per (block, channel).
 #include "kernels.cuh"
+#include "ptx.cuh"
 
 #include <cstdio>
 
@@ -182,17 +183,17 @@ template <int MODE>
 __global__ void __launch_bounds__(256) k_blur_act_stats(const __half* __restrict__ raw, __half* __restrict__ y, int h,
                                                         int w, int c, const float* __restrict__ noise,
                                                         const float* __restrict__ noise_w,
-                                                        const float* __restrict__ bias, float* __restrict__ gsum,
-                                                        float* __restrict__ gsq) {
-  __shared__ float s_sum[512], s_sq[512];
+                                                        const float* __restrict__ bias, stat_t* __restrict__ gsum,
+                                                        stat_t* __restrict__ gsq) {
+  __shared__ stat_t s_sum[512], s_sq[512];
   const int n = blockIdx.y;
   const int c8 = c >> 3;
   const int ppb = 256 / c8;                 // pixels per block step (c8 <= 64)
   const int cg = threadIdx.x % c8, pl = threadIdx.x / c8;
   const int ch = cg * 8;
   for (int i = threadIdx.x; i < c; i += 256) {
-    s_sum[i] = 0.f;
-    s_sq[i] = 0.f;
+    s_sum[i] = 0ull;
+    s_sq[i] = 0ull;
   }
   __syncthreads();
   float nw[8], bs[8], acc[8], acc2[8];
@@ -245,8 +246,8 @@ __global__ void __launch_bounds__(256) k_blur_act_stats(const __half* __restrict
     }
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      atomicAdd(&s_sum[ch + i], acc[i]);
-      atomicAdd(&s_sq[ch + i], acc2[i]);
+      atomicAdd(&s_sum[ch + i], stat_fx(acc[i]));
+      atomicAdd(&s_sq[ch + i], stat_fx(acc2[i]));
     }
   }
   __syncthreads();
@@ -290,8 +291,8 @@ __device__ __forceinline__ void hblur8(const Raw3& t, float (&h)[8]) {
 __global__ void __launch_bounds__(256, 3) k_blur_rows(const __half* __restrict__ raw, __half* __restrict__ y, int h, int w,
                                                       int c, const float* __restrict__ noise,
                                                       const float* __restrict__ noise_w, const float* __restrict__ bias,
-                                                      float* __restrict__ gsum, float* __restrict__ gsq) {
-  __shared__ float s_sum[512], s_sq[512];
+                                                      stat_t* __restrict__ gsum, stat_t* __restrict__ gsq) {
+  __shared__ stat_t s_sum[512], s_sq[512];
   const int n = blockIdx.z;
   const int c8 = c >> 3;
   const int ppb = 256 / c8;
@@ -300,8 +301,8 @@ __global__ void __launch_bounds__(256, 3) k_blur_rows(const __half* __restrict__
   const int px = blockIdx.x * ppb + pl;
   const int y0 = blockIdx.y * kBlurRows;
   for (int i = threadIdx.x; i < c; i += 256) {
-    s_sum[i] = 0.f;
-    s_sq[i] = 0.f;
+    s_sum[i] = 0ull;
+    s_sq[i] = 0ull;
   }
   __syncthreads();
   if (px < w) {
@@ -346,8 +347,8 @@ __global__ void __launch_bounds__(256, 3) k_blur_rows(const __half* __restrict__
     }
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      atomicAdd(&s_sum[ch + i], acc[i]);
-      atomicAdd(&s_sq[ch + i], acc2[i]);
+      atomicAdd(&s_sum[ch + i], stat_fx(acc[i]));
+      atomicAdd(&s_sq[ch + i], stat_fx(acc2[i]));
     }
   }
   __syncthreads();
@@ -358,7 +359,9 @@ __global__ void __launch_bounds__(256, 3) k_blur_rows(const __half* __restrict__
 }
 
 int launch_blur_act_stats(const __half* raw, __half* y, int n, int h, int w, int c, const float* noise,
-                          const float* noise_w, const float* bias, float* sum, float* sq, int mode, cudaStream_t st) {
+                          const float* noise_w, const float* bias, void* sum_v, void* sq_v, int mode, cudaStream_t st) {
+  stat_t* sum = static_cast<stat_t*>(sum_v);
+  stat_t* sq = static_cast<stat_t*>(sq_v);
   if (c % 8 != 0 || c > 512) { set_error("blur_act_stats: C=%d unsupported", c); return 2; }
   const int ppb = 256 / (c / 8);
   if (mode == 0) {
@@ -378,14 +381,15 @@ int launch_blur_act_stats(const __half* raw, __half* y, int n, int h, int w, int
 }
 
 // ------------------------------------------------------------------------------------------
-__global__ void k_finalize_stats(const float* __restrict__ sum, const float* __restrict__ sq,
+__global__ void k_finalize_stats(const long long* __restrict__ sum, const long long* __restrict__ sq,
                                  const float* __restrict__ styles, int style_stride, int style_off, int n, int c,
                                  float inv_count, float* __restrict__ A, float* __restrict__ B) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n * c) return;
   const int s = i / c, ch = i - s * c;
-  const float mean = sum[i] * inv_count;
-  float var = sq[i] * inv_count - mean * mean;
+  const double meand = static_cast<double>(sum[i]) * (1.0 / kStatScale) * inv_count;
+  const float mean = static_cast<float>(meand);
+  float var = static_cast<float>(static_cast<double>(sq[i]) * (1.0 / kStatScale) * inv_count - meand * meand);
   var = var > 0.f ? var : 0.f;
   const float rstd = 1.0f / sqrtf(var + 1e-8f);
   const float s0 = styles[static_cast<size_t>(s) * style_stride + style_off + ch];
@@ -394,9 +398,9 @@ __global__ void k_finalize_stats(const float* __restrict__ sum, const float* __r
   A[i] = a;
   B[i] = s1 - mean * a;
 }
-int launch_finalize_stats(const float* sum, const float* sq, const float* styles, int style_stride, int style_off,
+int launch_finalize_stats(const void* sum, const void* sq, const float* styles, int style_stride, int style_off,
                           int n, int c, float inv_count, float* A, float* B, cudaStream_t st) {
-  k_finalize_stats<<<(n * c + 255) / 256, 256, 0, st>>>(sum, sq, styles, style_stride, style_off, n, c, inv_count, A, B);
+  k_finalize_stats<<<(n * c + 255) / 256, 256, 0, st>>>(static_cast<const long long*>(sum), static_cast<const long long*>(sq), styles, style_stride, style_off, n, c, inv_count, A, B);
   CFR_LAUNCH_CHECK("finalize_stats");
   return 0;
 }

@@ -25,10 +25,10 @@ int launch_layer0(const float* xhat0, const float* styles, int style_stride, int
 // BlurLayer :463 + EpilogueBlock :560-562 (+noise*w +bias, lrelu) + per-(n,c) sums for IN.  mode 0: blur+act+write;
 // mode 1: statistics of an existing tensor only.
 int launch_blur_act_stats(const __half* raw, __half* y, int n, int h, int w, int c, const float* noise,
-                          const float* noise_w, const float* bias, float* sum, float* sq, int mode, cudaStream_t st);
+                          const float* noise_w, const float* bias, void* sum, void* sq, int mode, cudaStream_t st);
 
 // InstanceNormLayer :420-422 + StyleModulationLayer :505 ->  x = y*A + B,  A = rstd*(s0+1),  B = s1 - mean*A
-int launch_finalize_stats(const float* sum, const float* sq, const float* styles, int style_stride, int style_off,
+int launch_finalize_stats(const void* sum, const void* sq, const float* styles, int style_stride, int style_off,
                           int n, int c, float inv_count, float* A, float* B, cudaStream_t st);
 int launch_affine(const __half* y, const float* A, const float* B, int n, int hw, int c, __half* x, cudaStream_t st);
 

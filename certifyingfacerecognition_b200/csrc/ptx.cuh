@@ -173,6 +173,14 @@ __host__ __device__ __forceinline__ uint32_t make_idesc_f16(uint32_t M, uint32_t
   return d;
 }
 
+// Per-(n,c) InstanceNorm sums are accumulated as Q43.20 fixed point in 64-bit integers: integer atomics commute, so
+// the statistics -- and with them every downstream vote -- are bit-reproducible run to run.
+typedef unsigned long long stat_t;
+constexpr double kStatScale = 1048576.0;
+__device__ __forceinline__ stat_t stat_fx(float v) {
+  return static_cast<stat_t>(__double2ll_rn(static_cast<double>(v) * kStatScale));
+}
+
 __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }

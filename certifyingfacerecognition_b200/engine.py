@@ -258,7 +258,7 @@ class SynthesisProgram(Program):
 
         # ---- statistics / affine buffers, zeroed at the start of every run
         total_c = sum(layer_channels(l) for l in range(NUM_LAYERS))
-        self.stats = self.hold(torch.zeros(2, chunk * total_c, device=dev))
+        self.stats = self.hold(torch.zeros(2, chunk * total_c, dtype=torch.int64, device=dev))   # Q43.20 fixed point
         self.memset(self.stats)
         self.AB = [(self.hold(torch.zeros(chunk * 512, device=dev)), self.hold(torch.zeros(chunk * 512, device=dev)))
                    for _ in range(2)]

@@ -54,7 +54,8 @@ typedef struct cfr_conv_desc {
   const float* noise; const float* noise_w;   /* [outH*outW], [Cout] or NULL */
   int32_t act; float slope; const float* alpha;
   const void* resid; int32_t residC;          /* fp16 [N,outH,outW,residC] or NULL */
-  float* stat_sum; float* stat_sq;            /* [N,Cout] per-(n,c) sum / sum of squares, or NULL */
+  int64_t* stat_sum; int64_t* stat_sq;        /* [N,Cout] per-(n,c) sum / sum of squares, Q43.20 fixed point
+                                                 (integer atomics: bit-reproducible), or NULL */
 } cfr_conv_desc;
 
 CFR_API const char* cfr_last_error(void);
@@ -94,10 +95,10 @@ CFR_API int cfr_program_add_layer0(cfr_program* p, const float* xhat0, const flo
                            int style_off, int b, void* out_f16);
 /* BlurLayer :463 + noise/bias/LeakyReLU :560-562 + InstanceNorm sums :420-422.  mode 1 = sums only */
 CFR_API int cfr_program_add_blur_act_stats(cfr_program* p, const void* raw_f16, void* y_f16, int n, int h, int w, int c,
-                                   const float* noise, const float* noise_w, const float* bias, float* sum,
-                                   float* sq, int mode);
+                                   const float* noise, const float* noise_w, const float* bias, int64_t* sum,
+                                   int64_t* sq, int mode);
 /* InstanceNorm + AdaIN coefficients: x = y*A + B  (:420-422, :505) */
-CFR_API int cfr_program_add_finalize_stats(cfr_program* p, const float* sum, const float* sq, const float* styles,
+CFR_API int cfr_program_add_finalize_stats(cfr_program* p, const int64_t* sum, const int64_t* sq, const float* styles,
                                    int style_stride, int style_off, int n, int c, float inv_count, float* A,
                                    float* B);
 CFR_API int cfr_program_add_affine(cfr_program* p, const void* y_f16, const float* A, const float* B, int n, int hw, int c,

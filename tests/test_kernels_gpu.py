@@ -33,6 +33,15 @@ def _sync():
     torch.cuda.synchronize()
 
 
+def _stats(n, c):
+    """per-(n,c) sum / sum-of-squares accumulators: Q43.20 fixed point in int64 (integer atomics are reproducible)"""
+    return torch.zeros(n, c, dtype=torch.int64, device="cuda"), torch.zeros(n, c, dtype=torch.int64, device="cuda")
+
+
+def _fx(t):
+    return t.double() / 2 ** 20
+
+
 CONV_CASES = [
     # n, cin, cout, res, stride, ksize
     (2, 64, 64, 16, 1, 3),
@@ -85,8 +94,7 @@ def test_conv_epilogue_noise_lrelu_stats(E):
     ref = F.leaky_relu(F.conv2d(x, w, padding=1) + noise.view(1, 1, res, res) * nw.view(1, -1, 1, 1)
                        + bias.view(1, -1, 1, 1), 0.2)
     out = torch.zeros(n * res * res * c, dtype=torch.float16, device="cuda")
-    ssum = torch.zeros(n, c, device="cuda")
-    ssq = torch.zeros(n, c, device="cuda")
+    ssum, ssq = _stats(n, c)
     prog = E.Program()
     prog.conv(inp=_nhwc16(x), n=n, hin=res, win=res, cin=c, w=E.pack_conv_weight(w.cpu()).cuda().half(), cout=c,
               hout=res, wout=res, tile=E.tile_for(res), out=out, out_hwc=(res, res, c), taps=[E.TAPS3], bias=bias,
@@ -95,8 +103,8 @@ def test_conv_epilogue_noise_lrelu_stats(E):
     _sync()
     got = _from_nhwc(out, n, res, res, c)
     assert (got - ref).abs().max().item() < 2e-2
-    assert torch.allclose(ssum, ref.sum(dim=[2, 3]), rtol=1e-4, atol=1e-2)
-    assert torch.allclose(ssq, (ref * ref).sum(dim=[2, 3]), rtol=1e-4, atol=1e-2)
+    assert torch.allclose(_fx(ssum), ref.double().sum(dim=[2, 3]), rtol=1e-4, atol=1e-2)
+    assert torch.allclose(_fx(ssq), (ref * ref).double().sum(dim=[2, 3]), rtol=1e-4, atol=1e-2)
 
 
 def test_conv_prelu_residual_classbias(E):
@@ -185,7 +193,7 @@ def test_blur_act_stats(E):
     ref = F.conv2d(raw, k, padding=1, groups=c) + noise.view(1, 1, res, res) * nw.view(1, -1, 1, 1) + bias.view(1, -1, 1, 1)
     ref = F.leaky_relu(ref, 0.2)
     y = torch.zeros(n * res * res * c, dtype=torch.float16, device="cuda")
-    ssum, ssq = torch.zeros(n, c, device="cuda"), torch.zeros(n, c, device="cuda")
+    ssum, ssq = _stats(n, c)
     raw_keep = _nhwc16(raw)
     prog2 = E.Program()
     L.check(lib.cfr_program_add_blur_act_stats(prog2.handle, L.ptr(raw_keep), L.ptr(y), n, res, res, c, L.ptr(noise),
@@ -194,16 +202,16 @@ def test_blur_act_stats(E):
     _sync()
     got = _from_nhwc(y, n, res, res, c)
     assert (got - ref).abs().max().item() < 1e-2
-    assert torch.allclose(ssum, ref.sum(dim=[2, 3]), rtol=1e-4, atol=1e-2)
-    assert torch.allclose(ssq, (ref * ref).sum(dim=[2, 3]), rtol=1e-4, atol=1e-2)
+    assert torch.allclose(_fx(ssum), ref.double().sum(dim=[2, 3]), rtol=1e-4, atol=1e-2)
+    assert torch.allclose(_fx(ssq), (ref * ref).double().sum(dim=[2, 3]), rtol=1e-4, atol=1e-2)
     # statistics-only mode on the produced tensor
-    s2, q2 = torch.zeros(n, c, device="cuda"), torch.zeros(n, c, device="cuda")
+    s2, q2 = _stats(n, c)
     prog3 = E.Program()
     L.check(lib.cfr_program_add_blur_act_stats(prog3.handle, L.ptr(y), None, n, res, res, c, None, None, None,
                                                L.ptr(s2), L.ptr(q2), 1))
     prog3.run()
     _sync()
-    assert torch.allclose(s2, got.sum(dim=[2, 3]), rtol=1e-4, atol=1e-2)
+    assert torch.allclose(_fx(s2), got.double().sum(dim=[2, 3]), rtol=1e-4, atol=1e-2)
 
 
 def test_finalize_and_affine(E):
@@ -214,7 +222,8 @@ def test_finalize_and_affine(E):
     y = (torch.randn(n, hw, c, generator=g) * 2 + 1).cuda().half()
     yf = y.float()
     styles = torch.randn(n, 2 * c + 10, generator=g).cuda()
-    ssum, ssq = yf.sum(1).contiguous(), (yf * yf).sum(1).contiguous()
+    ssum = (yf.double().sum(1) * 2 ** 20).round().long().contiguous()
+    ssq = ((yf.double() * yf.double()).sum(1) * 2 ** 20).round().long().contiguous()
     A, B = torch.zeros(n, c, device="cuda"), torch.zeros(n, c, device="cuda")
     x = torch.zeros_like(y)
     prog = E.Program()
@@ -330,7 +339,7 @@ def test_halo_conv_matches_torch(E, n, cin, cout, h, w, affine, fold):
     ref = F.leaky_relu(F.conv2d(xin, wt, padding=1) + noise.view(1, 1, h, w) * nw.view(1, -1, 1, 1)
                        + bias.view(1, -1, 1, 1), 0.2)
     out = torch.full((n * h * w * cout,), float("nan"), dtype=torch.float16, device="cuda")
-    ssum, ssq = torch.zeros(n, cout, device="cuda"), torch.zeros(n, cout, device="cuda")
+    ssum, ssq = _stats(n, cout)
     prog = E.Program()
     wpk = E.pack_halo_weight(wt.cpu()).cuda()
     prog.conv(inp=_nhwc16(yprev), n=n, hin=h, win=w, cin=cin, w=wpk.float().contiguous() if fold else wpk.half(), cout=cout,
@@ -349,8 +358,8 @@ def test_halo_conv_matches_torch(E, n, cin, cout, h, w, affine, fold):
     assert (got - ref).abs().mean().item() < 2e-3 * max(1.0, ref.abs().max().item())
     # sums over 2*h*w pixels: allow a per-pixel systematic 1e-4 for the folded variant (fp16 noise gain / weights)
     atol = 1e-4 * 2 * h * w if fold else 5e-2
-    assert torch.allclose(ssum, 2 * ref.sum(dim=[2, 3]), rtol=2e-3, atol=atol)
-    assert torch.allclose(ssq, 2 * (ref * ref).sum(dim=[2, 3]), rtol=2e-3, atol=4 * atol)
+    assert torch.allclose(_fx(ssum), 2 * ref.double().sum(dim=[2, 3]), rtol=2e-3, atol=atol)
+    assert torch.allclose(_fx(ssq), 2 * (ref * ref).double().sum(dim=[2, 3]), rtol=2e-3, atol=4 * atol)
 
 
 @pytest.mark.parametrize("n,cin,cout,lo_h,lo_w,fold", [(2, 64, 32, 12, 128, False), (1, 32, 16, 20, 256, False),

@@ -108,6 +108,17 @@ def test_far_regime_disagreements_are_near_ties(setup):
         assert d_our <= d_ref * 1.005, (i, d_ref, d_our)
 
 
+def test_bit_reproducible_run_to_run(setup):
+    """Integer (fixed-point) InstanceNorm statistics + first-index argmin: identical inputs give identical bits."""
+    from oracle import fixtures
+    eng = setup[0]
+    w = torch.from_numpy(fixtures.latents(48)[40:48])
+    e1 = eng.embed_latents(w).clone()
+    e2 = eng.embed_latents(w).clone()
+    torch.cuda.synchronize()
+    assert torch.equal(e1, e2)
+
+
 def test_philox_votes_are_offset_consistent(setup):
     """Sharding contract: sample i always uses Philox counter i, so splitting [0,n) across calls (ranks) sums to
     the unsplit result exactly."""
