@@ -141,7 +141,7 @@ CFR_API int cfr_program_add_conv_halo(cfr_program* p, const cfr_conv_desc* d, co
 }
 
 CFR_API int cfr_program_add_conv_halo_folded(cfr_program* p, const cfr_conv_desc* d, const float* base_w, const float* inA,
-                                             const float* inB, int center_tap, void* w_main_f16, void* w_aux_f16) {
+                                             const float* inB, void* w_main_f16, void* w_aux_f16) {
   std::unique_ptr<HaloOp> op(new HaloOp());
   cfr_conv_desc dd = *d;
   dd.w = w_main_f16;
@@ -152,12 +152,13 @@ CFR_API int cfr_program_add_conv_halo_folded(cfr_program* p, const cfr_conv_desc
   if (r != 0) return r;
   HaloOp* raw = op.get();
   p->halos.push_back(std::move(op));
-  const int n = d->N, cout = d->Cout, cin = d->Cin;
+  const int n = d->N, cout = d->Cout, cin = d->Cin, phases = d->numPhases, ntaps = d->ntaps;
   const float* bias = d->bias;
   const float* noise_w = d->noise_w;
+  cfr_conv_desc keep = *d;                       // tap tables live in the closure
   p->add([=](cudaStream_t st) {
-    return launch_fold_weights(base_w, inA, inB, bias, noise_w, center_tap, n, pt, cout, cin,
-                               static_cast<__half*>(w_main_f16), static_cast<__half*>(w_aux_f16), st);
+    return launch_fold_weights(base_w, inA, inB, bias, noise_w, &keep.tap_dy[0][0], &keep.tap_dx[0][0], n, phases, ntaps,
+                               cout, cin, static_cast<__half*>(w_main_f16), static_cast<__half*>(w_aux_f16), st);
   }, "fold_weights");
   char lab[160];
   snprintf(lab, sizeof(lab), "halo-folded %dx%d taps%dx%d Cin%d Cout%d n%d TH%d", d->Hout, d->Wout, d->numPhases,

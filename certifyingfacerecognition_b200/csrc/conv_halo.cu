@@ -45,7 +45,8 @@ __device__ __forceinline__ Band decode_band(const HaloParams& p, int b) {
 }
 
 // FOLD: the previous layer's IN+AdaIN scale is folded into per-sample weights, and its shift, this layer's bias and
-// noise ride on an auxiliary 16-channel band {noise, inside-image indicator, 0..} consumed by one extra MMA per tap,
+// noise ride on an auxiliary 16-channel row per OUTPUT pixel {noise, inside-image indicators of its 3x3 input
+// neighbourhood, 0..} consumed by ONE extra MMA per tile,
 // so neither the loaders nor the epilogue touch them.
 template <int COUT, bool FOLD>
 __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid_constant__ HaloParams p) {
@@ -140,21 +141,14 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
     const uint32_t row_step = kHaloW * rb16;
     const uint32_t dhi_aux = smem_desc_hi(256, 32);        // aux operands: 32-byte rows, SWIZZLE_32B
     const uint32_t wa_lo = smem_desc_lo(smem_u32(wasm));
-    const uint32_t aux_row_step = kHaloW * 2;
-    uint32_t atoff[4][9];                                  // aux-band offsets (32-byte rows)
-#pragma unroll
-    for (int ph = 0; ph < 4; ++ph)
-#pragma unroll
-      for (int t = 0; t < 9; ++t)
-        atoff[ph][t] = (FOLD && ph < p.numPhases && t < p.ntaps)
-                           ? ((1 + p.tap_dy[ph][t]) * kHaloW + 1 + p.tap_dx[ph][t]) * 2u : 0u;
+    const uint32_t aux_row_step = 128 * 2;                 // one aux row (32 B) per output pixel, 128 pixels per tile row
     auto load_weights = [&](int n) {      // every (phase, tap) tile; FOLD: the per-sample set of image n
       const int row_base = FOLD ? n * p.wRows : 0;
-      mbar_expect_tx(wbar, p.wRows * p.rowBytes + (FOLD ? p.wRows * 32 : 0));
-      for (int r0 = 0; r0 < p.wRows; r0 += p.wBoxRows) {
+      const int aux_rows = p.numPhases * COUT;             // one aux B tile per phase
+      mbar_expect_tx(wbar, p.wRows * p.rowBytes + (FOLD ? aux_rows * 32 : 0));
+      for (int r0 = 0; r0 < p.wRows; r0 += p.wBoxRows)
         tma_load_2d(wsm + static_cast<size_t>(r0) * p.rowBytes, &p.tmW, wbar, 0, row_base + r0);
-        if (FOLD) tma_load_2d(wasm + static_cast<size_t>(r0) * 32, &p.tmWa, wbar, 0, row_base + r0);
-      }
+      if (FOLD) tma_load_2d(wasm, &p.tmWa, wbar, 0, n * aux_rows);
     };
     uint32_t wphase = 0, dphase = 0;
     int cur_n = -1;
@@ -212,14 +206,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
               }
             }
             if constexpr (FOLD) {
-              uint32_t ba_lo = wa_lo + ph * p.ntaps * (COUT * 2);
-#pragma unroll
-              for (int t = 0; t < 9; ++t) {
-                if (t < p.ntaps) {
-                  if (leader) umma_f16_lohi(d_tmem, x_row + atoff[ph][t], dhi_aux, ba_lo, dhi_aux, idesc, 1u);
-                  ba_lo += COUT * 2;
-                }
-              }
+              if (leader) umma_f16_lohi(d_tmem, x_row, dhi_aux, wa_lo + ph * (COUT * 2), dhi_aux, idesc, 1u);
             }
             if (leader) umma_commit(&tfull[as]);
             __syncwarp();
@@ -272,21 +259,31 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
         }
       }
       cp_async_commit();
-      if constexpr (FOLD) {                 // aux band: first 16-byte chunk of every pixel row = {noise, inside?, 0..}
+      if constexpr (FOLD) {
+        // aux rows, one per OUTPUT pixel of the band: k0 = noise, k(1 + 3*(dy+1) + (dx+1)) = 1 if input pixel
+        // (y+dy, x+dx) lies inside the image (so the folded IN/AdaIN shift respects the zero padding), rest 0
         const uint32_t xb_addr = smem_u32(aux + hs * p.auxBytes);
-        const int npix = (p.TH + 2) * kHaloW;
+        const int npix = p.TH * 128;
         for (int px = tt; px < npix; px += LT) {
-          const int row = px / kHaloW, col = px - row * kHaloW;
-          const int gy = bd.y0 - 1 + row, gx = bd.x0 - 1 + col;
-          const bool ok = static_cast<unsigned>(gy) < static_cast<unsigned>(p.H) &&
-                          static_cast<unsigned>(gx) < static_cast<unsigned>(p.W);
-          const float nzv = (ok && p.noise != nullptr) ? __ldg(&p.noise[gy * p.W + gx]) : 0.f;
-          const __half2 h01 = __floats2half2_rn(nzv, ok ? 1.f : 0.f);      // {noise, inside}
-          const __half2 h23 = __floats2half2_rn(ok ? 1.f : 0.f, 0.f);       // {inside (for the fp16 residual of the shift), 0}
+          const int r = px >> 7, cx = px & 127;
+          const int gy = bd.y0 + r, gx = bd.x0 + cx;
+          const bool in = gy < p.H && gx < p.W;
+          const float nzv = (in && p.noise != nullptr) ? __ldg(&p.noise[gy * p.W + gx]) : 0.f;
+          const float ru = gy > 0 ? 1.f : 0.f, rd = gy < p.H - 1 ? 1.f : 0.f;
+          const float cl = gx > 0 ? 1.f : 0.f, cr = gx < p.W - 1 ? 1.f : 0.f;
+          const __half2 h01 = __floats2half2_rn(nzv, ru * cl);          // k0 noise, k1 (-1,-1)
+          const __half2 h23 = __floats2half2_rn(ru, ru * cr);           // k2 (-1,0), k3 (-1,+1)
+          const __half2 h45 = __floats2half2_rn(cl, 1.f);               // k4 (0,-1), k5 (0,0)
+          const __half2 h67 = __floats2half2_rn(cr, rd * cl);           // k6 (0,+1), k7 (+1,-1)
+          const __half2 h89 = __floats2half2_rn(rd, rd * cr);           // k8 (+1,0), k9 (+1,+1)
           const uint32_t lin = xb_addr + (static_cast<uint32_t>(px) << 5);
-          const uint32_t dst = lin ^ (((lin >> 7) & 1u) << 4);
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %3};" ::"r"(dst), "r"(*reinterpret_cast<const uint32_t*>(&h01)),
-                       "r"(*reinterpret_cast<const uint32_t*>(&h23)), "r"(0u)
+          const uint32_t sw = ((lin >> 7) & 1u) << 4;
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(lin ^ sw),
+                       "r"(*reinterpret_cast<const uint32_t*>(&h01)), "r"(*reinterpret_cast<const uint32_t*>(&h23)),
+                       "r"(*reinterpret_cast<const uint32_t*>(&h45)), "r"(*reinterpret_cast<const uint32_t*>(&h67))
+                       : "memory");
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %2, %2};" ::"r"((lin + 16) ^ sw),
+                       "r"(*reinterpret_cast<const uint32_t*>(&h89)), "r"(0u)
                        : "memory");
         }
       }
@@ -528,39 +525,46 @@ static CUtensorMapSwizzle swz(int bytes) {
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// Per-sample weight folding (FOLD variant).  For image n and (phase,tap) pt:
-//   w_main[n][pt][co][ci] = fp16( W[pt][co][ci] * A[n][ci] )                       -- IN+AdaIN scale of the input
-//   w_aux [n][pt][co][0]  = noise_w[co]            if pt == center_tap else 0        -- x aux channel 0 (noise image)
-//   w_aux [n][pt][co][1]  = sum_ci W[pt][co][ci]*B[n][ci]  (+ bias[co] at the center tap)  -- x aux channel 1 (inside?)
-//   w_aux [n][pt][co][2]  = fp16 rounding residual of the previous entry                     -- x aux channel 2 (inside?)
-// so that  conv_W(A*y + B, zero padded) + noise*w + bias  ==  conv_wmain(y) + conv_waux({noise, inside}).
+// Per-sample weight folding (FOLD variant).  For image n, phase ph, tap t (input offset (dy,dx)):
+//   w_main[n][ph][t][co][ci]  = fp16( W[ph][t][co][ci] * A[n][ci] )                  -- IN+AdaIN scale of the input
+//   w_aux [n][ph][co][0]      = noise_w[co]                                            x aux k0 (noise at the pixel)
+//   w_aux [n][ph][co][1+3(dy+1)+(dx+1)] = sum_ci W[ph][t][co][ci]*B[n][ci] (+ bias[co] at (0,0))
+//                                                                                      x aux "input (y+dy,x+dx) inside?"
+// so that  conv_W(A*y + B, zero padded) + noise*w + bias  ==  conv_wmain(y) + <aux row, w_aux>   exactly at borders.
 // ---------------------------------------------------------------------------------------------------------
+struct FoldTaps {
+  int8_t k[4][9];      // aux K index of (phase, tap), -1 = unused
+};
 __global__ void k_fold_weights(const float* __restrict__ base_w, const float* __restrict__ inA,
                                const float* __restrict__ inB, const float* __restrict__ bias,
-                               const float* __restrict__ noise_w, int center_tap, int pt_count, int cout, int cin,
+                               const float* __restrict__ noise_w, FoldTaps ft, int phases, int ntaps, int cout, int cin,
                                __half* __restrict__ w_main, __half* __restrict__ w_aux) {
-  const int n = blockIdx.y, pt = blockIdx.x;
+  const int n = blockIdx.y, ph = blockIdx.x;
   const int co = threadIdx.x / cin, ci = threadIdx.x % cin;          // cin in {16, 32}: a group never straddles a warp
-  const size_t widx = (static_cast<size_t>(pt) * cout + co) * cin + ci;
-  const float w = base_w[widx];
   const float a = inA != nullptr ? inA[n * cin + ci] : 1.f;
   const float b = inB != nullptr ? inB[n * cin + ci] : 0.f;
-  w_main[(static_cast<size_t>(n) * pt_count) * cout * cin + widx] = __float2half_rn(w * a);
-  float sh = w * b;
-  for (int o = cin >> 1; o > 0; o >>= 1) sh += __shfl_xor_sync(0xffffffffu, sh, o);
-  if (ci < 16) {
-    float v = 0.f;
-    const float shift = sh + ((pt == center_tap && bias != nullptr) ? bias[co] : 0.f);
-    if (ci == 0 && pt == center_tap && noise_w != nullptr) v = noise_w[co];
-    if (ci == 1) v = shift;
-    if (ci == 2) v = shift - __half2float(__float2half_rn(shift));      // fp16 residual: shift is carried to ~2^-22
-    w_aux[((static_cast<size_t>(n) * pt_count + pt) * cout + co) * 16 + ci] = __float2half_rn(v);
+  __half* aux_row = w_aux + ((static_cast<size_t>(n) * phases + ph) * cout + co) * 16;
+  if (ci < 16) aux_row[ci] = __float2half_rn((ci == 0 && noise_w != nullptr) ? noise_w[co] : 0.f);
+  __syncwarp();
+  for (int t = 0; t < ntaps; ++t) {
+    const size_t widx = ((static_cast<size_t>(ph) * ntaps + t) * cout + co) * cin + ci;
+    const float w = base_w[widx];
+    w_main[static_cast<size_t>(n) * phases * ntaps * cout * cin + widx] = __float2half_rn(w * a);
+    float sh = w * b;
+    for (int o = cin >> 1; o > 0; o >>= 1) sh += __shfl_xor_sync(0xffffffffu, sh, o);
+    const int k = ft.k[ph][t];
+    if (ci == 0 && k >= 0) aux_row[k] = __float2half_rn(sh + ((k == 5 && bias != nullptr) ? bias[co] : 0.f));
   }
 }
 int launch_fold_weights(const float* base_w, const float* inA, const float* inB, const float* bias, const float* noise_w,
-                        int center_tap, int n, int pt, int cout, int cin, __half* w_main, __half* w_aux, cudaStream_t st) {
+                        const int8_t* tap_dy, const int8_t* tap_dx, int n, int phases, int ntaps, int cout, int cin,
+                        __half* w_main, __half* w_aux, cudaStream_t st) {
   if (cout * cin > 1024 || (cin != 16 && cin != 32)) { set_error("fold_weights: Cout*Cin=%d unsupported", cout * cin); return 2; }
-  k_fold_weights<<<dim3(pt, n), cout * cin, 0, st>>>(base_w, inA, inB, bias, noise_w, center_tap, pt, cout, cin, w_main, w_aux);
+  FoldTaps ft;
+  for (int ph = 0; ph < 4; ++ph)
+    for (int t = 0; t < 9; ++t)
+      ft.k[ph][t] = (ph < phases && t < ntaps) ? static_cast<int8_t>(1 + 3 * (tap_dy[ph * 9 + t] + 1) + (tap_dx[ph * 9 + t] + 1)) : -1;
+  k_fold_weights<<<dim3(phases, n), cout * cin, 0, st>>>(base_w, inA, inB, bias, noise_w, ft, phases, ntaps, cout, cin, w_main, w_aux);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { set_error("fold_weights launch: %s", cudaGetErrorString(e)); return 4; }
   count_launch();
@@ -589,13 +593,13 @@ int halo_build(const cfr_conv_desc& s, const float* inA, const float* inB, const
   if (p.fold && s.Cin > 32) { set_error("halo conv: folded variant needs Cin <= 32"); return 2; }
   p.rowBytes = s.Cin * 2;
   p.wRows = s.numPhases * s.ntaps * s.Cout;
-  p.wAuxBytes = p.fold ? (p.wRows * 32 + 1023) / 1024 * 1024 : 0;
+  p.wAuxBytes = p.fold ? (s.numPhases * s.Cout * 32 + 1023) / 1024 * 1024 : 0;
   p.wBytes = (p.wRows * p.rowBytes + 1023) / 1024 * 1024;
   p.wBoxRows = p.wRows;
   while (p.wBoxRows > 256 || p.wRows % p.wBoxRows != 0) --p.wBoxRows;
   const int ctrl = 8 * 44 + 16 + 2 * 64 * 4 + 2 * 64 * 8 + 64;
   const int budget = 227 * 1024 - 1024 - ctrl - p.wBytes - p.wAuxBytes;
-  auto aux_bytes = [&](int th) { return p.fold ? ((th + 2) * kHaloW * 32 + 1023) / 1024 * 1024 : 0; };
+  auto aux_bytes = [&](int th) { return p.fold ? (th * 128 * 32 + 1023) / 1024 * 1024 : 0; };
   auto halo_bytes = [&](int th) { return ((th + 2) * kHaloW * p.rowBytes + 1023) / 1024 * 1024 + aux_bytes(th); };
   // three band buffers (prefetch distance 2) with the tallest band that fits, but at least 4 rows per band;
   // otherwise fall back to two buffers
@@ -637,9 +641,9 @@ int halo_build(const cfr_conv_desc& s, const float* inA, const float* inB, const
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("halo conv: encode(W) failed: %d", (int)r); return 3; }
     if (p.fold) {
-      cuuint64_t adims[2] = {16, (cuuint64_t)totalRows};
+      cuuint64_t adims[2] = {16, (cuuint64_t)s.N * s.numPhases * s.Cout};
       cuuint64_t astr[1] = {32};
-      cuuint32_t abox[2] = {16, (cuuint32_t)p.wBoxRows};
+      cuuint32_t abox[2] = {16, (cuuint32_t)(s.numPhases * s.Cout)};
       r = enc(&p.tmWa, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(w_aux), adims, astr, abox, estr,
               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);

@@ -64,7 +64,8 @@ struct HaloOp {
 int halo_build(const cfr_conv_desc& s, const float* inA, const float* inB, const void* w_aux, HaloOp* op);
 // per-sample weight folding for the FOLD variant (see conv_halo.cu)
 int launch_fold_weights(const float* base_w, const float* inA, const float* inB, const float* bias, const float* noise_w,
-                        int center_tap, int n, int pt, int cout, int cin, __half* w_main, __half* w_aux, cudaStream_t st);
+                        const int8_t* tap_dy, const int8_t* tap_dx, int n, int phases, int ntaps, int cout, int cin,
+                        __half* w_main, __half* w_aux, cudaStream_t st);
 int halo_launch(const HaloOp& op, cudaStream_t stream);
 
 }  // namespace cfr

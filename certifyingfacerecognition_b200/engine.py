@@ -210,9 +210,9 @@ class Program:
                 assert w.dtype == torch.float32
                 rows = n * w.shape[0]
                 w_main = self.hold(torch.zeros(rows, cin, dtype=torch.float16, device=w.device))
-                w_aux = self.hold(torch.zeros(rows, 16, dtype=torch.float16, device=w.device))
+                w_aux = self.hold(torch.zeros(n * len(taps) * cout, 16, dtype=torch.float16, device=w.device))
                 L.check(self.lib.cfr_program_add_conv_halo_folded(self.handle, C.byref(d), L.ptr(w), L.ptr(a), L.ptr(b),
-                                                                  fold_center_tap, L.ptr(w_main), L.ptr(w_aux)))
+                                                                  L.ptr(w_main), L.ptr(w_aux)))
             else:
                 L.check(self.lib.cfr_program_add_conv_halo(self.handle, C.byref(d), L.ptr(a), L.ptr(b)))
         else:

@@ -79,13 +79,14 @@ CFR_API int cfr_program_add_conv(cfr_program* p, const cfr_conv_desc* d);
  * (Kpad == Cin).  inA/inB (may be NULL): per-(n, cin) affine x = y*A + B applied on load -- the previous layer's
  * InstanceNorm + AdaIN (stylegan_generator_model.py:420-422,:505) -- with the conv's zero padding left at zero. */
 CFR_API int cfr_program_add_conv_halo(cfr_program* p, const cfr_conv_desc* d, const float* inA, const float* inB);
-/* Folded variant (Cin <= 32): records (1) a per-sample weight-folding kernel -- w_main[n] = fp16(base_w * A[n]),
- * aux tiles carrying sum_ci base_w*B[n] (+ bias, noise gain at center_tap) -- and (2) the halo conv reading an extra
- * {noise, inside-image} band through one more MMA per tap, so IN+AdaIN, noise and bias cost nothing on the CUDA cores.
- * base_w: fp32 [phases*taps][Cout][Cin]; w_main_f16: [N][phases*taps*Cout][Cin]; w_aux_f16: [N][phases*taps*Cout][16].
+/* Folded variant (Cin <= 32): records (1) a per-sample weight-folding kernel -- w_main[n] = fp16(base_w * A[n]); one aux
+ * tile per phase carrying the noise gain, and per 3x3-neighbourhood position sum_ci base_w*B[n] (+ bias at the centre) --
+ * and (2) the halo conv, which feeds one extra 16-channel row per output pixel {noise, inside-image indicators} through
+ * ONE more MMA per tile, so IN+AdaIN, noise and bias cost nothing on the CUDA cores and stay exact at the borders.
+ * base_w: fp32 [phases*taps][Cout][Cin]; w_main_f16: [N][phases*taps*Cout][Cin]; w_aux_f16: [N][phases*Cout][16] (zeroed).
  * d->bias / d->noise / d->noise_w are consumed by the fold; d->w is ignored. */
 CFR_API int cfr_program_add_conv_halo_folded(cfr_program* p, const cfr_conv_desc* d, const float* base_w, const float* inA,
-                                     const float* inB, int center_tap, void* w_main_f16, void* w_aux_f16);
+                                     const float* inB, void* w_main_f16, void* w_aux_f16);
 CFR_API int cfr_program_add_memset(cfr_program* p, void* ptr, int value, size_t bytes);
 /* StyleModulationLayer dense, stylegan_generator_model.py:503 (all 18 layers): styles[b][rows] */
 CFR_API int cfr_program_add_styles(cfr_program* p, const float* wp2, const float* w_style, const float* b_style,
