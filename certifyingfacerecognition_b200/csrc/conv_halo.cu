@@ -233,29 +233,25 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
     const int tt = threadIdx.x - 256;
     const int nchLog = p.rowBytes == 32 ? 1 : (p.rowBytes == 64 ? 2 : 3);
     const int nch = 1 << nchLog;
-    const int totalChunks = (p.TH + 2) * kHaloW * nch;
+    const int RC = kHaloW * nch;               // 16-byte chunks per band row (260 / 520 / 1040)
     const size_t imgStride = static_cast<size_t>(p.H) * p.W * p.Cin;
-    const int lc = tt & (nch - 1);            // this thread's 8-channel group (LT % nch == 0: constant)
-    const int pstep = LT >> nchLog;           // pixels advanced per iteration (<= 128 < kHaloW)
-    const int pix0 = tt >> nchLog;
-    const int row0 = pix0 / kHaloW, col0 = pix0 - row0 * kHaloW;
+    const size_t rowStride = static_cast<size_t>(p.W) * p.Cin;
+    const int lc = tt & (nch - 1);             // this thread's 8-channel group (LT % nch == 0: constant)
 
+    // Thread t owns chunks q = t, t + LT, .. (< RC) of EVERY band row: per chunk the inner loop is an address add,
+    // a swizzle XOR and one cp.async (consecutive threads -> consecutive 16-byte chunks of one image row).
     auto issue = [&](const Band& bd, int hs) {
       const uint32_t hb_addr = smem_u32(smem + hs * p.haloBytes);
       const __half* img = p.in + static_cast<size_t>(bd.n) * imgStride + lc * 8;
-      int row = row0, col = col0;
-      for (int c = tt; c < totalChunks; c += LT) {
-        const int gy = bd.y0 - 1 + row, gx = bd.x0 - 1 + col;
-        const bool ok = static_cast<unsigned>(gy) < static_cast<unsigned>(p.H) &&
-                        static_cast<unsigned>(gx) < static_cast<unsigned>(p.W);
-        const uint32_t lin = hb_addr + (static_cast<uint32_t>(c) << 4);
-        const uint32_t dst = lin ^ (((lin >> 7) & (nch - 1)) << 4);
-        const __half* src = ok ? img + (static_cast<size_t>(gy) * p.W + gx) * p.Cin : p.in;
-        cp_async16(dst, src, ok ? 16u : 0u);
-        col += pstep;
-        if (col >= kHaloW) {
-          col -= kHaloW;
-          ++row;
+      for (int q = tt; q < RC; q += LT) {
+        const int gx = bd.x0 - 1 + (q >> nchLog);
+        const bool colok = static_cast<unsigned>(gx) < static_cast<unsigned>(p.W);
+        const __half* src = img + static_cast<size_t>(gx) * p.Cin + static_cast<long long>(bd.y0 - 1) * static_cast<long long>(rowStride);
+        uint32_t lin = hb_addr + (static_cast<uint32_t>(q) << 4);
+        int gy = bd.y0 - 1;
+        for (int row = 0; row < p.TH + 2; ++row, ++gy, lin += RC << 4, src += rowStride) {
+          const bool ok = colok && static_cast<unsigned>(gy) < static_cast<unsigned>(p.H);
+          cp_async16(lin ^ (((lin >> 7) & (nch - 1)) << 4), ok ? src : p.in, ok ? 16u : 0u);
         }
       }
       cp_async_commit();
@@ -263,20 +259,22 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
         // aux rows, one per OUTPUT pixel of the band: k0 = noise, k(1 + 3*(dy+1) + (dx+1)) = 1 if input pixel
         // (y+dy, x+dx) lies inside the image (so the folded IN/AdaIN shift respects the zero padding), rest 0
         const uint32_t xb_addr = smem_u32(aux + hs * p.auxBytes);
-        const int npix = p.TH * 128;
-        for (int px = tt; px < npix; px += LT) {
-          const int r = px >> 7, cx = px & 127;
-          const int gy = bd.y0 + r, gx = bd.x0 + cx;
-          const bool in = gy < p.H && gx < p.W;
-          const float nzv = (in && p.noise != nullptr) ? __ldg(&p.noise[gy * p.W + gx]) : 0.f;
+        const int cx = tt & 127;
+        const int gx = bd.x0 + cx;
+        const float cl = gx > 0 ? 1.f : 0.f, cr = gx < p.W - 1 ? 1.f : 0.f;
+        const bool colin = gx < p.W;
+        const bool has_nz = p.noise != nullptr;
+        const __half2 h45 = __floats2half2_rn(cl, 1.f);                  // k4 (0,-1), k5 (0,0)
+        for (int r = tt >> 7; r < p.TH; r += LT >> 7) {
+          const int gy = bd.y0 + r;
+          const bool in = colin && gy < p.H;
+          const float nzv = (in && has_nz) ? __ldg(&p.noise[gy * p.W + gx]) : 0.f;
           const float ru = gy > 0 ? 1.f : 0.f, rd = gy < p.H - 1 ? 1.f : 0.f;
-          const float cl = gx > 0 ? 1.f : 0.f, cr = gx < p.W - 1 ? 1.f : 0.f;
           const __half2 h01 = __floats2half2_rn(nzv, ru * cl);          // k0 noise, k1 (-1,-1)
           const __half2 h23 = __floats2half2_rn(ru, ru * cr);           // k2 (-1,0), k3 (-1,+1)
-          const __half2 h45 = __floats2half2_rn(cl, 1.f);               // k4 (0,-1), k5 (0,0)
           const __half2 h67 = __floats2half2_rn(cr, rd * cl);           // k6 (0,+1), k7 (+1,-1)
           const __half2 h89 = __floats2half2_rn(rd, rd * cr);           // k8 (+1,0), k9 (+1,+1)
-          const uint32_t lin = xb_addr + (static_cast<uint32_t>(px) << 5);
+          const uint32_t lin = xb_addr + (static_cast<uint32_t>(r * 128 + cx) << 5);
           const uint32_t sw = ((lin >> 7) & 1u) << 4;
           asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(lin ^ sw),
                        "r"(*reinterpret_cast<const uint32_t*>(&h01)), "r"(*reinterpret_cast<const uint32_t*>(&h23)),
@@ -312,29 +310,25 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
         }
         uint8_t* hb = smem + hs * p.haloBytes;
         const uint32_t hb_addr = smem_u32(hb);
-        int row = row0, col = col0;
-        for (int c = tt; c < totalChunks; c += LT) {        // same chunks this thread copied: no barrier needed
-          const int gy = bd.y0 - 1 + row, gx = bd.x0 - 1 + col;
-          const bool ok = static_cast<unsigned>(gy) < static_cast<unsigned>(p.H) &&
-                          static_cast<unsigned>(gx) < static_cast<unsigned>(p.W);
-          col += pstep;
-          if (col >= kHaloW) {
-            col -= kHaloW;
-            ++row;
-          }
-          if (!ok) continue;                                   // zero padding stays zero
-          const uint32_t lin = hb_addr + (static_cast<uint32_t>(c) << 4);
-          const uint32_t off = (lin ^ (((lin >> 7) & (nch - 1)) << 4)) - hb_addr;
-          uint4 v = *reinterpret_cast<uint4*>(hb + off);
-          __half2* h2 = reinterpret_cast<__half2*>(&v);
+        for (int q = tt; q < RC; q += LT) {                  // same chunks this thread copied: no barrier needed
+          const int gx = bd.x0 - 1 + (q >> nchLog);
+          if (static_cast<unsigned>(gx) >= static_cast<unsigned>(p.W)) continue;     // zero padding stays zero
+          uint32_t lin = hb_addr + (static_cast<uint32_t>(q) << 4);
+          int gy = bd.y0 - 1;
+          for (int row = 0; row < p.TH + 2; ++row, ++gy, lin += RC << 4) {
+            if (static_cast<unsigned>(gy) >= static_cast<unsigned>(p.H)) continue;
+            const uint32_t off = (lin ^ (((lin >> 7) & (nch - 1)) << 4)) - hb_addr;
+            uint4 v = *reinterpret_cast<uint4*>(hb + off);
+            __half2* h2 = reinterpret_cast<__half2*>(&v);
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            float2 f = __half22float2(h2[i]);
-            f.x = fmaf(f.x, ca[2 * i], cb[2 * i]);
-            f.y = fmaf(f.y, ca[2 * i + 1], cb[2 * i + 1]);
-            h2[i] = __floats2half2_rn(f.x, f.y);
+            for (int i = 0; i < 4; ++i) {
+              float2 f = __half22float2(h2[i]);
+              f.x = fmaf(f.x, ca[2 * i], cb[2 * i]);
+              f.y = fmaf(f.y, ca[2 * i + 1], cb[2 * i + 1]);
+              h2[i] = __floats2half2_rn(f.x, f.y);
+            }
+            *reinterpret_cast<uint4*>(hb + off) = v;
           }
-          *reinterpret_cast<uint4*>(hb + off) = v;
         }
       }
       fence_proxy_async();                 // generic-proxy writes -> visible to the tensor core (async proxy)
@@ -371,8 +365,9 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
         hbs[i] = has_bias ? p.bias[i] : 0.f;
       }
     }
-    uint32_t tcount = 0;
-    uint32_t as = 0, aphase = 0;
+    uint32_t tbase = 0;                     // tile counter at the start of the band
+    const int asLog = AS == 16 ? 4 : (AS == 8 ? 3 : 2);
+    const int phLog = p.numPhases == 4 ? 2 : 0;
     int cur_n = -1;
     for (int b = band0; b < band1; ++b) {
       const Band bd = decode_band(p, b);
@@ -389,15 +384,14 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
       cur_n = bd.n;
       const int gx = bd.x0 + q * 32 + static_cast<int>(lane);
       const bool colok = gx < p.W;
-      for (int r = 0; r < bd.rows; ++r) {
-        const int gy = bd.y0 + r;
-        for (int ph = 0; ph < p.numPhases; ++ph, ++tcount) {
-          const uint32_t my_as = as, my_ph = aphase;
-          if (++as == static_cast<uint32_t>(AS)) {
-            as = 0;
-            aphase ^= 1;
-          }
-          if ((tcount & 1) != static_cast<uint32_t>(grp)) continue;
+      const int ntiles = bd.rows << phLog;
+      {
+        // this warp group's tiles of the band: tile index tbase + i with (tbase + i) & 1 == grp
+        for (int i = (grp - static_cast<int>(tbase)) & 1; i < ntiles; i += 2) {
+          const uint32_t tcount = tbase + i;
+          const uint32_t my_as = tcount & (AS - 1), my_ph = (tcount >> asLog) & 1;
+          const int r = i >> phLog, ph = i & (p.numPhases - 1);
+          const int gy = bd.y0 + r;
           const int oy = gy * p.oscale + p.ooff_y[ph];
           const int ox = gx * p.oscale + p.ooff_x[ph];
           const size_t pix = (static_cast<size_t>(bd.n) * p.outH + oy) * p.outW + ox;
@@ -474,6 +468,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
           if (lane == 0) mbar_arrive(&tempty[my_as]);
         }
       }
+      tbase += ntiles;
       if constexpr (REG_STATS) {
         if (do_stats) {                      // once per band: registers -> shared
 #pragma unroll

@@ -52,6 +52,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 // Bounded wait: a pipeline bug traps (kernel error) instead of hanging the GPU box.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   for (uint32_t it = 0; !mbar_try_wait(bar, parity); ++it) {
+    __nanosleep(32);                       // keep polling warps off the issue slots
     if (it > (1u << 22)) __trap();
   }
 }
