@@ -128,6 +128,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=250, help="MC samples per step (BASELINE config 2: 250)")
     ap.add_argument("--chunk", type=int, default=125, help="samples per GAN+FRM program run")
+    ap.add_argument("--frm-group", type=int, default=2, help="synthesis chunks per ArcFace program run")
     ap.add_argument("--shard", default="identities", choices=["identities", "samples"])
     ap.add_argument("--cpu-sample", type=int, default=4, help="MC samples per CPU-baseline step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -169,7 +170,7 @@ def main():
     lib = L.load()
     n_ids = 64
     g_sd, f_sd, dirs, lat, fixtures = build_fixture(n_ids)
-    eng = Engine(g_sd, f_sd, dirs, torch.zeros(1, 512), chunk=args.chunk)
+    eng = Engine(g_sd, f_sd, dirs, torch.zeros(1, 512), chunk=args.chunk, frm_group=args.frm_group)
     true_rows = eng.embed_latents(lat).cpu()
     eng.set_gallery(fixtures.synthetic_gallery(true_rows, N_GALLERY))
     dev = eng.device
@@ -276,7 +277,7 @@ def main():
         "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps, "higher_is_better": True,
         "scaling": "weak" if args.shard == "identities" else "strong", "vs_baseline": None,
         "dtype": "fp16 operands / fp32 accumulate", "data": "synthetic",
-        "config": {"workload": workload, "chunk": args.chunk, "shard": args.shard, "gallery": N_GALLERY,
+        "config": {"workload": workload, "chunk": args.chunk, "frm_group": args.frm_group, "shard": args.shard, "gallery": N_GALLERY,
                    "l2": "working set per step (activations, GBs) far exceeds the 126 MB L2; no flush needed",
                    "gflop_per_sample_algorithmic": GFLOP_PER_SAMPLE_SUBPIXEL_FORM,
                    "pipeline_tflops": value * GFLOP_PER_SAMPLE_SUBPIXEL_FORM / 1e3,

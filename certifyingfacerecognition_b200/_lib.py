@@ -41,6 +41,7 @@ class SamplerDesc(C.Structure):
         ("synth", C.c_void_p), ("frm", C.c_void_p), ("chunk", C.c_int32),
         ("wp2", C.c_void_p), ("emb", C.c_void_p), ("dir_mat", C.c_void_p), ("w_avg", C.c_void_p),
         ("psi", C.c_float), ("gallery", C.c_void_p), ("n_gallery", C.c_int32),
+        ("frm_group", C.c_int32), ("frm_big", C.c_void_p), ("emb_big", C.c_void_p), ("out_slot", C.c_void_p),
     ]
 
 
@@ -66,7 +67,7 @@ SIGNATURES = {
     "cfr_program_add_blur_act_stats": (_I, [_P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _I]),
     "cfr_program_add_finalize_stats": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _F, _P, _P]),
     "cfr_program_add_affine": (_I, [_P, _P, _P, _P, _I, _I, _I, _P]),
-    "cfr_program_add_torgb_resize": (_I, [_P, _P, _P, _P, _I, _I, _I, _P, _P, _I, _F, _F, _P, _P]),
+    "cfr_program_add_torgb_resize": (_I, [_P, _P, _P, _P, _I, _I, _I, _P, _P, _I, _F, _F, _P, _P, _P]),
     "cfr_noise_project": (_I, [_P, _P, _P, _I, _P, _P, _P, _F, _U64, _U64, _I, _P, _P, _P]),
     "cfr_truncate": (_I, [_P, _P, _F, _I, _P, _P]),
     "cfr_match_vote": (_I, [_P, _I, _P, _I, _P, _P, _P, _P]),

@@ -218,10 +218,10 @@ CFR_API int cfr_program_add_affine(cfr_program* p, const void* y_f16, const floa
 
 CFR_API int cfr_program_add_torgb_resize(cfr_program* p, const void* x_f16, const float* A, const float* B, int n, int hin,
                                  int c, const float* w_rgb, const float* b_rgb, int rout, float mean, float stdv,
-                                 void* out_f16_nhwc16, float* out_planar_f32) {
+                                 void* out_f16_nhwc16, float* out_planar_f32, const int32_t* out_slot) {
   p->add([=](cudaStream_t st) {
     return launch_torgb_resize(static_cast<const __half*>(x_f16), A, B, n, hin, c, w_rgb, b_rgb, rout, mean, stdv,
-                               static_cast<__half*>(out_f16_nhwc16), out_planar_f32, st);
+                               static_cast<__half*>(out_f16_nhwc16), out_planar_f32, out_slot, st);
   }, "torgb_resize");
   return 0;
 }
@@ -246,8 +246,9 @@ CFR_API int cfr_sampler_create(const cfr_sampler_desc* d, cfr_sampler** out) {
   if (d->chunk <= 0 || d->n_gallery <= 0) { set_error("sampler: bad chunk / gallery size"); return 2; }
   std::unique_ptr<cfr_sampler> s(new cfr_sampler());
   s->d = *d;
-  CFR_CUDA(cudaMalloc(&s->keys, sizeof(unsigned long long) * d->chunk));
-  CFR_CUDA(cudaMemset(s->keys, 0xFF, sizeof(unsigned long long) * d->chunk));
+  const size_t nkeys = static_cast<size_t>(d->chunk) * (d->frm_group > 1 ? d->frm_group : 1);
+  CFR_CUDA(cudaMalloc(&s->keys, sizeof(unsigned long long) * nkeys));
+  CFR_CUDA(cudaMemset(s->keys, 0xFF, sizeof(unsigned long long) * nkeys));
   CFR_CUDA(cudaMalloc(&s->dev_in, sizeof(float) * 528));
   CFR_CUDA(cudaMalloc(&s->dev_counts, sizeof(long long) * d->n_gallery));
   CFR_CUDA(cudaMallocHost(&s->pin_in, sizeof(float) * 528));
@@ -270,20 +271,32 @@ CFR_API int cfr_sample_votes(cfr_sampler* s, const float* z, const float* x, con
                      int32_t* pred_out, float* emb_out, float* noise_out, cfr_stream_t stream) {
   const cfr_sampler_desc& d = s->d;
   if (sigma_len != 1 && sigma_len != 5) { set_error("sigma_len must be 1 or 5"); return 2; }
-  for (int64_t done = 0; done < num; done += d.chunk) {
-    const int b = static_cast<int>(num - done < d.chunk ? num - done : d.chunk);
-    int r = launch_noise_project(z, x, sigma, sigma_len, noise_in ? noise_in + done * 5 : nullptr, d.dir_mat, d.w_avg,
-                                 d.psi, seed, sample_offset + done, b, noise_out ? noise_out + done * 5 : nullptr,
-                                 d.wp2, S(stream));
-    if (r) return r;
-    if ((r = cfr_program_run(d.synth, stream)) != 0) return r;
-    if ((r = cfr_program_run(d.frm, stream)) != 0) return r;
-    if (emb_out) {
-      CFR_CUDA(cudaMemcpyAsync(emb_out + done * 512, d.emb, sizeof(float) * 512 * b, cudaMemcpyDeviceToDevice, S(stream)));
+  const int K = (d.frm_group > 1 && d.frm_big != nullptr && d.out_slot != nullptr) ? d.frm_group : 1;
+  int64_t done = 0;
+  while (done < num) {
+    // a full group of K chunks goes through the big ArcFace program (better SM fill); the tail chunk by chunk
+    const int g = (num - done >= static_cast<int64_t>(K) * d.chunk) ? K : 1;
+    const int b = static_cast<int>(num - done < static_cast<int64_t>(g) * d.chunk ? num - done : static_cast<int64_t>(g) * d.chunk);
+    for (int k = 0; k < g; ++k) {
+      const int64_t off = done + static_cast<int64_t>(k) * d.chunk;
+      const int bk = static_cast<int>(num - off < d.chunk ? num - off : d.chunk);
+      int r = 0;
+      if (d.out_slot != nullptr && (r = launch_set_int(d.out_slot, k, S(stream))) != 0) return r;
+      r = launch_noise_project(z, x, sigma, sigma_len, noise_in ? noise_in + off * 5 : nullptr, d.dir_mat, d.w_avg, d.psi,
+                               seed, sample_offset + off, bk, noise_out ? noise_out + off * 5 : nullptr, d.wp2, S(stream));
+      if (r) return r;
+      if ((r = cfr_program_run(d.synth, stream)) != 0) return r;
     }
-    r = launch_match_vote(d.emb, b, d.gallery, d.n_gallery, s->keys, pred_out ? pred_out + done : nullptr,
+    int r = cfr_program_run(g == K && K > 1 ? d.frm_big : d.frm, stream);
+    if (r) return r;
+    const float* emb = (g == K && K > 1) ? d.emb_big : d.emb;
+    if (emb_out) {
+      CFR_CUDA(cudaMemcpyAsync(emb_out + done * 512, emb, sizeof(float) * 512 * b, cudaMemcpyDeviceToDevice, S(stream)));
+    }
+    r = launch_match_vote(emb, b, d.gallery, d.n_gallery, s->keys, pred_out ? pred_out + done : nullptr,
                           reinterpret_cast<long long*>(counts), S(stream));
     if (r) return r;
+    done += b;
   }
   return 0;
 }

@@ -439,9 +439,14 @@ int launch_affine(const __half* y, const float* A, const float* B, int n, int hw
 __global__ void k_torgb_resize(const __half* __restrict__ x, const float* __restrict__ A, const float* __restrict__ B,
                                int n, int hin, int c, const float* __restrict__ w_rgb, const float* __restrict__ b_rgb,
                                int rout, float mean, float stdv, __half* __restrict__ out,
-                               float* __restrict__ out_planar) {
+                               float* __restrict__ out_planar, const int* __restrict__ slot) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n * rout * rout) return;
+  if (slot != nullptr) {                    // write into the slot-th group of n images of a larger buffer
+    const size_t g = static_cast<size_t>(*slot) * n * rout * rout;
+    if (out != nullptr) out += g * 16;
+    if (out_planar != nullptr) out_planar += g * 3;
+  }
   const int ox = i % rout, oy = (i / rout) % rout, s = i / (rout * rout);
   const float scale = static_cast<float>(hin) / static_cast<float>(rout);
   float sy = scale * (oy + 0.5f) - 0.5f;
@@ -498,9 +503,9 @@ __global__ void k_torgb_resize(const __half* __restrict__ x, const float* __rest
 }
 int launch_torgb_resize(const __half* x, const float* A, const float* B, int n, int hin, int c, const float* w_rgb,
                         const float* b_rgb, int rout, float mean, float stdv, __half* out, float* out_planar,
-                        cudaStream_t st) {
+                        const int* slot, cudaStream_t st) {
   const int total = n * rout * rout;
-  k_torgb_resize<<<(total + 127) / 128, 128, 0, st>>>(x, A, B, n, hin, c, w_rgb, b_rgb, rout, mean, stdv, out, out_planar);
+  k_torgb_resize<<<(total + 127) / 128, 128, 0, st>>>(x, A, B, n, hin, c, w_rgb, b_rgb, rout, mean, stdv, out, out_planar, slot);
   CFR_LAUNCH_CHECK("torgb_resize");
   return 0;
 }
@@ -561,6 +566,13 @@ __global__ void k_vote(unsigned long long* __restrict__ keys, int b, int* __rest
   if (pred != nullptr) pred[i] = pr;
   if (counts != nullptr) atomicAdd(&counts[pr], 1ull);
 }
+__global__ void k_set_int(int* p, int v) { *p = v; }
+int launch_set_int(int* p, int v, cudaStream_t st) {
+  k_set_int<<<1, 1, 0, st>>>(p, v);
+  CFR_LAUNCH_CHECK("set_int");
+  return 0;
+}
+
 int launch_match_vote(const float* emb, int b, const float* gallery, int n, unsigned long long* keys, int* pred,
                       long long* counts, cudaStream_t st) {
   if (b <= 0) return 0;

@@ -36,7 +36,8 @@ int launch_affine(const __half* y, const float* A, const float* B, int n, int hw
 // x [n,H,W,C] fp16 (optionally still un-normalised: per-(n,c) A,B applied on load) -> img [n,R,R,16] fp16 (ch 0..2)
 int launch_torgb_resize(const __half* x, const float* A, const float* B, int n, int hin, int c, const float* w_rgb,
                         const float* b_rgb, int rout, float mean, float stdv, __half* out, float* out_planar,
-                        cudaStream_t st);
+                        const int* slot, cudaStream_t st);
+int launch_set_int(int* p, int v, cudaStream_t st);
 
 // smoothing_model.py:56-61 + smooth.py:135,140-146: argmin_j ||e - g_j||_2 (exact differences, fp32), votes
 int launch_match_vote(const float* emb, int b, const float* gallery, int n, unsigned long long* keys, int* pred,

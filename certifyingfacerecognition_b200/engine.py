@@ -230,7 +230,7 @@ class Program:
 class SynthesisProgram(Program):
     def __init__(self, g_sd: Dict[str, Tensor], chunk: int, out_res: int = 112, device="cuda",
                  keep_planar: bool = False, mean: float = 0.5, std: float = 0.5, halo: bool = True,
-                 fold_small: bool = True):
+                 fold_small: bool = True, groups: int = 1):
         super().__init__()
         dev = torch.device(device)
         self.chunk, self.out_res = chunk, out_res
@@ -336,11 +336,14 @@ class SynthesisProgram(Program):
         wrgb = sd["synthesis.output8.conv.weight"].reshape(3, 16) * (1.0 / math.sqrt(16))
         w_rgb = self.hold(_f32(wrgb, dev))
         b_rgb = self.hold(_f32(sd["synthesis.output8.bias"], dev))
-        self.img = self.hold(torch.zeros(chunk, out_res, out_res, 16, dtype=torch.float16, device=dev))
-        self.img_planar = self.hold(torch.zeros(chunk, 3, out_res, out_res, device=dev)) if keep_planar else None
+        # the image buffer holds `groups` chunks; the op writes group *out_slot (set by the sampler between runs)
+        self.groups = groups
+        self.out_slot = self.hold(torch.zeros(1, dtype=torch.int32, device=dev))
+        self.img = self.hold(torch.zeros(groups * chunk, out_res, out_res, 16, dtype=torch.float16, device=dev))
+        self.img_planar = self.hold(torch.zeros(groups * chunk, 3, out_res, out_res, device=dev)) if keep_planar else None
         L.check(lib.cfr_program_add_torgb_resize(h, L.ptr(y), L.ptr(pending[0]), L.ptr(pending[1]), chunk, 1024, 16,
                                                  L.ptr(w_rgb), L.ptr(b_rgb), out_res, mean, std, L.ptr(self.img),
-                                                 L.ptr(self.img_planar)))
+                                                 L.ptr(self.img_planar), L.ptr(self.out_slot)))
         self.last_y = y
 
 
@@ -430,14 +433,16 @@ class Engine:
     """StyleGAN -> resize -> iresnet50 -> gallery vote, for one GPU."""
 
     def __init__(self, g_sd, f_sd, dir_mat: Tensor, gallery: Tensor, chunk: int = 32, device="cuda",
-                 keep_planar: bool = False):
+                 keep_planar: bool = False, frm_group: int = 1):
         if not torch.cuda.is_available():
             raise RuntimeError("certifyingfacerecognition_b200 needs a CUDA device (no CPU fallback)")
         self.lib = L.load()
         self.device = torch.device(device)
         self.chunk = chunk
-        self.synth = SynthesisProgram(g_sd, chunk, 112, device, keep_planar=keep_planar)
+        self.frm_group = max(1, int(frm_group))
+        self.synth = SynthesisProgram(g_sd, chunk, 112, device, keep_planar=keep_planar, groups=self.frm_group)
         self.frm = ArcFaceProgram(f_sd, chunk, self.synth.img, device)
+        self.frm_big = ArcFaceProgram(f_sd, chunk * self.frm_group, self.synth.img, device) if self.frm_group > 1 else None
         self.dir_mat = _f32(dir_mat, self.device)
         self.set_gallery(gallery)
 
@@ -448,6 +453,10 @@ class Engine:
         d.wp2, d.emb = L.ptr(self.synth.wp2), L.ptr(self.frm.emb)
         d.dir_mat, d.w_avg, d.psi = L.ptr(self.dir_mat), L.ptr(self.synth.w_avg), PSI
         d.gallery, d.n_gallery = L.ptr(self.gallery), self.gallery.shape[0]
+        d.frm_group = self.frm_group
+        d.frm_big = self.frm_big.handle if self.frm_big is not None else None
+        d.emb_big = L.ptr(self.frm_big.emb) if self.frm_big is not None else None
+        d.out_slot = L.ptr(self.synth.out_slot)
         if getattr(self, "sampler", None):
             self.lib.cfr_sampler_destroy(self.sampler)
         h = C.c_void_p()
@@ -475,6 +484,7 @@ class Engine:
         out = torch.empty(w.shape[0], 512, device=self.device)
         for i in range(0, w.shape[0], self.chunk):
             b = min(self.chunk, w.shape[0] - i)
+            self.synth.out_slot.zero_()
             L.check(self.lib.cfr_truncate(L.ptr(w[i:i + b]), L.ptr(self.synth.w_avg), PSI, b, L.ptr(self.synth.wp2),
                                           self._stream()))
             self.synth.run()

@@ -107,7 +107,8 @@ CFR_API int cfr_program_add_affine(cfr_program* p, const void* y_f16, const floa
 /* LastConvBlock :759-762 + postprocess (mod_stylegan_generator.py:303-307) + get_transform (gen_utils.py:77-85) */
 CFR_API int cfr_program_add_torgb_resize(cfr_program* p, const void* x_f16, const float* A, const float* B, int n, int hin,
                                  int c, const float* w_rgb, const float* b_rgb, int rout, float mean, float stdv,
-                                 void* out_f16_nhwc16, float* out_planar_f32);
+                                 void* out_f16_nhwc16, float* out_planar_f32, const int32_t* out_slot);
+/* out_slot (device int, may be NULL): the n images are written at group *out_slot of a [groups*n, R, R, 16] buffer */
 
 /* ---- immediate ops ------------------------------------------------------------------------------------ */
 /* L2Certificate.sample_noise (certificate.py:64-67) + WrappedModel.forward latent perturbation
@@ -134,6 +135,11 @@ typedef struct cfr_sampler_desc {
   float psi;
   const float* gallery;   /* [n_gallery,512] */
   int32_t n_gallery;
+  /* optional: run the FRM once per frm_group synthesis chunks (better SM fill for the small ArcFace layers) */
+  int32_t frm_group;      /* K >= 1 */
+  cfr_program* frm_big;   /* image [K*chunk] -> embeddings, or NULL */
+  const float* emb_big;   /* [K*chunk,512] */
+  int32_t* out_slot;      /* device int read by the synthesis program's torgb_resize op */
 } cfr_sampler_desc;
 CFR_API int cfr_sampler_create(const cfr_sampler_desc* d, cfr_sampler** out);
 CFR_API void cfr_sampler_destroy(cfr_sampler* s);

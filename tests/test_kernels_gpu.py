@@ -253,7 +253,7 @@ def test_torgb_resize_matches_torch(E):
     xin = _nhwc16(x)
     prog = E.Program()
     L.check(lib.cfr_program_add_torgb_resize(prog.handle, L.ptr(xin), None, None, n, hin, c, L.ptr(wr.contiguous()),
-                                             L.ptr(br), rout, 0.5, 0.5, L.ptr(out), L.ptr(planar)))
+                                             L.ptr(br), rout, 0.5, 0.5, L.ptr(out), L.ptr(planar), None))
     prog.run()
     _sync()
     assert (planar - ref).abs().max().item() < 1e-5          # fp32 math on identical fp16 inputs

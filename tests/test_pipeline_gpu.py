@@ -147,3 +147,16 @@ def test_host_entry_matches_device_entry(setup):
     dev, _ = eng.sample_votes(z, torch.zeros(1, 5), torch.tensor([SIGMA]), 16, seed=11)
     torch.cuda.synchronize()
     assert np.array_equal(counts, dev.cpu().numpy())
+
+
+def test_frm_grouping_is_transparent(setup, golden, models):
+    """Running ArcFace once per 2 synthesis chunks (better SM fill) must not change any embedding or vote."""
+    from certifyingfacerecognition_b200.engine import Engine
+    eng, g_sd, f_sd, dirs, gallery, z = setup
+    eng2 = Engine(g_sd, f_sd, dirs, gallery, chunk=8, frm_group=2)
+    x, sigma = torch.zeros(1, 5), torch.tensor([SIGMA])
+    c1, e1 = eng.sample_votes(z, x, sigma, 21, seed=3, want_emb=True, want_pred=True)
+    c2, e2 = eng2.sample_votes(z, x, sigma, 21, seed=3, want_emb=True, want_pred=True)
+    torch.cuda.synchronize()
+    assert torch.equal(e1["emb"], e2["emb"])
+    assert torch.equal(e1["pred"], e2["pred"]) and torch.equal(c1, c2)
