@@ -265,24 +265,34 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
         const bool colin = gx < p.W;
         const bool has_nz = p.noise != nullptr;
         const __half2 h45 = __floats2half2_rn(cl, 1.f);                  // k4 (0,-1), k5 (0,0)
-        for (int r = tt >> 7; r < p.TH; r += LT >> 7) {
-          const int gy = bd.y0 + r;
-          const bool in = colin && gy < p.H;
-          const float nzv = (in && has_nz) ? __ldg(&p.noise[gy * p.W + gx]) : 0.f;
-          const float ru = gy > 0 ? 1.f : 0.f, rd = gy < p.H - 1 ? 1.f : 0.f;
-          const __half2 h01 = __floats2half2_rn(nzv, ru * cl);          // k0 noise, k1 (-1,-1)
-          const __half2 h23 = __floats2half2_rn(ru, ru * cr);           // k2 (-1,0), k3 (-1,+1)
-          const __half2 h67 = __floats2half2_rn(cr, rd * cl);           // k6 (0,+1), k7 (+1,-1)
-          const __half2 h89 = __floats2half2_rn(rd, rd * cr);           // k8 (+1,0), k9 (+1,+1)
-          const uint32_t lin = xb_addr + (static_cast<uint32_t>(r * 128 + cx) << 5);
-          const uint32_t sw = ((lin >> 7) & 1u) << 4;
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(lin ^ sw),
-                       "r"(*reinterpret_cast<const uint32_t*>(&h01)), "r"(*reinterpret_cast<const uint32_t*>(&h23)),
-                       "r"(*reinterpret_cast<const uint32_t*>(&h45)), "r"(*reinterpret_cast<const uint32_t*>(&h67))
-                       : "memory");
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %2, %2};" ::"r"((lin + 16) ^ sw),
-                       "r"(*reinterpret_cast<const uint32_t*>(&h89)), "r"(0u)
-                       : "memory");
+        constexpr int RS = LT >> 7;                                     // rows advanced per step (2)
+        for (int r0 = tt >> 7; r0 < p.TH; r0 += 4 * RS) {
+          float nzv[4];                                                  // 4 independent noise loads in flight
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int gy = bd.y0 + r0 + u * RS;
+            nzv[u] = (has_nz && colin && r0 + u * RS < p.TH && gy < p.H) ? __ldg(&p.noise[gy * p.W + gx]) : 0.f;
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int r = r0 + u * RS;
+            if (r >= p.TH) break;
+            const int gy = bd.y0 + r;
+            const float ru = gy > 0 ? 1.f : 0.f, rd = gy < p.H - 1 ? 1.f : 0.f;
+            const __half2 h01 = __floats2half2_rn(nzv[u], ru * cl);       // k0 noise, k1 (-1,-1)
+            const __half2 h23 = __floats2half2_rn(ru, ru * cr);           // k2 (-1,0), k3 (-1,+1)
+            const __half2 h67 = __floats2half2_rn(cr, rd * cl);           // k6 (0,+1), k7 (+1,-1)
+            const __half2 h89 = __floats2half2_rn(rd, rd * cr);           // k8 (+1,0), k9 (+1,+1)
+            const uint32_t lin = xb_addr + (static_cast<uint32_t>(r * 128 + cx) << 5);
+            const uint32_t sw = ((lin >> 7) & 1u) << 4;
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(lin ^ sw),
+                         "r"(*reinterpret_cast<const uint32_t*>(&h01)), "r"(*reinterpret_cast<const uint32_t*>(&h23)),
+                         "r"(*reinterpret_cast<const uint32_t*>(&h45)), "r"(*reinterpret_cast<const uint32_t*>(&h67))
+                         : "memory");
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %2, %2};" ::"r"((lin + 16) ^ sw),
+                         "r"(*reinterpret_cast<const uint32_t*>(&h89)), "r"(0u)
+                         : "memory");
+          }
         }
       }
     };
