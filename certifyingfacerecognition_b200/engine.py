@@ -230,7 +230,7 @@ class Program:
 class SynthesisProgram(Program):
     def __init__(self, g_sd: Dict[str, Tensor], chunk: int, out_res: int = 112, device="cuda",
                  keep_planar: bool = False, mean: float = 0.5, std: float = 0.5, halo: bool = True,
-                 fold_small: bool = True, groups: int = 1):
+                 fold_small: bool = True, groups: int = 1, blur_on_tensor_cores: bool = True):
         super().__init__()
         dev = torch.device(device)
         self.chunk, self.out_res = chunk, out_res
@@ -318,8 +318,19 @@ class SynthesisProgram(Program):
                           tile=tile_for(lo), out=raw, out_hwc=(res, res, cout), taps=taps, oscale=2,
                           ooff=[(0, 0), (0, 1), (1, 0), (1, 1)], w_rows_per_phase=0 if hk else cout,
                           halo=hk, in_affine=pending, fold_center_tap=-1 if fold else None)
-                L.check(lib.cfr_program_add_blur_act_stats(h, L.ptr(raw), L.ptr(y), chunk, res, res, cout, L.ptr(noise),
-                                                           L.ptr(noise_w), L.ptr(bias), L.ptr(ssum), L.ptr(ssq), 0))
+                if fold and cout <= 16 and blur_on_tensor_cores:
+                    # BlurLayer :463 as a depthwise conv on the tensor cores: W[tap] = k[tap] * I (1/16, 1/8, 1/4 are exact
+                    # in fp16, accumulation is fp32 => same numerics as the CUDA-core blur), + noise/bias/LeakyReLU/stats
+                    k1 = torch.tensor([1.0, 2.0, 1.0]) / 4.0
+                    wb = torch.einsum("a,b,oi->oiab", k1, k1, torch.eye(cout))
+                    self.conv(inp=raw, n=chunk, hin=res, win=res, cin=cout, w=self.hold(_f32(pack_halo_weight(wb), dev)),
+                              cout=cout, hout=res, wout=res, tile=tile_for(res), out=y, out_hwc=(res, res, cout),
+                              taps=[TAPS3], noise=noise, noise_w=noise_w, bias=bias, act=L.ACT_LRELU, slope=0.2,
+                              stat_sum=ssum, stat_sq=ssq, halo=True, fold_center_tap=4)
+                else:
+                    L.check(lib.cfr_program_add_blur_act_stats(h, L.ptr(raw), L.ptr(y), chunk, res, res, cout,
+                                                               L.ptr(noise), L.ptr(noise_w), L.ptr(bias), L.ptr(ssum),
+                                                               L.ptr(ssq), 0))
             # A/B double-buffered by layer parity: the consumer of layer l reads them while layer l+1's are written
             A, B = self.AB[l % 2]
             L.check(lib.cfr_program_add_finalize_stats(h, L.ptr(ssum), L.ptr(ssq), L.ptr(self.styles), off,
