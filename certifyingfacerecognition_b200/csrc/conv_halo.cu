@@ -3,6 +3,7 @@
 #include "conv_igemm.cuh"
 #include "ptx.cuh"
 
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -395,17 +396,22 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
       const int gx = bd.x0 + q * 32 + static_cast<int>(lane);
       const bool colok = gx < p.W;
       const int ntiles = bd.rows << phLog;
+      // output pixel of (row r, phase ph): band origin + r * row pitch + per-phase offset (all precomputed)
+      const size_t pix_band = (static_cast<size_t>(bd.n) * p.outH + bd.y0 * p.oscale) * p.outW + gx * p.oscale;
+      const size_t pix_row = static_cast<size_t>(p.oscale) * p.outW;
       {
         // this warp group's tiles of the band: tile index tbase + i with (tbase + i) & 1 == grp
         for (int i = (grp - static_cast<int>(tbase)) & 1; i < ntiles; i += 2) {
           const uint32_t tcount = tbase + i;
           const uint32_t my_as = tcount & (AS - 1), my_ph = (tcount >> asLog) & 1;
           const int r = i >> phLog, ph = i & (p.numPhases - 1);
-          const int gy = bd.y0 + r;
-          const int oy = gy * p.oscale + p.ooff_y[ph];
-          const int ox = gx * p.oscale + p.ooff_x[ph];
-          const size_t pix = (static_cast<size_t>(bd.n) * p.outH + oy) * p.outW + ox;
-          const float nz = (has_noise && colok) ? __ldg(&p.noise[oy * p.outW + ox]) : 0.f;
+          const size_t pix = pix_band + r * pix_row + static_cast<size_t>(p.ooff_y[ph]) * p.outW + p.ooff_x[ph];
+          float nz = 0.f;
+          if (has_noise && colok) {
+            const int oy = (bd.y0 + r) * p.oscale + p.ooff_y[ph];
+            const int ox = gx * p.oscale + p.ooff_x[ph];
+            nz = __ldg(&p.noise[oy * p.outW + ox]);
+          }
           mbar_wait(&tfull[my_as], my_ph);
           tc_fence_after();
           const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + my_as * ACC_COLS;
@@ -608,7 +614,10 @@ int halo_build(const cfr_conv_desc& s, const float* inA, const float* inB, const
   auto halo_bytes = [&](int th) { return ((th + 2) * kHaloW * p.rowBytes + 1023) / 1024 * 1024 + aux_bytes(th); };
   // three band buffers (prefetch distance 2) with the tallest band that fits, but at least 4 rows per band;
   // otherwise fall back to two buffers
-  int ns = 3, th = 16;
+  // two band buffers with tall bands beat three with short ones (per-band overhead and halo re-reads dominate):
+  // profiles/ops_r01_*.tsv.  CFR_HALO_STAGES=3 switches back for experiments.
+  int ns = 2, th = 16;
+  if (const char* e = getenv("CFR_HALO_STAGES")) ns = atoi(e) == 3 ? 3 : 2;
   while (th > 1 && ns * halo_bytes(th) > budget) --th;
   if (th < 4) {
     ns = 2;

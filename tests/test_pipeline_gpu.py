@@ -160,3 +160,50 @@ def test_frm_grouping_is_transparent(setup, golden, models):
     torch.cuda.synchronize()
     assert torch.equal(e1["emb"], e2["emb"])
     assert torch.equal(e1["pred"], e2["pred"]) and torch.equal(c1, c2)
+
+
+def test_edge_sizes(setup):
+    """num = 0 (no launch, zero counts), num = 1, and num one past a chunk boundary."""
+    eng, _, _, _, _, z = setup
+    x, sigma = torch.zeros(1, 5), torch.tensor([SIGMA])
+    c0, _ = eng.sample_votes(z, x, sigma, 0, seed=9)
+    c1, e1 = eng.sample_votes(z, x, sigma, 1, seed=9, want_pred=True)
+    c9, e9 = eng.sample_votes(z, x, sigma, 9, seed=9, want_pred=True)
+    torch.cuda.synchronize()
+    assert c0.sum().item() == 0 and c1.sum().item() == 1 and c9.sum().item() == 9
+    assert e9["pred"][0].item() == e1["pred"][0].item()          # sample 0 is the same draw in both calls
+    assert int(torch.bincount(e9["pred"].long(), minlength=N_GALLERY).sum()) == 9
+
+
+def test_smooth_api_end_to_end(setup, golden, models):
+    """The drop-in Python classes on the device path: certify / predict return types and the certified radius
+    against the oracle run on the noise the device actually drew (radius within 1 %)."""
+    from certifyingfacerecognition_b200.models.smoothing_model import WrappedModel
+    from certifyingfacerecognition_b200.smoothing import L2Certificate, Smooth
+    from oracle import mc_path as M
+    eng, g_sd, f_sd, dirs, gallery, z = setup
+    dev = torch.device("cuda")
+    model = WrappedModel(dirs.to(dev), "insightface", generator_state=g_sd, frm_state=f_sd,
+                         latents=torch.from_numpy(golden["w_all"]), orig_embs=gallery, chunk=8)
+    sm = Smooth(model, N_GALLERY, torch.tensor([SIGMA], device=dev), L2Certificate(1, device=dev), seed=21)
+    x = torch.zeros(1, 5, device=dev)
+    pred, gap = sm.certify(z.to(dev), x, torch.tensor([0], device=dev), 8, 24, 0.001, 8, device=dev)
+    assert isinstance(pred, int) and isinstance(gap, float)
+    # replay the very same noise through the oracle
+    _, extra = model.engine.sample_votes(z, x, torch.tensor([SIGMA]), 8, seed=21, sample_offset=0, want_noise=True)
+    n0 = extra["noise"].cpu()
+    _, extra = model.engine.sample_votes(z, x, torch.tensor([SIGMA]), 24, seed=21, sample_offset=8, want_noise=True)
+    n1 = extra["noise"].cpu()
+    classify = lambda p: M.wrapped_forward(z, p, dirs, gallery, g_sd, f_sd, literal=False)
+    c0 = M.count_arr(classify(n0.view(8, 1, 1, 5)).argmax(1), N_GALLERY)
+    ref_pred = int(c0.argmax())
+    if ref_pred != 0:
+        assert (pred, gap) == (ref_pred, 0.0)
+    else:
+        c1 = M.count_arr(classify(n1.view(24, 1, 1, 5)).argmax(1), N_GALLERY)
+        pbar = M.lower_confidence_bound(int(c1[0]), 24, 0.001)
+        ref = (M.ABSTAIN, 0.0) if pbar < 0.5 else (0, M.compute_gap(pbar))
+        assert pred == ref[0] and gap == pytest.approx(ref[1], rel=1e-2, abs=1e-9)
+    probs = model(z.to(dev), n0.view(8, 1, 1, 5).to(dev))
+    assert probs.shape == (8, N_GALLERY) and torch.allclose(probs.sum(1), torch.ones(8, device=dev), atol=1e-4)
+    assert sm.predict(z.to(dev), x, 16, 0.001, 8, device=dev) in (Smooth.ABSTAIN, 0, *range(8, 18))
