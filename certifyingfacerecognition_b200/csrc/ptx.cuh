@@ -51,8 +51,10 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 }
 // Bounded wait: a pipeline bug traps (kernel error) instead of hanging the GPU box.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ns = 32;
   for (uint32_t it = 0; !mbar_try_wait(bar, parity); ++it) {
-    __nanosleep(32);                       // keep polling warps off the issue slots
+    __nanosleep(ns);                       // exponential back-off keeps polling warps off the issue slots
+    if (ns < 256) ns <<= 1;
     if (it > (1u << 22)) __trap();
   }
 }

