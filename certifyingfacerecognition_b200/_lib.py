@@ -42,6 +42,7 @@ class SamplerDesc(C.Structure):
         ("wp2", C.c_void_p), ("emb", C.c_void_p), ("dir_mat", C.c_void_p), ("w_avg", C.c_void_p),
         ("psi", C.c_float), ("gallery", C.c_void_p), ("n_gallery", C.c_int32),
         ("frm_group", C.c_int32), ("frm_big", C.c_void_p), ("emb_big", C.c_void_p), ("out_slot", C.c_void_p),
+        ("matcher", C.c_void_p),
     ]
 
 
@@ -71,6 +72,9 @@ SIGNATURES = {
     "cfr_noise_project": (_I, [_P, _P, _P, _I, _P, _P, _P, _F, _U64, _U64, _I, _P, _P, _P]),
     "cfr_truncate": (_I, [_P, _P, _F, _I, _P, _P]),
     "cfr_match_vote": (_I, [_P, _I, _P, _I, _P, _P, _P, _P]),
+    "cfr_matcher_create": (_I, [_P, _I, _I, _P, C.POINTER(_P)]),
+    "cfr_matcher_destroy": (None, [_P]),
+    "cfr_matcher_run": (_I, [_P, _P, _I, _P, _P, _P]),
     "cfr_sampler_create": (_I, [C.POINTER(SamplerDesc), C.POINTER(_P)]),
     "cfr_sampler_destroy": (None, [_P]),
     "cfr_sample_votes": (_I, [_P, _P, _P, _P, _I, _P, _I64, _U64, _U64, _P, _P, _P, _P, _P]),

@@ -30,6 +30,15 @@ struct cfr_program {
   }
 };
 
+struct cfr_matcher {
+  int n_gallery = 0, n_pad = 0, max_b = 0;
+  __half* g_split = nullptr;            // [n_pad][1536]  = [g_h, g_l, g_h]
+  float* g_bias = nullptr;              // [n_pad]        = -|g|^2
+  __half* q_split = nullptr;            // [max_b][1536]  = [2e_h, 2e_h, 2e_l]
+  unsigned long long* keys = nullptr;   // [max_b]
+  ConvOp op;
+};
+
 struct cfr_sampler {
   cfr_sampler_desc d;
   unsigned long long* keys = nullptr;   // [chunk]
@@ -242,6 +251,55 @@ CFR_API int cfr_match_vote(const float* emb, int b, const float* gallery, int n,
                            reinterpret_cast<long long*>(counts), S(stream));
 }
 
+CFR_API int cfr_matcher_create(const float* gallery, int n_gallery, int max_b, cfr_stream_t stream, cfr_matcher** out) {
+  if (n_gallery <= 0 || max_b <= 0) { set_error("matcher: bad sizes"); return 2; }
+  std::unique_ptr<cfr_matcher> m(new cfr_matcher());
+  m->n_gallery = n_gallery;
+  m->n_pad = (n_gallery + 255) / 256 * 256;
+  m->max_b = max_b;
+  CFR_CUDA(cudaMalloc(&m->g_split, sizeof(__half) * 1536 * static_cast<size_t>(m->n_pad)));
+  CFR_CUDA(cudaMalloc(&m->g_bias, sizeof(float) * m->n_pad));
+  CFR_CUDA(cudaMalloc(&m->q_split, sizeof(__half) * 1536 * static_cast<size_t>(max_b)));
+  CFR_CUDA(cudaMalloc(&m->keys, sizeof(unsigned long long) * max_b));
+  CFR_CUDA(cudaMemsetAsync(m->keys, 0, sizeof(unsigned long long) * max_b, S(stream)));
+  int r = launch_split_hilo(gallery, n_gallery, m->n_pad, 0, m->g_split, m->g_bias, S(stream));
+  if (r) return r;
+  cfr_conv_desc d;
+  memset(&d, 0, sizeof(d));
+  d.in = m->q_split; d.N = max_b; d.Hin = 1; d.Win = 1; d.Cin = 1536;
+  d.w = m->g_split; d.wRows = m->n_pad; d.Kpad = 1536; d.Cout = m->n_pad;
+  d.Hout = 1; d.Wout = 1; d.TW = 1; d.TH = 1; d.TN = 128;
+  d.stride = 1; d.ntaps = 1; d.numPhases = 1;
+  d.out = m->q_split;            // never written in argmax mode
+  d.outIsF32 = 0; d.outH = 1; d.outW = 1; d.outC = m->n_pad; d.oscale = 1;
+  d.bias = m->g_bias;
+  r = conv_build(d, &m->op);
+  if (r) return r;
+  conv_set_argmax(&m->op, m->keys);
+  *out = m.release();
+  return 0;
+}
+CFR_API void cfr_matcher_destroy(cfr_matcher* m) {
+  if (!m) return;
+  cudaFree(m->g_split);
+  cudaFree(m->g_bias);
+  cudaFree(m->q_split);
+  cudaFree(m->keys);
+  delete m;
+}
+CFR_API int cfr_matcher_run(cfr_matcher* m, const float* emb, int b, int32_t* pred, int64_t* counts, cfr_stream_t stream) {
+  if (b > m->max_b) { set_error("matcher: b=%d exceeds max_b=%d", b, m->max_b); return 2; }
+  if (b <= 0) return 0;
+  int r = launch_split_hilo(emb, b, m->max_b, 1, m->q_split, nullptr, S(stream));
+  if (r) return r;
+  if ((r = conv_launch(m->op, S(stream))) != 0) return r;
+  // rows >= b are zero queries: their keys are reset below without being counted
+  r = launch_vote_argmax(m->keys, b, pred, reinterpret_cast<long long*>(counts), S(stream));
+  if (r) return r;
+  if (b < m->max_b) CFR_CUDA(cudaMemsetAsync(m->keys + b, 0, sizeof(unsigned long long) * (m->max_b - b), S(stream)));
+  return 0;
+}
+
 CFR_API int cfr_sampler_create(const cfr_sampler_desc* d, cfr_sampler** out) {
   if (d->chunk <= 0 || d->n_gallery <= 0) { set_error("sampler: bad chunk / gallery size"); return 2; }
   std::unique_ptr<cfr_sampler> s(new cfr_sampler());
@@ -293,8 +351,12 @@ CFR_API int cfr_sample_votes(cfr_sampler* s, const float* z, const float* x, con
     if (emb_out) {
       CFR_CUDA(cudaMemcpyAsync(emb_out + done * 512, emb, sizeof(float) * 512 * b, cudaMemcpyDeviceToDevice, S(stream)));
     }
-    r = launch_match_vote(emb, b, d.gallery, d.n_gallery, s->keys, pred_out ? pred_out + done : nullptr,
-                          reinterpret_cast<long long*>(counts), S(stream));
+    if (d.matcher != nullptr) {
+      r = cfr_matcher_run(d.matcher, emb, b, pred_out ? pred_out + done : nullptr, counts, stream);
+    } else {
+      r = launch_match_vote(emb, b, d.gallery, d.n_gallery, s->keys, pred_out ? pred_out + done : nullptr,
+                            reinterpret_cast<long long*>(counts), S(stream));
+    }
     if (r) return r;
     done += b;
   }

@@ -251,6 +251,35 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
       mbar_wait(&tfull_bar[as], aphase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * p.BN;
+      if (p.argmax_keys != nullptr) {
+        // gallery match: score = acc + bias[j] (= 2 e.g_j - |g_j|^2); keep the best column of this tile per row and
+        // fold it into the global per-query key (max score, then lowest index == torch.argmax tie-break)
+        float best = -3.4e38f;
+        int best_j = 0;
+        for (int c0 = 0; c0 < p.BN; c0 += 16) {
+          float v[16];
+          tmem_ld16(t_row + c0, v);
+          const int ch0 = t.ntile * p.BN + c0;
+#pragma unroll
+          for (int i = 0; i < 16; i += 4) {
+            const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + ch0 + i));
+            v[i] += b4.x; v[i + 1] += b4.y; v[i + 2] += b4.z; v[i + 3] += b4.w;
+          }
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            if (v[i] > best) {
+              best = v[i];
+              best_j = ch0 + i;
+            }
+          }
+        }
+        if (valid) {
+          uint32_t u = __float_as_uint(best);
+          u ^= (u >> 31) ? 0xFFFFFFFFu : 0x80000000u;                      // order-preserving float -> uint
+          const unsigned long long key = (static_cast<unsigned long long>(u) << 32) | (0xFFFFFFFFu - static_cast<uint32_t>(best_j));
+          atomicMax(&p.argmax_keys[n], key);
+        }
+      } else
       for (int c0 = 0; c0 < p.BN; c0 += 16) {
         float v[16];
         tmem_ld16(t_row + c0, v);
@@ -398,6 +427,8 @@ static EncodeTiledFn get_encode() {
   });
   return fn;
 }
+
+void conv_set_argmax(ConvOp* op, unsigned long long* keys) { op->p.argmax_keys = keys; }
 
 void* get_encode_tiled() { return reinterpret_cast<void*>(get_encode()); }
 

@@ -67,6 +67,7 @@ struct ConvParams {
   int residC;
   unsigned long long* stat_sum;  // [N, Cout] Q43.20 fixed point, or null (requires TN == 1, numPhases == 1)
   unsigned long long* stat_sq;
+  unsigned long long* argmax_keys;   // [N] or null: no store; per-"image" argmax over output channels (gallery match)
   int CoutTotal;
 };
 
@@ -82,6 +83,8 @@ struct ConvOp {
 typedef ::cfr_conv_desc ConvSpec;
 
 int conv_build(const ConvSpec& s, ConvOp* op);
+// after conv_build: switch the epilogue to argmax mode (keys[n] = max over channels of (score, first index))
+void conv_set_argmax(ConvOp* op, unsigned long long* keys);
 int conv_launch(const ConvOp& op, cudaStream_t stream);
 void set_error(const char* fmt, ...);
 const char* last_error();

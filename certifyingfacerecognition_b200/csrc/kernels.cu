@@ -566,6 +566,56 @@ __global__ void k_vote(unsigned long long* __restrict__ keys, int b, int* __rest
   if (pred != nullptr) pred[i] = pr;
   if (counts != nullptr) atomicAdd(&counts[pr], 1ull);
 }
+// ------------------------------------------------------------------------------------------
+// Tensor-core gallery match (large galleries): fp32 rows are split into fp16 hi + lo parts so that
+//   e.g = e_h.g_h + e_h.g_l + e_l.g_h  (+ O(2^-22)),  one K = 3*512 GEMM:  A = [e_h, e_h, e_l],  B = [g_h, g_l, g_h].
+// mode 0 (gallery): dst = [h, l, h], bias[row] = -|g|^2 (exact fp32; padded rows get -3e38);
+// mode 1 (queries): dst = [2h, 2h, 2l]  (the factor 2 of 2 e.g - |g|^2 is exact in fp16).
+// ------------------------------------------------------------------------------------------
+__global__ void k_split_hilo(const float* __restrict__ src, int rows, int rows_pad, int mode, __half* __restrict__ dst,
+                             float* __restrict__ bias) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows_pad) return;
+  __half* d = dst + static_cast<size_t>(row) * 1536;
+  float nrm = 0.f;
+  for (int k = lane; k < 512; k += 32) {
+    const float v = row < rows ? src[static_cast<size_t>(row) * 512 + k] : 0.f;
+    const float s = mode == 1 ? 2.f * v : v;
+    const __half h = __float2half_rn(s);
+    const __half l = __float2half_rn(s - __half2float(h));
+    d[k] = h;
+    d[512 + k] = mode == 1 ? h : l;
+    d[1024 + k] = mode == 1 ? l : h;
+    nrm += v * v;
+  }
+  if (bias != nullptr) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) nrm += __shfl_xor_sync(0xffffffffu, nrm, o);
+    if (lane == 0) bias[row] = row < rows ? -nrm : -3.0e38f;
+  }
+}
+int launch_split_hilo(const float* src, int rows, int rows_pad, int mode, __half* dst, float* bias, cudaStream_t st) {
+  k_split_hilo<<<(rows_pad + 7) / 8, 256, 0, st>>>(src, rows, rows_pad, mode, dst, bias);
+  CFR_LAUNCH_CHECK("split_hilo");
+  return 0;
+}
+__global__ void k_vote_argmax(unsigned long long* __restrict__ keys, int b, int* __restrict__ pred,
+                              unsigned long long* __restrict__ counts) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= b) return;
+  const int pr = static_cast<int>(0xFFFFFFFFu - static_cast<uint32_t>(keys[i] & 0xffffffffull));
+  keys[i] = 0ull;                  // re-arm (atomicMax identity)
+  if (pred != nullptr) pred[i] = pr;
+  if (counts != nullptr) atomicAdd(&counts[pr], 1ull);
+}
+int launch_vote_argmax(unsigned long long* keys, int b, int* pred, long long* counts, cudaStream_t st) {
+  if (b <= 0) return 0;
+  k_vote_argmax<<<(b + 127) / 128, 128, 0, st>>>(keys, b, pred, reinterpret_cast<unsigned long long*>(counts));
+  CFR_LAUNCH_CHECK("vote_argmax");
+  return 0;
+}
+
 __global__ void k_set_int(int* p, int v) { *p = v; }
 int launch_set_int(int* p, int v, cudaStream_t st) {
   k_set_int<<<1, 1, 0, st>>>(p, v);

@@ -443,8 +443,10 @@ class ArcFaceProgram(Program):
 class Engine:
     """StyleGAN -> resize -> iresnet50 -> gallery vote, for one GPU."""
 
+    TC_MATCH_MIN_ROWS = 32768      # galleries at least this large use the tensor-core matcher (cfr_matcher_*)
+
     def __init__(self, g_sd, f_sd, dir_mat: Tensor, gallery: Tensor, chunk: int = 32, device="cuda",
-                 keep_planar: bool = False, frm_group: int = 1):
+                 keep_planar: bool = False, frm_group: int = 1, tc_match: Optional[bool] = None):
         if not torch.cuda.is_available():
             raise RuntimeError("certifyingfacerecognition_b200 needs a CUDA device (no CPU fallback)")
         self.lib = L.load()
@@ -455,6 +457,8 @@ class Engine:
         self.frm = ArcFaceProgram(f_sd, chunk, self.synth.img, device)
         self.frm_big = ArcFaceProgram(f_sd, chunk * self.frm_group, self.synth.img, device) if self.frm_group > 1 else None
         self.dir_mat = _f32(dir_mat, self.device)
+        self.tc_match = tc_match
+        self.matcher = None
         self.set_gallery(gallery)
 
     def set_gallery(self, gallery: Tensor) -> None:
@@ -468,6 +472,16 @@ class Engine:
         d.frm_big = self.frm_big.handle if self.frm_big is not None else None
         d.emb_big = L.ptr(self.frm_big.emb) if self.frm_big is not None else None
         d.out_slot = L.ptr(self.synth.out_slot)
+        if getattr(self, "matcher", None):
+            self.lib.cfr_matcher_destroy(self.matcher)
+            self.matcher = None
+        use_tc = self.tc_match if self.tc_match is not None else self.gallery.shape[0] >= self.TC_MATCH_MIN_ROWS
+        if use_tc:
+            m = C.c_void_p()
+            L.check(self.lib.cfr_matcher_create(L.ptr(self.gallery), self.gallery.shape[0], self.chunk * self.frm_group,
+                                                self._stream(), C.byref(m)))
+            self.matcher = m
+        d.matcher = self.matcher
         if getattr(self, "sampler", None):
             self.lib.cfr_sampler_destroy(self.sampler)
         h = C.c_void_p()
@@ -479,6 +493,9 @@ class Engine:
             if getattr(self, "sampler", None):
                 self.lib.cfr_sampler_destroy(self.sampler)
                 self.sampler = None
+            if getattr(self, "matcher", None):
+                self.lib.cfr_matcher_destroy(self.matcher)
+                self.matcher = None
         except Exception:
             pass
 

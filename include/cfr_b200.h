@@ -29,6 +29,7 @@ extern "C" {
 typedef struct CUstream_st* cfr_stream_t; /* == cudaStream_t */
 typedef struct cfr_program cfr_program;   /* ordered list of kernel launches with baked-in tensor maps */
 typedef struct cfr_sampler cfr_sampler;   /* the whole Smooth._sample_noise body */
+typedef struct cfr_matcher cfr_matcher;   /* tensor-core gallery match for large galleries */
 
 #define CFR_MAX_PHASES 4
 #define CFR_MAX_TAPS 9
@@ -123,6 +124,14 @@ CFR_API int cfr_truncate(const float* w, const float* w_avg, float psi, int b, f
 CFR_API int cfr_match_vote(const float* emb, int b, const float* gallery, int n, uint64_t* keys, int32_t* pred,
                    int64_t* counts, cfr_stream_t stream);
 
+/* Large-gallery variant of cfr_match_vote (BASELINE config 5, up to 1 M identities): argmax_j (2 e.g_j - |g_j|^2) as one
+ * tcgen05 GEMM over fp16 hi/lo splits of both operands (e.g = e_h.g_h + e_h.g_l + e_l.g_h, i.e. ~2^-22 relative --
+ * fp32-class scores), with the running argmax (first index on ties) fused into the GEMM epilogue; nothing of size
+ * [b, N] is ever written.  create() splits the gallery once ([N,1536] fp16 + |g|^2). */
+CFR_API int cfr_matcher_create(const float* gallery, int n_gallery, int max_b, cfr_stream_t stream, cfr_matcher** out);
+CFR_API void cfr_matcher_destroy(cfr_matcher* m);
+CFR_API int cfr_matcher_run(cfr_matcher* m, const float* emb, int b, int32_t* pred, int64_t* counts, cfr_stream_t stream);
+
 /* ---- Smooth._sample_noise (smooth.py:109-138) as one call --------------------------------------------- */
 typedef struct cfr_sampler_desc {
   cfr_program* synth;     /* wp2 -> image at FRM resolution (one chunk) */
@@ -140,6 +149,7 @@ typedef struct cfr_sampler_desc {
   cfr_program* frm_big;   /* image [K*chunk] -> embeddings, or NULL */
   const float* emb_big;   /* [K*chunk,512] */
   int32_t* out_slot;      /* device int read by the synthesis program's torgb_resize op */
+  cfr_matcher* matcher;   /* optional: tensor-core match (max_b >= frm_group*chunk) instead of the exact SIMT kernel */
 } cfr_sampler_desc;
 CFR_API int cfr_sampler_create(const cfr_sampler_desc* d, cfr_sampler** out);
 CFR_API void cfr_sampler_destroy(cfr_sampler* s);

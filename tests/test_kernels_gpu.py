@@ -385,3 +385,31 @@ def test_halo_upconv_matches_torch(E, n, cin, cout, lo_h, lo_w, fold):
     got = _from_nhwc(out, n, H, W, cout)
     assert torch.isfinite(got).all()
     assert (got - ref).abs().max().item() < 3e-2 * max(1.0, ref.abs().max().item())
+
+
+# ------------------------------------------------------------------------------------------------------------
+# tensor-core gallery matcher (BASELINE config 5)
+# ------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n_gallery,b", [(20000, 37), (1000, 128), (70001, 250)])
+def test_tc_matcher_equals_exact_match(E, n_gallery, b):
+    L = E.L
+    lib = L.load()
+    g = torch.Generator().manual_seed(n_gallery)
+    gal = (torch.randn(n_gallery, 512, generator=g) * 1.3 + 0.2).cuda()
+    idx = torch.randint(0, n_gallery, (b,), generator=g).cuda()
+    emb = (gal[idx] + 0.5 * torch.randn(b, 512, generator=g).cuda()).contiguous()
+    gal[123] = gal[n_gallery - 7]                               # exact duplicate rows: the first index must win
+    emb[0] = gal[n_gallery - 7]
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    m = C.c_void_p()
+    L.check(lib.cfr_matcher_create(L.ptr(gal), n_gallery, 256, st, C.byref(m)))
+    pred = torch.zeros(b, dtype=torch.int32, device="cuda")
+    counts = torch.zeros(n_gallery, dtype=torch.int64, device="cuda")
+    for _ in range(2):
+        L.check(lib.cfr_matcher_run(m, L.ptr(emb), b, L.ptr(pred), L.ptr(counts), st))
+    _sync()
+    lib.cfr_matcher_destroy(m)
+    ref = torch.cdist(emb, gal, compute_mode="donot_use_mm_for_euclid_dist").argmin(1)
+    assert pred[0].item() == 123
+    assert torch.equal(pred.long(), ref)
+    assert torch.equal(counts, torch.bincount(ref, minlength=n_gallery) * 2)
