@@ -207,3 +207,15 @@ def test_smooth_api_end_to_end(setup, golden, models):
     probs = model(z.to(dev), n0.view(8, 1, 1, 5).to(dev))
     assert probs.shape == (8, N_GALLERY) and torch.allclose(probs.sum(1), torch.ones(8, device=dev), atol=1e-4)
     assert sm.predict(z.to(dev), x, 16, 0.001, 8, device=dev) in (Smooth.ABSTAIN, 0, *range(8, 18))
+
+
+def test_tensor_core_matcher_in_the_sampler(setup, models):
+    """The large-gallery matcher (config 5) plugged into cfr_sample_votes gives the exact kernel's votes."""
+    from certifyingfacerecognition_b200.engine import Engine
+    eng, g_sd, f_sd, dirs, gallery, z = setup
+    eng_tc = Engine(g_sd, f_sd, dirs, gallery, chunk=8, tc_match=True)
+    x, sigma = torch.zeros(1, 5), torch.tensor([3 * SIGMA])
+    c1, e1 = eng.sample_votes(z, x, sigma, 19, seed=5, want_pred=True)
+    c2, e2 = eng_tc.sample_votes(z, x, sigma, 19, seed=5, want_pred=True)
+    torch.cuda.synchronize()
+    assert torch.equal(e1["pred"], e2["pred"]) and torch.equal(c1, c2)
