@@ -53,7 +53,10 @@ template <int COUT, bool FOLD>
 __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid_constant__ HaloParams p) {
   constexpr int NCH = COUT / 16;                 // 16-column epilogue chunks
   constexpr bool REG_STATS = COUT <= 32;         // keep per-thread channel sums in registers across a band
-  constexpr int ACC_COLS = COUT;                 // TMEM columns per accumulator stage
+  constexpr int ACC_COLS = COUT;                 // TMEM columns per accumulator
+  constexpr int G = COUT == 64 ? 2 : 4;          // tiles per accumulator group (one mbarrier handshake per group)
+  constexpr int AS = 512 / (G * COUT);           // accumulator groups resident in TMEM (8 / 4 / 4)
+  constexpr int asLog = AS == 8 ? 3 : 2;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int NS = p.haloStages;                                   // 2 or 3 halo band buffers
@@ -75,14 +78,12 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
 
   const int warp = threadIdx.x >> 5;
   const uint32_t lane = lane_id();
-  const int AS = p.accStages;
   const int totalBands = p.N * p.bandsY * p.bandsX;
   const int per = (totalBands + gridDim.x - 1) / gridDim.x;
   const int band0 = blockIdx.x * per;
   const int band1 = min(totalBands, band0 + per);
   const bool affine = p.inA != nullptr;
-  uint32_t tmemCols = 32;
-  while (tmemCols < static_cast<uint32_t>(AS * ACC_COLS)) tmemCols <<= 1;
+  constexpr uint32_t tmemCols = 512;
 
   if (warp == kHaloMmaWarp0 && lane == 0) {
     tma_prefetch_desc(&p.tmW);
@@ -160,7 +161,31 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
     }
     int hs = 0;
     uint32_t hphase = 0;
-    uint32_t as = 0, aphase = 0, tsel = 0;
+    uint32_t gbase = 0;                    // accumulator-group counter at the start of the band
+    // One tfull/tempty handshake covers a GROUP of G tiles (G accumulators of COUT columns side by side in TMEM):
+    // with 4 KB tiles the per-tile mbarrier round trips were ~3/4 of the kernel time (profiles/ablation_r01.log).
+    // numPhases == 4: group = the 4 sub-pixel phases of one low-res row;  numPhases == 1: group = G consecutive rows.
+    auto issue_tile = [&](uint32_t d_tmem, uint32_t a_row, uint32_t x_row, uint32_t b_lo, uint32_t ba_lo,
+                          const uint32_t (&to)[9]) {
+#pragma unroll
+      for (int t = 0; t < 9; ++t) {
+        if (t < p.ntaps) {
+          const uint32_t a_lo = a_row + to[t];
+          if (leader && !(p.dbg & 8)) {
+            umma_f16_lohi(d_tmem, a_lo, dhi, b_lo, dhi, idesc, t != 0 ? 1u : 0u);
+            if (kPer > 1) umma_f16_lohi(d_tmem, a_lo + 2, dhi, b_lo + 2, dhi, idesc, 1u);
+            if (kPer > 2) {
+              umma_f16_lohi(d_tmem, a_lo + 4, dhi, b_lo + 4, dhi, idesc, 1u);
+              umma_f16_lohi(d_tmem, a_lo + 6, dhi, b_lo + 6, dhi, idesc, 1u);
+            }
+          }
+          b_lo += w_tap;
+        }
+      }
+      if constexpr (FOLD) {
+        if (leader) umma_f16_lohi(d_tmem, x_row, dhi_aux, ba_lo, dhi_aux, idesc, 1u);
+      }
+    };
     for (int b = band0; b < band1; ++b) {
       const Band bd = decode_band(p, b);
       if (FOLD && bd.n != cur_n) {
@@ -178,47 +203,33 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
       }
       mbar_wait(&hready[hs], hphase);
       tc_fence_after();
-      uint32_t a_row = smem_desc_lo(smem_u32(smem + hs * p.haloBytes));
-      uint32_t x_row = smem_desc_lo(smem_u32(aux + hs * p.auxBytes));
-      for (int r = 0; r < bd.rows; ++r, a_row += row_step, x_row += aux_row_step) {
+      const uint32_t a_band = smem_desc_lo(smem_u32(smem + hs * p.haloBytes));
+      const uint32_t x_band = smem_desc_lo(smem_u32(aux + hs * p.auxBytes));
+      const int ngroups = p.numPhases == 4 ? bd.rows : (bd.rows + G - 1) / G;
+      for (int j = 0; j < ngroups; ++j) {
+        const uint32_t gc = gbase + j;
+        if ((gc & (kMmaWarps - 1)) != mw) continue;
+        const uint32_t slot = gc & (AS - 1);
+        mbar_wait(&tempty[slot], ((gc >> asLog) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d0 = tmem_base + slot * (G * ACC_COLS);
+        if (p.numPhases == 4) {            // G == 4: tile k of the group == phase k of low-res row j
+          const uint32_t a_row = a_band + j * row_step, x_row = x_band + j * aux_row_step;
 #pragma unroll
-        for (int ph = 0; ph < 4; ++ph) {
-          if (ph < p.numPhases) {
-            const bool mine = tsel == mw;
-            tsel = (tsel + 1) & (kMmaWarps - 1);
-            if (mine) {
-            mbar_wait(&tempty[as], aphase ^ 1);
-            tc_fence_after();
-            const uint32_t d_tmem = tmem_base + as * ACC_COLS;
-            uint32_t b_lo = w_lo + ph * p.ntaps * w_tap;
+          for (int k = 0; k < 4; ++k)
+            issue_tile(d0 + k * ACC_COLS, a_row, x_row, w_lo + k * p.ntaps * w_tap, wa_lo + k * (COUT * 2), toff[k]);
+        } else {                           // tile k of the group == output row j*G + k
 #pragma unroll
-            for (int t = 0; t < 9; ++t) {
-              if (t < p.ntaps) {
-                const uint32_t a_lo = a_row + toff[ph][t];
-                if (leader) {
-                  umma_f16_lohi(d_tmem, a_lo, dhi, b_lo, dhi, idesc, t != 0 ? 1u : 0u);
-                  if (kPer > 1) umma_f16_lohi(d_tmem, a_lo + 2, dhi, b_lo + 2, dhi, idesc, 1u);
-                  if (kPer > 2) {
-                    umma_f16_lohi(d_tmem, a_lo + 4, dhi, b_lo + 4, dhi, idesc, 1u);
-                    umma_f16_lohi(d_tmem, a_lo + 6, dhi, b_lo + 6, dhi, idesc, 1u);
-                  }
-                }
-                b_lo += w_tap;
-              }
-            }
-            if constexpr (FOLD) {
-              if (leader) umma_f16_lohi(d_tmem, x_row, dhi_aux, wa_lo + ph * (COUT * 2), dhi_aux, idesc, 1u);
-            }
-            if (leader) umma_commit(&tfull[as]);
-            __syncwarp();
-            }
-            if (++as == static_cast<uint32_t>(AS)) {
-              as = 0;
-              aphase ^= 1;
-            }
+          for (int k = 0; k < G; ++k) {
+            const int r = j * G + k;
+            if (r < bd.rows)
+              issue_tile(d0 + k * ACC_COLS, a_band + r * row_step, x_band + r * aux_row_step, w_lo, wa_lo, toff[0]);
           }
         }
+        if (leader) umma_commit(&tfull[slot]);
+        __syncwarp();
       }
+      gbase += ngroups;
       if (leader) umma_commit(&hempty[hs]);          // halo stage free once every MMA of this band has read it
       __syncwarp();
       if (++hs == NS) {
@@ -226,12 +237,12 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
         hphase ^= 1;
       }
     }
-  } else if (warp >= 8) {
+  } else if (warp >= kEpiWarps) {
     // ================================================================ band loader + affine-on-load (warps 8..15)
     // cp.async 16-byte chunks straight into the swizzled operand layout (TMA boxes with 32..128-byte rows are
     // row-rate bound: profiles/ncu_r01_halo_tma.txt), zero-filling out-of-image pixels == the conv padding.
     constexpr int LT = kLoaderWarps * 32;
-    const int tt = threadIdx.x - 256;
+    const int tt = threadIdx.x - kEpiWarps * 32;
     const int nchLog = p.rowBytes == 32 ? 1 : (p.rowBytes == 64 ? 2 : 3);
     const int nch = 1 << nchLog;
     const int RC = kHaloW * nch;               // 16-byte chunks per band row (260 / 520 / 1040)
@@ -244,6 +255,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
     auto issue = [&](const Band& bd, int hs) {
       const uint32_t hb_addr = smem_u32(smem + hs * p.haloBytes);
       const __half* img = p.in + static_cast<size_t>(bd.n) * imgStride + lc * 8;
+      if (!(p.dbg & 2))
       for (int q = tt; q < RC; q += LT) {
         const int gx = bd.x0 - 1 + (q >> nchLog);
         const bool colok = static_cast<unsigned>(gx) < static_cast<unsigned>(p.W);
@@ -256,7 +268,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
         }
       }
       cp_async_commit();
-      if constexpr (FOLD) {
+      if (FOLD && !(p.dbg & 4)) {
         // aux rows, one per OUTPUT pixel of the band: k0 = noise, k(1 + 3*(dy+1) + (dx+1)) = 1 if input pixel
         // (y+dy, x+dx) lies inside the image (so the folded IN/AdaIN shift respects the zero padding), rest 0
         const uint32_t xb_addr = smem_u32(aux + hs * p.auxBytes);
@@ -359,7 +371,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
     // ================================================================ epilogue (warps 0..7)
     constexpr bool HOIST = COUT == 16 && !FOLD;     // per-channel noise gain / bias live in registers
     const int q = warp & 3;                // TMEM lane quarter
-    const int grp = warp >> 2;             // handles tiles with (tcount & 1) == grp
+    const int grp = warp >> 2;             // handles tiles with tcount % kEpiGroups == grp
     const int et = threadIdx.x;            // 0..255
     const bool do_stats = p.stat_sum != nullptr;
     const bool has_noise = !FOLD && p.noise != nullptr, has_bias = !FOLD && p.bias != nullptr;
@@ -376,35 +388,38 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
         hbs[i] = has_bias ? p.bias[i] : 0.f;
       }
     }
-    uint32_t tbase = 0;                     // tile counter at the start of the band
-    const int asLog = AS == 16 ? 4 : (AS == 8 ? 3 : 2);
-    const int phLog = p.numPhases == 4 ? 2 : 0;
+    uint32_t gbase = 0;                     // accumulator-group counter at the start of the band
     int cur_n = -1;
     for (int b = band0; b < band1; ++b) {
       const Band bd = decode_band(p, b);
       if (do_stats && cur_n >= 0 && bd.n != cur_n) {
-        named_bar_sync(1, 256);
+        named_bar_sync(1, kEpiWarps * 32);
         if (et < COUT) {
           atomicAdd(&p.stat_sum[cur_n * COUT + et], s_sum[et]);
           atomicAdd(&p.stat_sq[cur_n * COUT + et], s_sq[et]);
           s_sum[et] = 0ull;
           s_sq[et] = 0ull;
         }
-        named_bar_sync(1, 256);
+        named_bar_sync(1, kEpiWarps * 32);
       }
       cur_n = bd.n;
       const int gx = bd.x0 + q * 32 + static_cast<int>(lane);
       const bool colok = gx < p.W;
-      const int ntiles = bd.rows << phLog;
+      const int ngroups = p.numPhases == 4 ? bd.rows : (bd.rows + G - 1) / G;
       // output pixel of (row r, phase ph): band origin + r * row pitch + per-phase offset (all precomputed)
       const size_t pix_band = (static_cast<size_t>(bd.n) * p.outH + bd.y0 * p.oscale) * p.outW + gx * p.oscale;
       const size_t pix_row = static_cast<size_t>(p.oscale) * p.outW;
-      {
-        // this warp group's tiles of the band: tile index tbase + i with (tbase + i) & 1 == grp
-        for (int i = (grp - static_cast<int>(tbase)) & 1; i < ntiles; i += 2) {
-          const uint32_t tcount = tbase + i;
-          const uint32_t my_as = tcount & (AS - 1), my_ph = (tcount >> asLog) & 1;
-          const int r = i >> phLog, ph = i & (p.numPhases - 1);
+      // this warp group's accumulator groups of the band: index gbase + j with (gbase + j) % kEpiGroups == grp
+      for (int j = (grp - static_cast<int>(gbase)) & (kEpiGroups - 1); j < ngroups; j += kEpiGroups) {
+        const uint32_t gc = gbase + j;
+        const uint32_t slot = gc & (AS - 1);
+        mbar_wait(&tfull[slot], (gc >> asLog) & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < G; ++k) {
+          const int r = p.numPhases == 4 ? j : j * G + k;
+          const int ph = p.numPhases == 4 ? k : 0;
+          if (r >= bd.rows) break;
           const size_t pix = pix_band + r * pix_row + static_cast<size_t>(p.ooff_y[ph]) * p.outW + p.ooff_x[ph];
           float nz = 0.f;
           if (has_noise && colok) {
@@ -412,9 +427,8 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
             const int ox = gx * p.oscale + p.ooff_x[ph];
             nz = __ldg(&p.noise[oy * p.outW + ox]);
           }
-          mbar_wait(&tfull[my_as], my_ph);
-          tc_fence_after();
-          const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + my_as * ACC_COLS;
+          const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + (slot * G + k) * ACC_COLS;
+          if (!(p.dbg & 1))
 #pragma unroll
           for (int ci = 0; ci < NCH; ++ci) {
             float v[16];
@@ -479,12 +493,12 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
               }
             }
           }
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&tempty[my_as]);
         }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty[slot]);
       }
-      tbase += ntiles;
+      gbase += ngroups;
       if constexpr (REG_STATS) {
         if (do_stats) {                      // once per band: registers -> shared
 #pragma unroll
@@ -509,7 +523,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
       }
     }
     if (do_stats && cur_n >= 0) {
-      named_bar_sync(1, 256);
+      named_bar_sync(1, kEpiWarps * 32);
       if (et < COUT) {
         atomicAdd(&p.stat_sum[cur_n * COUT + et], s_sum[et]);
         atomicAdd(&p.stat_sq[cur_n * COUT + et], s_sq[et]);
@@ -601,6 +615,7 @@ int halo_build(const cfr_conv_desc& s, const float* inA, const float* inB, const
   memcpy(p.tap_dy, s.tap_dy, sizeof(p.tap_dy));
   memcpy(p.tap_dx, s.tap_dx, sizeof(p.tap_dx));
   p.fold = w_aux != nullptr;
+  if (const char* e = getenv("CFR_HALO_DBG")) p.dbg = atoi(e);
   if (p.fold && s.Cin > 32) { set_error("halo conv: folded variant needs Cin <= 32"); return 2; }
   p.rowBytes = s.Cin * 2;
   p.wRows = s.numPhases * s.ntaps * s.Cout;
@@ -632,8 +647,9 @@ int halo_build(const cfr_conv_desc& s, const float* inA, const float* inB, const
   p.haloBytes = halo_bytes(th) - p.auxBytes;
   p.bandsX = (s.Wout + 127) / 128;
   p.bandsY = (s.Hout + th - 1) / th;
-  p.accStages = 512 / s.Cout;
-  if (p.accStages > 16) p.accStages = 16;
+  p.accStages = 0;   // (fixed per template: 512 / (G * Cout) groups of G accumulators)
+  if (s.numPhases != 1 && s.numPhases != 4) { set_error("halo conv: 1 or 4 phases"); return 2; }
+  if (s.numPhases == 4 && s.Cout == 64) { set_error("halo conv: 4-phase up-conv needs Cout <= 32"); return 2; }
   p.inA = inA; p.inB = inB;
   p.out = static_cast<__half*>(s.out);
   p.outH = s.outH; p.outW = s.outW; p.outC = s.outC; p.oscale = s.oscale;

@@ -23,8 +23,13 @@ namespace cfr {
 constexpr int kLoaderWarps = 8;
 constexpr int kMmaWarps = 4;          // tcgen05.mma issue is per-thread serial (~30 SASS instr per MMA incl. R2UR moves);
                                       // with N = 16..64 the MMAs are tiny, so several warps issue alternate tiles
-constexpr int kHaloMmaWarp0 = 8 + kLoaderWarps;      // warps 0-7 epilogue, 8-15 loader/transform, 16-19 MMA issuers
-constexpr int kHaloThreads = (8 + kLoaderWarps + kMmaWarps) * 32;
+#ifndef CFR_HALO_EPI_GROUPS
+#define CFR_HALO_EPI_GROUPS 2
+#endif
+constexpr int kEpiGroups = CFR_HALO_EPI_GROUPS;       // each group = 4 warps (one per TMEM lane quarter); tile t -> group t % kEpiGroups
+constexpr int kEpiWarps = 4 * kEpiGroups;
+constexpr int kHaloMmaWarp0 = kEpiWarps + kLoaderWarps;   // [epilogue warps][loader/transform warps][MMA issuers]
+constexpr int kHaloThreads = (kEpiWarps + kLoaderWarps + kMmaWarps) * 32;
 constexpr int kHaloW = 130;         // 128 output columns + 1 halo column each side
 
 struct HaloParams {
@@ -32,6 +37,8 @@ struct HaloParams {
   CUtensorMap tmW;                  // weights (Cin, [n *] phases*taps*Cout), box {Cin, wBoxRows}
   CUtensorMap tmWa;                 // FOLD: aux weight tiles (16, n*phases*taps*Cout), box {16, wBoxRows}
   int fold;                         // per-sample folded weights + aux band
+  int dbg;                          // ablation bits for profiling only (env CFR_HALO_DBG): 1 skip epilogue math/store,
+                                    // 2 skip band cp.async, 4 skip aux rows, 8 skip MMAs (results are then garbage)
   int auxBytes, wAuxBytes;          // aux band bytes per stage / aux weight bytes (0 unless fold)
   int N, H, W;                      // conv output grid == input grid (stride 1)
   int Cin, Cout;
