@@ -62,6 +62,7 @@ SIGNATURES = {
     "cfr_program_add_conv": (_I, [_P, C.POINTER(ConvDesc)]),
     "cfr_program_add_conv_halo": (_I, [_P, C.POINTER(ConvDesc), _P, _P]),
     "cfr_program_add_conv_halo_folded": (_I, [_P, C.POINTER(ConvDesc), _P, _P, _P, _P, _P]),
+    "cfr_program_add_upconv_blur_folded": (_I, [_P, C.POINTER(ConvDesc), _P, _P, _P, _P, _P, _P, _P]),
     "cfr_program_add_memset": (_I, [_P, _P, _I, _SZ]),
     "cfr_program_add_styles": (_I, [_P, _P, _P, _P, _I, _I, _I, _P]),
     "cfr_program_add_layer0": (_I, [_P, _P, _P, _I, _I, _I, _P]),

@@ -138,7 +138,7 @@ CFR_API int cfr_program_add_conv(cfr_program* p, const cfr_conv_desc* d) {
 
 CFR_API int cfr_program_add_conv_halo(cfr_program* p, const cfr_conv_desc* d, const float* inA, const float* inB) {
   std::unique_ptr<HaloOp> op(new HaloOp());
-  int r = halo_build(*d, inA, inB, nullptr, op.get());
+  int r = halo_build(*d, inA, inB, nullptr, 0, nullptr, op.get());
   if (r != 0) return r;
   HaloOp* raw = op.get();
   p->halos.push_back(std::move(op));
@@ -149,15 +149,15 @@ CFR_API int cfr_program_add_conv_halo(cfr_program* p, const cfr_conv_desc* d, co
   return 0;
 }
 
-CFR_API int cfr_program_add_conv_halo_folded(cfr_program* p, const cfr_conv_desc* d, const float* base_w, const float* inA,
-                                             const float* inB, void* w_main_f16, void* w_aux_f16) {
+static int add_folded(cfr_program* p, const cfr_conv_desc* d, const float* base_w, const float* inA, const float* inB,
+                      void* w_main_f16, void* w_aux_f16, int composite, const float* corr_d, float* corr_buf) {
   std::unique_ptr<HaloOp> op(new HaloOp());
   cfr_conv_desc dd = *d;
   dd.w = w_main_f16;
-  const int pt = d->numPhases * d->ntaps;
-  dd.wRows = d->N * pt * d->Cout;
+  const int wsets = composite ? 8 : d->numPhases;
+  dd.wRows = d->N * wsets * d->ntaps * d->Cout;
   dd.Kpad = d->Cin;
-  int r = halo_build(dd, nullptr, nullptr, w_aux_f16, op.get());
+  int r = halo_build(dd, nullptr, nullptr, w_aux_f16, composite, composite ? corr_buf : nullptr, op.get());
   if (r != 0) return r;
   HaloOp* raw = op.get();
   p->halos.push_back(std::move(op));
@@ -167,13 +167,28 @@ CFR_API int cfr_program_add_conv_halo_folded(cfr_program* p, const cfr_conv_desc
   cfr_conv_desc keep = *d;                       // tap tables live in the closure
   p->add([=](cudaStream_t st) {
     return launch_fold_weights(base_w, inA, inB, bias, noise_w, &keep.tap_dy[0][0], &keep.tap_dx[0][0], n, phases, ntaps,
-                               cout, cin, static_cast<__half*>(w_main_f16), static_cast<__half*>(w_aux_f16), st);
+                               cout, cin, composite, static_cast<__half*>(w_main_f16), static_cast<__half*>(w_aux_f16), st);
   }, "fold_weights");
+  if (composite) {
+    const __half* yin = static_cast<const __half*>(d->in);
+    const int h = d->Hin, w = d->Win;
+    p->add([=](cudaStream_t st) { return launch_upblur_corr(yin, inA, inB, corr_d, n, h, w, cin, cout, corr_buf, st); },
+           "upblur_corr");
+  }
   char lab[160];
-  snprintf(lab, sizeof(lab), "halo-folded %dx%d taps%dx%d Cin%d Cout%d n%d TH%d", d->Hout, d->Wout, d->numPhases,
-           d->ntaps, d->Cin, d->Cout, d->N, raw->p.TH);
+  snprintf(lab, sizeof(lab), "halo-%s %dx%d taps%dx%d Cin%d Cout%d n%d TH%d", composite ? "upblur" : "folded", d->Hout,
+           d->Wout, d->numPhases, d->ntaps, d->Cin, d->Cout, d->N, raw->p.TH);
   p->add([raw](cudaStream_t st) { return halo_launch(*raw, st); }, lab, raw->flops);
   return 0;
+}
+CFR_API int cfr_program_add_conv_halo_folded(cfr_program* p, const cfr_conv_desc* d, const float* base_w, const float* inA,
+                                             const float* inB, void* w_main_f16, void* w_aux_f16) {
+  return add_folded(p, d, base_w, inA, inB, w_main_f16, w_aux_f16, 0, nullptr, nullptr);
+}
+CFR_API int cfr_program_add_upconv_blur_folded(cfr_program* p, const cfr_conv_desc* d, const float* base_w,
+                                               const float* corr_d, const float* inA, const float* inB, void* w_main_f16,
+                                               void* w_aux_f16, float* corr_buf) {
+  return add_folded(p, d, base_w, inA, inB, w_main_f16, w_aux_f16, 1, corr_d, corr_buf);
 }
 
 CFR_API int cfr_program_add_memset(cfr_program* p, void* ptr, int value, size_t bytes) {

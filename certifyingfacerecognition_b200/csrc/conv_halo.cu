@@ -146,7 +146,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
     const uint32_t aux_row_step = 128 * 2;                 // one aux row (32 B) per output pixel, 128 pixels per tile row
     auto load_weights = [&](int n) {      // every (phase, tap) tile; FOLD: the per-sample set of image n
       const int row_base = FOLD ? n * p.wRows : 0;
-      const int aux_rows = p.numPhases * COUT;             // one aux B tile per phase
+      const int aux_rows = p.wsets * COUT;                 // one aux B tile per weight set
       mbar_expect_tx(wbar, p.wRows * p.rowBytes + (FOLD ? aux_rows * 32 : 0));
       for (int r0 = 0; r0 < p.wRows; r0 += p.wBoxRows)
         tma_load_2d(wsm + static_cast<size_t>(r0) * p.rowBytes, &p.tmW, wbar, 0, row_base + r0);
@@ -215,9 +215,14 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
         const uint32_t d0 = tmem_base + slot * (G * ACC_COLS);
         if (p.numPhases == 4) {            // G == 4: tile k of the group == phase k of low-res row j
           const uint32_t a_row = a_band + j * row_step, x_row = x_band + j * aux_row_step;
+          const int gy = bd.y0 + j;
+          // composite blur o up-conv: the first / last hi-res row use their own weight sets (4 + phase)
+          const bool top = p.composite && gy == 0, bot = p.composite && gy == p.H - 1;
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            issue_tile(d0 + k * ACC_COLS, a_row, x_row, w_lo + k * p.ntaps * w_tap, wa_lo + k * (COUT * 2), toff[k]);
+          for (int k = 0; k < 4; ++k) {
+            const int ws = ((top && k < 2) || (bot && k >= 2)) ? 4 + k : k;
+            issue_tile(d0 + k * ACC_COLS, a_row, x_row, w_lo + ws * p.ntaps * w_tap, wa_lo + ws * (COUT * 2), toff[k]);
+          }
         } else {                           // tile k of the group == output row j*G + k
 #pragma unroll
           for (int k = 0; k < G; ++k) {
@@ -277,6 +282,33 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
         const float cl = gx > 0 ? 1.f : 0.f, cr = gx < p.W - 1 ? 1.f : 0.f;
         const bool colin = gx < p.W;
         const bool has_nz = p.noise != nullptr;
+        if (p.composite) {
+          // aux row of a low-res pixel: k0..k3 = noise at its 4 hi-res phases, k4..k12 = inside-image indicators
+          for (int r = tt >> 7; r < p.TH; r += LT >> 7) {
+            const int gy = bd.y0 + r;
+            float2 n0 = make_float2(0.f, 0.f), n1 = n0;
+            if (has_nz && colin && gy < p.H) {
+              const float* np = p.noise + static_cast<size_t>(2 * gy) * p.outW + 2 * gx;
+              n0 = __ldg(reinterpret_cast<const float2*>(np));
+              n1 = __ldg(reinterpret_cast<const float2*>(np + p.outW));
+            }
+            const float ru = gy > 0 ? 1.f : 0.f, rd = gy < p.H - 1 ? 1.f : 0.f;
+            const __half2 q0 = __floats2half2_rn(n0.x, n0.y), q1 = __floats2half2_rn(n1.x, n1.y);
+            const __half2 q2 = __floats2half2_rn(ru * cl, ru), q3 = __floats2half2_rn(ru * cr, cl);      // k4 k5 | k6 k7
+            const __half2 q4 = __floats2half2_rn(1.f, cr), q5 = __floats2half2_rn(rd * cl, rd);          // k8 k9 | k10 k11
+            const __half2 q6 = __floats2half2_rn(rd * cr, 0.f);                                          // k12
+            const uint32_t lin = xb_addr + (static_cast<uint32_t>(r * 128 + cx) << 5);
+            const uint32_t sw = ((lin >> 7) & 1u) << 4;
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(lin ^ sw),
+                         "r"(*reinterpret_cast<const uint32_t*>(&q0)), "r"(*reinterpret_cast<const uint32_t*>(&q1)),
+                         "r"(*reinterpret_cast<const uint32_t*>(&q2)), "r"(*reinterpret_cast<const uint32_t*>(&q3))
+                         : "memory");
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"((lin + 16) ^ sw),
+                         "r"(*reinterpret_cast<const uint32_t*>(&q4)), "r"(*reinterpret_cast<const uint32_t*>(&q5)),
+                         "r"(*reinterpret_cast<const uint32_t*>(&q6)), "r"(0u)
+                         : "memory");
+          }
+        } else {
         const __half2 h45 = __floats2half2_rn(cl, 1.f);                  // k4 (0,-1), k5 (0,0)
         constexpr int RS = LT >> 7;                                     // rows advanced per step (2)
         for (int r0 = tt >> 7; r0 < p.TH; r0 += 4 * RS) {
@@ -306,6 +338,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
                          "r"(*reinterpret_cast<const uint32_t*>(&h89)), "r"(0u)
                          : "memory");
           }
+        }
         }
       }
     };
@@ -454,6 +487,15 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
                 }
               }
             }
+            if (p.corr != nullptr) {          // composite: exact first / last hi-res column
+              const bool left = gx == 0 && (ph & 1) == 0, right = gx == p.W - 1 && (ph & 1) == 1;
+              if (left || right) {
+                const int oy = (bd.y0 + r) * p.oscale + p.ooff_y[ph];
+                const float* cp = p.corr + ((static_cast<size_t>(bd.n) * 2 + (right ? 1 : 0)) * p.outH + oy) * COUT + ch0;
+#pragma unroll
+                for (int i = 0; i < 16; ++i) v[i] += cp[i];
+              }
+            }
             if (lrelu) {
 #pragma unroll
               for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], v[i] * slope);      // slope < 1
@@ -558,45 +600,96 @@ static CUtensorMapSwizzle swz(int bytes) {
 // so that  conv_W(A*y + B, zero padded) + noise*w + bias  ==  conv_wmain(y) + <aux row, w_aux>   exactly at borders.
 // ---------------------------------------------------------------------------------------------------------
 struct FoldTaps {
-  int8_t k[4][9];      // aux K index of (phase, tap), -1 = unused
+  int8_t k[8][9];      // aux K index of the "input (y+dy, x+dx) inside?" indicator of (weight set, tap), -1 = unused
+  int8_t noise_k[8];   // aux K index of the noise value used by the weight set
+  int8_t center_k;     // aux K index of the (0,0) indicator (carries the bias)
 };
 __global__ void k_fold_weights(const float* __restrict__ base_w, const float* __restrict__ inA,
                                const float* __restrict__ inB, const float* __restrict__ bias,
-                               const float* __restrict__ noise_w, FoldTaps ft, int phases, int ntaps, int cout, int cin,
+                               const float* __restrict__ noise_w, FoldTaps ft, int wsets, int ntaps, int cout, int cin,
                                __half* __restrict__ w_main, __half* __restrict__ w_aux) {
-  const int n = blockIdx.y, ph = blockIdx.x;
+  const int n = blockIdx.y, ws = blockIdx.x;
   const int co = threadIdx.x / cin, ci = threadIdx.x % cin;          // cin in {16, 32}: a group never straddles a warp
   const float a = inA != nullptr ? inA[n * cin + ci] : 1.f;
   const float b = inB != nullptr ? inB[n * cin + ci] : 0.f;
-  __half* aux_row = w_aux + ((static_cast<size_t>(n) * phases + ph) * cout + co) * 16;
-  if (ci < 16) aux_row[ci] = __float2half_rn((ci == 0 && noise_w != nullptr) ? noise_w[co] : 0.f);
+  __half* aux_row = w_aux + ((static_cast<size_t>(n) * wsets + ws) * cout + co) * 16;
+  if (ci < 16) aux_row[ci] = __float2half_rn((ci == ft.noise_k[ws] && noise_w != nullptr) ? noise_w[co] : 0.f);
   __syncwarp();
   for (int t = 0; t < ntaps; ++t) {
-    const size_t widx = ((static_cast<size_t>(ph) * ntaps + t) * cout + co) * cin + ci;
+    const size_t widx = ((static_cast<size_t>(ws) * ntaps + t) * cout + co) * cin + ci;
     const float w = base_w[widx];
-    w_main[static_cast<size_t>(n) * phases * ntaps * cout * cin + widx] = __float2half_rn(w * a);
+    w_main[static_cast<size_t>(n) * wsets * ntaps * cout * cin + widx] = __float2half_rn(w * a);
     float sh = w * b;
     for (int o = cin >> 1; o > 0; o >>= 1) sh += __shfl_xor_sync(0xffffffffu, sh, o);
-    const int k = ft.k[ph][t];
-    if (ci == 0 && k >= 0) aux_row[k] = __float2half_rn(sh + ((k == 5 && bias != nullptr) ? bias[co] : 0.f));
+    const int k = ft.k[ws][t];
+    if (ci == 0 && k >= 0) aux_row[k] = __float2half_rn(sh + ((k == ft.center_k && bias != nullptr) ? bias[co] : 0.f));
   }
 }
 int launch_fold_weights(const float* base_w, const float* inA, const float* inB, const float* bias, const float* noise_w,
                         const int8_t* tap_dy, const int8_t* tap_dx, int n, int phases, int ntaps, int cout, int cin,
-                        __half* w_main, __half* w_aux, cudaStream_t st) {
+                        int composite, __half* w_main, __half* w_aux, cudaStream_t st) {
   if (cout * cin > 1024 || (cin != 16 && cin != 32)) { set_error("fold_weights: Cout*Cin=%d unsupported", cout * cin); return 2; }
   FoldTaps ft;
-  for (int ph = 0; ph < 4; ++ph)
+  const int wsets = composite ? 8 : phases;
+  const int m_off = composite ? 4 : 1;            // indicators follow the noise slots in the aux row
+  for (int ws = 0; ws < 8; ++ws) {
+    const int ph = ws < 4 ? ws : ws - 4;          // weight sets 4..7 are the first/last-row variants of phases 0..3
+    ft.noise_k[ws] = static_cast<int8_t>(composite ? ph : 0);
     for (int t = 0; t < 9; ++t)
-      ft.k[ph][t] = (ph < phases && t < ntaps) ? static_cast<int8_t>(1 + 3 * (tap_dy[ph * 9 + t] + 1) + (tap_dx[ph * 9 + t] + 1)) : -1;
-  k_fold_weights<<<dim3(phases, n), cout * cin, 0, st>>>(base_w, inA, inB, bias, noise_w, ft, phases, ntaps, cout, cin, w_main, w_aux);
+      ft.k[ws][t] = (ws < wsets && t < ntaps)
+                        ? static_cast<int8_t>(m_off + 3 * (tap_dy[(ph % phases) * 9 + t] + 1) + (tap_dx[(ph % phases) * 9 + t] + 1)) : -1;
+  }
+  ft.center_k = static_cast<int8_t>(m_off + 4);
+  k_fold_weights<<<dim3(wsets, n), cout * cin, 0, st>>>(base_w, inA, inB, bias, noise_w, ft, wsets, ntaps, cout, cin, w_main, w_aux);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { set_error("fold_weights launch: %s", cudaGetErrorString(e)); return 4; }
   count_launch();
   return 0;
 }
 
-int halo_build(const cfr_conv_desc& s, const float* inA, const float* inB, const void* w_aux, HaloOp* op) {
+// ---------------------------------------------------------------------------------------------------------
+// composite blur o up-conv: exact-value correction for hi-res column 0 (side 0) and 2W-1 (side 1).
+//   corr[n][side][Y][co] = sum_{dy,ci} D[side][a][rc][dy][co][ci] * x(i+dy, col),  Y = 2i+a, col = 0 / W-1,
+//   x = A[n][ci]*y + B[n][ci] inside the image, 0 outside; rc = first / last hi-res row variant.
+// One thread per (Y, co); a few MFLOP per image.
+// ---------------------------------------------------------------------------------------------------------
+__global__ void k_upblur_corr(const __half* __restrict__ y, const float* __restrict__ inA, const float* __restrict__ inB,
+                              const float* __restrict__ corr_d, int h, int w, int cin, int cout,
+                              float* __restrict__ corr) {
+  const int n = blockIdx.z, side = blockIdx.y;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= 2 * h * cout) return;
+  const int co = idx % cout, Y = idx / cout;
+  const int i = Y >> 1, a = Y & 1;
+  const int rc = (Y == 0) ? 1 : (Y == 2 * h - 1 ? 2 : 0);
+  const int col = side == 0 ? 0 : w - 1;
+  const float* d = corr_d + ((((static_cast<size_t>(side) * 2 + a) * 3 + rc) * 3) * cout + co) * cin;
+  float acc = 0.f;
+  for (int dy = -1; dy <= 1; ++dy) {
+    const int r = i + dy;
+    if (r < 0 || r >= h) continue;
+    const __half* px = y + ((static_cast<size_t>(n) * h + r) * w + col) * cin;
+    const float* dd = d + static_cast<size_t>(dy + 1) * cout * cin;
+    for (int ci = 0; ci < cin; ++ci) {
+      float xv = __half2float(px[ci]);
+      if (inA != nullptr) xv = __half2float(__float2half_rn(fmaf(xv, inA[n * cin + ci], inB[n * cin + ci])));
+      acc = fmaf(dd[ci], xv, acc);
+    }
+  }
+  corr[((static_cast<size_t>(n) * 2 + side) * (2 * h) + Y) * cout + co] = acc;
+}
+int launch_upblur_corr(const __half* y, const float* inA, const float* inB, const float* corr_d, int n, int h, int w,
+                       int cin, int cout, float* corr, cudaStream_t st) {
+  dim3 grid((2 * h * cout + 127) / 128, 2, n);
+  k_upblur_corr<<<grid, 128, 0, st>>>(y, inA, inB, corr_d, h, w, cin, cout, corr);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { set_error("upblur_corr launch: %s", cudaGetErrorString(e)); return 4; }
+  count_launch();
+  return 0;
+}
+
+int halo_build(const cfr_conv_desc& s, const float* inA, const float* inB, const void* w_aux, int composite,
+               const float* corr, HaloOp* op) {
   EncodeTiledFn enc = reinterpret_cast<EncodeTiledFn>(get_encode_tiled());
   if (enc == nullptr) { set_error("cuTensorMapEncodeTiled not available (no CUDA driver?)"); return 1; }
   HaloParams& p = op->p;
@@ -609,17 +702,20 @@ int halo_build(const cfr_conv_desc& s, const float* inA, const float* inB, const
     set_error("halo conv: unsupported option (stride/out grid/f32/cbias/resid/per-sample weights)");
     return 2;
   }
-  if (s.stat_sum != nullptr && s.numPhases != 1) { set_error("halo conv: stats need one phase"); return 2; }
   p.N = s.N; p.H = s.Hout; p.W = s.Wout; p.Cin = s.Cin; p.Cout = s.Cout;
   p.numPhases = s.numPhases; p.ntaps = s.ntaps;
   memcpy(p.tap_dy, s.tap_dy, sizeof(p.tap_dy));
   memcpy(p.tap_dx, s.tap_dx, sizeof(p.tap_dx));
   p.fold = w_aux != nullptr;
+  p.composite = composite;
+  p.corr = corr;
+  if (composite && (!p.fold || s.numPhases != 4 || s.ntaps != 9)) { set_error("halo conv: composite needs fold, 4 phases, 9 taps"); return 2; }
+  p.wsets = composite ? 8 : s.numPhases;
   if (const char* e = getenv("CFR_HALO_DBG")) p.dbg = atoi(e);
   if (p.fold && s.Cin > 32) { set_error("halo conv: folded variant needs Cin <= 32"); return 2; }
   p.rowBytes = s.Cin * 2;
-  p.wRows = s.numPhases * s.ntaps * s.Cout;
-  p.wAuxBytes = p.fold ? (s.numPhases * s.Cout * 32 + 1023) / 1024 * 1024 : 0;
+  p.wRows = p.wsets * s.ntaps * s.Cout;
+  p.wAuxBytes = p.fold ? (p.wsets * s.Cout * 32 + 1023) / 1024 * 1024 : 0;
   p.wBytes = (p.wRows * p.rowBytes + 1023) / 1024 * 1024;
   p.wBoxRows = p.wRows;
   while (p.wBoxRows > 256 || p.wRows % p.wBoxRows != 0) --p.wBoxRows;
@@ -671,9 +767,9 @@ int halo_build(const cfr_conv_desc& s, const float* inA, const float* inB, const
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("halo conv: encode(W) failed: %d", (int)r); return 3; }
     if (p.fold) {
-      cuuint64_t adims[2] = {16, (cuuint64_t)s.N * s.numPhases * s.Cout};
+      cuuint64_t adims[2] = {16, (cuuint64_t)s.N * p.wsets * s.Cout};
       cuuint64_t astr[1] = {32};
-      cuuint32_t abox[2] = {16, (cuuint32_t)(s.numPhases * s.Cout)};
+      cuuint32_t abox[2] = {16, (cuuint32_t)(p.wsets * s.Cout)};
       r = enc(&p.tmWa, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(w_aux), adims, astr, abox, estr,
               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);

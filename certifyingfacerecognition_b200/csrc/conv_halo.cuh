@@ -37,6 +37,9 @@ struct HaloParams {
   CUtensorMap tmW;                  // weights (Cin, [n *] phases*taps*Cout), box {Cin, wBoxRows}
   CUtensorMap tmWa;                 // FOLD: aux weight tiles (16, n*phases*taps*Cout), box {16, wBoxRows}
   int fold;                         // per-sample folded weights + aux band
+  int composite;                    // blur o up-conv: 4 phases x 9 taps, 8 weight sets (first/last-row variants), 4 noise slots
+  int wsets;                        // weight sets resident in smem (numPhases, or 8 when composite)
+  const float* corr;                // composite: border-column correction [N][2 sides][outH][Cout] fp32
   int dbg;                          // ablation bits for profiling only (env CFR_HALO_DBG): 1 skip epilogue math/store,
                                     // 2 skip band cp.async, 4 skip aux rows, 8 skip MMAs (results are then garbage)
   int auxBytes, wAuxBytes;          // aux band bytes per stage / aux weight bytes (0 unless fold)
@@ -68,11 +71,15 @@ struct HaloOp {
   double bytes;   // algorithmic HBM traffic per launch
 };
 
-int halo_build(const cfr_conv_desc& s, const float* inA, const float* inB, const void* w_aux, HaloOp* op);
+int halo_build(const cfr_conv_desc& s, const float* inA, const float* inB, const void* w_aux, int composite,
+               const float* corr, HaloOp* op);
 // per-sample weight folding for the FOLD variant (see conv_halo.cu)
 int launch_fold_weights(const float* base_w, const float* inA, const float* inB, const float* bias, const float* noise_w,
                         const int8_t* tap_dy, const int8_t* tap_dx, int n, int phases, int ntaps, int cout, int cin,
-                        __half* w_main, __half* w_aux, cudaStream_t st);
+                        int composite, __half* w_main, __half* w_aux, cudaStream_t st);
+// composite up-conv+blur: exact values for the first / last hi-res column (see engine.composite_upconv_weights)
+int launch_upblur_corr(const __half* y, const float* inA, const float* inB, const float* corr_d, int n, int h, int w,
+                       int cin, int cout, float* corr, cudaStream_t st);
 int halo_launch(const HaloOp& op, cudaStream_t stream);
 
 }  // namespace cfr

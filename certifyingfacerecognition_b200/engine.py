@@ -131,6 +131,48 @@ def pack_halo_upconv(weq: Tensor) -> Tuple[Tensor, List[List[Tuple[int, int]]]]:
     return torch.cat(mats, dim=0).contiguous(), taps
 
 
+# ---- blur o up-conv as ONE convolution on the low-res grid (StyleGAN UpConvBlock :665-676 incl. BlurLayer :463) ----
+# out(2i+a, 2j+b) = sum_{u,v} k_u k_v raw(2i+a+u, 2j+b+v) [inside], raw = conv3x3(nearest_x2(x)).  Both the up-sampling
+# and the blur are linear, so per phase (a,b) this is a 3x3 conv on x with weights  Wc = R_a (x) C_b (x) Weq,
+# R_a[dy][s] = sum_u k_u [floor((a+u+s)/2) == dy].  The blur zero-pads the *raw* image, so the first / last hi-res row
+# (column) simply drop u = -1 / u = +1 from that sum: "first"/"last" variants (exact: test_composite_upconv_blur_*).
+def _blur_phase_matrix(a: int, cls: str) -> Tensor:
+    k = torch.tensor([1.0, 2.0, 1.0], dtype=torch.float64) / 4.0
+    m = torch.zeros(3, 3, dtype=torch.float64)
+    for u in (-1, 0, 1):
+        if (cls == "first" and u == -1) or (cls == "last" and u == 1):
+            continue
+        for s_ in (-1, 0, 1):
+            m[(a + u + s_) // 2 + 1][s_ + 1] += k[u + 1]
+    return m
+
+
+# weight sets of the composite kernel: 0..3 = phases (a,b) on interior rows, 4..5 = first hi-res row (a=0, b=0/1),
+# 6..7 = last hi-res row (a=1, b=0/1); columns always use the interior form (border columns get `corr`, below)
+COMPOSITE_WSETS = [(0, 0, "int"), (0, 1, "int"), (1, 0, "int"), (1, 1, "int"),
+                   (0, 0, "first"), (0, 1, "first"), (1, 0, "last"), (1, 1, "last")]
+
+
+def composite_upconv_weights(weq: Tensor) -> Tuple[Tensor, Tensor]:
+    """weq [Cout,Cin,3,3] (fp32/64) -> (base [8*9*Cout, Cin] rows = (wset, tap=(dy,dx), cout),
+    corr_d [2 sides][2 a][3 row classes int/first/last][3 dy][Cout][Cin]).
+
+    corr: the MMA path uses interior column weights for every pixel; for hi-res column 0 (b=0, j=0) / 2W-1 (b=1, j=W-1)
+    the exact result differs by  -k_(-/+1) * sum_{dy,s} R_{a,rc}[dy][s] * Weq[s][t=+1/-1] . x(i+dy, 0 / W-1)."""
+    w = weq.double()
+    sets = []
+    for a, b, rc in COMPOSITE_WSETS:
+        wc = torch.einsum("ys,xt,oist->yxoi", _blur_phase_matrix(a, rc), _blur_phase_matrix(b, "int"), w)   # [3,3,Co,Ci]
+        sets.append(wc.reshape(9 * w.shape[0], w.shape[1]))
+    base = torch.cat(sets, dim=0)
+    corr = torch.zeros(2, 2, 3, 3, w.shape[0], w.shape[1], dtype=torch.float64)
+    for side, t in ((0, 2), (1, 0)):                     # left uses Weq[:, :, s, +1], right Weq[:, :, s, -1]
+        for a in (0, 1):
+            for rci, rc in enumerate(("int", "first", "last")):
+                corr[side, a, rci] = -0.25 * torch.einsum("ys,ois->yoi", _blur_phase_matrix(a, rc), w[:, :, :, t])
+    return base.float().contiguous(), corr.float().contiguous()
+
+
 class Program:
     """Owns a cfr_program handle plus every tensor its launches reference."""
 
@@ -170,7 +212,8 @@ class Program:
              noise: Optional[Tensor] = None, noise_w: Optional[Tensor] = None, act: int = L.ACT_NONE,
              slope: float = 0.2, alpha: Optional[Tensor] = None, resid: Optional[Tensor] = None, resid_c: int = 0,
              stat_sum: Optional[Tensor] = None, stat_sq: Optional[Tensor] = None, halo: bool = False,
-             in_affine: Optional[Tuple[Tensor, Tensor]] = None, fold_center_tap: Optional[int] = None) -> None:
+             in_affine: Optional[Tuple[Tensor, Tensor]] = None, fold_center_tap: Optional[int] = None,
+             composite_corr: Optional[Tensor] = None) -> None:
         """Record one convolution.  ``halo``: use the halo-resident kernel (Cin, Cout <= 64); ``in_affine`` (A, B):
         apply x = y*A + B on load; ``fold_center_tap`` (halo, Cin <= 32): fold A into per-sample weights and carry
         B / bias / noise on the auxiliary band -- ``w`` is then the fp32 base weight [phases*taps*Cout, Cin]."""
@@ -210,9 +253,17 @@ class Program:
                 assert w.dtype == torch.float32
                 rows = n * w.shape[0]
                 w_main = self.hold(torch.zeros(rows, cin, dtype=torch.float16, device=w.device))
-                w_aux = self.hold(torch.zeros(n * len(taps) * cout, 16, dtype=torch.float16, device=w.device))
-                L.check(self.lib.cfr_program_add_conv_halo_folded(self.handle, C.byref(d), L.ptr(w), L.ptr(a), L.ptr(b),
-                                                                  L.ptr(w_main), L.ptr(w_aux)))
+                if composite_corr is not None:          # blur o up-conv: 8 weight sets, border-column correction
+                    self.keep.append(composite_corr)
+                    w_aux = self.hold(torch.zeros(n * 8 * cout, 16, dtype=torch.float16, device=w.device))
+                    corr = self.hold(torch.zeros(n * 2 * out_hwc[0] * cout, device=w.device))
+                    L.check(self.lib.cfr_program_add_upconv_blur_folded(self.handle, C.byref(d), L.ptr(w),
+                                                                        L.ptr(composite_corr), L.ptr(a), L.ptr(b),
+                                                                        L.ptr(w_main), L.ptr(w_aux), L.ptr(corr)))
+                else:
+                    w_aux = self.hold(torch.zeros(n * len(taps) * cout, 16, dtype=torch.float16, device=w.device))
+                    L.check(self.lib.cfr_program_add_conv_halo_folded(self.handle, C.byref(d), L.ptr(w), L.ptr(a),
+                                                                      L.ptr(b), L.ptr(w_main), L.ptr(w_aux)))
             else:
                 L.check(self.lib.cfr_program_add_conv_halo(self.handle, C.byref(d), L.ptr(a), L.ptr(b)))
         else:
@@ -230,7 +281,8 @@ class Program:
 class SynthesisProgram(Program):
     def __init__(self, g_sd: Dict[str, Tensor], chunk: int, out_res: int = 112, device="cuda",
                  keep_planar: bool = False, mean: float = 0.5, std: float = 0.5, halo: bool = True,
-                 fold_small: bool = True, groups: int = 1, blur_on_tensor_cores: bool = True):
+                 fold_small: bool = True, groups: int = 1, blur_on_tensor_cores: bool = True,
+                 fused_upblur: bool = True):
         super().__init__()
         dev = torch.device(device)
         self.chunk, self.out_res = chunk, out_res
@@ -312,25 +364,34 @@ class SynthesisProgram(Program):
             else:
                 lo = res // 2
                 weq = upconv_equiv_weight(sd, l)
-                wp, taps = pack_halo_upconv(weq) if hk else pack_upconv_phases(weq)
-                wp = self.hold(_f32(wp, dev) if fold else _f16(wp, dev))
-                self.conv(inp=x, n=chunk, hin=lo, win=lo, cin=cin, w=wp, cout=cout, hout=lo, wout=lo,
-                          tile=tile_for(lo), out=raw, out_hwc=(res, res, cout), taps=taps, oscale=2,
-                          ooff=[(0, 0), (0, 1), (1, 0), (1, 1)], w_rows_per_phase=0 if hk else cout,
-                          halo=hk, in_affine=pending, fold_center_tap=-1 if fold else None)
-                if fold and cout <= 16 and blur_on_tensor_cores:
-                    # BlurLayer :463 as a depthwise conv on the tensor cores: W[tap] = k[tap] * I (1/16, 1/8, 1/4 are exact
-                    # in fp16, accumulation is fp32 => same numerics as the CUDA-core blur), + noise/bias/LeakyReLU/stats
-                    k1 = torch.tensor([1.0, 2.0, 1.0]) / 4.0
-                    wb = torch.einsum("a,b,oi->oiab", k1, k1, torch.eye(cout))
-                    self.conv(inp=raw, n=chunk, hin=res, win=res, cin=cout, w=self.hold(_f32(pack_halo_weight(wb), dev)),
-                              cout=cout, hout=res, wout=res, tile=tile_for(res), out=y, out_hwc=(res, res, cout),
-                              taps=[TAPS3], noise=noise, noise_w=noise_w, bias=bias, act=L.ACT_LRELU, slope=0.2,
-                              stat_sum=ssum, stat_sq=ssq, halo=True, fold_center_tap=4)
+                if fold and cout <= 16 and fused_upblur:
+                    # UpConvBlock incl. BlurLayer + epilogue as ONE halo conv (composite 3x3 weights per phase)
+                    base, corr_d = composite_upconv_weights(weq)
+                    self.conv(inp=x, n=chunk, hin=lo, win=lo, cin=cin, w=self.hold(_f32(base, dev)), cout=cout, hout=lo,
+                              wout=lo, tile=tile_for(lo), out=y, out_hwc=(res, res, cout), taps=[TAPS3] * 4, oscale=2,
+                              ooff=[(0, 0), (0, 1), (1, 0), (1, 1)], noise=noise, noise_w=noise_w, bias=bias,
+                              act=L.ACT_LRELU, slope=0.2, stat_sum=ssum, stat_sq=ssq, halo=True, in_affine=pending,
+                              fold_center_tap=4, composite_corr=self.hold(_f32(corr_d, dev)))
                 else:
-                    L.check(lib.cfr_program_add_blur_act_stats(h, L.ptr(raw), L.ptr(y), chunk, res, res, cout,
-                                                               L.ptr(noise), L.ptr(noise_w), L.ptr(bias), L.ptr(ssum),
-                                                               L.ptr(ssq), 0))
+                    wp, taps = pack_halo_upconv(weq) if hk else pack_upconv_phases(weq)
+                    wp = self.hold(_f32(wp, dev) if fold else _f16(wp, dev))
+                    self.conv(inp=x, n=chunk, hin=lo, win=lo, cin=cin, w=wp, cout=cout, hout=lo, wout=lo,
+                              tile=tile_for(lo), out=raw, out_hwc=(res, res, cout), taps=taps, oscale=2,
+                              ooff=[(0, 0), (0, 1), (1, 0), (1, 1)], w_rows_per_phase=0 if hk else cout,
+                              halo=hk, in_affine=pending, fold_center_tap=-1 if fold else None)
+                    if fold and cout <= 16 and blur_on_tensor_cores:
+                        # BlurLayer :463 as a depthwise conv on the tensor cores: W[tap] = k[tap] * I (1/16, 1/8, 1/4 are
+                        # exact in fp16, accumulation is fp32 => same numerics as the CUDA-core blur), + noise/bias/act/stats
+                        k1 = torch.tensor([1.0, 2.0, 1.0]) / 4.0
+                        wb = torch.einsum("a,b,oi->oiab", k1, k1, torch.eye(cout))
+                        self.conv(inp=raw, n=chunk, hin=res, win=res, cin=cout, w=self.hold(_f32(pack_halo_weight(wb), dev)),
+                                  cout=cout, hout=res, wout=res, tile=tile_for(res), out=y, out_hwc=(res, res, cout),
+                                  taps=[TAPS3], noise=noise, noise_w=noise_w, bias=bias, act=L.ACT_LRELU, slope=0.2,
+                                  stat_sum=ssum, stat_sq=ssq, halo=True, fold_center_tap=4)
+                    else:
+                        L.check(lib.cfr_program_add_blur_act_stats(h, L.ptr(raw), L.ptr(y), chunk, res, res, cout,
+                                                                   L.ptr(noise), L.ptr(noise_w), L.ptr(bias), L.ptr(ssum),
+                                                                   L.ptr(ssq), 0))
             # A/B double-buffered by layer parity: the consumer of layer l reads them while layer l+1's are written
             A, B = self.AB[l % 2]
             L.check(lib.cfr_program_add_finalize_stats(h, L.ptr(ssum), L.ptr(ssq), L.ptr(self.styles), off,

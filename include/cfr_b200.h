@@ -88,6 +88,16 @@ CFR_API int cfr_program_add_conv_halo(cfr_program* p, const cfr_conv_desc* d, co
  * d->bias / d->noise / d->noise_w are consumed by the fold; d->w is ignored. */
 CFR_API int cfr_program_add_conv_halo_folded(cfr_program* p, const cfr_conv_desc* d, const float* base_w, const float* inA,
                                      const float* inB, void* w_main_f16, void* w_aux_f16);
+/* UpConvBlock INCLUDING its BlurLayer and epilogue (stylegan_generator_model.py:665-678, :463, :559-562) as ONE
+ * halo conv: nearest-x2, 3x3 conv and the [1,2,1]^2 blur are linear, so each sub-pixel phase is a 3x3 conv on the
+ * low-res grid with composite weights (engine.composite_upconv_weights); the blur's zero padding of the raw image is
+ * reproduced exactly by separate weight sets for the first / last hi-res row and a small per-column correction.
+ * d: 4 phases x 9 taps (3x3), noise/bias/act/stats as for add_conv.  base_w: fp32 [8 sets * 9 taps * Cout][Cin];
+ * corr_d: fp32 [2][2][3][3][Cout][Cin]; w_main_f16 [N][8*9*Cout][Cin]; w_aux_f16 [N][8*Cout][16]; corr_buf
+ * fp32 [N][2][outH][Cout]. */
+CFR_API int cfr_program_add_upconv_blur_folded(cfr_program* p, const cfr_conv_desc* d, const float* base_w,
+                                       const float* corr_d, const float* inA, const float* inB, void* w_main_f16,
+                                       void* w_aux_f16, float* corr_buf);
 CFR_API int cfr_program_add_memset(cfr_program* p, void* ptr, int value, size_t bytes);
 /* StyleModulationLayer dense, stylegan_generator_model.py:503 (all 18 layers): styles[b][rows] */
 CFR_API int cfr_program_add_styles(cfr_program* p, const float* wp2, const float* w_style, const float* b_style,

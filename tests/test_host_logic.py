@@ -159,3 +159,36 @@ def test_cli_surface_matches_reference():
         p.parse_args(["--face-recog-model", "vgg", "--outfile", "o", "--sigma", "1"])
     row = "{}\t{}\t{}\t{}\t{:.3}\t{:.3}\t{}".format(3, 3, 3, 1, 1.9780096, 0.19780096, "0:00:01.5")
     assert row == "3\t3\t3\t1\t1.98\t0.198\t0:00:01.5"
+
+
+def test_composite_upconv_blur_weights_are_exact():
+    """blur o nearest-x2 o conv3x3 as per-phase 3x3 convs on the low-res grid with first/last-row weight sets and the
+    border-column correction == the reference op order (UpConvBlock :665-676), borders included."""
+    g = torch.Generator().manual_seed(3)
+    H, W, ci, co = 5, 6, 4, 3
+    x = torch.randn(2, ci, H, W, generator=g).double()
+    weq = torch.randn(co, ci, 3, 3, generator=g).double()
+    ref = M._blur(F.conv2d(F.interpolate(x, scale_factor=2, mode="nearest"), weq, padding=1))
+    base, corr = E.composite_upconv_weights(weq)
+    base = base.double().reshape(8, 9, co, ci)
+    corr = corr.double()
+    xp = F.pad(x, (1, 1, 1, 1))
+    out = torch.zeros_like(ref)
+    for a in (0, 1):
+        for b in (0, 1):
+            for i in range(H):
+                ws = a * 2 + b
+                rci = 0
+                if i == 0 and a == 0:
+                    ws, rci = 4 + b, 1
+                if i == H - 1 and a == 1:
+                    ws, rci = 6 + b, 2
+                wc = base[ws].reshape(3, 3, co, ci)
+                for j in range(W):
+                    v = torch.einsum("yxoi,niyx->no", wc, xp[:, :, i:i + 3, j:j + 3])
+                    if j == 0 and b == 0:
+                        v = v + torch.einsum("yoi,niy->no", corr[0, a, rci], xp[:, :, i:i + 3, 1])
+                    if j == W - 1 and b == 1:
+                        v = v + torch.einsum("yoi,niy->no", corr[1, a, rci], xp[:, :, i:i + 3, W])
+                    out[:, :, 2 * i + a, 2 * j + b] = v
+    assert (out - ref).abs().max().item() < 1e-5

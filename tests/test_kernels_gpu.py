@@ -413,3 +413,44 @@ def test_tc_matcher_equals_exact_match(E, n_gallery, b):
     assert pred[0].item() == 123
     assert torch.equal(pred.long(), ref)
     assert torch.equal(counts, torch.bincount(ref, minlength=n_gallery) * 2)
+
+
+@pytest.mark.parametrize("n,cin,cout,lo_h,lo_w", [(2, 32, 16, 12, 128), (3, 32, 16, 9, 200), (1, 16, 16, 4, 64)])
+def test_halo_upconv_blur_composite_matches_torch(E, n, cin, cout, lo_h, lo_w):
+    """UpConvBlock incl. BlurLayer and epilogue (up x2 -> conv3x3 -> blur -> +noise*w +bias -> LeakyReLU) as ONE kernel,
+    with the previous layer's IN/AdaIN folded in; borders must be exact."""
+    g = torch.Generator().manual_seed(cin + lo_h)
+    yprev = torch.randn(n, cin, lo_h, lo_w, generator=g).cuda().half().float()
+    weq = torch.randn(cout, cin, 3, 3, generator=g) / math.sqrt(cin * 9)
+    A = (torch.rand(n, cin, generator=g) + 0.5).cuda()
+    B = torch.randn(n, cin, generator=g).cuda()
+    H, W = 2 * lo_h, 2 * lo_w
+    bias, nw = torch.randn(cout, generator=g).cuda(), torch.randn(cout, generator=g).cuda()
+    noise = torch.randn(H, W, generator=g).cuda()
+    xin = yprev * A.view(n, cin, 1, 1) + B.view(n, cin, 1, 1)
+    raw = F.conv2d(F.interpolate(xin, scale_factor=2, mode="nearest"), weq.cuda(), padding=1)
+    k = torch.tensor([1.0, 2.0, 1.0])
+    kk = ((k[:, None] * k[None, :]) / 16).view(1, 1, 3, 3).repeat(cout, 1, 1, 1).cuda()
+    ref = F.leaky_relu(F.conv2d(raw, kk, padding=1, groups=cout) + noise.view(1, 1, H, W) * nw.view(1, -1, 1, 1)
+                       + bias.view(1, -1, 1, 1), 0.2)
+    base, corr_d = E.composite_upconv_weights(weq)
+    out = torch.full((n * H * W * cout,), float("nan"), dtype=torch.float16, device="cuda")
+    ssum, ssq = _stats(n, cout)
+    prog = E.Program()
+    prog.conv(inp=_nhwc16(yprev), n=n, hin=lo_h, win=lo_w, cin=cin, w=base.cuda(), cout=cout, hout=lo_h, wout=lo_w,
+              tile=(16, 8, 1), out=out, out_hwc=(H, W, cout), taps=[E.TAPS3] * 4, oscale=2,
+              ooff=[(0, 0), (0, 1), (1, 0), (1, 1)], noise=noise.reshape(-1).contiguous(), noise_w=nw, bias=bias,
+              act=E.L.ACT_LRELU, slope=0.2, stat_sum=ssum, stat_sq=ssq, halo=True,
+              in_affine=(A.contiguous(), B.contiguous()), fold_center_tap=4, composite_corr=corr_d.cuda())
+    prog.run()
+    _sync()
+    got = _from_nhwc(out, n, H, W, cout)
+    assert torch.isfinite(got).all()
+    err = (got - ref).abs()
+    scale = max(1.0, ref.abs().max().item())
+    assert err.max().item() < 4e-2 * scale
+    # borders are as accurate as the interior
+    border = torch.cat([err[:, :, 0].flatten(), err[:, :, -1].flatten(), err[:, :, :, 0].flatten(), err[:, :, :, -1].flatten()])
+    assert border.max().item() < 4e-2 * scale and border.mean().item() < 3e-3 * scale
+    assert err.mean().item() < 2e-3 * scale
+    assert torch.allclose(_fx(ssum), ref.double().sum(dim=[2, 3]), rtol=2e-3, atol=1e-4 * H * W)
