@@ -49,7 +49,9 @@ __device__ __forceinline__ Band decode_band(const HaloParams& p, int b) {
 // noise ride on an auxiliary 16-channel row per OUTPUT pixel {noise, inside-image indicators of its 3x3 input
 // neighbourhood, 0..} consumed by ONE extra MMA per tile,
 // so neither the loaders nor the epilogue touch them.
-template <int COUT, bool FOLD>
+// COMP: composite blur o up-conv (4 phases x 9 taps, first/last-row weight sets, border-column correction); a separate
+// instantiation so that the plain conv paths keep their register allocation / schedule.
+template <int COUT, bool FOLD, bool COMP = false>
 __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid_constant__ HaloParams p) {
   constexpr int NCH = COUT / 16;                 // 16-column epilogue chunks
   constexpr bool REG_STATS = COUT <= 32;         // keep per-thread channel sums in registers across a band
@@ -217,7 +219,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
           const uint32_t a_row = a_band + j * row_step, x_row = x_band + j * aux_row_step;
           const int gy = bd.y0 + j;
           // composite blur o up-conv: the first / last hi-res row use their own weight sets (4 + phase)
-          const bool top = p.composite && gy == 0, bot = p.composite && gy == p.H - 1;
+          const bool top = COMP && gy == 0, bot = COMP && gy == p.H - 1;
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             const int ws = ((top && k < 2) || (bot && k >= 2)) ? 4 + k : k;
@@ -282,7 +284,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
         const float cl = gx > 0 ? 1.f : 0.f, cr = gx < p.W - 1 ? 1.f : 0.f;
         const bool colin = gx < p.W;
         const bool has_nz = p.noise != nullptr;
-        if (p.composite) {
+        if constexpr (COMP) {
           // aux row of a low-res pixel: k0..k3 = noise at its 4 hi-res phases, k4..k12 = inside-image indicators
           for (int r = tt >> 7; r < p.TH; r += LT >> 7) {
             const int gy = bd.y0 + r;
@@ -487,7 +489,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
                 }
               }
             }
-            if (p.corr != nullptr) {          // composite: exact first / last hi-res column
+            if constexpr (COMP) {             // composite: exact first / last hi-res column
               const bool left = gx == 0 && (ph & 1) == 0, right = gx == p.W - 1 && (ph & 1) == 1;
               if (left || right) {
                 const int oy = (bd.y0 + r) * p.oscale + p.ooff_y[ph];
@@ -653,35 +655,57 @@ int launch_fold_weights(const float* base_w, const float* inA, const float* inB,
 //   x = A[n][ci]*y + B[n][ci] inside the image, 0 outside; rc = first / last hi-res row variant.
 // One thread per (Y, co); a few MFLOP per image.
 // ---------------------------------------------------------------------------------------------------------
-__global__ void k_upblur_corr(const __half* __restrict__ y, const float* __restrict__ inA, const float* __restrict__ inB,
-                              const float* __restrict__ corr_d, int h, int w, int cin, int cout,
-                              float* __restrict__ corr) {
-  const int n = blockIdx.z, side = blockIdx.y;
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= 2 * h * cout) return;
-  const int co = idx % cout, Y = idx / cout;
-  const int i = Y >> 1, a = Y & 1;
-  const int rc = (Y == 0) ? 1 : (Y == 2 * h - 1 ? 2 : 0);
+constexpr int kCorrRows = 64;       // low-res rows per block
+__global__ void __launch_bounds__(256) k_upblur_corr(const __half* __restrict__ y, const float* __restrict__ inA,
+                                                     const float* __restrict__ inB, const float* __restrict__ corr_d,
+                                                     int h, int w, int cin, int cout, float* __restrict__ corr) {
+  extern __shared__ float csm[];
+  float* xcol = csm;                                   // [kCorrRows + 2][cin] transformed border column (0 outside)
+  float* dsm = csm + (kCorrRows + 2) * cin;            // [a][dy][ci][co] interior-row coefficients (co fastest)
+  const int n = blockIdx.z, side = blockIdx.y, i0 = blockIdx.x * kCorrRows;
   const int col = side == 0 ? 0 : w - 1;
-  const float* d = corr_d + ((((static_cast<size_t>(side) * 2 + a) * 3 + rc) * 3) * cout + co) * cin;
-  float acc = 0.f;
-  for (int dy = -1; dy <= 1; ++dy) {
-    const int r = i + dy;
-    if (r < 0 || r >= h) continue;
-    const __half* px = y + ((static_cast<size_t>(n) * h + r) * w + col) * cin;
-    const float* dd = d + static_cast<size_t>(dy + 1) * cout * cin;
-    for (int ci = 0; ci < cin; ++ci) {
-      float xv = __half2float(px[ci]);
+  for (int t = threadIdx.x; t < (kCorrRows + 2) * cin; t += blockDim.x) {
+    const int r = i0 - 1 + t / cin, ci = t % cin;
+    float xv = 0.f;
+    if (r >= 0 && r < h) {
+      xv = __half2float(y[((static_cast<size_t>(n) * h + r) * w + col) * cin + ci]);
       if (inA != nullptr) xv = __half2float(__float2half_rn(fmaf(xv, inA[n * cin + ci], inB[n * cin + ci])));
-      acc = fmaf(dd[ci], xv, acc);
     }
+    xcol[t] = xv;
   }
-  corr[((static_cast<size_t>(n) * 2 + side) * (2 * h) + Y) * cout + co] = acc;
+  for (int t = threadIdx.x; t < 2 * 3 * cin * cout; t += blockDim.x) {
+    const int co = t % cout, ci = (t / cout) % cin, dy = (t / (cout * cin)) % 3, a = t / (cout * cin * 3);
+    dsm[t] = corr_d[((((static_cast<size_t>(side) * 2 + a) * 3 + 0) * 3 + dy) * cout + co) * cin + ci];
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < 2 * kCorrRows * cout; idx += blockDim.x) {
+    const int co = idx % cout, Yl = idx / cout;
+    const int Y = 2 * i0 + Yl, il = Yl >> 1, a = Yl & 1;
+    if (Y >= 2 * h) break;
+    const int rc = (Y == 0) ? 1 : (Y == 2 * h - 1 ? 2 : 0);
+    float acc = 0.f;
+    if (rc == 0) {
+      for (int dy = 0; dy < 3; ++dy) {
+        const float* xr = xcol + (il + dy) * cin;
+        const float* dd = dsm + ((a * 3 + dy) * cin) * cout + co;
+        for (int ci = 0; ci < cin; ++ci) acc = fmaf(dd[ci * cout], xr[ci], acc);
+      }
+    } else {                                           // first / last hi-res row: two rows per image, read D directly
+      const float* d = corr_d + ((((static_cast<size_t>(side) * 2 + a) * 3 + rc) * 3) * cout + co) * cin;
+      for (int dy = 0; dy < 3; ++dy) {
+        const float* xr = xcol + (il + dy) * cin;
+        for (int ci = 0; ci < cin; ++ci) acc = fmaf(d[dy * cout * cin + ci], xr[ci], acc);
+      }
+    }
+    corr[((static_cast<size_t>(n) * 2 + side) * (2 * h) + Y) * cout + co] = acc;
+  }
 }
 int launch_upblur_corr(const __half* y, const float* inA, const float* inB, const float* corr_d, int n, int h, int w,
                        int cin, int cout, float* corr, cudaStream_t st) {
-  dim3 grid((2 * h * cout + 127) / 128, 2, n);
-  k_upblur_corr<<<grid, 128, 0, st>>>(y, inA, inB, corr_d, h, w, cin, cout, corr);
+  dim3 grid((h + kCorrRows - 1) / kCorrRows, 2, n);
+  const size_t smem = (static_cast<size_t>(kCorrRows + 2) * cin + 2 * 3 * cin * cout) * sizeof(float);
+  if (smem > 48 * 1024) { set_error("upblur_corr: Cin*Cout too large"); return 2; }
+  k_upblur_corr<<<grid, 256, smem, st>>>(y, inA, inB, corr_d, h, w, cin, cout, corr);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { set_error("upblur_corr launch: %s", cudaGetErrorString(e)); return 4; }
   count_launch();
@@ -709,7 +733,7 @@ int halo_build(const cfr_conv_desc& s, const float* inA, const float* inB, const
   p.fold = w_aux != nullptr;
   p.composite = composite;
   p.corr = corr;
-  if (composite && (!p.fold || s.numPhases != 4 || s.ntaps != 9)) { set_error("halo conv: composite needs fold, 4 phases, 9 taps"); return 2; }
+  if (composite && (!p.fold || s.numPhases != 4 || s.ntaps != 9 || s.Cout != 16)) { set_error("halo conv: composite needs fold, 4 phases, 9 taps"); return 2; }
   p.wsets = composite ? 8 : s.numPhases;
   if (const char* e = getenv("CFR_HALO_DBG")) p.dbg = atoi(e);
   if (p.fold && s.Cin > 32) { set_error("halo conv: folded variant needs Cin <= 32"); return 2; }
@@ -791,7 +815,7 @@ int halo_launch(const HaloOp& op, cudaStream_t stream) {
   std::call_once(once, [] {
     const void* fns[] = {(const void*)conv_halo_kernel<16, false>, (const void*)conv_halo_kernel<32, false>,
                          (const void*)conv_halo_kernel<64, false>, (const void*)conv_halo_kernel<16, true>,
-                         (const void*)conv_halo_kernel<32, true>};
+                         (const void*)conv_halo_kernel<32, true>, (const void*)conv_halo_kernel<16, true, true>};
     for (const void* f : fns)
       if (attr_err == cudaSuccess)
         attr_err = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
@@ -804,7 +828,8 @@ int halo_launch(const HaloOp& op, cudaStream_t stream) {
   }
   switch (op.p.Cout) {
     case 16:
-      if (op.p.fold) conv_halo_kernel<16, true><<<op.grid, kHaloThreads, op.smemBytes, stream>>>(op.p);
+      if (op.p.composite) conv_halo_kernel<16, true, true><<<op.grid, kHaloThreads, op.smemBytes, stream>>>(op.p);
+      else if (op.p.fold) conv_halo_kernel<16, true><<<op.grid, kHaloThreads, op.smemBytes, stream>>>(op.p);
       else conv_halo_kernel<16, false><<<op.grid, kHaloThreads, op.smemBytes, stream>>>(op.p);
       break;
     case 32:

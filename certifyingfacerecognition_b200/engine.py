@@ -286,6 +286,9 @@ class SynthesisProgram(Program):
         super().__init__()
         dev = torch.device(device)
         self.chunk, self.out_res = chunk, out_res
+        import os as _os
+        if _os.environ.get("CFR_FUSED_UPBLUR") is not None:          # A/B knob for profiling
+            fused_upblur = _os.environ["CFR_FUSED_UPBLUR"] != "0"
         sd = {k: v.detach().float().cpu() for k, v in g_sd.items()}
         lib, h = self.lib, self.handle
 
