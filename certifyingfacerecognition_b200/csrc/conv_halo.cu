@@ -75,8 +75,9 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 16);
   float* sA = reinterpret_cast<float*>(tmem_slot + 4);     // [64]
   float* sB = sA + 64;                                     // [64]
-  stat_t* s_sum = reinterpret_cast<stat_t*>(sB + 64);      // [64]
-  stat_t* s_sq = s_sum + 64;                               // [64]
+  // per-(epilogue warp, channel) float partials; each warp owns its slice (64-bit shared atomics are CAS spin loops)
+  float* s_sum = sB + 64;                                  // [kEpiWarps][COUT]
+  float* s_sq = s_sum + kEpiWarps * COUT;                  // [kEpiWarps][COUT]
 
   const int warp = threadIdx.x >> 5;
   const uint32_t lane = lane_id();
@@ -109,10 +110,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
     tmem_alloc(tmem_slot, tmemCols);
     tmem_relinquish();
   }
-  if (threadIdx.x < 64) {
-    s_sum[threadIdx.x] = 0ull;
-    s_sq[threadIdx.x] = 0ull;
-  }
+  for (int i = threadIdx.x; i < 2 * kEpiWarps * COUT; i += kHaloThreads) s_sum[i] = 0.f;
   if constexpr (FOLD) {                      // aux rows are {noise, indicator, 0 x14}: zero everything once
     const uint4 z = make_uint4(0u, 0u, 0u, 0u);
     for (int i = threadIdx.x; i < (NS * p.auxBytes) >> 4; i += kHaloThreads) reinterpret_cast<uint4*>(aux)[i] = z;
@@ -423,6 +421,18 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
         hbs[i] = has_bias ? p.bias[i] : 0.f;
       }
     }
+    auto flush_channel = [&](int img) {      // thread et < COUT: all warps' partials (fixed order) -> Q43.20 -> global
+      float a = 0.f, b = 0.f;
+#pragma unroll
+      for (int w = 0; w < kEpiWarps; ++w) {
+        a += s_sum[w * COUT + et];
+        b += s_sq[w * COUT + et];
+        s_sum[w * COUT + et] = 0.f;
+        s_sq[w * COUT + et] = 0.f;
+      }
+      atomicAdd(&p.stat_sum[img * COUT + et], stat_fx(a));
+      atomicAdd(&p.stat_sq[img * COUT + et], stat_fx(b));
+    };
     uint32_t gbase = 0;                     // accumulator-group counter at the start of the band
     int cur_n = -1;
     for (int b = band0; b < band1; ++b) {
@@ -430,10 +440,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
       if (do_stats && cur_n >= 0 && bd.n != cur_n) {
         named_bar_sync(1, kEpiWarps * 32);
         if (et < COUT) {
-          atomicAdd(&p.stat_sum[cur_n * COUT + et], s_sum[et]);
-          atomicAdd(&p.stat_sq[cur_n * COUT + et], s_sq[et]);
-          s_sum[et] = 0ull;
-          s_sq[et] = 0ull;
+          flush_channel(cur_n);
         }
         named_bar_sync(1, kEpiWarps * 32);
       }
@@ -531,8 +538,8 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
                 const float ssq = warp_reduce16h(sq, lane);
                 if ((lane & 1) == 0) {
                   const int ch = ch0 + reduce16_channel_h(lane);
-                  atomicAdd(&s_sum[ch], stat_fx(ssum));
-                  atomicAdd(&s_sq[ch], stat_fx(ssq));
+                  s_sum[warp * COUT + ch] += ssum;
+                  s_sq[warp * COUT + ch] += ssq;
                 }
               }
             }
@@ -559,8 +566,8 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
             const float ssq = warp_reduce16h(a2, lane);
             if ((lane & 1) == 0) {
               const int ch = ci * 16 + reduce16_channel_h(lane);
-              atomicAdd(&s_sum[ch], stat_fx(ssum));
-              atomicAdd(&s_sq[ch], stat_fx(ssq));
+              s_sum[warp * COUT + ch] += ssum;
+              s_sq[warp * COUT + ch] += ssq;
             }
           }
         }
@@ -569,8 +576,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
     if (do_stats && cur_n >= 0) {
       named_bar_sync(1, kEpiWarps * 32);
       if (et < COUT) {
-        atomicAdd(&p.stat_sum[cur_n * COUT + et], s_sum[et]);
-        atomicAdd(&p.stat_sq[cur_n * COUT + et], s_sq[et]);
+        flush_channel(cur_n);
       }
     }
   }
@@ -743,7 +749,7 @@ int halo_build(const cfr_conv_desc& s, const float* inA, const float* inB, const
   p.wBytes = (p.wRows * p.rowBytes + 1023) / 1024 * 1024;
   p.wBoxRows = p.wRows;
   while (p.wBoxRows > 256 || p.wRows % p.wBoxRows != 0) --p.wBoxRows;
-  const int ctrl = 8 * 44 + 16 + 2 * 64 * 4 + 2 * 64 * 8 + 64;
+  const int ctrl = 8 * 44 + 16 + 2 * 64 * 4 + 2 * kEpiWarps * s.Cout * 4 + 64;
   const int budget = 227 * 1024 - 1024 - ctrl - p.wBytes - p.wAuxBytes;
   auto aux_bytes = [&](int th) { return p.fold ? (th * 128 * 32 + 1023) / 1024 * 1024 : 0; };
   auto halo_bytes = [&](int th) { return ((th + 2) * kHaloW * p.rowBytes + 1023) / 1024 * 1024 + aux_bytes(th); };

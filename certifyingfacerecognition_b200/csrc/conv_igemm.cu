@@ -62,6 +62,19 @@ __device__ __forceinline__ int reduce16_channel(uint32_t lane) {
   return ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
 }
 
+// channel c of image img: the four epilogue warps' partial sums (fixed order) -> Q43.20 fixed point -> global accumulate
+__device__ __forceinline__ void flush_stats(const ConvParams& p, float* s_sum, float* s_sq, int img, int c) {
+  const float a = (s_sum[c] + s_sum[kStatsMaxC + c]) + (s_sum[2 * kStatsMaxC + c] + s_sum[3 * kStatsMaxC + c]);
+  const float b = (s_sq[c] + s_sq[kStatsMaxC + c]) + (s_sq[2 * kStatsMaxC + c] + s_sq[3 * kStatsMaxC + c]);
+  atomicAdd(&p.stat_sum[img * p.CoutTotal + c], stat_fx(a));
+  atomicAdd(&p.stat_sq[img * p.CoutTotal + c], stat_fx(b));
+#pragma unroll
+  for (int w = 0; w < 4; ++w) {
+    s_sum[w * kStatsMaxC + c] = 0.f;
+    s_sq[w * kStatsMaxC + c] = 0.f;
+  }
+}
+
 __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __grid_constant__ ConvParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -72,8 +85,10 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
   uint64_t* tfull_bar = empty_bar + S;
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
-  stat_t* s_sum = reinterpret_cast<stat_t*>(tmem_slot + 4);
-  stat_t* s_sq = s_sum + kStatsMaxC;
+  // per-(epilogue warp, channel) float partial sums: every warp owns its slice, so no shared-memory atomics (64-bit
+  // shared atomics compile to ATOMS.CAST.SPIN loops); the tile -> warp order is static, hence still bit-reproducible
+  float* s_sum = reinterpret_cast<float*>(tmem_slot + 4);      // [4][kStatsMaxC]
+  float* s_sq = s_sum + 4 * kStatsMaxC;                        // [4][kStatsMaxC]
 
   const int warp = threadIdx.x >> 5;
   const uint32_t lane = lane_id();
@@ -110,7 +125,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
     tmem_relinquish();
   }
   if (p.stat_sum != nullptr) {
-    for (int i = threadIdx.x; i < 2 * kStatsMaxC; i += blockDim.x) s_sum[i] = 0ull;
+    for (int i = threadIdx.x; i < 8 * kStatsMaxC; i += blockDim.x) s_sum[i] = 0.f;
   }
   tc_fence_before();
   __syncthreads();
@@ -227,10 +242,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
       if (do_stats && cur_img >= 0 && t.n0 != cur_img) {
         named_bar_sync(1, 128);
         for (int c = et; c < p.CoutTotal; c += 128) {
-          atomicAdd(&p.stat_sum[cur_img * p.CoutTotal + c], s_sum[c]);
-          atomicAdd(&p.stat_sq[cur_img * p.CoutTotal + c], s_sq[c]);
-          s_sum[c] = 0ull;
-          s_sq[c] = 0ull;
+          flush_stats(p, s_sum, s_sq, cur_img, c);
         }
         named_bar_sync(1, 128);
       }
@@ -358,8 +370,8 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
           const float ssq = warp_reduce16(sq, lane);
           if ((lane & 1) == 0) {
             const int ch = ch0 + reduce16_channel(lane);
-            atomicAdd(&s_sum[ch], stat_fx(ssum));
-            atomicAdd(&s_sq[ch], stat_fx(ssq));
+            s_sum[q * kStatsMaxC + ch] += ssum;
+            s_sq[q * kStatsMaxC + ch] += ssq;
           }
         }
       }
@@ -372,8 +384,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
     if (do_stats && cur_img >= 0) {
       named_bar_sync(1, 128);
       for (int c = et; c < p.CoutTotal; c += 128) {
-        atomicAdd(&p.stat_sum[cur_img * p.CoutTotal + c], s_sum[c]);
-        atomicAdd(&p.stat_sq[cur_img * p.CoutTotal + c], s_sq[c]);
+        flush_stats(p, s_sum, s_sq, cur_img, c);
       }
     }
   }
@@ -477,7 +488,7 @@ int conv_build(const ConvSpec& s, ConvOp* op) {
   p.numNTiles = s.Cout / bn;
   p.CoutTotal = s.Cout;
   p.stageBytes = kBM * 128 + bn * 128;
-  const int ctrlBytes = 8 * (2 * 8 + 4) + 16 + 2 * kStatsMaxC * 8;
+  const int ctrlBytes = 8 * (2 * 8 + 4) + 16 + 8 * kStatsMaxC * 4;
   const int budget = 227 * 1024 - 1024 - ctrlBytes;
   p.numStages = budget / p.stageBytes;
   if (p.numStages > 8) p.numStages = 8;

@@ -4,6 +4,7 @@
 #include "ptx.cuh"
 
 #include <cstdio>
+#include <cstdlib>
 
 namespace cfr {
 void set_error(const char* fmt, ...);
@@ -179,23 +180,56 @@ __device__ __forceinline__ void store8(__half* p, const float (&f)[8]) {
   *reinterpret_cast<uint4*>(p) = o;
 }
 
+// Block-level reduction of per-thread channel sums for the InstanceNorm statistics.  256 threads; thread t owns the
+// 8 channels starting at (t % c8) * 8.  Warp shuffles, then one float slot per (warp-slice, channel) in `part`
+// ([2][2048] floats), then a fixed-order sum -> Q43.20 -> one global 64-bit RED per channel: deterministic, and no
+// 64-bit shared-memory atomics (those compile to ATOMS.CAST.SPIN loops; 64 contending threads made them the
+// dominant cost of the blur pass).  Must be called by all 256 threads; `part` must not be in use.
+__device__ __forceinline__ void block_flush_stats(float (&acc)[8], float (&acc2)[8], int c, int n,
+                                                  stat_t* __restrict__ gsum, stat_t* __restrict__ gsq, float* part) {
+  const int c8 = c >> 3;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int off = 16; off >= c8; off >>= 1) {             // lanes with equal lane % c8 own the same channels
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], off);
+      acc2[i] += __shfl_xor_sync(0xffffffffu, acc2[i], off);
+    }
+  }
+  const int wpc = c8 > 32 ? c8 >> 5 : 1;                 // warps that together cover one channel set
+  const int slices = 8 / wpc, slice = warp / wpc;
+  const int ch = (threadIdx.x % c8) * 8;
+  if (c8 >= 32 || lane < c8) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      part[slice * c + ch + i] = acc[i];
+      part[2048 + slice * c + ch + i] = acc2[i];
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < c; i += 256) {
+    float a = 0.f, b = 0.f;
+    for (int sl = 0; sl < slices; ++sl) {
+      a += part[sl * c + i];
+      b += part[2048 + sl * c + i];
+    }
+    atomicAdd(&gsum[n * c + i], stat_fx(a));
+    atomicAdd(&gsq[n * c + i], stat_fx(b));
+  }
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(256) k_blur_act_stats(const __half* __restrict__ raw, __half* __restrict__ y, int h,
                                                         int w, int c, const float* __restrict__ noise,
                                                         const float* __restrict__ noise_w,
                                                         const float* __restrict__ bias, stat_t* __restrict__ gsum,
                                                         stat_t* __restrict__ gsq) {
-  __shared__ stat_t s_sum[512], s_sq[512];
+  __shared__ float s_part[2 * 2048];
   const int n = blockIdx.y;
   const int c8 = c >> 3;
   const int ppb = 256 / c8;                 // pixels per block step (c8 <= 64)
   const int cg = threadIdx.x % c8, pl = threadIdx.x / c8;
   const int ch = cg * 8;
-  for (int i = threadIdx.x; i < c; i += 256) {
-    s_sum[i] = 0ull;
-    s_sq[i] = 0ull;
-  }
-  __syncthreads();
   float nw[8], bs[8], acc[8], acc2[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
@@ -244,17 +278,8 @@ __global__ void __launch_bounds__(256) k_blur_act_stats(const __half* __restrict
         acc2[i] += v[i] * v[i];
       }
     }
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      atomicAdd(&s_sum[ch + i], stat_fx(acc[i]));
-      atomicAdd(&s_sq[ch + i], stat_fx(acc2[i]));
-    }
   }
-  __syncthreads();
-  for (int i = threadIdx.x; i < c; i += 256) {
-    atomicAdd(&gsum[n * c + i], s_sum[i]);
-    atomicAdd(&gsq[n * c + i], s_sq[i]);
-  }
+  block_flush_stats(acc, acc2, c, n, gsum, gsq, s_part);
 }
 // Separable [1,2,1]/4 x [1,2,1]/4 blur with a 3-row sliding window in registers: every thread owns 8 channels of one
 // pixel column and walks down a band of kBlurRows rows, so each raw element is loaded ~3x from L1 and ~1x from
@@ -292,7 +317,7 @@ __global__ void __launch_bounds__(256, 3) k_blur_rows(const __half* __restrict__
                                                       int c, const float* __restrict__ noise,
                                                       const float* __restrict__ noise_w, const float* __restrict__ bias,
                                                       stat_t* __restrict__ gsum, stat_t* __restrict__ gsq) {
-  __shared__ stat_t s_sum[512], s_sq[512];
+  __shared__ float s_part[2 * 2048];
   const int n = blockIdx.z;
   const int c8 = c >> 3;
   const int ppb = 256 / c8;
@@ -300,19 +325,18 @@ __global__ void __launch_bounds__(256, 3) k_blur_rows(const __half* __restrict__
   const int ch = cg * 8;
   const int px = blockIdx.x * ppb + pl;
   const int y0 = blockIdx.y * kBlurRows;
-  for (int i = threadIdx.x; i < c; i += 256) {
-    s_sum[i] = 0ull;
-    s_sq[i] = 0ull;
+  float acc[8], acc2[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    acc[i] = 0.f;
+    acc2[i] = 0.f;
   }
-  __syncthreads();
   if (px < w) {
-    float nw[8], bs[8], acc[8], acc2[8];
+    float nw[8], bs[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       nw[i] = noise_w[ch + i];
       bs[i] = bias[ch + i];
-      acc[i] = 0.f;
-      acc2[i] = 0.f;
     }
     const __half* img = raw + static_cast<size_t>(n) * h * w * c;
     const size_t rstride = static_cast<size_t>(w) * c;
@@ -345,28 +369,121 @@ __global__ void __launch_bounds__(256, 3) k_blur_rows(const __half* __restrict__
       }
       store8(y + ((static_cast<size_t>(n) * h + yy) * w + px) * c + ch, v);
     }
+  }
+  block_flush_stats(acc, acc2, c, n, gsum, gsq, s_part);
+}
+
+// cp.async-pipelined variant of k_blur_rows: the loads of the next kBlurStages-1 rows of a block's strip are in flight
+// as 16-byte LDGSTS into a shared-memory ring (zero-filled outside the image == the blur's zero padding), so the bytes
+// in flight per SM no longer depend on how many registers a thread can devote to prefetching, and every raw element
+// is fetched from L2/HBM once instead of three times.  The noise row rides in the same ring.
+constexpr int kBlurStages = 6;
+__global__ void __launch_bounds__(256, 3) k_blur_pipe(const __half* __restrict__ raw, __half* __restrict__ y, int h, int w,
+                                                      int c, const float* __restrict__ noise,
+                                                      const float* __restrict__ noise_w, const float* __restrict__ bias,
+                                                      stat_t* __restrict__ gsum, stat_t* __restrict__ gsq) {
+  extern __shared__ uint4 ring[];                       // [stage][(ppb + 2) * c8] uint4, then [stage][ppb] noise floats
+  const int n = blockIdx.z;
+  const int c8 = c >> 3;
+  const int ppb = 256 / c8;
+  const int cg = threadIdx.x % c8, pl = threadIdx.x / c8;
+  const int ch = cg * 8;
+  const int px0 = blockIdx.x * ppb, px = px0 + pl;
+  const int y0 = blockIdx.y * kBlurRows, y1 = min(h, y0 + kBlurRows);
+  const int stage_u4 = (ppb + 2) * c8;
+  float* nring = reinterpret_cast<float*>(ring + kBlurStages * stage_u4);
+  const __half* img = raw + static_cast<size_t>(n) * h * w * c;
+  const size_t rstride = static_cast<size_t>(w) * c;
+  // halo pixels (left of the first / right of the last pixel of the block) are fetched by the first 2*c8 threads
+  const bool is_halo = threadIdx.x < 2 * c8;
+  const int hside = threadIdx.x / c8;                   // 0 left, 1 right (only meaningful if is_halo)
+  const int hpx = hside == 0 ? px0 - 1 : px0 + ppb;
+  const int hslot = hside == 0 ? 0 : ppb + 1;
+  auto issue = [&](int r, int st) {                     // raw row r (and the noise of output row r - 1) -> stage st
+    if (r <= y1) {
+      const bool rok = r >= 0 && r < h;
+      const bool ok = rok && px < w;
+      const __half* src = ok ? img + r * rstride + static_cast<size_t>(px) * c + ch : img;
+      cp_async16(smem_u32(ring + st * stage_u4 + (pl + 1) * c8 + cg), src, ok ? 16u : 0u);
+      if (is_halo) {
+        const bool hok = rok && hpx >= 0 && hpx < w;
+        const __half* hs = hok ? img + r * rstride + static_cast<size_t>(hpx) * c + (threadIdx.x % c8) * 8 : img;
+        cp_async16(smem_u32(ring + st * stage_u4 + hslot * c8 + (threadIdx.x % c8)), hs, hok ? 16u : 0u);
+      }
+      if (cg == 0 && px < w && r - 1 >= y0) {
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(nring + st * ppb + pl)),
+                     "l"(noise + static_cast<size_t>(r - 1) * w + px) : "memory");
+      }
+    }
+    cp_async_commit();
+  };
+#pragma unroll
+  for (int i = 0; i < kBlurStages - 1; ++i) issue(y0 - 1 + i, i);
+  float nw[8], bs[8], acc[8], acc2[8], hp[8], hc[8], hn[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    nw[i] = noise_w[ch + i];
+    bs[i] = bias[ch + i];
+    acc[i] = 0.f;
+    acc2[i] = 0.f;
+    hp[i] = 0.f;
+    hc[i] = 0.f;
+  }
+  const int rows = y1 - y0 + 2;
+  int st = 0, st_fill = kBlurStages - 1;
+  for (int k = 0; k < rows; ++k) {
+    cp_async_wait<kBlurStages - 2>();
+    __syncthreads();
+    issue(y0 - 1 + k + kBlurStages - 1, st_fill);
+    Raw3 t;
+    const uint4* rp = ring + st * stage_u4 + pl * c8 + cg;
+    t.l = rp[0];
+    t.c = rp[c8];
+    t.r = rp[2 * c8];
+    hblur8(t, hn);
+    if (k >= 2 && px < w) {
+      const int yy = y0 + k - 2;
+      const float nzc = nring[st * ppb + pl];
+      float v[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float u = 0.25f * (hp[i] + hn[i]) + 0.5f * hc[i];
+        u = fmaf(nzc, nw[i], u) + bs[i];
+        u = fmaxf(u, 0.2f * u);
+        v[i] = u;
+        acc[i] += u;
+        acc2[i] = fmaf(u, u, acc2[i]);
+      }
+      store8(y + ((static_cast<size_t>(n) * h + yy) * w + px) * c + ch, v);
+    }
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      atomicAdd(&s_sum[ch + i], stat_fx(acc[i]));
-      atomicAdd(&s_sq[ch + i], stat_fx(acc2[i]));
+      hp[i] = hc[i];
+      hc[i] = hn[i];
     }
+    st = st + 1 == kBlurStages ? 0 : st + 1;
+    st_fill = st_fill + 1 == kBlurStages ? 0 : st_fill + 1;
   }
-  __syncthreads();
-  for (int i = threadIdx.x; i < c; i += 256) {
-    atomicAdd(&gsum[n * c + i], s_sum[i]);
-    atomicAdd(&gsq[n * c + i], s_sq[i]);
-  }
+  cp_async_wait<0>();
+  __syncthreads();                                       // the ring is dead: reuse it for the block reduction
+  block_flush_stats(acc, acc2, c, n, gsum, gsq, reinterpret_cast<float*>(ring));
 }
 
 int launch_blur_act_stats(const __half* raw, __half* y, int n, int h, int w, int c, const float* noise,
                           const float* noise_w, const float* bias, void* sum_v, void* sq_v, int mode, cudaStream_t st) {
   stat_t* sum = static_cast<stat_t*>(sum_v);
   stat_t* sq = static_cast<stat_t*>(sq_v);
-  if (c % 8 != 0 || c > 512) { set_error("blur_act_stats: C=%d unsupported", c); return 2; }
+  if (c < 8 || c > 512 || (c & (c - 1)) != 0) { set_error("blur_act_stats: C=%d unsupported (power of two in 8..512)", c); return 2; }
   const int ppb = 256 / (c / 8);
   if (mode == 0) {
     dim3 grid((w + ppb - 1) / ppb, (h + kBlurRows - 1) / kBlurRows, n);
-    k_blur_rows<<<grid, 256, 0, st>>>(raw, y, h, w, c, noise, noise_w, bias, sum, sq);
+    static const bool legacy = getenv("CFR_BLUR_LEGACY") != nullptr;      // A/B knob for profiling
+    if (legacy || c > 256) {             // c8 > 32 would need > 2*c8 halo threads per 256; those layers are tiny anyway
+      k_blur_rows<<<grid, 256, 0, st>>>(raw, y, h, w, c, noise, noise_w, bias, sum, sq);
+    } else {
+      const size_t smem = static_cast<size_t>(kBlurStages) * ((ppb + 2) * (c / 8) * 16 + ppb * 4);
+      k_blur_pipe<<<grid, 256, smem, st>>>(raw, y, h, w, c, noise, noise_w, bias, sum, sq);
+    }
     CFR_LAUNCH_CHECK("blur_rows");
     return 0;
   }

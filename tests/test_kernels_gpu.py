@@ -180,10 +180,12 @@ def test_fc_as_conv(E):
     assert (out - ref).abs().max().item() < 2e-3
 
 
-def test_blur_act_stats(E):
+@pytest.mark.parametrize("n,c,res", [(2, 32, 64), (1, 64, 128), (2, 128, 40), (1, 256, 16), (1, 512, 8), (1, 32, 256)])
+def test_blur_act_stats(E, n, c, res):
+    """BlurLayer + noise/bias/LeakyReLU + IN sums; C <= 256 takes the cp.async ring kernel (strips of 32 rows, so
+    res = 40 / 128 / 256 cross strip boundaries), C = 512 the register sliding-window kernel."""
     L = E.L
     lib = L.load()
-    n, c, res = 2, 32, 64
     g = torch.Generator().manual_seed(11)
     raw = torch.randn(n, c, res, res, generator=g).cuda().half().float()
     noise = torch.randn(res * res, generator=g).cuda()
