@@ -4,6 +4,7 @@
 #include "ptx.cuh"
 
 #include <cstdio>
+#include <type_traits>
 #include <cstdlib>
 
 namespace cfr {
@@ -374,11 +375,44 @@ __global__ void __launch_bounds__(256, 3) k_blur_rows(const __half* __restrict__
 }
 
 // cp.async-pipelined variant of k_blur_rows: the loads of the next kBlurStages-1 rows of a block's strip are in flight
-// as 16-byte LDGSTS into a shared-memory ring (zero-filled outside the image == the blur's zero padding), so the bytes
-// in flight per SM no longer depend on how many registers a thread can devote to prefetching, and every raw element
-// is fetched from L2/HBM once instead of three times.  The noise row rides in the same ring.
+// as 16-byte LDGSTS into a shared-memory ring (zero-filled outside the image == the blur's zero padding), so every
+// raw element is fetched from L2/HBM once.  The noise row rides in the same ring.  ncu (profiles/ncu_r01_notes.md)
+// showed the first version issue-bound (IPC 3.1, 274 SASS instructions per row of which ~140 were address
+// arithmetic and register moves), hence: running pointers, the ring/role rotation unrolled 6x so stage offsets and
+// the three-row window are compile-time, and packed fp32x2 arithmetic (sm_100 FADD2/FFMA2/FMUL2).
 constexpr int kBlurStages = 6;
-__global__ void __launch_bounds__(256, 3) k_blur_pipe(const __half* __restrict__ raw, __half* __restrict__ y, int h, int w,
+typedef unsigned long long f2_t;                          // two packed fp32 (the .f32x2 PTX operand type)
+__device__ __forceinline__ f2_t f2_pack(float lo, float hi) {
+  f2_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ float2 f2_unpack(f2_t v) {
+  float2 r;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v));
+  return r;
+}
+__device__ __forceinline__ f2_t f2_add(f2_t a, f2_t b) {
+  f2_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ f2_t f2_mul(f2_t a, f2_t b) {
+  f2_t d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ f2_t f2_fma(f2_t a, f2_t b, f2_t c) {
+  f2_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ f2_t f2_from_half2(uint32_t h2) {
+  const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&h2));
+  return f2_pack(f.x, f.y);
+}
+
+__global__ void __launch_bounds__(256, 2) k_blur_pipe(const __half* __restrict__ raw, __half* __restrict__ y, int h, int w,
                                                       int c, const float* __restrict__ noise,
                                                       const float* __restrict__ noise_w, const float* __restrict__ bias,
                                                       stat_t* __restrict__ gsum, stat_t* __restrict__ gsq) {
@@ -390,83 +424,123 @@ __global__ void __launch_bounds__(256, 3) k_blur_pipe(const __half* __restrict__
   const int ch = cg * 8;
   const int px0 = blockIdx.x * ppb, px = px0 + pl;
   const int y0 = blockIdx.y * kBlurRows, y1 = min(h, y0 + kBlurRows);
-  const int stage_u4 = (ppb + 2) * c8;
-  float* nring = reinterpret_cast<float*>(ring + kBlurStages * stage_u4);
+  const uint32_t stage_bytes = static_cast<uint32_t>((ppb + 2) * c8) * 16u;
+  const uint32_t ring_base = smem_u32(ring);
+  const uint32_t nring_base = ring_base + kBlurStages * stage_bytes;
   const __half* img = raw + static_cast<size_t>(n) * h * w * c;
-  const size_t rstride = static_cast<size_t>(w) * c;
+  const long long rstride_b = static_cast<long long>(w) * c * 2;          // bytes per image row
+  const bool colok = px < w;
   // halo pixels (left of the first / right of the last pixel of the block) are fetched by the first 2*c8 threads
   const bool is_halo = threadIdx.x < 2 * c8;
   const int hside = threadIdx.x / c8;                   // 0 left, 1 right (only meaningful if is_halo)
   const int hpx = hside == 0 ? px0 - 1 : px0 + ppb;
-  const int hslot = hside == 0 ? 0 : ppb + 1;
-  auto issue = [&](int r, int st) {                     // raw row r (and the noise of output row r - 1) -> stage st
-    if (r <= y1) {
-      const bool rok = r >= 0 && r < h;
-      const bool ok = rok && px < w;
-      const __half* src = ok ? img + r * rstride + static_cast<size_t>(px) * c + ch : img;
-      cp_async16(smem_u32(ring + st * stage_u4 + (pl + 1) * c8 + cg), src, ok ? 16u : 0u);
-      if (is_halo) {
-        const bool hok = rok && hpx >= 0 && hpx < w;
-        const __half* hs = hok ? img + r * rstride + static_cast<size_t>(hpx) * c + (threadIdx.x % c8) * 8 : img;
-        cp_async16(smem_u32(ring + st * stage_u4 + hslot * c8 + (threadIdx.x % c8)), hs, hok ? 16u : 0u);
-      }
-      if (cg == 0 && px < w && r - 1 >= y0) {
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(nring + st * ppb + pl)),
-                     "l"(noise + static_cast<size_t>(r - 1) * w + px) : "memory");
-      }
-    }
+  const bool hcolok = is_halo && hpx >= 0 && hpx < w;
+  // running state of the producer side: raw row r_next goes to the stage the unrolled loop names statically
+  int r_next = y0 - 1;
+  const char* src = reinterpret_cast<const char*>(img) + r_next * rstride_b + (static_cast<long long>(px) * c + ch) * 2;
+  const char* hsrc = reinterpret_cast<const char*>(img) + r_next * rstride_b +
+                     (static_cast<long long>(hpx) * c + (threadIdx.x % c8) * 8) * 2;
+  const float* nsrc = noise + static_cast<long long>(r_next - 1) * w + px;  // noise of output row r_next - 1
+  const uint32_t own_dst = ring_base + static_cast<uint32_t>((pl + 1) * c8 + cg) * 16u;
+  const uint32_t halo_dst = ring_base + static_cast<uint32_t>((hside == 0 ? 0 : ppb + 1) * c8 + (threadIdx.x % c8)) * 16u;
+  const uint32_t noise_dst = nring_base + static_cast<uint32_t>(pl) * 4u;
+  const bool noise_thr = cg == 0 && colok;
+  const int r_last = min(y1, h - 1);                    // last raw row this strip needs that lies inside the image
+  auto issue = [&](int st) {                            // raw row r_next (+ noise of output row r_next - 1) -> stage st
+    const bool rok = r_next >= 0 && r_next <= r_last;
+    cp_async16(own_dst + st * stage_bytes, (rok && colok) ? src : reinterpret_cast<const char*>(img), (rok && colok) ? 16u : 0u);
+    if (is_halo)
+      cp_async16(halo_dst + st * stage_bytes, (rok && hcolok) ? hsrc : reinterpret_cast<const char*>(img), (rok && hcolok) ? 16u : 0u);
+    if (noise_thr && r_next > y0 && r_next <= y1)
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(noise_dst + st * (ppb * 4)), "l"(nsrc) : "memory");
     cp_async_commit();
+    ++r_next;
+    src += rstride_b;
+    hsrc += rstride_b;
+    nsrc += w;
   };
 #pragma unroll
-  for (int i = 0; i < kBlurStages - 1; ++i) issue(y0 - 1 + i, i);
-  float nw[8], bs[8], acc[8], acc2[8], hp[8], hc[8], hn[8];
+  for (int i = 0; i < kBlurStages - 1; ++i) issue(i);
+
+  f2_t nw2[4], bs2[4], acc[4], acc2[4], H[3][4];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    nw[i] = noise_w[ch + i];
-    bs[i] = bias[ch + i];
-    acc[i] = 0.f;
-    acc2[i] = 0.f;
-    hp[i] = 0.f;
-    hc[i] = 0.f;
+  for (int i = 0; i < 4; ++i) {
+    // threads right of the image (colok false) compute with zero gains: their u is 0, so the sums need no masking
+    nw2[i] = colok ? f2_pack(noise_w[ch + 2 * i], noise_w[ch + 2 * i + 1]) : f2_pack(0.f, 0.f);
+    bs2[i] = colok ? f2_pack(bias[ch + 2 * i], bias[ch + 2 * i + 1]) : f2_pack(0.f, 0.f);
+    acc[i] = f2_pack(0.f, 0.f);
+    acc2[i] = acc[i];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) H[j][i] = acc[i];
   }
-  const int rows = y1 - y0 + 2;
-  int st = 0, st_fill = kBlurStages - 1;
-  for (int k = 0; k < rows; ++k) {
+  const float sx = colok ? 0.0625f : 0.f;
+  const f2_t two2 = f2_pack(2.f, 2.f), sixteenth2 = f2_pack(sx, sx), slope2 = f2_pack(0.2f, 0.2f);
+  const uint32_t rd_base = ring_base + static_cast<uint32_t>(pl * c8 + cg) * 16u;
+  const uint32_t nrd_base = nring_base + static_cast<uint32_t>(pl) * 4u;
+  __half* outp = y + ((static_cast<size_t>(n) * h + y0) * w + (colok ? px : 0)) * c + ch;   // output row y0 + (k - 2)
+  const size_t ostride = static_cast<size_t>(w) * c;
+  // one row step: wait for raw row k (stage J), refill the stage freed by the previous step, horizontal blur of row k
+  // into H[J % 3]; if OUT, emit output row k - 2 from the three-row window
+  auto step = [&](auto Jc, auto OUTc) {
+    constexpr int J = decltype(Jc)::value;
+    constexpr bool OUT = decltype(OUTc)::value;
     cp_async_wait<kBlurStages - 2>();
     __syncthreads();
-    issue(y0 - 1 + k + kBlurStages - 1, st_fill);
-    Raw3 t;
-    const uint4* rp = ring + st * stage_u4 + pl * c8 + cg;
-    t.l = rp[0];
-    t.c = rp[c8];
-    t.r = rp[2 * c8];
-    hblur8(t, hn);
-    if (k >= 2 && px < w) {
-      const int yy = y0 + k - 2;
-      const float nzc = nring[st * ppb + pl];
-      float v[8];
+    issue((J + kBlurStages - 1) % kBlurStages);
+    uint32_t lw[4], mw[4], rw[4];
+    const uint32_t a0 = rd_base + J * stage_bytes;
+    asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(lw[0]), "=r"(lw[1]), "=r"(lw[2]), "=r"(lw[3]) : "r"(a0));
+    asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(mw[0]), "=r"(mw[1]), "=r"(mw[2]), "=r"(mw[3]) : "r"(a0 + c8 * 16));
+    asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(rw[0]), "=r"(rw[1]), "=r"(rw[2]), "=r"(rw[3]) : "r"(a0 + c8 * 32));
+    f2_t(&hn)[4] = H[J % 3];
+    f2_t(&hc)[4] = H[(J + 2) % 3];
+    f2_t(&hp)[4] = H[(J + 1) % 3];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        float u = 0.25f * (hp[i] + hn[i]) + 0.5f * hc[i];
-        u = fmaf(nzc, nw[i], u) + bs[i];
-        u = fmaxf(u, 0.2f * u);
-        v[i] = u;
-        acc[i] += u;
-        acc2[i] = fmaf(u, u, acc2[i]);
+    for (int i = 0; i < 4; ++i)                         // horizontal blur x4: (l + r) + 2 m
+      hn[i] = f2_fma(two2, f2_from_half2(mw[i]), f2_add(f2_from_half2(lw[i]), f2_from_half2(rw[i])));
+    if constexpr (OUT) {
+      float nz;
+      asm volatile("ld.shared.f32 %0, [%1];" : "=f"(nz) : "r"(nrd_base + J * (ppb * 4)));
+      const f2_t nz2 = f2_pack(nz, nz);
+      uint32_t o[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const f2_t vs = f2_fma(two2, hc[i], f2_add(hp[i], hn[i]));              // 16 x blurred value
+        const f2_t t = f2_fma(vs, sixteenth2, f2_fma(nz2, nw2[i], bs2[i]));
+        const float2 tf = f2_unpack(t), sf = f2_unpack(f2_mul(t, slope2));
+        const float u0 = fmaxf(tf.x, sf.x), u1 = fmaxf(tf.y, sf.y);
+        const f2_t u = f2_pack(u0, u1);
+        acc[i] = f2_add(acc[i], u);
+        acc2[i] = f2_fma(u, u, acc2[i]);
+        const __half2 hh = __floats2half2_rn(u0, u1);
+        o[i] = *reinterpret_cast<const uint32_t*>(&hh);
       }
-      store8(y + ((static_cast<size_t>(n) * h + yy) * w + px) * c + ch, v);
+      if (colok) *reinterpret_cast<uint4*>(outp) = make_uint4(o[0], o[1], o[2], o[3]);
+      outp += ostride;
     }
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      hp[i] = hc[i];
-      hc[i] = hn[i];
-    }
-    st = st + 1 == kBlurStages ? 0 : st + 1;
-    st_fill = st_fill + 1 == kBlurStages ? 0 : st_fill + 1;
+  };
+  using std::integral_constant;
+  step(integral_constant<int, 0>{}, std::false_type{});          // raw rows y0 - 1 and y0 only fill the window
+  step(integral_constant<int, 1>{}, std::false_type{});
+  const int rows = y1 - y0 + 2;
+  for (int k0 = 2; k0 < rows; k0 += kBlurStages) {              // `k0 + j < rows` is block-uniform
+    step(integral_constant<int, 2>{}, std::true_type{});
+    if (k0 + 1 < rows) step(integral_constant<int, 3>{}, std::true_type{});
+    if (k0 + 2 < rows) step(integral_constant<int, 4>{}, std::true_type{});
+    if (k0 + 3 < rows) step(integral_constant<int, 5>{}, std::true_type{});
+    if (k0 + 4 < rows) step(integral_constant<int, 0>{}, std::true_type{});
+    if (k0 + 5 < rows) step(integral_constant<int, 1>{}, std::true_type{});
   }
   cp_async_wait<0>();
   __syncthreads();                                       // the ring is dead: reuse it for the block reduction
-  block_flush_stats(acc, acc2, c, n, gsum, gsq, reinterpret_cast<float*>(ring));
+  float facc[8], facc2[8];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 a = f2_unpack(acc[i]), b = f2_unpack(acc2[i]);
+    facc[2 * i] = a.x; facc[2 * i + 1] = a.y;
+    facc2[2 * i] = b.x; facc2[2 * i + 1] = b.y;
+  }
+  block_flush_stats(facc, facc2, c, n, gsum, gsq, reinterpret_cast<float*>(ring));
 }
 
 int launch_blur_act_stats(const __half* raw, __half* y, int n, int h, int w, int c, const float* noise,
