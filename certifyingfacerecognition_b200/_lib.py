@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libcfr_b200.so")
+LIB_PATH = os.environ.get("CFR_LIB_PATH") or os.path.join(HERE, "libcfr_b200.so")   # env: A/B builds when profiling
 
 MAX_PHASES, MAX_TAPS = 4, 9
 ACT_NONE, ACT_LRELU, ACT_PRELU = 0, 1, 2

@@ -12,6 +12,8 @@ LIB = os.path.join(HERE, "libcfr_b200.so")
 SOURCES = ["conv_igemm.cu", "conv_halo.cu", "kernels.cu", "api.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden"]
+for _d in os.environ.get("CFR_NVCC_DEFS", "").split():      # experiment knobs, e.g. CFR_NVCC_DEFS="CFR_MBAR_SLEEP_MAX=0"
+    NVCC_FLAGS.append("-D" + _d)
 if os.environ.get("CFR_HALO_EPI_GROUPS"):
     NVCC_FLAGS.append("-DCFR_HALO_EPI_GROUPS=" + os.environ["CFR_HALO_EPI_GROUPS"])
 

@@ -1,5 +1,6 @@
 // Halo-resident tcgen05 convolution kernel -- see conv_halo.cuh.
 #include "conv_halo.cuh"
+#include <type_traits>
 #include "conv_igemm.cuh"
 #include "ptx.cuh"
 
@@ -128,6 +129,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
     const uint32_t mw = warp - kHaloMmaWarp0;
     const bool leader = elect_one();
     const uint32_t idesc = make_idesc_f16(128, COUT);
+    [[maybe_unused]] const uint32_t idesc2 = make_idesc_f16(128, 2 * COUT), idesc4 = make_idesc_f16(128, 4 * COUT);
     const uint32_t dhi = smem_desc_hi(8 * p.rowBytes, p.rowBytes);
     const int kPer = p.Cin / 16;
     const uint32_t rb16 = p.rowBytes >> 4;                 // row pitch in 16-byte units
@@ -165,26 +167,36 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
     // One tfull/tempty handshake covers a GROUP of G tiles (G accumulators of COUT columns side by side in TMEM):
     // with 4 KB tiles the per-tile mbarrier round trips were ~3/4 of the kernel time (profiles/ablation_r01.log).
     // numPhases == 4: group = the 4 sub-pixel phases of one low-res row;  numPhases == 1: group = G consecutive rows.
-    auto issue_tile = [&](uint32_t d_tmem, uint32_t a_row, uint32_t x_row, uint32_t b_lo, uint32_t ba_lo,
-                          const uint32_t (&to)[9]) {
+    // One tile = ntaps x (Cin/16) MMAs (+1 aux MMA when FOLD).  The (ntaps, Cin/16) pair is dispatched ONCE per tile to
+    // a fully unrolled, branch-free sequence of predicated MMAs (only the elected lane issues): the generic loop with
+    // per-MMA run-time checks cost ~40 SASS instructions per MMA and kept the issuing warps 70 % busy (ncu, r2r).
+    const uint32_t lead = (leader && !(p.dbg & 8)) ? 1u : 0u;
+    auto issue_tile_t = [&](auto NTc, auto KPc, uint32_t d_tmem, uint32_t a_row, uint32_t x_row, uint32_t b_lo,
+                            uint32_t ba_lo, const uint32_t (&to)[9]) {
+      constexpr int NT = decltype(NTc)::value, KP = decltype(KPc)::value;
 #pragma unroll
-      for (int t = 0; t < 9; ++t) {
-        if (t < p.ntaps) {
-          const uint32_t a_lo = a_row + to[t];
-          if (leader && !(p.dbg & 8)) {
-            umma_f16_lohi(d_tmem, a_lo, dhi, b_lo, dhi, idesc, t != 0 ? 1u : 0u);
-            if (kPer > 1) umma_f16_lohi(d_tmem, a_lo + 2, dhi, b_lo + 2, dhi, idesc, 1u);
-            if (kPer > 2) {
-              umma_f16_lohi(d_tmem, a_lo + 4, dhi, b_lo + 4, dhi, idesc, 1u);
-              umma_f16_lohi(d_tmem, a_lo + 6, dhi, b_lo + 6, dhi, idesc, 1u);
-            }
-          }
-          b_lo += w_tap;
+      for (int t = 0; t < NT; ++t) {
+        const uint32_t a_lo = a_row + to[t];
+#pragma unroll
+        for (int k = 0; k < KP; ++k) {
+          if (t == 0 && k == 0) umma_f16_pred<false>(d_tmem, a_lo, dhi, b_lo, dhi, idesc, lead);
+          else umma_f16_pred<true>(d_tmem, a_lo + 2 * k, dhi, b_lo + t * w_tap + 2 * k, dhi, idesc, lead);
         }
       }
-      if constexpr (FOLD) {
-        if (leader) umma_f16_lohi(d_tmem, x_row, dhi_aux, ba_lo, dhi_aux, idesc, 1u);
-      }
+      if constexpr (FOLD) umma_f16_pred<true>(d_tmem, x_row, dhi_aux, ba_lo, dhi_aux, idesc, leader ? 1u : 0u);
+    };
+    using std::integral_constant;
+    auto issue_tile = [&](uint32_t d_tmem, uint32_t a_row, uint32_t x_row, uint32_t b_lo, uint32_t ba_lo,
+                          const uint32_t (&to)[9]) {
+      if (p.ntaps == 9) {
+        if (kPer == 1) issue_tile_t(integral_constant<int, 9>{}, integral_constant<int, 1>{}, d_tmem, a_row, x_row, b_lo, ba_lo, to);
+        else if (kPer == 2) issue_tile_t(integral_constant<int, 9>{}, integral_constant<int, 2>{}, d_tmem, a_row, x_row, b_lo, ba_lo, to);
+        else issue_tile_t(integral_constant<int, 9>{}, integral_constant<int, 4>{}, d_tmem, a_row, x_row, b_lo, ba_lo, to);
+      } else if (p.ntaps == 4) {
+        if (kPer == 1) issue_tile_t(integral_constant<int, 4>{}, integral_constant<int, 1>{}, d_tmem, a_row, x_row, b_lo, ba_lo, to);
+        else if (kPer == 2) issue_tile_t(integral_constant<int, 4>{}, integral_constant<int, 2>{}, d_tmem, a_row, x_row, b_lo, ba_lo, to);
+        else issue_tile_t(integral_constant<int, 4>{}, integral_constant<int, 4>{}, d_tmem, a_row, x_row, b_lo, ba_lo, to);
+      }                                     // (halo_build only admits 4 or 9 taps)
     };
     for (int b = band0; b < band1; ++b) {
       const Band bd = decode_band(p, b);
@@ -213,16 +225,44 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
         mbar_wait(&tempty[slot], ((gc >> asLog) & 1) ^ 1);
         tc_fence_after();
         const uint32_t d0 = tmem_base + slot * (G * ACC_COLS);
-        if (p.numPhases == 4) {            // G == 4: tile k of the group == phase k of low-res row j
+        if constexpr (COMP) {
+          // composite blur o up-conv: all four phases are 3x3 convs of the SAME low-res window, so they share the A
+          // operand: one N = 4*COUT MMA per (tap, k-step) fills the four side-by-side accumulators of the group
+          // (weights are tap-major, sets ordered [4 5 | 0 1 2 3 | 6 7]).  The first / last image row swap in their
+          // own sets for phases 0,1 / 2,3: two N = 2*COUT MMAs there.
           const uint32_t a_row = a_band + j * row_step, x_row = x_band + j * aux_row_step;
           const int gy = bd.y0 + j;
-          // composite blur o up-conv: the first / last hi-res row use their own weight sets (4 + phase)
-          const bool top = COMP && gy == 0, bot = COMP && gy == p.H - 1;
+          const uint32_t set_u = COUT * rb16;                       // one weight set of one tap, 16-byte units
+          const uint32_t tap_u = 8 * set_u;
+          if (gy != 0 && gy != p.H - 1) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const int ws = ((top && k < 2) || (bot && k >= 2)) ? 4 + k : k;
-            issue_tile(d0 + k * ACC_COLS, a_row, x_row, w_lo + ws * p.ntaps * w_tap, wa_lo + ws * (COUT * 2), toff[k]);
+            for (int t = 0; t < 9; ++t) {
+              const uint32_t a_lo = a_row + toff[0][t], b_lo = w_lo + t * tap_u + 2 * set_u;
+              if (t == 0) umma_f16_pred<false>(d0, a_lo, dhi, b_lo, dhi, idesc4, lead);
+              else umma_f16_pred<true>(d0, a_lo, dhi, b_lo, dhi, idesc4, lead);
+              if (kPer > 1) umma_f16_pred<true>(d0, a_lo + 2, dhi, b_lo + 2, dhi, idesc4, lead);
+            }
+            umma_f16_pred<true>(d0, x_row, dhi_aux, wa_lo + 2 * (COUT * 2), dhi_aux, idesc4, leader ? 1u : 0u);
+          } else {
+            const uint32_t s_lo = gy == 0 ? 0u : 2u, s_hi = gy == 0 ? 4u : 6u;   // first set of the (0,1) / (2,3) pair
+#pragma unroll
+            for (int hf = 0; hf < 2; ++hf) {
+              const uint32_t so = hf == 0 ? s_lo : s_hi, dd = d0 + hf * 2 * ACC_COLS;
+#pragma unroll
+              for (int t = 0; t < 9; ++t) {
+                const uint32_t a_lo = a_row + toff[0][t], b_lo = w_lo + t * tap_u + so * set_u;
+                if (t == 0) umma_f16_pred<false>(dd, a_lo, dhi, b_lo, dhi, idesc2, lead);
+                else umma_f16_pred<true>(dd, a_lo, dhi, b_lo, dhi, idesc2, lead);
+                if (kPer > 1) umma_f16_pred<true>(dd, a_lo + 2, dhi, b_lo + 2, dhi, idesc2, lead);
+              }
+              umma_f16_pred<true>(dd, x_row, dhi_aux, wa_lo + so * (COUT * 2), dhi_aux, idesc2, leader ? 1u : 0u);
+            }
           }
+        } else if (p.numPhases == 4) {     // G == 4: tile k of the group == phase k of low-res row j
+          const uint32_t a_row = a_band + j * row_step, x_row = x_band + j * aux_row_step;
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            issue_tile(d0 + k * ACC_COLS, a_row, x_row, w_lo + k * p.ntaps * w_tap, wa_lo + k * (COUT * 2), toff[k]);
         } else {                           // tile k of the group == output row j*G + k
 #pragma unroll
           for (int k = 0; k < G; ++k) {
@@ -615,18 +655,22 @@ struct FoldTaps {
 __global__ void k_fold_weights(const float* __restrict__ base_w, const float* __restrict__ inA,
                                const float* __restrict__ inB, const float* __restrict__ bias,
                                const float* __restrict__ noise_w, FoldTaps ft, int wsets, int ntaps, int cout, int cin,
-                               __half* __restrict__ w_main, __half* __restrict__ w_aux) {
+                               int composite, __half* __restrict__ w_main, __half* __restrict__ w_aux) {
   const int n = blockIdx.y, ws = blockIdx.x;
+  // composite: tap-major output with the weight sets ordered [4 5 | 0 1 2 3 | 6 7] inside a tap, so that the four
+  // interior phases are ONE contiguous N = 4*cout operand (and the first / last-row variants contiguous pairs)
+  const int pos = composite ? (ws < 4 ? ws + 2 : (ws < 6 ? ws - 4 : ws)) : ws;
   const int co = threadIdx.x / cin, ci = threadIdx.x % cin;          // cin in {16, 32}: a group never straddles a warp
   const float a = inA != nullptr ? inA[n * cin + ci] : 1.f;
   const float b = inB != nullptr ? inB[n * cin + ci] : 0.f;
-  __half* aux_row = w_aux + ((static_cast<size_t>(n) * wsets + ws) * cout + co) * 16;
+  __half* aux_row = w_aux + ((static_cast<size_t>(n) * wsets + pos) * cout + co) * 16;
   if (ci < 16) aux_row[ci] = __float2half_rn((ci == ft.noise_k[ws] && noise_w != nullptr) ? noise_w[co] : 0.f);
   __syncwarp();
   for (int t = 0; t < ntaps; ++t) {
     const size_t widx = ((static_cast<size_t>(ws) * ntaps + t) * cout + co) * cin + ci;
     const float w = base_w[widx];
-    w_main[static_cast<size_t>(n) * wsets * ntaps * cout * cin + widx] = __float2half_rn(w * a);
+    const size_t oidx = composite ? ((static_cast<size_t>(t) * wsets + pos) * cout + co) * cin + ci : widx;
+    w_main[static_cast<size_t>(n) * wsets * ntaps * cout * cin + oidx] = __float2half_rn(w * a);
     float sh = w * b;
     for (int o = cin >> 1; o > 0; o >>= 1) sh += __shfl_xor_sync(0xffffffffu, sh, o);
     const int k = ft.k[ws][t];
@@ -648,7 +692,7 @@ int launch_fold_weights(const float* base_w, const float* inA, const float* inB,
                         ? static_cast<int8_t>(m_off + 3 * (tap_dy[(ph % phases) * 9 + t] + 1) + (tap_dx[(ph % phases) * 9 + t] + 1)) : -1;
   }
   ft.center_k = static_cast<int8_t>(m_off + 4);
-  k_fold_weights<<<dim3(wsets, n), cout * cin, 0, st>>>(base_w, inA, inB, bias, noise_w, ft, wsets, ntaps, cout, cin, w_main, w_aux);
+  k_fold_weights<<<dim3(wsets, n), cout * cin, 0, st>>>(base_w, inA, inB, bias, noise_w, ft, wsets, ntaps, cout, cin, composite, w_main, w_aux);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { set_error("fold_weights launch: %s", cudaGetErrorString(e)); return 4; }
   count_launch();
@@ -739,7 +783,7 @@ int halo_build(const cfr_conv_desc& s, const float* inA, const float* inB, const
   p.fold = w_aux != nullptr;
   p.composite = composite;
   p.corr = corr;
-  if (composite && (!p.fold || s.numPhases != 4 || s.ntaps != 9 || s.Cout != 16)) { set_error("halo conv: composite needs fold, 4 phases, 9 taps"); return 2; }
+  if (composite && (!p.fold || s.numPhases != 4 || s.ntaps != 9 || s.Cout != 16 || s.Cin > 32)) { set_error("halo conv: composite needs fold, 4 phases, 9 taps"); return 2; }
   p.wsets = composite ? 8 : s.numPhases;
   if (const char* e = getenv("CFR_HALO_DBG")) p.dbg = atoi(e);
   if (p.fold && s.Cin > 32) { set_error("halo conv: folded variant needs Cin <= 32"); return 2; }
@@ -775,6 +819,7 @@ int halo_build(const cfr_conv_desc& s, const float* inA, const float* inB, const
   p.bandsY = (s.Hout + th - 1) / th;
   p.accStages = 0;   // (fixed per template: 512 / (G * Cout) groups of G accumulators)
   if (s.numPhases != 1 && s.numPhases != 4) { set_error("halo conv: 1 or 4 phases"); return 2; }
+  if (s.ntaps != 4 && s.ntaps != 9) { set_error("halo conv: 4 or 9 taps per phase"); return 2; }
   if (s.numPhases == 4 && s.Cout == 64) { set_error("halo conv: 4-phase up-conv needs Cout <= 32"); return 2; }
   p.inA = inA; p.inB = inB;
   p.out = static_cast<__half*>(s.out);

@@ -50,13 +50,22 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   return ok != 0;
 }
 // Bounded wait: a pipeline bug traps (kernel error) instead of hanging the GPU box.
+#ifndef CFR_MBAR_SLEEP_MAX
+#define CFR_MBAR_SLEEP_MAX 256
+#endif
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+#if CFR_MBAR_SLEEP_MAX > 0
   uint32_t ns = 32;
   for (uint32_t it = 0; !mbar_try_wait(bar, parity); ++it) {
     __nanosleep(ns);                       // exponential back-off keeps polling warps off the issue slots
-    if (ns < 256) ns <<= 1;
+    if (ns < CFR_MBAR_SLEEP_MAX) ns <<= 1;
     if (it > (1u << 22)) __trap();
   }
+#else
+  // try_wait itself suspends the warp until the phase flips or its time hint expires: no extra sleep on top
+  for (uint32_t it = 0; !mbar_try_wait(bar, parity); ++it)
+    if (it > (1u << 26)) __trap();
+#endif
 }
 
 // ---------------------------------------------------------------- TMA
@@ -162,6 +171,35 @@ __device__ __forceinline__ void umma_f16_lohi(uint32_t d_tmem, uint32_t a_lo, ui
       "mov.b64 db, {%3, %4};\n\t"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}\n" ::"r"(d_tmem),
       "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+// Same, issued only where `issue` != 0 (a predicated instruction: no branch, so a whole warp can run an unrolled
+// sequence of these with one elected lane issuing); ACC is a compile-time accumulate flag.
+template <bool ACC>
+__device__ __forceinline__ void umma_f16_pred(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                              uint32_t idesc, uint32_t issue) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t.reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "setp.ne.b32 q, %7, 0;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}\n" ::"r"(d_tmem),
+      "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(ACC ? 1u : 0u), "r"(issue)
+      : "memory");
+}
+
+__device__ __forceinline__ void umma_f16_lohi_pred(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo,
+                                                   uint32_t b_hi, uint32_t idesc, uint32_t accumulate, uint32_t issue) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t.reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "setp.ne.b32 q, %7, 0;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}\n" ::"r"(d_tmem),
+      "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate), "r"(issue)
       : "memory");
 }
 
