@@ -126,6 +126,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
     // ================================================================ MMA issuers (kMmaWarps warps, alternate tiles)
     // The whole warp runs the loop (so descriptor words stay warp-uniform); one elected lane issues
     // tcgen05.mma / commit.  Warp m issues the tiles with (tile index mod kMmaWarps) == m.
+    setmaxnreg_dec<kRegsMma>();
     const uint32_t mw = warp - kHaloMmaWarp0;
     const bool leader = elect_one();
     const uint32_t idesc = make_idesc_f16(128, COUT);
@@ -286,6 +287,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
     // ================================================================ band loader + affine-on-load (warps 8..15)
     // cp.async 16-byte chunks straight into the swizzled operand layout (TMA boxes with 32..128-byte rows are
     // row-rate bound: profiles/ncu_r01_halo_tma.txt), zero-filling out-of-image pixels == the conv padding.
+    setmaxnreg_dec<kRegsLoader>();
     constexpr int LT = kLoaderWarps * 32;
     const int tt = threadIdx.x - kEpiWarps * 32;
     const int nchLog = p.rowBytes == 32 ? 1 : (p.rowBytes == 64 ? 2 : 3);
@@ -442,6 +444,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
     }
   } else {
     // ================================================================ epilogue (warps 0..7)
+    setmaxnreg_inc<kRegsEpi>();
     constexpr bool HOIST = COUT == 16 && !FOLD;     // per-channel noise gain / bias live in registers
     const int q = warp & 3;                // TMEM lane quarter
     const int grp = warp >> 2;             // handles tiles with tcount % kEpiGroups == grp

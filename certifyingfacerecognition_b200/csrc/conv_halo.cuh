@@ -30,6 +30,10 @@ constexpr int kEpiGroups = CFR_HALO_EPI_GROUPS;       // each group = 4 warps (o
 constexpr int kEpiWarps = 4 * kEpiGroups;
 constexpr int kHaloMmaWarp0 = kEpiWarps + kLoaderWarps;   // [epilogue warps][loader/transform warps][MMA issuers]
 constexpr int kHaloThreads = (kEpiWarps + kLoaderWarps + kMmaWarps) * 32;
+// Register re-allocation between the roles (setmaxnreg; each role is a whole number of 4-warp groups): the kernel starts
+// with 96 registers per thread (640 threads); the MMA issuers and loaders hand registers to the epilogue warps, whose
+// per-channel accumulators otherwise spill.  8*32*kRegsEpi + 8*32*kRegsLoader + 4*32*kRegsMma <= 640 * 96.
+constexpr int kRegsEpi = 128, kRegsLoader = 72, kRegsMma = 56;
 constexpr int kHaloW = 130;         // 128 output columns + 1 halo column each side
 
 struct HaloParams {
