@@ -302,16 +302,40 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
     auto issue = [&](const Band& bd, int hs) {
       const uint32_t hb_addr = smem_u32(smem + hs * p.haloBytes);
       const __half* img = p.in + static_cast<size_t>(bd.n) * imgStride + lc * 8;
-      if (!(p.dbg & 2))
-      for (int q = tt; q < RC; q += LT) {
-        const int gx = bd.x0 - 1 + (q >> nchLog);
-        const bool colok = static_cast<unsigned>(gx) < static_cast<unsigned>(p.W);
-        const __half* src = img + static_cast<size_t>(gx) * p.Cin + static_cast<long long>(bd.y0 - 1) * static_cast<long long>(rowStride);
-        uint32_t lin = hb_addr + (static_cast<uint32_t>(q) << 4);
-        int gy = bd.y0 - 1;
-        for (int row = 0; row < p.TH + 2; ++row, ++gy, lin += RC << 4, src += rowStride) {
-          const bool ok = colok && static_cast<unsigned>(gy) < static_cast<unsigned>(p.H);
-          cp_async16(lin ^ (((lin >> 7) & (nch - 1)) << 4), ok ? src : p.in, ok ? 16u : 0u);
+      if (!(p.dbg & 2)) {
+        // rows of the band that lie inside the image: [r_lo, r_hi) of TH + 2; the others are zero-filled
+        const int R = p.TH + 2;
+        const int r_lo = bd.y0 == 0 ? 1 : 0;
+        const int r_hi = min(R, p.H - (bd.y0 - 1));
+        const uint32_t rowB = static_cast<uint32_t>(RC) << 4;             // smem bytes per band row
+        const uint32_t swm = static_cast<uint32_t>(nch - 1);
+        // (a) whole multiples of LT chunks per row: a thread keeps its column(s), walks down the rows with an address
+        //     add, a swizzle XOR and one cp.async per chunk (all checks hoisted out of the row loop)
+        const int nfull = RC / LT;
+        for (int c = 0; c < nfull; ++c) {
+          const int q = tt + c * LT;
+          const int gx = bd.x0 - 1 + (q >> nchLog);
+          const bool colok = static_cast<unsigned>(gx) < static_cast<unsigned>(p.W);
+          const uint32_t sz = colok ? 16u : 0u;
+          const __half* src = img + static_cast<size_t>(colok ? gx : 0) * p.Cin +
+                              static_cast<long long>(bd.y0 - 1 + r_lo) * static_cast<long long>(rowStride);
+          uint32_t lin = hb_addr + (static_cast<uint32_t>(q) << 4);
+          int row = 0;
+          for (; row < r_lo; ++row, lin += rowB) cp_async16(lin ^ (((lin >> 7) & swm) << 4), p.in, 0u);
+#pragma unroll 2
+          for (; row < r_hi; ++row, lin += rowB, src += rowStride) cp_async16(lin ^ (((lin >> 7) & swm) << 4), src, sz);
+          for (; row < R; ++row, lin += rowB) cp_async16(lin ^ (((lin >> 7) & swm) << 4), p.in, 0u);
+        }
+        // (b) the RC % LT left-over chunks of every row (4 / 8 / 16), spread as (row, chunk) pairs over the threads
+        const int left = RC - nfull * LT, leftLog = nchLog + 1;            // left == 2 * nch
+        for (int idx = tt; idx < R * left; idx += LT) {
+          const int row = idx >> leftLog, q = nfull * LT + (idx & (left - 1));
+          const int gx = bd.x0 - 1 + (q >> nchLog), gy = bd.y0 - 1 + row;
+          const bool ok = static_cast<unsigned>(gx) < static_cast<unsigned>(p.W) && row >= r_lo && row < r_hi;
+          const __half* src = img + static_cast<size_t>(ok ? gx : 0) * p.Cin +
+                              static_cast<long long>(ok ? gy : 0) * static_cast<long long>(rowStride);
+          const uint32_t lin = hb_addr + static_cast<uint32_t>(row) * rowB + (static_cast<uint32_t>(q) << 4);
+          cp_async16(lin ^ (((lin >> 7) & swm) << 4), src, ok ? 16u : 0u);
         }
       }
       cp_async_commit();
@@ -408,25 +432,37 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
         }
         uint8_t* hb = smem + hs * p.haloBytes;
         const uint32_t hb_addr = smem_u32(hb);
-        for (int q = tt; q < RC; q += LT) {                  // same chunks this thread copied: no barrier needed
+        auto xform = [&](uint32_t lin) {                      // y*A + B on one 16-byte chunk, in place
+          const uint32_t off = (lin ^ (((lin >> 7) & (nch - 1)) << 4)) - hb_addr;
+          uint4 v = *reinterpret_cast<uint4*>(hb + off);
+          __half2* h2 = reinterpret_cast<__half2*>(&v);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            float2 f = __half22float2(h2[i]);
+            f.x = fmaf(f.x, ca[2 * i], cb[2 * i]);
+            f.y = fmaf(f.y, ca[2 * i + 1], cb[2 * i + 1]);
+            h2[i] = __floats2half2_rn(f.x, f.y);
+          }
+          *reinterpret_cast<uint4*>(hb + off) = v;
+        };
+        // exactly the chunks this thread copied in issue() (so its own cp.async wait suffices: no barrier needed)
+        const int R = p.TH + 2;
+        const int r_lo = bd.y0 == 0 ? 1 : 0, r_hi = min(R, p.H - (bd.y0 - 1));
+        const uint32_t rowB = static_cast<uint32_t>(RC) << 4;
+        const int nfull = RC / LT;
+        for (int c = 0; c < nfull; ++c) {
+          const int q = tt + c * LT;
           const int gx = bd.x0 - 1 + (q >> nchLog);
           if (static_cast<unsigned>(gx) >= static_cast<unsigned>(p.W)) continue;     // zero padding stays zero
-          uint32_t lin = hb_addr + (static_cast<uint32_t>(q) << 4);
-          int gy = bd.y0 - 1;
-          for (int row = 0; row < p.TH + 2; ++row, ++gy, lin += RC << 4) {
-            if (static_cast<unsigned>(gy) >= static_cast<unsigned>(p.H)) continue;
-            const uint32_t off = (lin ^ (((lin >> 7) & (nch - 1)) << 4)) - hb_addr;
-            uint4 v = *reinterpret_cast<uint4*>(hb + off);
-            __half2* h2 = reinterpret_cast<__half2*>(&v);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              float2 f = __half22float2(h2[i]);
-              f.x = fmaf(f.x, ca[2 * i], cb[2 * i]);
-              f.y = fmaf(f.y, ca[2 * i + 1], cb[2 * i + 1]);
-              h2[i] = __floats2half2_rn(f.x, f.y);
-            }
-            *reinterpret_cast<uint4*>(hb + off) = v;
-          }
+          uint32_t lin = hb_addr + (static_cast<uint32_t>(q) << 4) + r_lo * rowB;
+          for (int row = r_lo; row < r_hi; ++row, lin += rowB) xform(lin);
+        }
+        const int left = RC - nfull * LT, leftLog = nchLog + 1;
+        for (int idx = tt; idx < R * left; idx += LT) {
+          const int row = idx >> leftLog, q = nfull * LT + (idx & (left - 1));
+          const int gx = bd.x0 - 1 + (q >> nchLog);
+          if (static_cast<unsigned>(gx) < static_cast<unsigned>(p.W) && row >= r_lo && row < r_hi)
+            xform(hb_addr + static_cast<uint32_t>(row) * rowB + (static_cast<uint32_t>(q) << 4));
         }
       }
       fence_proxy_async();                 // generic-proxy writes -> visible to the tensor core (async proxy)
