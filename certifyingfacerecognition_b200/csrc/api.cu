@@ -20,6 +20,7 @@ struct cfr_program {
   std::vector<std::unique_ptr<ConvOp>> convs;
   std::vector<std::unique_ptr<HaloOp>> halos;
   std::vector<cudaEvent_t> events;
+  std::vector<void*> owned;            // device buffers the program allocated itself (packed noise tables)
   void add(std::function<int(cudaStream_t)> f, std::string label, double fl = 0.0) {
     ops.push_back(std::move(f));
     labels.push_back(std::move(label));
@@ -27,6 +28,7 @@ struct cfr_program {
   }
   ~cfr_program() {
     for (auto e : events) cudaEventDestroy(e);
+    for (auto q : owned) cudaFree(q);
   }
 };
 
@@ -161,6 +163,16 @@ static int add_folded(cfr_program* p, const cfr_conv_desc* d, const float* base_
   if (r != 0) return r;
   HaloOp* raw = op.get();
   p->halos.push_back(std::move(op));
+  {                                              // packed aux-row heads (noise [+ corner indicator]) for the loader
+    void* tab = nullptr;
+    const size_t tab_bytes = static_cast<size_t>(d->Hout) * d->Wout * (composite ? 8 : 4);
+    if (cudaMalloc(&tab, tab_bytes) != cudaSuccess) { set_error("folded conv: cudaMalloc(noise table) failed"); return 5; }
+    p->owned.push_back(tab);
+    raw->p.noise_tab = tab;
+    const float* nz = d->noise;
+    const int h = d->Hout, w = d->Wout;
+    p->add([=](cudaStream_t st) { return launch_pack_noise(nz, h, w, composite, tab, st); }, "pack_noise");
+  }
   const int n = d->N, cout = d->Cout, cin = d->Cin, phases = d->numPhases, ntaps = d->ntaps;
   const float* bias = d->bias;
   const float* noise_w = d->noise_w;

@@ -338,35 +338,31 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
           cp_async16(lin ^ (((lin >> 7) & swm) << 4), src, ok ? 16u : 0u);
         }
       }
-      cp_async_commit();
       if (FOLD && !(p.dbg & 4)) {
         // aux rows, one per OUTPUT pixel of the band: k0 = noise, k(1 + 3*(dy+1) + (dx+1)) = 1 if input pixel
-        // (y+dy, x+dx) lies inside the image (so the folded IN/AdaIN shift respects the zero padding), rest 0
+        // (y+dy, x+dx) lies inside the image (so the folded IN/AdaIN shift respects the zero padding), rest 0.
+        // The head of the row that depends on memory ({noise, k1} / composite: 4 noise values) is cp.async'ed from
+        // the packed table; the position-only indicators are plain shared stores to the other bytes of the row.
         const uint32_t xb_addr = smem_u32(aux + hs * p.auxBytes);
         const int cx = tt & 127;
         const int gx = bd.x0 + cx;
         const float cl = gx > 0 ? 1.f : 0.f, cr = gx < p.W - 1 ? 1.f : 0.f;
         const bool colin = gx < p.W;
-        const bool has_nz = p.noise != nullptr;
         if constexpr (COMP) {
           // aux row of a low-res pixel: k0..k3 = noise at its 4 hi-res phases, k4..k12 = inside-image indicators
+          const uint2* tab = static_cast<const uint2*>(p.noise_tab);
           for (int r = tt >> 7; r < p.TH; r += LT >> 7) {
             const int gy = bd.y0 + r;
-            float2 n0 = make_float2(0.f, 0.f), n1 = n0;
-            if (has_nz && colin && gy < p.H) {
-              const float* np = p.noise + static_cast<size_t>(2 * gy) * p.outW + 2 * gx;
-              n0 = __ldg(reinterpret_cast<const float2*>(np));
-              n1 = __ldg(reinterpret_cast<const float2*>(np + p.outW));
-            }
+            const bool ok = colin && gy < p.H;
             const float ru = gy > 0 ? 1.f : 0.f, rd = gy < p.H - 1 ? 1.f : 0.f;
-            const __half2 q0 = __floats2half2_rn(n0.x, n0.y), q1 = __floats2half2_rn(n1.x, n1.y);
             const __half2 q2 = __floats2half2_rn(ru * cl, ru), q3 = __floats2half2_rn(ru * cr, cl);      // k4 k5 | k6 k7
             const __half2 q4 = __floats2half2_rn(1.f, cr), q5 = __floats2half2_rn(rd * cl, rd);          // k8 k9 | k10 k11
             const __half2 q6 = __floats2half2_rn(rd * cr, 0.f);                                          // k12
             const uint32_t lin = xb_addr + (static_cast<uint32_t>(r * 128 + cx) << 5);
             const uint32_t sw = ((lin >> 7) & 1u) << 4;
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(lin ^ sw),
-                         "r"(*reinterpret_cast<const uint32_t*>(&q0)), "r"(*reinterpret_cast<const uint32_t*>(&q1)),
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(lin ^ sw),
+                         "l"(ok ? tab + static_cast<size_t>(gy) * p.W + gx : tab), "r"(ok ? 8u : 0u) : "memory");
+            asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"((lin ^ sw) + 8),
                          "r"(*reinterpret_cast<const uint32_t*>(&q2)), "r"(*reinterpret_cast<const uint32_t*>(&q3))
                          : "memory");
             asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"((lin + 16) ^ sw),
@@ -375,29 +371,22 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
                          : "memory");
           }
         } else {
-        const __half2 h45 = __floats2half2_rn(cl, 1.f);                  // k4 (0,-1), k5 (0,0)
-        constexpr int RS = LT >> 7;                                     // rows advanced per step (2)
-        for (int r0 = tt >> 7; r0 < p.TH; r0 += 4 * RS) {
-          float nzv[4];                                                  // 4 independent noise loads in flight
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const int gy = bd.y0 + r0 + u * RS;
-            nzv[u] = (has_nz && colin && r0 + u * RS < p.TH && gy < p.H) ? __ldg(&p.noise[gy * p.W + gx]) : 0.f;
-          }
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const int r = r0 + u * RS;
-            if (r >= p.TH) break;
+          const uint32_t* tab = static_cast<const uint32_t*>(p.noise_tab);
+          const __half2 h45 = __floats2half2_rn(cl, 1.f);                  // k4 (0,-1), k5 (0,0)
+          for (int r = tt >> 7; r < p.TH; r += LT >> 7) {
             const int gy = bd.y0 + r;
+            const bool ok = colin && gy < p.H;
             const float ru = gy > 0 ? 1.f : 0.f, rd = gy < p.H - 1 ? 1.f : 0.f;
-            const __half2 h01 = __floats2half2_rn(nzv[u], ru * cl);       // k0 noise, k1 (-1,-1)
             const __half2 h23 = __floats2half2_rn(ru, ru * cr);           // k2 (-1,0), k3 (-1,+1)
             const __half2 h67 = __floats2half2_rn(cr, rd * cl);           // k6 (0,+1), k7 (+1,-1)
             const __half2 h89 = __floats2half2_rn(rd, rd * cr);           // k8 (+1,0), k9 (+1,+1)
             const uint32_t lin = xb_addr + (static_cast<uint32_t>(r * 128 + cx) << 5);
             const uint32_t sw = ((lin >> 7) & 1u) << 4;
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(lin ^ sw),
-                         "r"(*reinterpret_cast<const uint32_t*>(&h01)), "r"(*reinterpret_cast<const uint32_t*>(&h23)),
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(lin ^ sw),      // k0 noise, k1 (-1,-1)
+                         "l"(ok ? tab + static_cast<size_t>(gy) * p.W + gx : tab), "r"(ok ? 4u : 0u) : "memory");
+            asm volatile("st.shared.b32 [%0], %1;" ::"r"((lin ^ sw) + 4), "r"(*reinterpret_cast<const uint32_t*>(&h23))
+                         : "memory");
+            asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"((lin ^ sw) + 8),
                          "r"(*reinterpret_cast<const uint32_t*>(&h45)), "r"(*reinterpret_cast<const uint32_t*>(&h67))
                          : "memory");
             asm volatile("st.shared.v4.b32 [%0], {%1, %2, %2, %2};" ::"r"((lin + 16) ^ sw),
@@ -405,8 +394,8 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
                          : "memory");
           }
         }
-        }
       }
+      cp_async_commit();
     };
 
     int cur_n = -1;
@@ -797,6 +786,34 @@ int launch_upblur_corr(const __half* y, const float* inA, const float* inB, cons
   k_upblur_corr<<<grid, 256, smem, st>>>(y, inA, inB, corr_d, h, w, cin, cout, corr);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { set_error("upblur_corr launch: %s", cudaGetErrorString(e)); return 4; }
+  count_launch();
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// packed aux-row heads for the FOLD variants (see conv_halo.cuh)
+// ---------------------------------------------------------------------------------------------------------
+__global__ void k_pack_noise(const float* __restrict__ noise, int h, int w, int mode, void* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= h * w) return;
+  const int y = i / w, x = i - y * w;
+  if (mode == 0) {
+    const __half2 v = __floats2half2_rn(noise != nullptr ? noise[i] : 0.f, (y > 0 && x > 0) ? 1.f : 0.f);
+    static_cast<uint32_t*>(out)[i] = *reinterpret_cast<const uint32_t*>(&v);
+  } else {
+    float n00 = 0.f, n01 = 0.f, n10 = 0.f, n11 = 0.f;
+    if (noise != nullptr) {
+      const float* np = noise + static_cast<size_t>(2 * y) * (2 * w) + 2 * x;
+      n00 = np[0]; n01 = np[1]; n10 = np[2 * w]; n11 = np[2 * w + 1];
+    }
+    const __half2 a = __floats2half2_rn(n00, n01), b = __floats2half2_rn(n10, n11);
+    static_cast<uint2*>(out)[i] = make_uint2(*reinterpret_cast<const uint32_t*>(&a), *reinterpret_cast<const uint32_t*>(&b));
+  }
+}
+int launch_pack_noise(const float* noise, int h, int w, int mode, void* out, cudaStream_t st) {
+  k_pack_noise<<<(h * w + 255) / 256, 256, 0, st>>>(noise, h, w, mode, out);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { set_error("pack_noise launch: %s", cudaGetErrorString(e)); return 4; }
   count_launch();
   return 0;
 }

@@ -64,6 +64,7 @@ struct HaloParams {
   __half* out; int outH, outW, outC, oscale;
   int8_t ooff_y[4], ooff_x[4];
   const float* bias; const float* noise; const float* noise_w;
+  const void* noise_tab;            // FOLD: packed per-pixel aux-row head (see launch_pack_noise), filled by cp.async
   int act; float slope;
   unsigned long long* stat_sum; unsigned long long* stat_sq;  // [N, Cout] Q43.20 fixed point, or null
 };
@@ -84,6 +85,10 @@ int launch_fold_weights(const float* base_w, const float* inA, const float* inB,
 // composite up-conv+blur: exact values for the first / last hi-res column (see engine.composite_upconv_weights)
 int launch_upblur_corr(const __half* y, const float* inA, const float* inB, const float* corr_d, int n, int h, int w,
                        int cin, int cout, float* corr, cudaStream_t st);
+// FOLD aux rows: the part of an aux row that comes from memory, pre-packed once per run so the loader can cp.async it
+// (no register-staged noise loads on its critical path).  mode 0: out[y][x] = {half noise(y,x), half (y>0 && x>0)};
+// mode 1 (composite, low-res grid h x w, noise is 2h x 2w): out[y][x] = 4 halves noise(2y+a, 2x+b), (a,b) row-major.
+int launch_pack_noise(const float* noise, int h, int w, int mode, void* out, cudaStream_t st);
 int halo_launch(const HaloOp& op, cudaStream_t stream);
 
 }  // namespace cfr
