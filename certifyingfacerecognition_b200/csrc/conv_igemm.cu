@@ -4,6 +4,7 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <vector>
@@ -22,12 +23,13 @@ struct TileCoord {
   int n0, y0, x0, phase, ntile;
 };
 
-__device__ __forceinline__ TileCoord decode_item(const ConvParams& p, int item) {
+// MT == 2: `item` indexes PAIRS of adjacent M tiles; `sub` selects the tile of the pair
+__device__ __forceinline__ TileCoord decode_item(const ConvParams& p, int item, int sub) {
   TileCoord t;
   t.ntile = item % p.numNTiles;
   int r = item / p.numNTiles;
   t.phase = r % p.numPhases;
-  int m = r / p.numPhases;
+  int m = (r / p.numPhases) * p.MT + sub;
   int tx = m % p.tilesX;
   m /= p.tilesX;
   int ty = m % p.tilesY;
@@ -63,19 +65,27 @@ __device__ __forceinline__ int reduce16_channel(uint32_t lane) {
 }
 
 // channel c of image img: the four epilogue warps' partial sums (fixed order) -> Q43.20 fixed point -> global accumulate
+// (s_sum / s_sq point at the four slices of ONE epilogue group; slices are CoutTotal floats apart)
 __device__ __forceinline__ void flush_stats(const ConvParams& p, float* s_sum, float* s_sq, int img, int c) {
-  const float a = (s_sum[c] + s_sum[kStatsMaxC + c]) + (s_sum[2 * kStatsMaxC + c] + s_sum[3 * kStatsMaxC + c]);
-  const float b = (s_sq[c] + s_sq[kStatsMaxC + c]) + (s_sq[2 * kStatsMaxC + c] + s_sq[3 * kStatsMaxC + c]);
-  atomicAdd(&p.stat_sum[img * p.CoutTotal + c], stat_fx(a));
-  atomicAdd(&p.stat_sq[img * p.CoutTotal + c], stat_fx(b));
+  const int C = p.CoutTotal;
+  const float a = (s_sum[c] + s_sum[C + c]) + (s_sum[2 * C + c] + s_sum[3 * C + c]);
+  const float b = (s_sq[c] + s_sq[C + c]) + (s_sq[2 * C + c] + s_sq[3 * C + c]);
+  atomicAdd(&p.stat_sum[img * C + c], stat_fx(a));
+  atomicAdd(&p.stat_sq[img * C + c], stat_fx(b));
 #pragma unroll
   for (int w = 0; w < 4; ++w) {
-    s_sum[w * kStatsMaxC + c] = 0.f;
-    s_sq[w * kStatsMaxC + c] = 0.f;
+    s_sum[w * C + c] = 0.f;
+    s_sq[w * C + c] = 0.f;
   }
 }
 
-__global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __grid_constant__ ConvParams p) {
+// MT == 2: the CTA works on two adjacent M tiles at once.  Both tiles' A boxes and ONE weight box make a pipeline
+// stage, and every K step issues two MMAs (one per accumulator) against the same B operand: the bytes the SM pulls from
+// L2 per FLOP drop by 1/4 - 1/3.  These layers are bound by the chip-wide L2 -> SM feed (ncu: ~12 TB/s delivered,
+// tensor pipe 17-55 % busy), not by the tensor cores.  A second group of four epilogue warps drains the second tile.
+template <int MT>
+__global__ void __launch_bounds__(MT == 2 ? kConvThreadsMT2 : kConvThreads, 1)
+conv_igemm_kernel(const __grid_constant__ ConvParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int S = p.numStages;
@@ -87,13 +97,13 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
   // per-(epilogue warp, channel) float partial sums: every warp owns its slice, so no shared-memory atomics (64-bit
   // shared atomics compile to ATOMS.CAST.SPIN loops); the tile -> warp order is static, hence still bit-reproducible
-  float* s_sum = reinterpret_cast<float*>(tmem_slot + 4);      // [4][kStatsMaxC]
-  float* s_sq = s_sum + 4 * kStatsMaxC;                        // [4][kStatsMaxC]
+  float* s_sum = reinterpret_cast<float*>(tmem_slot + 4);      // [MT][4][CoutTotal]
+  float* s_sq = s_sum + MT * 4 * p.CoutTotal;                  // [MT][4][CoutTotal]
 
   const int warp = threadIdx.x >> 5;
   const uint32_t lane = lane_id();
 
-  const int totalItems = p.tilesX * p.tilesY * p.tilesN * p.numPhases * p.numNTiles;
+  const int totalItems = (p.tilesX * p.tilesY * p.tilesN / MT) * p.numPhases * p.numNTiles;
   const int per = (totalItems + gridDim.x - 1) / gridDim.x;
   const int item0 = blockIdx.x * per;
   const int item1 = min(totalItems, item0 + per);
@@ -102,7 +112,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
   const int stagesPerTile = (chunksTotal + p.G - 1) / p.G;
   const uint32_t subBytes = kBM * p.CB * 2;
   uint32_t tmemCols = 32;
-  while (tmemCols < 2u * p.BN) tmemCols <<= 1;
+  while (tmemCols < static_cast<uint32_t>(p.nAcc * MT * p.BN)) tmemCols <<= 1;
 
   if (warp == kProducerWarp && lane == 0) {
     tma_prefetch_desc(&p.tmA);
@@ -116,7 +126,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
       }
       for (int i = 0; i < 2; ++i) {
         mbar_init(&tfull_bar[i], 1);
-        mbar_init(&tempty_bar[i], 4);
+        mbar_init(&tempty_bar[i], 4 * MT);
       }
       fence_barrier_init();
     }
@@ -125,7 +135,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
     tmem_relinquish();
   }
   if (p.stat_sum != nullptr) {
-    for (int i = threadIdx.x; i < 8 * kStatsMaxC; i += blockDim.x) s_sum[i] = 0.f;
+    for (int i = threadIdx.x; i < MT * 8 * p.CoutTotal; i += blockDim.x) s_sum[i] = 0.f;
   }
   tc_fence_before();
   __syncthreads();
@@ -139,24 +149,29 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
     int stage = 0;
     uint32_t phase = 0;
     for (int item = item0; item < item1; ++item) {
-      const TileCoord t = decode_item(p, item);
+      const TileCoord t = decode_item(p, item, 0);
+      const TileCoord t1 = decode_item(p, item, MT - 1);          // second tile of the pair (== t when MT == 1)
       const int wrow = t.n0 * p.wRowsPerSample + t.phase * p.wRowsPerPhase + t.ntile * p.BN;
       const int xb = t.x0 * p.stride, yb = t.y0 * p.stride;
+      const int xb1 = t1.x0 * p.stride, yb1 = t1.y0 * p.stride;
       int chunk = 0;
       for (int s = 0; s < stagesPerTile; ++s) {
         mbar_wait(&empty_bar[stage], phase ^ 1);
         const int nch = min(p.G, chunksTotal - chunk);
         uint8_t* a_dst = smem + static_cast<size_t>(stage) * p.stageBytes;
         if (leader) {
-          mbar_expect_tx(&full_bar[stage], nch * subBytes + p.BN * 128);
+          mbar_expect_tx(&full_bar[stage], MT * nch * subBytes + p.BN * 128);
           for (int g = 0; g < nch; ++g) {
             const int c = chunk + g;
             const int tap = c / p.nCB;
             const int cb = c - tap * p.nCB;
             tma_load_4d(a_dst + g * subBytes, &p.tmA, &full_bar[stage], cb * p.CB, xb + p.tap_dx[t.phase][tap],
                         yb + p.tap_dy[t.phase][tap], t.n0);
+            if (MT == 2)
+              tma_load_4d(a_dst + kBM * 128 + g * subBytes, &p.tmA, &full_bar[stage], cb * p.CB,
+                          xb1 + p.tap_dx[t.phase][tap], yb1 + p.tap_dy[t.phase][tap], t1.n0);
           }
-          tma_load_2d(a_dst + kBM * 128, &p.tmB, &full_bar[stage], s * 64, wrow);
+          tma_load_2d(a_dst + MT * kBM * 128, &p.tmB, &full_bar[stage], s * 64, wrow);
         }
         __syncwarp();
         chunk += nch;
@@ -183,7 +198,9 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
     for (int item = item0; item < item1; ++item) {
       mbar_wait(&tempty_bar[as], aphase ^ 1);
       tc_fence_after();
-      const uint32_t d_tmem = tmem_base + as * p.BN;
+      const uint32_t d_tmem = tmem_base + as * MT * p.BN;
+      const uint32_t d_tmem1 = d_tmem + p.BN;                      // accumulator of the second tile (MT == 2)
+      constexpr uint32_t a1off = kBM * 128 >> 4;
       uint32_t acc = 0;
       int remaining = chunksTotal;
       for (int s = 0; s < stagesPerTile; ++s) {
@@ -192,18 +209,23 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
         const int nk = (remaining < p.G ? remaining : p.G) * kPer;     // K=16 steps in this stage
         remaining -= p.G;
         const uint32_t a0 = smem_lo + stage * stage16;
-        const uint32_t b0 = a0 + (kBM * 128 >> 4);
+        const uint32_t b0 = a0 + MT * (kBM * 128 >> 4);
         if (leader) {
           if (kPer == 4) {                 // one 64-channel chunk per stage: 4 K-steps inside the 128B swizzle row
             umma_f16_lohi(d_tmem, a0, a_hi, b0, b_hi, idesc, acc);
+            if (MT == 2) umma_f16_lohi(d_tmem1, a0 + a1off, a_hi, b0, b_hi, idesc, acc);
             umma_f16_lohi(d_tmem, a0 + 2, a_hi, b0 + 2, b_hi, idesc, 1u);
+            if (MT == 2) umma_f16_lohi(d_tmem1, a0 + a1off + 2, a_hi, b0 + 2, b_hi, idesc, 1u);
             umma_f16_lohi(d_tmem, a0 + 4, a_hi, b0 + 4, b_hi, idesc, 1u);
+            if (MT == 2) umma_f16_lohi(d_tmem1, a0 + a1off + 4, a_hi, b0 + 4, b_hi, idesc, 1u);
             umma_f16_lohi(d_tmem, a0 + 6, a_hi, b0 + 6, b_hi, idesc, 1u);
+            if (MT == 2) umma_f16_lohi(d_tmem1, a0 + a1off + 6, a_hi, b0 + 6, b_hi, idesc, 1u);
           } else {
             uint32_t a_lo = a0;
             uint32_t accl = acc;
             for (int k = 0, j = 0; k < nk; ++k) {
               umma_f16_lohi(d_tmem, a_lo + 2 * j, a_hi, b0 + 2 * k, b_hi, idesc, accl);
+              if (MT == 2) umma_f16_lohi(d_tmem1, a_lo + a1off + 2 * j, a_hi, b0 + 2 * k, b_hi, idesc, accl);
               accl = 1;
               if (++j == kPer) {
                 j = 0;
@@ -220,31 +242,37 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
           phase ^= 1;
         }
       }
-      if (leader) umma_commit(&tfull_bar[as]);        // accumulator complete -> epilogue
+      if (leader) umma_commit(&tfull_bar[as]);        // accumulator(s) complete -> epilogue
       __syncwarp();
-      as ^= 1;
-      if (as == 0) aphase ^= 1;
+      if (++as == p.nAcc) {
+        as = 0;
+        aphase ^= 1;
+      }
     }
   } else {
-    // ===================================================================== epilogue (warps 0..3)
+    // ===================================================================== epilogue (warps 0..3; MT == 2: + warps 6..9)
+    const int sub = warp >= 6 ? 1 : 0;           // which tile of the pair this group drains
     const int q = warp & 3;                      // TMEM lane quarter this warp may read
     const int row = q * 32 + lane;               // M row == pixel index inside the tile box
     const int tx = row % p.TW;
     const int ty = (row / p.TW) % p.TH;
     const int tn = row / (p.TW * p.TH);
-    const int et = threadIdx.x;                  // 0..127
+    const int et = sub ? threadIdx.x - 192 : threadIdx.x;       // 0..127 inside the group
+    const int gbar = 1 + sub;                    // named barrier of this group
+    s_sum += sub * 4 * p.CoutTotal;              // this group's four slices
+    s_sq += sub * 4 * p.CoutTotal;
     int as = 0;
     uint32_t aphase = 0;
     int cur_img = -1;
     const bool do_stats = p.stat_sum != nullptr;
     for (int item = item0; item < item1; ++item) {
-      const TileCoord t = decode_item(p, item);
+      const TileCoord t = decode_item(p, item, sub);
       if (do_stats && cur_img >= 0 && t.n0 != cur_img) {
-        named_bar_sync(1, 128);
+        named_bar_sync(gbar, 128);
         for (int c = et; c < p.CoutTotal; c += 128) {
           flush_stats(p, s_sum, s_sq, cur_img, c);
         }
-        named_bar_sync(1, 128);
+        named_bar_sync(gbar, 128);
       }
       cur_img = t.n0;
       const int gx = t.x0 + tx, gy = t.y0 + ty, n = t.n0 + tn;
@@ -262,7 +290,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
 
       mbar_wait(&tfull_bar[as], aphase);
       tc_fence_after();
-      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * p.BN;
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + (as * MT + sub) * p.BN;
       if (p.argmax_keys != nullptr) {
         // gallery match: score = acc + bias[j] (= 2 e.g_j - |g_j|^2); keep the best column of this tile per row and
         // fold it into the global per-query key (max score, then lowest index == torch.argmax tie-break)
@@ -370,19 +398,21 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
           const float ssq = warp_reduce16(sq, lane);
           if ((lane & 1) == 0) {
             const int ch = ch0 + reduce16_channel(lane);
-            s_sum[q * kStatsMaxC + ch] += ssum;
-            s_sq[q * kStatsMaxC + ch] += ssq;
+            s_sum[q * p.CoutTotal + ch] += ssum;
+            s_sq[q * p.CoutTotal + ch] += ssq;
           }
         }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[as]);
-      as ^= 1;
-      if (as == 0) aphase ^= 1;
+      if (++as == p.nAcc) {
+        as = 0;
+        aphase ^= 1;
+      }
     }
     if (do_stats && cur_img >= 0) {
-      named_bar_sync(1, 128);
+      named_bar_sync(gbar, 128);
       for (int c = et; c < p.CoutTotal; c += 128) {
         flush_stats(p, s_sum, s_sq, cur_img, c);
       }
@@ -487,13 +517,32 @@ int conv_build(const ConvSpec& s, ConvOp* op) {
   p.BN = bn;
   p.numNTiles = s.Cout / bn;
   p.CoutTotal = s.Cout;
-  p.stageBytes = kBM * 128 + bn * 128;
-  const int ctrlBytes = 8 * (2 * 8 + 4) + 16 + 8 * kStatsMaxC * 4;
+  // two M tiles per CTA step (shared weight stage) whenever the tile list pairs up and still fills the machine
+  {
+    const int mTiles = p.tilesX * p.tilesY * p.tilesN;
+    static const int force = getenv("CFR_IGEMM_MT") != nullptr ? atoi(getenv("CFR_IGEMM_MT")) : 0;   // A/B knob: 1 or 2
+    const bool same_rows = s.wRowsPerSample == 0 || (p.tilesX * p.tilesY) % 2 == 0;   // a pair reads ONE weight tile
+    const long long pairItems = static_cast<long long>(mTiles / 2) * s.numPhases * (s.Cout / bn);
+    bool mt2 = mTiles % 2 == 0 && same_rows && 2 * bn <= 512 && pairItems >= num_sms() / 2;
+    if (force == 1) mt2 = false;
+    p.MT = mt2 ? 2 : 1;
+    p.nAcc = (2 * p.MT * bn <= 512) ? 2 : 1;
+  }
+  p.stageBytes = p.MT * kBM * 128 + bn * 128;
+  const int statBytes = s.stat_sum != nullptr ? p.MT * 8 * s.Cout * 4 : 0;
+  const int ctrlBytes = 8 * (2 * 8 + 4) + 16 + statBytes;
   const int budget = 227 * 1024 - 1024 - ctrlBytes;
   p.numStages = budget / p.stageBytes;
   if (p.numStages > 8) p.numStages = 8;
+  if (p.numStages < 3 && p.MT == 2) {                   // not enough stages to pipeline: fall back to one tile per step
+    p.MT = 1;
+    p.nAcc = 2;
+    p.stageBytes = kBM * 128 + bn * 128;
+    p.numStages = (227 * 1024 - 1024 - (8 * (2 * 8 + 4) + 16 + (s.stat_sum != nullptr ? 8 * s.Cout * 4 : 0))) / p.stageBytes;
+    if (p.numStages > 8) p.numStages = 8;
+  }
   if (p.numStages < 2) { set_error("conv: not enough shared memory for 2 stages"); return 2; }
-  op->smemBytes = p.numStages * p.stageBytes + ctrlBytes + 1024;
+  op->smemBytes = p.numStages * p.stageBytes + (8 * (2 * 8 + 4) + 16 + (s.stat_sum != nullptr ? p.MT * 8 * s.Cout * 4 : 0)) + 1024;
   p.wRowsPerSample = s.wRowsPerSample;
   p.wRowsPerPhase = s.wRowsPerPhase;
   if (s.outIsF32) p.out32 = static_cast<float*>(s.out); else p.out = static_cast<__half*>(s.out);
@@ -530,7 +579,7 @@ int conv_build(const ConvSpec& s, ConvOp* op) {
   }
   if (s.Kpad % 64 != 0 || s.Kpad < s.ntaps * s.Cin) { set_error("conv: Kpad=%d must be a multiple of 64 and >= taps*Cin", s.Kpad); return 2; }
 
-  const int total = p.tilesX * p.tilesY * p.tilesN * p.numPhases * p.numNTiles;
+  const int total = (p.tilesX * p.tilesY * p.tilesN / p.MT) * p.numPhases * p.numNTiles;
   op->grid = total < num_sms() ? total : num_sms();
   // algorithmic FLOPs of this launch: 2 * (valid output-grid pixels) * phases * taps * Cin * Cout
   op->flops = 2.0 * s.N * s.Hout * s.Wout * s.numPhases * s.ntaps * static_cast<double>(s.Cin) * s.Cout;
@@ -590,7 +639,9 @@ int conv_launch(const ConvOp& op, cudaStream_t stream) {
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(conv_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    attr_err = cudaFuncSetAttribute(conv_igemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (attr_err == cudaSuccess)
+      attr_err = cudaFuncSetAttribute(conv_igemm_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   });
   if (attr_err != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(attr_err)); return 4; }
   cudaEvent_t e1 = nullptr;
@@ -598,7 +649,8 @@ int conv_launch(const ConvOp& op, cudaStream_t stream) {
     cudaEventRecord(profile_event(0), stream);
     e1 = profile_event(0);
   }
-  conv_igemm_kernel<<<op.grid, kConvThreads, op.smemBytes, stream>>>(op.p);
+  if (op.p.MT == 2) conv_igemm_kernel<2><<<op.grid, kConvThreadsMT2, op.smemBytes, stream>>>(op.p);
+  else conv_igemm_kernel<1><<<op.grid, kConvThreads, op.smemBytes, stream>>>(op.p);
   if (profile_on()) {
     cudaEventRecord(e1, stream);
     profile_account(0, op.flops);

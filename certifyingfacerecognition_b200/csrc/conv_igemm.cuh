@@ -23,6 +23,7 @@
 namespace cfr {
 
 constexpr int kConvThreads = 192;   // warps0-3: epilogue, warp4: TMA producer, warp5: MMA issuer + TMEM owner
+constexpr int kConvThreadsMT2 = 320;  // + warps 6-9: epilogue of the second M tile (MT == 2)
 constexpr int kBM = 128;
 constexpr int kMaxPhases = 4;
 constexpr int kMaxTaps = 9;
@@ -46,6 +47,8 @@ struct ConvParams {
   int BN;                        // output channels per tile (multiple of 16, <= 256)
   int swizzleA;                  // bytes: 32 / 64 / 128 (= CB*2)
   int numStages, stageBytes;
+  int MT;                        // M tiles per CTA step (1 or 2): two adjacent tiles share every weight stage
+  int nAcc;                      // TMEM accumulator sets (of MT x BN columns) in flight: 2, or 1 when MT*BN == 512
   int wRowsPerSample;            // 0: weights shared by all samples
   int wRowsPerPhase;
   // output
