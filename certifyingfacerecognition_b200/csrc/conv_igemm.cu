@@ -103,7 +103,9 @@ conv_igemm_kernel(const __grid_constant__ ConvParams p) {
   const int warp = threadIdx.x >> 5;
   const uint32_t lane = lane_id();
 
-  const int totalItems = (p.tilesX * p.tilesY * p.tilesN / MT) * p.numPhases * p.numNTiles;
+  // (an odd tile count leaves the last pair with a dummy second tile: its sample index is >= N, so TMA zero-fills its
+  //  A box and the epilogue only keeps the barriers in step)
+  const int totalItems = ((p.tilesX * p.tilesY * p.tilesN + MT - 1) / MT) * p.numPhases * p.numNTiles;
   const int per = (totalItems + gridDim.x - 1) / gridDim.x;
   const int item0 = blockIdx.x * per;
   const int item1 = min(totalItems, item0 + per);
@@ -267,6 +269,18 @@ conv_igemm_kernel(const __grid_constant__ ConvParams p) {
     const bool do_stats = p.stat_sum != nullptr;
     for (int item = item0; item < item1; ++item) {
       const TileCoord t = decode_item(p, item, sub);
+      if (MT == 2 && t.n0 >= p.N) {              // dummy tile of an odd tile count
+        mbar_wait(&tfull_bar[as], aphase);
+        tc_fence_after();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty_bar[as]);
+        if (++as == p.nAcc) {
+          as = 0;
+          aphase ^= 1;
+        }
+        continue;
+      }
       if (do_stats && cur_img >= 0 && t.n0 != cur_img) {
         named_bar_sync(gbar, 128);
         for (int c = et; c < p.CoutTotal; c += 128) {
@@ -523,7 +537,7 @@ int conv_build(const ConvSpec& s, ConvOp* op) {
     static const int force = getenv("CFR_IGEMM_MT") != nullptr ? atoi(getenv("CFR_IGEMM_MT")) : 0;   // A/B knob: 1 or 2
     const bool same_rows = s.wRowsPerSample == 0 || (p.tilesX * p.tilesY) % 2 == 0;   // a pair reads ONE weight tile
     const long long pairItems = static_cast<long long>(mTiles / 2) * s.numPhases * (s.Cout / bn);
-    bool mt2 = mTiles % 2 == 0 && same_rows && 2 * bn <= 512 && pairItems >= num_sms() / 2;
+    bool mt2 = mTiles >= 2 && same_rows && 2 * bn <= 512 && pairItems >= num_sms() / 2;
     if (force == 1) mt2 = false;
     p.MT = mt2 ? 2 : 1;
     p.nAcc = (2 * p.MT * bn <= 512) ? 2 : 1;
@@ -579,7 +593,7 @@ int conv_build(const ConvSpec& s, ConvOp* op) {
   }
   if (s.Kpad % 64 != 0 || s.Kpad < s.ntaps * s.Cin) { set_error("conv: Kpad=%d must be a multiple of 64 and >= taps*Cin", s.Kpad); return 2; }
 
-  const int total = (p.tilesX * p.tilesY * p.tilesN / p.MT) * p.numPhases * p.numNTiles;
+  const int total = ((p.tilesX * p.tilesY * p.tilesN + p.MT - 1) / p.MT) * p.numPhases * p.numNTiles;
   op->grid = total < num_sms() ? total : num_sms();
   // algorithmic FLOPs of this launch: 2 * (valid output-grid pixels) * phases * taps * Cin * Cout
   op->flops = 2.0 * s.N * s.Hout * s.Wout * s.numPhases * s.ntaps * static_cast<double>(s.Cin) * s.Cout;

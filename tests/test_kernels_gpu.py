@@ -58,6 +58,9 @@ CONV_CASES = [
     (3, 256, 512, 14, 2, 3),
     (5, 512, 512, 7, 1, 3),
     (2, 64, 320, 16, 1, 3),
+    (297, 16, 32, 8, 1, 3),      # 149 M tiles (odd): paired-tile (MT=2) path with a dummy last tile
+    (150, 64, 128, 16, 1, 3),    # 300 M tiles: paired-tile path, two accumulator sets in flight
+    (160, 128, 256, 16, 1, 3),   # paired tiles with BN=256 (single accumulator set)
 ]
 
 
