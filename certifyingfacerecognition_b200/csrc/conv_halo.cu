@@ -264,6 +264,22 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
 #pragma unroll
           for (int k = 0; k < 4; ++k)
             issue_tile(d0 + k * ACC_COLS, a_row, x_row, w_lo + k * p.ntaps * w_tap, wa_lo + k * (COUT * 2), toff[k]);
+        } else if (FOLD && p.ntaps == 9 && kPer == 1 && j * G + G <= bd.rows && !(p.dbg & 16)) {
+          // tile k of the group == output row j*G + k.  Tap-major over the G tiles: consecutive MMAs write DIFFERENT
+          // accumulators, so the tensor pipe is not serialised on one accumulate chain (N = 16 MMAs are latency-,
+          // not throughput-limited)
+          const uint32_t a0 = a_band + j * G * row_step, x0 = x_band + j * G * aux_row_step;
+#pragma unroll
+          for (int t = 0; t < 9; ++t) {
+#pragma unroll
+            for (int k = 0; k < G; ++k) {
+              if (t == 0) umma_f16_pred<false>(d0 + k * ACC_COLS, a0 + k * row_step + toff[0][t], dhi, w_lo, dhi, idesc, lead);
+              else umma_f16_pred<true>(d0 + k * ACC_COLS, a0 + k * row_step + toff[0][t], dhi, w_lo + t * w_tap, dhi, idesc, lead);
+            }
+          }
+#pragma unroll
+          for (int k = 0; k < G; ++k)
+            umma_f16_pred<true>(d0 + k * ACC_COLS, x0 + k * aux_row_step, dhi_aux, wa_lo, dhi_aux, idesc, leader ? 1u : 0u);
         } else {                           // tile k of the group == output row j*G + k
 #pragma unroll
           for (int k = 0; k < G; ++k) {
