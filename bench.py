@@ -90,8 +90,9 @@ class ClockSampler:
 
 
 def build_fixture(n_ids: int):
-    from oracle import fixtures
-    g_sd, f_sd = fixtures.build_models(cache_dir=os.path.join(ROOT, ".fixture_cache"))
+    """Seeded random-init weights of the named architectures + synthetic latents (package module, no oracle code)."""
+    from certifyingfacerecognition_b200 import synthetic as fixtures
+    g_sd, f_sd = fixtures.build_models()
     dirs = torch.from_numpy(np.load(os.path.join(ROOT, "tests", "golden", "dirs.npy")))
     lat = torch.from_numpy(fixtures.latents(n_ids))
     return g_sd, f_sd, dirs, lat, fixtures

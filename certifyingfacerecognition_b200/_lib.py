@@ -72,6 +72,7 @@ SIGNATURES = {
     "cfr_program_add_torgb_resize": (_I, [_P, _P, _P, _P, _I, _I, _I, _P, _P, _I, _F, _F, _P, _P, _P]),
     "cfr_noise_project": (_I, [_P, _P, _P, _I, _P, _P, _P, _F, _U64, _U64, _I, _P, _P, _P]),
     "cfr_truncate": (_I, [_P, _P, _F, _I, _P, _P]),
+    "cfr_mapping": (_I, [_P, _P, _P, _I, _P, _P]),
     "cfr_match_vote": (_I, [_P, _I, _P, _I, _P, _P, _P, _P]),
     "cfr_matcher_create": (_I, [_P, _I, _I, _P, C.POINTER(_P)]),
     "cfr_matcher_destroy": (None, [_P]),

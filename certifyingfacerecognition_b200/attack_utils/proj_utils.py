@@ -22,6 +22,17 @@ ATTRS["pose"] = 0.5
 ATTRS["smile"] = 0.8
 
 
+def set_seed(device, seed=111):
+    """proj_utils.py:28-33."""
+    import random
+    import torch
+    random.seed(seed)
+    np.random.seed(seed)
+    torch.manual_seed(seed)
+    if str(device).startswith("cuda"):
+        torch.cuda.manual_seed_all(seed)
+
+
 def get_full_points(points, fill_with_null=False):
     """Mirror the point set through the origin, optionally completing it with a null-space basis first."""
     if fill_with_null:

@@ -272,6 +272,10 @@ CFR_API int cfr_noise_project(const float* z, const float* x, const float* sigma
 CFR_API int cfr_truncate(const float* w, const float* w_avg, float psi, int b, float* wp2, cfr_stream_t stream) {
   return launch_truncate(w, w_avg, psi, b, wp2, S(stream));
 }
+CFR_API int cfr_mapping(const float* z, const float* wt, const float* bias, int b, float* w_out, cfr_stream_t stream) {
+  if (z == nullptr || wt == nullptr || bias == nullptr || w_out == nullptr) { set_error("cfr_mapping: null pointer"); return 2; }
+  return launch_mapping(z, wt, bias, b, w_out, S(stream));
+}
 CFR_API int cfr_match_vote(const float* emb, int b, const float* gallery, int n, uint64_t* keys, int32_t* pred, int64_t* counts,
                    cfr_stream_t stream) {
   return launch_match_vote(emb, b, gallery, n, reinterpret_cast<unsigned long long*>(keys), pred,

@@ -161,6 +161,67 @@ int launch_layer0(const float* xhat0, const float* styles, int style_stride, int
 }
 
 // ------------------------------------------------------------------------------------------
+// Mapping network Z -> W (generate_data.py path).  8 dense 512x512 layers in fp32 on the CUDA cores: 4.2 MFLOP per
+// latent, weights (8 MB) L2-resident and read coalesced through the transposed layout; one block = kMapRows latents,
+// thread o owns output feature o of every layer.
+// ------------------------------------------------------------------------------------------
+constexpr int kMapRows = 8;
+__global__ void __launch_bounds__(512) k_mapping(const float* __restrict__ z, const float* __restrict__ wt,
+                                                 const float* __restrict__ bias, int b, float* __restrict__ w_out) {
+  __shared__ float xs[2][kMapRows][512];
+  __shared__ float red[kMapRows][16];
+  const int o = threadIdx.x, r0 = blockIdx.x * kMapRows;
+  const int lane = o & 31, warp = o >> 5;
+  // PixelNormLayer: x / sqrt(mean(x^2) + 1e-8)
+  float v[kMapRows];
+#pragma unroll
+  for (int s = 0; s < kMapRows; ++s) {
+    v[s] = (r0 + s < b) ? z[static_cast<size_t>(r0 + s) * 512 + o] : 0.f;
+    float q = v[s] * v[s];
+    for (int off = 16; off > 0; off >>= 1) q += __shfl_xor_sync(0xffffffffu, q, off);
+    if (lane == 0) red[s][warp] = q;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int s = 0; s < kMapRows; ++s) {
+    float q = 0.f;
+    for (int w = 0; w < 16; ++w) q += red[s][w];
+    xs[0][s][o] = v[s] / sqrtf(q * (1.0f / 512.0f) + 1e-8f);
+  }
+  __syncthreads();
+  int cur = 0;
+  for (int l = 0; l < 8; ++l) {
+    const float* wl = wt + static_cast<size_t>(l) * 512 * 512 + o;
+    float acc[kMapRows];
+#pragma unroll
+    for (int s = 0; s < kMapRows; ++s) acc[s] = 0.f;
+#pragma unroll 4
+    for (int i = 0; i < 512; ++i) {
+      const float wv = __ldg(wl + static_cast<size_t>(i) * 512);
+#pragma unroll
+      for (int s = 0; s < kMapRows; ++s) acc[s] = fmaf(xs[cur][s][i], wv, acc[s]);
+    }
+    const float bv = bias[l * 512 + o];
+#pragma unroll
+    for (int s = 0; s < kMapRows; ++s) {
+      const float t = acc[s] + bv;
+      xs[cur ^ 1][s][o] = t >= 0.f ? t : 0.2f * t;
+    }
+    __syncthreads();
+    cur ^= 1;
+  }
+#pragma unroll
+  for (int s = 0; s < kMapRows; ++s)
+    if (r0 + s < b) w_out[static_cast<size_t>(r0 + s) * 512 + o] = xs[cur][s][o];
+}
+int launch_mapping(const float* z, const float* wt, const float* bias, int b, float* w_out, cudaStream_t st) {
+  if (b <= 0) return 0;
+  k_mapping<<<(b + kMapRows - 1) / kMapRows, 512, 0, st>>>(z, wt, bias, b, w_out);
+  CFR_LAUNCH_CHECK("mapping");
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
 // blur [1,2,1]x[1,2,1]/16 (zero pad) + noise*w + bias + lrelu(0.2) + per-(n,c) sum / sumsq
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ void load8(const __half* p, float (&f)[8]) {

@@ -14,6 +14,10 @@ int launch_noise_project(const float* z, const float* x, const float* sigma, int
 // plain latents (gallery building): wp2 from w[b,512] directly
 int launch_truncate(const float* w, const float* w_avg, float psi, int b, float* wp2, cudaStream_t st);
 
+// MappingModule (stylegan_generator_model.py:265-295): PixelNorm (:398-406) + 8 x {Linear(512,512) * scale + b, LeakyReLU(0.2)}
+//   wt [8][512 in][512 out] = W^T * (sqrt(2)/sqrt(512) * lr_mul), bias [8][512] = b * lr_mul;  z [b,512] -> w [b,512] (fp32)
+int launch_mapping(const float* z, const float* wt, const float* bias, int b, float* w_out, cudaStream_t st);
+
 // stylegan_generator_model.py:503 via DenseBlock :811-815  -- all 18 layers' style vectors at once
 int launch_styles(const float* wp2, const float* w_style, const float* b_style, int rows, int rows_trunc, int b,
                   float* styles, cudaStream_t st);

@@ -282,7 +282,7 @@ class SynthesisProgram(Program):
     def __init__(self, g_sd: Dict[str, Tensor], chunk: int, out_res: int = 112, device="cuda",
                  keep_planar: bool = False, mean: float = 0.5, std: float = 0.5, halo: bool = True,
                  fold_small: bool = True, groups: int = 1, blur_on_tensor_cores: bool = True,
-                 fused_upblur: bool = True):
+                 fused_upblur: bool = True, nhwc_out: bool = True):
         super().__init__()
         dev = torch.device(device)
         self.chunk, self.out_res = chunk, out_res
@@ -414,7 +414,8 @@ class SynthesisProgram(Program):
         # the image buffer holds `groups` chunks; the op writes group *out_slot (set by the sampler between runs)
         self.groups = groups
         self.out_slot = self.hold(torch.zeros(1, dtype=torch.int32, device=dev))
-        self.img = self.hold(torch.zeros(groups * chunk, out_res, out_res, 16, dtype=torch.float16, device=dev))
+        self.img = (self.hold(torch.zeros(groups * chunk, out_res, out_res, 16, dtype=torch.float16, device=dev))
+                    if nhwc_out else None)
         self.img_planar = self.hold(torch.zeros(groups * chunk, 3, out_res, out_res, device=dev)) if keep_planar else None
         L.check(lib.cfr_program_add_torgb_resize(h, L.ptr(y), L.ptr(pending[0]), L.ptr(pending[1]), chunk, 1024, 16,
                                                  L.ptr(w_rgb), L.ptr(b_rgb), out_res, mean, std, L.ptr(self.img),

@@ -129,6 +129,10 @@ CFR_API int cfr_noise_project(const float* z, const float* x, const float* sigma
                       const float* dir_mat, const float* w_avg, float psi, uint64_t seed, uint64_t sample_offset,
                       int b, float* noise_out, float* wp2, cfr_stream_t stream);
 CFR_API int cfr_truncate(const float* w, const float* w_avg, float psi, int b, float* wp2, cfr_stream_t stream);
+/* MappingModule.forward (stylegan_generator_model.py:265-295; PixelNormLayer :398-406, DenseBlock :765-815, WScaleLayer
+ * :508-535) -- the Z -> W step of generate_data.py:58-123 / ModStyleGANGenerator.synthesize 'Z' (mod_stylegan_generator.py
+ * :228-236).  wt: [8][512 in][512 out] fp32 = W_l^T * (sqrt(2)/sqrt(512) * 0.01); bias: [8][512] = b_l * 0.01. */
+CFR_API int cfr_mapping(const float* z, const float* wt, const float* bias, int b, float* w_out, cfr_stream_t stream);
 /* WrappedModel.compute_probs + .argmax(1) + Smooth._count_arr (smoothing_model.py:56-61, smooth.py:135-146).
  * keys: b uint64 scratch, all-ones before the first call (re-armed by the call). */
 CFR_API int cfr_match_vote(const float* emb, int b, const float* gallery, int n, uint64_t* keys, int32_t* pred,

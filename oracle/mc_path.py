@@ -44,6 +44,30 @@ def layer_res(layer: int) -> int:
 
 
 # --------------------------------------------------------------------------- #
+# StyleGAN v1 mapping network (generate_data.py path)     #
+# --------------------------------------------------------------------------- #
+def preprocess_z(z: Tensor) -> Tensor:
+    """ModStyleGANGenerator.preprocess, latent_space_type 'Z' (mod_stylegan_generator.py:177-180):
+    z / ||z|| * sqrt(512)."""
+    z = z.reshape(-1, W_DIM)
+    return z / z.norm(dim=1, keepdim=True) * math.sqrt(W_DIM)
+
+
+def mapping(z: Tensor, sd: SD) -> Tensor:
+    """MappingModule.forward, stylegan_generator_model.py:265-295: PixelNormLayer (:398-406, eps 1e-8) then 8 x
+    DenseBlock (:765-815) = Linear(no bias) -> WScaleLayer (:508-535: x*gain/sqrt(fan_in)*lr_mul + b*lr_mul with
+    gain sqrt(2), lr_mul 0.01) -> LeakyReLU(0.2).   [B,512] -> [B,512]."""
+    x = z / torch.sqrt(torch.mean(z * z, dim=1, keepdim=True) + 1e-8)
+    lr_mul = 0.01
+    scale = math.sqrt(2.0) / math.sqrt(W_DIM) * lr_mul
+    for i in range(8):
+        x = F.linear(x, sd[f"mapping.dense{i}.linear.weight"])
+        x = x * scale + sd[f"mapping.dense{i}.wscale.bias"].view(1, -1) * lr_mul
+        x = F.leaky_relu(x, 0.2)
+    return x
+
+
+# --------------------------------------------------------------------------- #
 # StyleGAN v1 synthesis                                                        #
 # --------------------------------------------------------------------------- #
 def truncation(w: Tensor, sd: SD, psi: float = 0.7, trunc_layers: int = 8) -> Tensor:

@@ -49,3 +49,31 @@ def test_certify_cli_writes_reference_tsv(tmp_path, golden, models):
     # 24 votes for the true identity -> pABar = 0.001^(1/24) -> gap 0.674 printed with 3 significant digits
     certified = [r_ for r_ in rows if r_[3] == "1"]
     assert certified, rows
+
+
+@pytest.mark.gpu
+def test_gallery_builder_tool_roundtrip(tmp_path):
+    """latents -> embs file (main_attack.py:210-216), read back through WrappedModel(load_embs=True)."""
+    import json
+    import subprocess
+    import sys
+    from certifyingfacerecognition_b200 import synthetic
+    from certifyingfacerecognition_b200.models.smoothing_model import WrappedModel
+    out = tmp_path / "embeddings" / "embs_insightface.pth"
+    wnpy = tmp_path / "w.npy"
+    np.save(wnpy, synthetic.latents(6))
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "build_gallery.py"), "--latents", str(wnpy), "--num", "6",
+                        "--chunk", "4", "--out", str(out)], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert line["identities"] == 6 and line["value"] > 0
+    embs = torch.load(out)
+    assert embs.shape == (6, 512) and torch.isfinite(embs).all()
+    g_sd, f_sd = synthetic.build_models()
+    dirs = torch.from_numpy(np.load(os.path.join(ROOT, "tests", "golden", "dirs.npy"))).cuda()
+    m = WrappedModel(dirs, "insightface", n_embs=-1, load_embs=True, embs_file=str(out), generator_state=g_sd,
+                     frm_state=f_sd, latents=torch.from_numpy(synthetic.latents(6)), chunk=4)
+    assert torch.allclose(m.orig_embs.cpu(), embs, atol=0, rtol=0)
+    # the gallery rows are the embeddings of the unperturbed latents: identity i must match row i
+    probs = m(m.latents[2:3], torch.zeros(1, 1, 1, 5, device="cuda"))
+    assert int(probs.argmax(1)) == 2

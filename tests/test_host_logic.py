@@ -192,3 +192,23 @@ def test_composite_upconv_blur_weights_are_exact():
                         v = v + torch.einsum("yoi,niy->no", corr[1, a, rci], xp[:, :, i:i + 3, W])
                     out[:, :, 2 * i + a, 2 * j + b] = v
     assert (out - ref).abs().max().item() < 1e-5
+
+
+def test_package_synthetic_weights_equal_the_test_fixtures(models):
+    """bench.py / tools draw their random-init weights from certifyingfacerecognition_b200/synthetic.py (the product
+    side may not import oracle/); they must be the very tensors the parity tests and golden vectors were made with."""
+    from certifyingfacerecognition_b200 import synthetic
+    from oracle import fixtures
+    g_ref, f_ref = models
+    g_sd, f_sd = synthetic.build_models()
+    assert set(g_sd) == set(g_ref) and set(f_sd) == set(f_ref)
+    for k in g_ref:
+        assert torch.equal(g_sd[k], g_ref[k]), k
+    for k in f_ref:
+        if k.endswith("running_mean") or k.endswith("running_var"):
+            assert torch.allclose(f_sd[k], f_ref[k].float(), rtol=0, atol=0), k      # stored as fp32 in the npz
+        else:
+            assert torch.equal(f_sd[k], f_ref[k]), k
+    assert np.array_equal(synthetic.latents(7), fixtures.latents(7))
+    rows = torch.randn(3, 512, generator=torch.Generator().manual_seed(0))
+    assert torch.equal(synthetic.synthetic_gallery(rows, 10), fixtures.synthetic_gallery(rows, 10))

@@ -1,12 +1,14 @@
 """Pin the CPU restatement (oracle/mc_path.py) against vectors produced by the UNMODIFIED reference
 (tests/golden/reference_vectors.npz, written by oracle/make_golden.py)."""
 import math
+import os
 
 import numpy as np
 import pytest
 import torch
 import torch.nn.functional as F
 
+from conftest import ROOT
 from oracle import mc_path as M
 
 
@@ -96,3 +98,15 @@ def test_count_arr_and_predict():
         out[:, 2] = 1.0
         return out
     assert M.predict(classify, torch.zeros(1, 5), torch.tensor([0.1]), 40, 0.001, 16, 4) == 2
+
+
+def test_mapping_network_against_reference():
+    """oracle restatement of MappingModule vs the unmodified reference module
+    (tests/golden/mapping_vectors.npz, written by oracle/make_golden_mapping.py)."""
+    from certifyingfacerecognition_b200 import synthetic
+    g = np.load(os.path.join(ROOT, "tests", "golden", "mapping_vectors.npz"))
+    sd = synthetic.mapping_weights()
+    z = M.preprocess_z(torch.from_numpy(g["z_raw"]))
+    assert torch.allclose(z, torch.from_numpy(g["z"]), atol=1e-5)
+    w = M.mapping(torch.from_numpy(g["z"]), sd)
+    assert torch.allclose(w, torch.from_numpy(g["w"]), atol=2e-5, rtol=1e-5)

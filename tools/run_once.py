@@ -16,9 +16,9 @@ def main():
     ap.add_argument("--chunk", type=int, default=8)
     ap.add_argument("--reps", type=int, default=2)
     args = ap.parse_args()
-    from oracle import fixtures
+    from certifyingfacerecognition_b200 import synthetic as fixtures
     from certifyingfacerecognition_b200.engine import Engine
-    g_sd, f_sd = fixtures.build_models(cache_dir=os.path.join(ROOT, ".fixture_cache"))
+    g_sd, f_sd = fixtures.build_models()
     dirs = torch.from_numpy(np.load(os.path.join(ROOT, "tests", "golden", "dirs.npy")))
     eng = Engine(g_sd, f_sd, dirs, torch.zeros(8, 512), chunk=args.chunk)
     w = torch.from_numpy(fixtures.latents(args.chunk))
