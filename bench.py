@@ -256,6 +256,16 @@ def main():
             dist.destroy_process_group()
         return
     pk = peaks()
+    # DRAM bytes per launch of the halo kernel from the committed `ncu --set full` capture of this very command
+    # (profiles/traffic_r01_halo.json; only meaningful for the chunk size it was captured at)
+    halo_traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic_r01_halo.json")) as fh:
+            tj = json.load(fh)
+        if args.chunk == 125:
+            halo_traffic = tj["avg_dram_bytes_per_launch"] / 1e6
+    except (OSError, KeyError, ValueError):
+        pass
     ig_ms, ig_flops, ig_n = prof["igemm"]
     ha_ms, ha_bytes, ha_n = prof["halo"]
     ig_tf = ig_flops / (ig_ms * 1e-3) / 1e12 if ig_ms > 0 else 0.0
@@ -264,7 +274,8 @@ def main():
     halo_roof = {"kernel": "conv_halo_kernel (tcgen05 halo-resident conv: StyleGAN layers 13-17, Cin<=64; HBM-bound "
                            "by arithmetic intensity, SURVEY.md section 8d)",
                  "bound": "hbm", "achieved": ha_gbs, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                 "frac": ha_gbs / pk["hbm_gbs"], "traffic": None, "peak_source": pk["source"],
+                 "frac": ha_gbs / pk["hbm_gbs"], "traffic": halo_traffic, "traffic_unit": "MB per launch (dram read+write, ncu)",
+                 "peak_source": pk["source"],
                  "launches_timed": int(ha_n), "avg_launch_ms": ha_ms / max(1, ha_n),
                  "alg_mbytes_per_launch": ha_bytes / max(1, ha_n) / 1e6, "share_of_step": ha_ms / ms if ms > 0 else None}
     igemm_roof = {"kernel": "conv_igemm_kernel (tcgen05 implicit GEMM: StyleGAN layers 1-12 + every iresnet50 conv / FC)",
