@@ -524,8 +524,9 @@ int conv_build(const ConvSpec& s, ConvOp* op) {
   p.swizzleA = p.CB * 2;
   // N tile: largest of 256/128/.. dividing Cout
   int bn = s.Cout;
-  if (bn > 256) {
-    bn = 256;
+  static const int bn_max = getenv("CFR_IGEMM_BN_MAX") != nullptr ? atoi(getenv("CFR_IGEMM_BN_MAX")) : 256;   // A/B knob
+  if (bn > bn_max) {
+    bn = bn_max;
     while (s.Cout % bn != 0) bn -= 16;
   }
   p.BN = bn;
