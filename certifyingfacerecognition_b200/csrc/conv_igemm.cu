@@ -524,7 +524,12 @@ int conv_build(const ConvSpec& s, ConvOp* op) {
   p.swizzleA = p.CB * 2;
   // N tile: largest of 256/128/.. dividing Cout
   int bn = s.Cout;
-  static const int bn_max = getenv("CFR_IGEMM_BN_MAX") != nullptr ? atoi(getenv("CFR_IGEMM_BN_MAX")) : 256;   // A/B knob
+  // N tile cap.  256 halves the A re-fetch per output channel, but two 256-column accumulators of a tile pair fill
+  // TMEM, so the epilogue cannot overlap the next tile; measured (profiles/ncu_r01_notes.md section 10): plain convs
+  // are faster with 128 (two accumulator sets in flight, twice the work items on the small ArcFace maps), the
+  // 4-phase up-convs (short K, Cin >= 256: ingest-bound) with 256.  CFR_IGEMM_BN_MAX overrides for A/B runs.
+  static const int bn_env = getenv("CFR_IGEMM_BN_MAX") != nullptr ? atoi(getenv("CFR_IGEMM_BN_MAX")) : 0;
+  const int bn_max = bn_env > 0 ? bn_env : (s.numPhases == 1 ? 128 : 256);
   if (bn > bn_max) {
     bn = bn_max;
     while (s.Cout % bn != 0) bn -= 16;
