@@ -219,3 +219,46 @@ def test_tensor_core_matcher_in_the_sampler(setup, models):
     c2, e2 = eng_tc.sample_votes(z, x, sigma, 19, seed=5, want_pred=True)
     torch.cuda.synchronize()
     assert torch.equal(e1["pred"], e2["pred"]) and torch.equal(c1, c2)
+
+
+def test_full_size_certification_step_properties(setup, golden, models):
+    """BASELINE config 2 sizes (250 MC samples per step, 5000-row gallery, chunk 125, two chunks per ArcFace run), checked
+    through size-independent properties: every sample votes exactly once, the Philox stream is offset-consistent (any
+    split over calls / ranks sums to the unsplit tally), identical inputs give identical bits, the host entry equals
+    the device entry, and the per-sample predictions agree with the small-chunk engine the other tests pin against
+    the oracle (chunking only changes the order of fp32 partial sums of the InstanceNorm statistics)."""
+    import ctypes as C
+    from certifyingfacerecognition_b200 import _lib as L
+    from certifyingfacerecognition_b200.engine import Engine
+    eng8, g_sd, f_sd, dirs, gallery, z = setup
+    big = Engine(g_sd, f_sd, dirs, gallery, chunk=125, frm_group=2)
+    x = torch.zeros(1, 5)
+    sigma = torch.tensor([2.0 * SIGMA])
+    num = 250
+    full, ex = big.sample_votes(z, x, sigma, num, seed=21, want_pred=True)
+    torch.cuda.synchronize()
+    assert full.sum().item() == num and full.min().item() >= 0
+    assert torch.equal(torch.bincount(ex["pred"].long(), minlength=N_GALLERY), full)
+    # offset-consistent split (what rank sharding relies on), ragged pieces
+    part = torch.zeros_like(full)
+    big.sample_votes(z, x, sigma, 100, seed=21, sample_offset=0, counts=part)
+    big.sample_votes(z, x, sigma, 37, seed=21, sample_offset=100, counts=part)
+    big.sample_votes(z, x, sigma, 113, seed=21, sample_offset=137, counts=part)
+    torch.cuda.synchronize()
+    assert torch.equal(full, part)
+    # bit-reproducible
+    again, _ = big.sample_votes(z, x, sigma, num, seed=21)
+    torch.cuda.synchronize()
+    assert torch.equal(full, again)
+    # host entry (host buffers, H2D / D2H inside the call)
+    counts = np.zeros(N_GALLERY, dtype=np.int64)
+    zh = z.numpy().reshape(-1).astype(np.float32)
+    xh, sh = np.zeros(5, dtype=np.float32), sigma.numpy().astype(np.float32)
+    L.check(big.lib.cfr_sample_votes_host(big.sampler, zh.ctypes.data, xh.ctypes.data, sh.ctypes.data, 1, num, 21, 0,
+                                          counts.ctypes.data, C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+    assert np.array_equal(counts, full.cpu().numpy())
+    # same Philox samples through the chunk-8 engine
+    _, ex8 = eng8.sample_votes(z, x, sigma, num, seed=21, want_pred=True)
+    torch.cuda.synchronize()
+    agree = (ex8["pred"] == ex["pred"]).float().mean().item()
+    assert agree >= 0.995, agree
