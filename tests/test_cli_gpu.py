@@ -62,7 +62,7 @@ def test_gallery_builder_tool_roundtrip(tmp_path):
     out = tmp_path / "embeddings" / "embs_insightface.pth"
     wnpy = tmp_path / "w.npy"
     np.save(wnpy, synthetic.latents(6))
-    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "build_gallery.py"), "--latents", str(wnpy), "--num", "6",
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "build_gallery.py"), "--latents", str(wnpy), "--identities", "6",
                         "--chunk", "4", "--out", str(out)], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stderr[-2000:]
     line = json.loads(r.stdout.strip().splitlines()[-1])

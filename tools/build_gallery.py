@@ -31,7 +31,7 @@ def main() -> None:
     ap.add_argument("--latents", default=None, help="w.npy ([N,512] or reshapable); default: synthetic fixture")
     ap.add_argument("--generator", default=None, help="stylegan_ffhq.pth state dict; default: synthetic fixture")
     ap.add_argument("--frm", default=None, help="iresnet50 backbone.pth state dict; default: synthetic fixture")
-    ap.add_argument("--num", type=int, default=512, help="identities (synthetic mode / truncation of --latents)")
+    ap.add_argument("--identities", dest="num", type=int, default=512, help="identities (synthetic mode / truncation of --latents)")
     ap.add_argument("--chunk", type=int, default=128)
     ap.add_argument("--out", default=None, help="embs .pth to write (rank 0)")
     args = ap.parse_args()
