@@ -55,7 +55,12 @@ __device__ __forceinline__ Band decode_band(const HaloParams& p, int b) {
 template <int COUT, bool FOLD, bool COMP = false>
 __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid_constant__ HaloParams p) {
   constexpr int NCH = COUT / 16;                 // 16-column epilogue chunks
-  constexpr bool REG_STATS = COUT <= 32;         // keep per-thread channel sums in registers across a band
+  // COUT == 64: both epilogue warp groups drain EVERY tile, each its own half of the channels, so that a thread's
+  // per-channel statistics (2 x 32 registers) stay in registers like in the narrower variants -- the per-chunk
+  // shuffle transpose-reduce it replaces was more than half of that epilogue's instructions
+  constexpr bool SPLIT = COUT == 64;
+  constexpr int NCH_T = SPLIT ? NCH / 2 : NCH;   // 16-column chunks per epilogue thread
+  constexpr bool REG_STATS = true;               // keep per-thread channel sums in registers across a band
   constexpr int ACC_COLS = COUT;                 // TMEM columns per accumulator
   constexpr int G = COUT == 64 ? 2 : 4;          // tiles per accumulator group (one mbarrier handshake per group)
   constexpr int AS = 512 / (G * COUT);           // accumulator groups resident in TMEM (8 / 4 / 4)
@@ -103,7 +108,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
       mbar_init(wdrain, kMmaWarps);
       for (int i = 0; i < 16; ++i) {
         mbar_init(&tfull[i], 1);
-        mbar_init(&tempty[i], 4);
+        mbar_init(&tempty[i], SPLIT ? 8 : 4);
       }
       fence_barrier_init();
     }
@@ -494,9 +499,10 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
     const bool has_noise = !FOLD && p.noise != nullptr, has_bias = !FOLD && p.bias != nullptr;
     const bool lrelu = p.act == CFR_ACT_LRELU;
     const float slope = p.slope;
-    float racc[REG_STATS ? COUT : 1], racc2[REG_STATS ? COUT : 1];
+    const int ci0 = SPLIT ? grp * NCH_T : 0;       // first chunk this thread handles
+    float racc[NCH_T * 16], racc2[NCH_T * 16];
 #pragma unroll
-    for (int i = 0; i < (REG_STATS ? COUT : 1); ++i) { racc[i] = 0.f; racc2[i] = 0.f; }
+    for (int i = 0; i < NCH_T * 16; ++i) { racc[i] = 0.f; racc2[i] = 0.f; }
     float hnw[HOIST ? COUT : 1], hbs[HOIST ? COUT : 1];
     if constexpr (HOIST) {
 #pragma unroll
@@ -536,7 +542,8 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
       const size_t pix_band = (static_cast<size_t>(bd.n) * p.outH + bd.y0 * p.oscale) * p.outW + gx * p.oscale;
       const size_t pix_row = static_cast<size_t>(p.oscale) * p.outW;
       // this warp group's accumulator groups of the band: index gbase + j with (gbase + j) % kEpiGroups == grp
-      for (int j = (grp - static_cast<int>(gbase)) & (kEpiGroups - 1); j < ngroups; j += kEpiGroups) {
+      for (int j = SPLIT ? 0 : ((grp - static_cast<int>(gbase)) & (kEpiGroups - 1)); j < ngroups;
+           j += SPLIT ? 1 : kEpiGroups) {
         const uint32_t gc = gbase + j;
         const uint32_t slot = gc & (AS - 1);
         mbar_wait(&tfull[slot], (gc >> asLog) & 1);
@@ -556,7 +563,8 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
           const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + (slot * G + k) * ACC_COLS;
           if (!(p.dbg & 1))
 #pragma unroll
-          for (int ci = 0; ci < NCH; ++ci) {
+          for (int cl = 0; cl < NCH_T; ++cl) {
+            const int ci = ci0 + cl;
             float v[16];
             tmem_ld16(t_row + ci * 16, v);
             const int ch0 = ci * 16;
@@ -607,8 +615,8 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
                 if (colok) {
 #pragma unroll
                   for (int i = 0; i < 16; ++i) {
-                    racc[ch0 + i] += v[i];
-                    racc2[ch0 + i] = fmaf(v[i], v[i], racc2[ch0 + i]);
+                    racc[cl * 16 + i] += v[i];
+                    racc2[cl * 16 + i] = fmaf(v[i], v[i], racc2[cl * 16 + i]);
                   }
                 }
               } else {
@@ -637,19 +645,19 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
       if constexpr (REG_STATS) {
         if (do_stats) {                      // once per band: registers -> shared
 #pragma unroll
-          for (int ci = 0; ci < NCH; ++ci) {
+          for (int cl = 0; cl < NCH_T; ++cl) {
             float a[16], a2[16];
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
-              a[i] = racc[ci * 16 + i];
-              a2[i] = racc2[ci * 16 + i];
-              racc[ci * 16 + i] = 0.f;
-              racc2[ci * 16 + i] = 0.f;
+              a[i] = racc[cl * 16 + i];
+              a2[i] = racc2[cl * 16 + i];
+              racc[cl * 16 + i] = 0.f;
+              racc2[cl * 16 + i] = 0.f;
             }
             const float ssum = warp_reduce16h(a, lane);
             const float ssq = warp_reduce16h(a2, lane);
             if ((lane & 1) == 0) {
-              const int ch = ci * 16 + reduce16_channel_h(lane);
+              const int ch = (ci0 + cl) * 16 + reduce16_channel_h(lane);
               s_sum[warp * COUT + ch] += ssum;
               s_sq[warp * COUT + ch] += ssq;
             }
