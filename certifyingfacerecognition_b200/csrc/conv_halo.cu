@@ -500,9 +500,10 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
     const bool lrelu = p.act == CFR_ACT_LRELU;
     const float slope = p.slope;
     const int ci0 = SPLIT ? grp * NCH_T : 0;       // first chunk this thread handles
-    float racc[NCH_T * 16], racc2[NCH_T * 16];
+    f2_t racc[NCH_T * 8], racc2[NCH_T * 8];          // per-thread channel sums, packed fp32 pairs (FADD2 / FFMA2)
 #pragma unroll
-    for (int i = 0; i < NCH_T * 16; ++i) { racc[i] = 0.f; racc2[i] = 0.f; }
+    for (int i = 0; i < NCH_T * 8; ++i) { racc[i] = f2_pack(0.f, 0.f); racc2[i] = racc[i]; }
+    const f2_t slope2 = f2_pack(p.slope, p.slope);
     float hnw[HOIST ? COUT : 1], hbs[HOIST ? COUT : 1];
     if constexpr (HOIST) {
 #pragma unroll
@@ -597,9 +598,17 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
                 for (int i = 0; i < 16; ++i) v[i] += cp[i];
               }
             }
+            f2_t vp[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) vp[i] = f2_pack(v[2 * i], v[2 * i + 1]);
             if (lrelu) {
 #pragma unroll
-              for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], v[i] * slope);      // slope < 1
+              for (int i = 0; i < 8; ++i) {                                          // max(v, v * slope), slope < 1
+                const float2 sv = f2_unpack(f2_mul(vp[i], slope2));
+                v[2 * i] = fmaxf(v[2 * i], sv.x);
+                v[2 * i + 1] = fmaxf(v[2 * i + 1], sv.y);
+                vp[i] = f2_pack(v[2 * i], v[2 * i + 1]);
+              }
             }
             if (colok) {
               uint4 o[2];
@@ -614,9 +623,9 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
               if constexpr (REG_STATS) {
                 if (colok) {
 #pragma unroll
-                  for (int i = 0; i < 16; ++i) {
-                    racc[cl * 16 + i] += v[i];
-                    racc2[cl * 16 + i] = fmaf(v[i], v[i], racc2[cl * 16 + i]);
+                  for (int i = 0; i < 8; ++i) {
+                    racc[cl * 8 + i] = f2_add(racc[cl * 8 + i], vp[i]);
+                    racc2[cl * 8 + i] = f2_fma(vp[i], vp[i], racc2[cl * 8 + i]);
                   }
                 }
               } else {
@@ -648,11 +657,12 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
           for (int cl = 0; cl < NCH_T; ++cl) {
             float a[16], a2[16];
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              a[i] = racc[cl * 16 + i];
-              a2[i] = racc2[cl * 16 + i];
-              racc[cl * 16 + i] = 0.f;
-              racc2[cl * 16 + i] = 0.f;
+            for (int i = 0; i < 8; ++i) {
+              const float2 s1 = f2_unpack(racc[cl * 8 + i]), s2 = f2_unpack(racc2[cl * 8 + i]);
+              a[2 * i] = s1.x; a[2 * i + 1] = s1.y;
+              a2[2 * i] = s2.x; a2[2 * i + 1] = s2.y;
+              racc[cl * 8 + i] = f2_pack(0.f, 0.f);
+              racc2[cl * 8 + i] = racc[cl * 8 + i];
             }
             const float ssum = warp_reduce16h(a, lane);
             const float ssq = warp_reduce16h(a2, lane);

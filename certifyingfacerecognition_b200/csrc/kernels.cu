@@ -457,32 +457,6 @@ __global__ void __launch_bounds__(256, 3) k_blur_rows(const __half* __restrict__
 // arithmetic and register moves), hence: running pointers, the ring/role rotation unrolled 6x so stage offsets and
 // the three-row window are compile-time, and packed fp32x2 arithmetic (sm_100 FADD2/FFMA2/FMUL2).
 constexpr int kBlurStages = 6;
-typedef unsigned long long f2_t;                          // two packed fp32 (the .f32x2 PTX operand type)
-__device__ __forceinline__ f2_t f2_pack(float lo, float hi) {
-  f2_t r;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
-  return r;
-}
-__device__ __forceinline__ float2 f2_unpack(f2_t v) {
-  float2 r;
-  asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v));
-  return r;
-}
-__device__ __forceinline__ f2_t f2_add(f2_t a, f2_t b) {
-  f2_t d;
-  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-  return d;
-}
-__device__ __forceinline__ f2_t f2_mul(f2_t a, f2_t b) {
-  f2_t d;
-  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-  return d;
-}
-__device__ __forceinline__ f2_t f2_fma(f2_t a, f2_t b, f2_t c) {
-  f2_t d;
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
-  return d;
-}
 __device__ __forceinline__ f2_t f2_from_half2(uint32_t h2) {
   const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&h2));
   return f2_pack(f.x, f.y);
