@@ -77,6 +77,9 @@ SIGNATURES = {
     "cfr_matcher_create": (_I, [_P, _I, _I, _P, C.POINTER(_P)]),
     "cfr_matcher_destroy": (None, [_P]),
     "cfr_matcher_run": (_I, [_P, _P, _I, _P, _P, _P]),
+    "cfr_match_keys": (_I, [_P, _I, _P, _I, C.c_uint32, _P, _P]),
+    "cfr_matcher_keys": (_I, [_P, _P, _I, C.c_uint32, _P, _P]),
+    "cfr_vote_keys": (_I, [_P, _I, _P, _P, _P]),
     "cfr_sampler_create": (_I, [C.POINTER(SamplerDesc), C.POINTER(_P)]),
     "cfr_sampler_destroy": (None, [_P]),
     "cfr_sample_votes": (_I, [_P, _P, _P, _P, _I, _P, _I64, _U64, _U64, _P, _P, _P, _P, _P]),

@@ -331,6 +331,29 @@ CFR_API int cfr_matcher_run(cfr_matcher* m, const float* emb, int b, int32_t* pr
   return 0;
 }
 
+// ---- gallery sharded over ranks (partition C) ----
+CFR_API int cfr_match_keys(const float* emb, int b, const float* gallery, int n, uint32_t row_offset, uint64_t* keys,
+                           cfr_stream_t stream) {
+  if (n <= 0) { set_error("match_keys: empty gallery shard"); return 2; }
+  return launch_match_keys(emb, b, gallery, n, row_offset, reinterpret_cast<unsigned long long*>(keys), S(stream));
+}
+CFR_API int cfr_matcher_keys(cfr_matcher* m, const float* emb, int b, uint32_t row_offset, uint64_t* keys,
+                             cfr_stream_t stream) {
+  if (b > m->max_b) { set_error("matcher: b=%d exceeds max_b=%d", b, m->max_b); return 2; }
+  if (b <= 0) return 0;
+  int r = launch_split_hilo(emb, b, m->max_b, 1, m->q_split, nullptr, S(stream));
+  if (r) return r;
+  if ((r = conv_launch(m->op, S(stream))) != 0) return r;
+  r = launch_export_argmax_keys(m->keys, b, row_offset, reinterpret_cast<unsigned long long*>(keys), S(stream));
+  if (r) return r;
+  if (b < m->max_b) CFR_CUDA(cudaMemsetAsync(m->keys + b, 0, sizeof(unsigned long long) * (m->max_b - b), S(stream)));
+  return 0;
+}
+CFR_API int cfr_vote_keys(const uint64_t* keys, int b, int32_t* pred, int64_t* counts, cfr_stream_t stream) {
+  return launch_vote_keys(reinterpret_cast<const unsigned long long*>(keys), b, pred, reinterpret_cast<long long*>(counts),
+                          S(stream));
+}
+
 CFR_API int cfr_sampler_create(const cfr_sampler_desc* d, cfr_sampler** out) {
   if (d->chunk <= 0 || d->n_gallery <= 0) { set_error("sampler: bad chunk / gallery size"); return 2; }
   std::unique_ptr<cfr_sampler> s(new cfr_sampler());

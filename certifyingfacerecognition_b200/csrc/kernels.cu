@@ -759,7 +759,7 @@ constexpr int kMatchEmb = 8;      // embeddings per block
 constexpr int kMatchRows = 64;    // gallery rows per block
 
 __global__ void __launch_bounds__(256) k_match(const float* __restrict__ emb, int b, const float* __restrict__ gallery,
-                                               int n, unsigned long long* __restrict__ keys) {
+                                               int n, unsigned long long* __restrict__ keys, unsigned row0) {
   __shared__ float4 s_emb[kMatchEmb][128];
   const int e0 = blockIdx.y * kMatchEmb;
   for (int i = threadIdx.x; i < kMatchEmb * 128; i += 256) {
@@ -788,7 +788,7 @@ __global__ void __launch_bounds__(256) k_match(const float* __restrict__ emb, in
       }
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-      const unsigned long long key = (static_cast<unsigned long long>(__float_as_uint(acc)) << 32) | static_cast<unsigned>(r);
+      const unsigned long long key = (static_cast<unsigned long long>(__float_as_uint(acc)) << 32) | (static_cast<unsigned>(r) + row0);
       best[e] = key < best[e] ? key : best[e];
     }
   }
@@ -868,10 +868,54 @@ int launch_match_vote(const float* emb, int b, const float* gallery, int n, unsi
                       long long* counts, cudaStream_t st) {
   if (b <= 0) return 0;
   dim3 grid((n + kMatchRows - 1) / kMatchRows, (b + kMatchEmb - 1) / kMatchEmb);
-  k_match<<<grid, 256, 0, st>>>(emb, b, gallery, n, keys);
+  k_match<<<grid, 256, 0, st>>>(emb, b, gallery, n, keys, 0u);
   CFR_LAUNCH_CHECK("match");
   k_vote<<<(b + 127) / 128, 128, 0, st>>>(keys, b, pred, reinterpret_cast<unsigned long long*>(counts));
   CFR_LAUNCH_CHECK("vote");
+  return 0;
+}
+
+// ---- gallery sharded over ranks (partition C) ----------------------------------------
+// Every rank reduces its own rows to one 64-bit key per query such that the UNSIGNED MINIMUM over ranks is the global
+// winner with torch.argmax's first-index tie-break:  exact matcher: (distance bits << 32) | global row;  tensor-core
+// matcher: ~((ordered score bits << 32) | (0xFFFFFFFF - global row)).  The low word is always the global row.
+int launch_match_keys(const float* emb, int b, const float* gallery, int n, unsigned row0, unsigned long long* keys,
+                      cudaStream_t st) {
+  if (b <= 0) return 0;
+  cudaError_t e = cudaMemsetAsync(keys, 0xFF, sizeof(unsigned long long) * b, st);
+  if (e != cudaSuccess) { set_error("match_keys memset: %s", cudaGetErrorString(e)); return 5; }
+  dim3 grid((n + kMatchRows - 1) / kMatchRows, (b + kMatchEmb - 1) / kMatchEmb);
+  k_match<<<grid, 256, 0, st>>>(emb, b, gallery, n, keys, row0);
+  CFR_LAUNCH_CHECK("match_keys");
+  return 0;
+}
+__global__ void k_export_argmax_keys(unsigned long long* __restrict__ keys, int b, unsigned row0,
+                                     unsigned long long* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= b) return;
+  const unsigned long long k = keys[i];
+  keys[i] = 0ull;                  // re-arm (atomicMax identity)
+  const unsigned col = 0xFFFFFFFFu - static_cast<unsigned>(k & 0xffffffffull);
+  out[i] = ~((k & 0xffffffff00000000ull) | (0xFFFFFFFFu - (col + row0)));
+}
+int launch_export_argmax_keys(unsigned long long* keys, int b, unsigned row0, unsigned long long* out, cudaStream_t st) {
+  if (b <= 0) return 0;
+  k_export_argmax_keys<<<(b + 127) / 128, 128, 0, st>>>(keys, b, row0, out);
+  CFR_LAUNCH_CHECK("export_argmax_keys");
+  return 0;
+}
+__global__ void k_vote_keys(const unsigned long long* __restrict__ keys, int b, int* __restrict__ pred,
+                            unsigned long long* __restrict__ counts) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= b) return;
+  const int pr = static_cast<int>(keys[i] & 0xffffffffull);
+  if (pred != nullptr) pred[i] = pr;
+  if (counts != nullptr) atomicAdd(&counts[pr], 1ull);
+}
+int launch_vote_keys(const unsigned long long* keys, int b, int* pred, long long* counts, cudaStream_t st) {
+  if (b <= 0) return 0;
+  k_vote_keys<<<(b + 127) / 128, 128, 0, st>>>(keys, b, pred, reinterpret_cast<unsigned long long*>(counts));
+  CFR_LAUNCH_CHECK("vote_keys");
   return 0;
 }
 

@@ -50,4 +50,10 @@ int launch_vote_argmax(unsigned long long* keys, int b, int* pred, long long* co
 int launch_match_vote(const float* emb, int b, const float* gallery, int n, unsigned long long* keys, int* pred,
                       long long* counts, cudaStream_t st);
 
+// gallery sharded over ranks (partition C): per-rank 64-bit keys whose unsigned minimum over ranks is the global winner
+int launch_match_keys(const float* emb, int b, const float* gallery, int n, unsigned row0, unsigned long long* keys,
+                      cudaStream_t st);
+int launch_export_argmax_keys(unsigned long long* keys, int b, unsigned row0, unsigned long long* out, cudaStream_t st);
+int launch_vote_keys(const unsigned long long* keys, int b, int* pred, long long* counts, cudaStream_t st);
+
 }  // namespace cfr

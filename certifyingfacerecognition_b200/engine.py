@@ -585,6 +585,18 @@ class Engine:
             out[i:i + b] = self.frm.emb[:b]
         return out
 
+    def sample_votes_sharded(self, shard, z: Tensor, x: Tensor, sigma: Tensor, num: int, seed: int = 0,
+                             sample_offset: int = 0, noise: Optional[Tensor] = None, want_pred: bool = False):
+        """Smooth._sample_noise body with the gallery sharded over ranks (partition C): every rank
+        synthesises and embeds the SAME samples (same seed / offsets), matches them against its own rows
+        (`gallery_shard.ShardedGallery`), the 8-byte keys are all-gathered and merged.  Returns (counts [N] int64, pred)."""
+        # the engine's own (placeholder) gallery is not consulted: only the embeddings are taken from this call
+        _, ex = self.sample_votes(z, x, sigma, num, seed=seed, sample_offset=sample_offset, noise=noise, want_emb=True,
+                                  counts=torch.zeros(self.num_classes, dtype=torch.int64, device=self.device))
+        counts = torch.zeros(shard.n_total, dtype=torch.int64, device=self.device)
+        pred = shard.match_vote(ex["emb"], counts, want_pred=want_pred)
+        return counts, pred
+
     def sample_votes(self, z: Tensor, x: Tensor, sigma: Tensor, num: int, seed: int = 0, sample_offset: int = 0,
                      noise: Optional[Tensor] = None, counts: Optional[Tensor] = None, want_pred: bool = False,
                      want_emb: bool = False, want_noise: bool = False):

@@ -146,6 +146,17 @@ CFR_API int cfr_matcher_create(const float* gallery, int n_gallery, int max_b, c
 CFR_API void cfr_matcher_destroy(cfr_matcher* m);
 CFR_API int cfr_matcher_run(cfr_matcher* m, const float* emb, int b, int32_t* pred, int64_t* counts, cfr_stream_t stream);
 
+/* Gallery sharded over ranks (partition C; the reference keeps the whole gallery on one device,
+ * smoothing_model.py:56-61).  Each rank matches the replicated queries against ITS rows [row_offset, row_offset + n) and
+ * emits one 64-bit key per query; the UNSIGNED MINIMUM of the keys over ranks (all-gather + min, done by the host side)
+ * is the global winner with torch.argmax's first-index tie-break, its low 32 bits the global row.  cfr_match_keys is the
+ * exact fp32 matcher, cfr_matcher_keys the tensor-core one (shards of 32 768+ rows); cfr_vote_keys tallies merged keys. */
+CFR_API int cfr_match_keys(const float* emb, int b, const float* gallery, int n, uint32_t row_offset, uint64_t* keys,
+                           cfr_stream_t stream);
+CFR_API int cfr_matcher_keys(cfr_matcher* m, const float* emb, int b, uint32_t row_offset, uint64_t* keys,
+                             cfr_stream_t stream);
+CFR_API int cfr_vote_keys(const uint64_t* keys, int b, int32_t* pred, int64_t* counts, cfr_stream_t stream);
+
 /* ---- Smooth._sample_noise (smooth.py:109-138) as one call --------------------------------------------- */
 typedef struct cfr_sampler_desc {
   cfr_program* synth;     /* wp2 -> image at FRM resolution (one chunk) */

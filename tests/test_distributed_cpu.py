@@ -57,3 +57,44 @@ def test_sample_sharding_two_ranks_equals_single_rank(tmp_path):
     assert np.array_equal(got["c2"], c2) and c2.sum() == 1000
     pred = ref.certify(None, None, torch.tensor([int(c2.argmax())]), 101, 1000, 0.001, 10, device=torch.device("cpu"))
     assert np.allclose(got["pred"], np.array(pred, dtype=np.float64))
+
+
+# ---- partition C: gallery rows sharded over ranks, 8-byte keys all-gathered and merged -------------------------------
+def _exact_keys(emb, rows, lo):
+    """Pure-torch restatement of cfr_match_keys: (fp32 bits of the squared distance << 32) | global row, minimum over
+    the local rows (ties -> lowest row), as int64 bit patterns."""
+    d2 = ((emb[:, None, :] - rows[None, :, :]) ** 2).sum(-1).float()
+    bits = d2.view(torch.int32).to(torch.int64) & 0xFFFFFFFF
+    keys = (bits << 32) | (torch.arange(rows.shape[0], dtype=torch.int64)[None, :] + lo)
+    return keys.min(dim=1).values           # distances are >= 0, so these keys are positive: signed == unsigned order
+
+
+def _gallery_fixture():
+    g = torch.Generator().manual_seed(9)
+    gal = torch.randn(41, 16, generator=g)
+    gal[30] = gal[7]                        # duplicate rows in different shards: the lower global index must win
+    emb = torch.cat([gal[[7, 30, 12, 40]] + 0.01 * torch.randn(4, 16, generator=g), gal[[7, 30]]])
+    return gal, emb
+
+
+def _shard_worker(rank, world, port, out):
+    from certifyingfacerecognition_b200.gallery_shard import allgather_merge, rows_of_keys, shard_bounds
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    gal, emb = _gallery_fixture()
+    lo, hi = shard_bounds(gal.shape[0], world, rank)
+    merged = allgather_merge(_exact_keys(emb, gal[lo:hi], lo), dist.group.WORLD)
+    if rank == 1:                           # every rank holds the same merged result; check a non-zero one
+        np.save(out, rows_of_keys(merged).numpy())
+    dist.destroy_process_group()
+
+
+def test_gallery_sharding_two_ranks_equals_single_rank(tmp_path):
+    out = str(tmp_path / "rows.npy")
+    mp.start_processes(_shard_worker, args=(2, _free_port(), out), nprocs=2, join=True, start_method="fork")
+    gal, emb = _gallery_fixture()
+    d = torch.cdist(emb, gal, compute_mode="donot_use_mm_for_euclid_dist")
+    ref = (-d).argmax(dim=1)                # the reference's softmax(-d).argmax(1): first index on ties
+    got = np.load(out)
+    assert np.array_equal(got, ref.numpy())
+    assert got[4] == 7 and got[5] == 7      # exact duplicates resolve to the lower global row

@@ -212,3 +212,21 @@ def test_package_synthetic_weights_equal_the_test_fixtures(models):
     assert np.array_equal(synthetic.latents(7), fixtures.latents(7))
     rows = torch.randn(3, 512, generator=torch.Generator().manual_seed(0))
     assert torch.equal(synthetic.synthetic_gallery(rows, 10), fixtures.synthetic_gallery(rows, 10))
+
+
+def test_sharded_gallery_key_merge_is_an_unsigned_min():
+    """Partition C host logic: keys are uint64 bit patterns carried in int64; the merge must order them unsigned."""
+    from certifyingfacerecognition_b200.gallery_shard import merge_keys_unsigned_min, rows_of_keys, shard_bounds
+    g = torch.Generator().manual_seed(5)
+    hi = torch.randint(0, 1 << 32, (4, 64), generator=g, dtype=torch.int64)
+    lo = torch.randint(0, 1 << 32, (4, 64), generator=g, dtype=torch.int64)
+    keys_u = (hi.numpy().astype(np.uint64) << np.uint64(32)) | lo.numpy().astype(np.uint64)
+    stack = torch.from_numpy(keys_u.view(np.int64).copy())
+    got = merge_keys_unsigned_min(stack).numpy().view(np.uint64)
+    assert np.array_equal(got, keys_u.min(axis=0))
+    assert np.array_equal(rows_of_keys(torch.from_numpy(got.view(np.int64).copy())).numpy(), (got & np.uint64(0xFFFFFFFF)).astype(np.int64))
+    # balanced contiguous shards covering [0, n) exactly, lower ranks lower rows
+    for n, w in ((10, 3), (5000, 8), (7, 7), (1_000_000, 8)):
+        b = [shard_bounds(n, w, r) for r in range(w)]
+        assert b[0][0] == 0 and b[-1][1] == n and all(b[i][1] == b[i + 1][0] for i in range(w - 1))
+        assert max(h - l for l, h in b) - min(h - l for l, h in b) <= 1
