@@ -133,6 +133,9 @@ def main():
     ap.add_argument("--shard", default="identities", choices=["identities", "samples"])
     ap.add_argument("--cpu-sample", type=int, default=4, help="MC samples per CPU-baseline step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--frm", default="insightface", choices=["insightface", "facenet"],
+                    help="face recognition model: ArcFace iresnet50 (headline, BASELINE config 2) or FaceNet "
+                         "InceptionResnetV1 at 160^2 (config 4; GPU arm only)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -140,6 +143,12 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     workload = (f"isotropic certify batch: {args.batch} MC samples/step, sigma={SIGMA}, StyleGAN-FFHQ-1024 + ArcFace "
                 f"iresnet50 random-init, {N_GALLERY}-row synthetic gallery (BASELINE config 2)")
+    gflop_per_sample = GFLOP_PER_SAMPLE_SUBPIXEL_FORM
+    if args.frm == "facenet":
+        workload = (f"isotropic certify batch: {args.batch} MC samples/step, sigma={SIGMA}, StyleGAN-FFHQ-1024 + FaceNet "
+                    f"InceptionResnetV1 @160 random-init, {N_GALLERY}-row synthetic gallery (BASELINE config 4)")
+        gflop_per_sample = GFLOP_PER_SAMPLE_SUBPIXEL_FORM - 12.62 + 2.835      # iresnet50 -> InceptionResnetV1 (counted
+        args.no_cpu_baseline = True                                           # from the layer table, models/facenet.py)
 
     # ------------------------------------------------------------------ reference arm (CPU, rank 0 only)
     if args.impl == "reference":
@@ -171,7 +180,10 @@ def main():
     lib = L.load()
     n_ids = 64
     g_sd, f_sd, dirs, lat, fixtures = build_fixture(n_ids)
-    eng = Engine(g_sd, f_sd, dirs, torch.zeros(1, 512), chunk=args.chunk, frm_group=args.frm_group)
+    if args.frm == "facenet":
+        f_sd = fixtures.facenet_weights()
+    eng = Engine(g_sd, f_sd, dirs, torch.zeros(1, 512), chunk=args.chunk, frm_group=args.frm_group,
+                 frm="insightface" if args.frm == "insightface" else "facenet-vggface2")
     true_rows = eng.embed_latents(lat).cpu()
     eng.set_gallery(fixtures.synthetic_gallery(true_rows, N_GALLERY))
     dev = eng.device
@@ -291,9 +303,9 @@ def main():
         "dtype": "fp16 operands / fp32 accumulate", "data": "synthetic",
         "config": {"workload": workload, "chunk": args.chunk, "frm_group": args.frm_group, "shard": args.shard, "gallery": N_GALLERY,
                    "l2": "working set per step (activations, GBs) far exceeds the 126 MB L2; no flush needed",
-                   "gflop_per_sample_algorithmic": GFLOP_PER_SAMPLE_SUBPIXEL_FORM,
-                   "pipeline_tflops": value * GFLOP_PER_SAMPLE_SUBPIXEL_FORM / 1e3,
-                   "pipeline_frac_of_bf16_sustained": value * GFLOP_PER_SAMPLE_SUBPIXEL_FORM / 1e3 / (pk["tf_sustained"] * world)},
+                   "gflop_per_sample_algorithmic": gflop_per_sample,
+                   "pipeline_tflops": value * gflop_per_sample / 1e3,
+                   "pipeline_frac_of_bf16_sustained": value * gflop_per_sample / 1e3 / (pk["tf_sustained"] * world)},
         "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": 528 * 4, "d2h_bytes_per_step": N_GALLERY * 8,
                 "api": "cfr_sample_votes_host (C ABI, host buffers, one call per step)"},
         "gpu_launches": int(launches),

@@ -44,6 +44,8 @@ _REFERENCE_FLAGS = (
 _EXTRA_FLAGS = (
     ("--seed", dict(type=int, default=1234, help="key of the device-side Philox noise stream")),
     ("--chunk", dict(type=int, default=32, help="samples per synthesis + recognition program run")),
+    ("--frm-weights", dict(type=str, default=None, help="state dict of the recognition network (needed for the FaceNet "
+                                                         "variants: the reference downloads those weights at run time)")),
 )
 
 
@@ -100,8 +102,9 @@ def main(argv=None) -> None:
     device = torch.device("cuda", torch.cuda.current_device())
 
     directions = get_all_matrices(device=device)[3].T.contiguous()       # [5, 512] attribute directions (:71)
+    frm_state = torch.load(args.frm_weights, map_location="cpu") if args.frm_weights else None
     model = WrappedModel(directions, args.face_recog_model, n_embs=args.load_n_embs, load_embs=True, embs_file=None,
-                         chunk=args.chunk)
+                         chunk=args.chunk, frm_state=frm_state)
     latents = model.latents.to(device)
     sigma = smoothing_scale(args, device)
     n_ids, n_dirs = latents.shape[0], directions.shape[0]

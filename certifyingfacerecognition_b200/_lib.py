@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("CFR_LIB_PATH") or os.path.join(HERE, "libcfr_b200.so")   # env: A/B builds when profiling
 
 MAX_PHASES, MAX_TAPS = 4, 9
-ACT_NONE, ACT_LRELU, ACT_PRELU = 0, 1, 2
+ACT_NONE, ACT_LRELU, ACT_PRELU, ACT_RELU_POST = 0, 1, 2, 3
 
 _i8_taps = (C.c_int8 * MAX_TAPS) * MAX_PHASES
 
@@ -70,6 +70,9 @@ SIGNATURES = {
     "cfr_program_add_finalize_stats": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _F, _P, _P]),
     "cfr_program_add_affine": (_I, [_P, _P, _P, _P, _I, _I, _I, _P]),
     "cfr_program_add_torgb_resize": (_I, [_P, _P, _P, _P, _I, _I, _I, _P, _P, _I, _F, _F, _P, _P, _P]),
+    "cfr_program_add_maxpool3s2": (_I, [_P, _P, _I, _I, _I, _I, _P, _I, _I]),
+    "cfr_program_add_avgpool": (_I, [_P, _P, _I, _I, _I, _P]),
+    "cfr_program_add_l2norm": (_I, [_P, _P, _I, _I, _P]),
     "cfr_noise_project": (_I, [_P, _P, _P, _I, _P, _P, _P, _F, _U64, _U64, _I, _P, _P, _P]),
     "cfr_truncate": (_I, [_P, _P, _F, _I, _P, _P]),
     "cfr_mapping": (_I, [_P, _P, _P, _I, _P, _P]),

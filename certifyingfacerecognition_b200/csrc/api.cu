@@ -252,6 +252,24 @@ CFR_API int cfr_program_add_affine(cfr_program* p, const void* y_f16, const floa
   return 0;
 }
 
+CFR_API int cfr_program_add_maxpool3s2(cfr_program* p, const void* in_f16, int n, int h, int w, int c, void* out_f16,
+                                       int out_c_total, int c_off) {
+  p->add([=](cudaStream_t st) {
+    return launch_maxpool3s2(static_cast<const __half*>(in_f16), n, h, w, c, static_cast<__half*>(out_f16), out_c_total, c_off, st);
+  }, "maxpool3s2");
+  return 0;
+}
+CFR_API int cfr_program_add_avgpool(cfr_program* p, const void* in_f16, int n, int hw, int c, void* out_f16) {
+  p->add([=](cudaStream_t st) {
+    return launch_avgpool(static_cast<const __half*>(in_f16), n, hw, c, static_cast<__half*>(out_f16), st);
+  }, "avgpool");
+  return 0;
+}
+CFR_API int cfr_program_add_l2norm(cfr_program* p, const float* in, int n, int c, float* out) {
+  p->add([=](cudaStream_t st) { return launch_l2norm(in, n, c, out, st); }, "l2norm");
+  return 0;
+}
+
 CFR_API int cfr_program_add_torgb_resize(cfr_program* p, const void* x_f16, const float* A, const float* B, int n, int hin,
                                  int c, const float* w_rgb, const float* b_rgb, int rout, float mean, float stdv,
                                  void* out_f16_nhwc16, float* out_planar_f32, const int32_t* out_slot) {

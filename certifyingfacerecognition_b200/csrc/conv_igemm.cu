@@ -386,6 +386,10 @@ conv_igemm_kernel(const __grid_constant__ ConvParams p) {
             }
           }
         }
+        if (p.act == ACT_RELU_POST) {             // Inception-ResNet blocks: relu(x + scale * conv(cat))
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
+        }
         if (valid) {
           if (p.out32 != nullptr) {
             float4* op = reinterpret_cast<float4*>(p.out32 + pix * p.outC + ch0);

@@ -29,7 +29,7 @@ constexpr int kMaxPhases = 4;
 constexpr int kMaxTaps = 9;
 constexpr int kStatsMaxC = 512;
 
-enum Act : int { ACT_NONE = 0, ACT_LRELU = 1, ACT_PRELU = 2 };
+enum Act : int { ACT_NONE = 0, ACT_LRELU = 1, ACT_PRELU = 2, ACT_RELU_POST = 3 };   // 3: ReLU AFTER the residual add
 
 struct ConvParams {
   CUtensorMap tmA;   // activations: dims (C, W, H, N)

@@ -875,6 +875,81 @@ int launch_match_vote(const float* emb, int b, const float* gallery, int n, unsi
   return 0;
 }
 
+// ---- InceptionResnetV1 glue kernels (tiny, HBM-trivial) ------------------------------------------------------
+__global__ void k_maxpool3s2(const __half* __restrict__ in, int n, int h, int w, int c, __half* __restrict__ out,
+                             int out_c_total, int c_off) {
+  const int ho = (h - 3) / 2 + 1, wo = (w - 3) / 2 + 1, c8 = c >> 3;
+  const size_t total = static_cast<size_t>(n) * ho * wo * c8;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int cg = static_cast<int>(i % c8);
+    size_t r = i / c8;
+    const int ox = static_cast<int>(r % wo);
+    r /= wo;
+    const int oy = static_cast<int>(r % ho), s = static_cast<int>(r / ho);
+    float m[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) m[k] = -3.0e38f;
+    for (int dy = 0; dy < 3; ++dy)
+      for (int dx = 0; dx < 3; ++dx) {
+        float v[8];
+        load8(in + ((static_cast<size_t>(s) * h + 2 * oy + dy) * w + 2 * ox + dx) * c + cg * 8, v);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) m[k] = fmaxf(m[k], v[k]);
+      }
+    store8(out + ((static_cast<size_t>(s) * ho + oy) * wo + ox) * out_c_total + c_off + cg * 8, m);
+  }
+}
+int launch_maxpool3s2(const __half* in, int n, int h, int w, int c, __half* out, int out_c_total, int c_off, cudaStream_t st) {
+  if (c % 8 != 0 || c_off % 8 != 0 || out_c_total % 8 != 0 || h < 3 || w < 3) { set_error("maxpool3s2: bad shape"); return 2; }
+  const size_t total = static_cast<size_t>(n) * ((h - 3) / 2 + 1) * ((w - 3) / 2 + 1) * (c / 8);
+  size_t blocks = (total + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  k_maxpool3s2<<<static_cast<unsigned>(blocks), 256, 0, st>>>(in, n, h, w, c, out, out_c_total, c_off);
+  CFR_LAUNCH_CHECK("maxpool3s2");
+  return 0;
+}
+__global__ void k_avgpool(const __half* __restrict__ in, int n, int hw, int c, __half* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;            // over n * c/8
+  const int c8 = c >> 3;
+  if (i >= n * c8) return;
+  const int cg = i % c8, s = i / c8;
+  float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (int p = 0; p < hw; ++p) {
+    float v[8];
+    load8(in + (static_cast<size_t>(s) * hw + p) * c + cg * 8, v);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) a[k] += v[k];
+  }
+  const float inv = 1.f / static_cast<float>(hw);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) a[k] *= inv;
+  store8(out + static_cast<size_t>(s) * c + cg * 8, a);
+}
+int launch_avgpool(const __half* in, int n, int hw, int c, __half* out, cudaStream_t st) {
+  if (c % 8 != 0) { set_error("avgpool: C=%d must be a multiple of 8", c); return 2; }
+  k_avgpool<<<(n * (c / 8) + 127) / 128, 128, 0, st>>>(in, n, hw, c, out);
+  CFR_LAUNCH_CHECK("avgpool");
+  return 0;
+}
+__global__ void k_l2norm(const float* __restrict__ in, int n, int c, float* __restrict__ out) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= n) return;
+  float q = 0.f;
+  for (int k = lane; k < c; k += 32) {
+    const float v = in[static_cast<size_t>(row) * c + k];
+    q = fmaf(v, v, q);
+  }
+  for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+  const float inv = 1.f / fmaxf(sqrtf(q), 1e-12f);                 // F.normalize: x / max(||x||, eps)
+  for (int k = lane; k < c; k += 32) out[static_cast<size_t>(row) * c + k] = in[static_cast<size_t>(row) * c + k] * inv;
+}
+int launch_l2norm(const float* in, int n, int c, float* out, cudaStream_t st) {
+  k_l2norm<<<(n + 7) / 8, 256, 0, st>>>(in, n, c, out);
+  CFR_LAUNCH_CHECK("l2norm");
+  return 0;
+}
+
 // ---- gallery sharded over ranks (partition C) ----------------------------------------
 // Every rank reduces its own rows to one 64-bit key per query such that the UNSIGNED MINIMUM over ranks is the global
 // winner with torch.argmax's first-index tie-break:  exact matcher: (distance bits << 32) | global row;  tensor-core

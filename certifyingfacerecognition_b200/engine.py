@@ -511,16 +511,27 @@ class Engine:
     TC_MATCH_MIN_ROWS = 32768      # galleries at least this large use the tensor-core matcher (cfr_matcher_*)
 
     def __init__(self, g_sd, f_sd, dir_mat: Tensor, gallery: Tensor, chunk: int = 32, device="cuda",
-                 keep_planar: bool = False, frm_group: int = 1, tc_match: Optional[bool] = None):
+                 keep_planar: bool = False, frm_group: int = 1, tc_match: Optional[bool] = None,
+                 frm: str = "insightface"):
         if not torch.cuda.is_available():
             raise RuntimeError("certifyingfacerecognition_b200 needs a CUDA device (no CPU fallback)")
         self.lib = L.load()
         self.device = torch.device(device)
         self.chunk = chunk
         self.frm_group = max(1, int(frm_group))
-        self.synth = SynthesisProgram(g_sd, chunk, 112, device, keep_planar=keep_planar, groups=self.frm_group)
-        self.frm = ArcFaceProgram(f_sd, chunk, self.synth.img, device)
-        self.frm_big = ArcFaceProgram(f_sd, chunk * self.frm_group, self.synth.img, device) if self.frm_group > 1 else None
+        # FRM: ArcFace iresnet50 at 112^2 (main_attack.py:123-125) or FaceNet InceptionResnetV1 at 160^2 (:126-129);
+        # gen_utils.py:17-21 INP_RESOLS gives the resize target, MEAN = STD = 0.5 for both
+        self.frm_name = frm
+        if frm == "insightface":
+            frm_cls, res = ArcFaceProgram, 112
+        elif frm in ("facenet", "facenet-vggface2"):
+            from .models.facenet import FaceNetProgram, INPUT_RES
+            frm_cls, res = FaceNetProgram, INPUT_RES
+        else:
+            raise ValueError(f"unknown face recognition model '{frm}'")
+        self.synth = SynthesisProgram(g_sd, chunk, res, device, keep_planar=keep_planar, groups=self.frm_group)
+        self.frm = frm_cls(f_sd, chunk, self.synth.img, device)
+        self.frm_big = frm_cls(f_sd, chunk * self.frm_group, self.synth.img, device) if self.frm_group > 1 else None
         self.dir_mat = _f32(dir_mat, self.device)
         self.tc_match = tc_match
         self.matcher = None

@@ -54,9 +54,12 @@ class WrappedModel(nn.Module):
                  latents: Optional[torch.Tensor] = None, orig_embs: Optional[torch.Tensor] = None,
                  chunk: int = 32) -> None:
         super().__init__()
-        if face_recog != "insightface":
-            raise NotImplementedError(f"face_recog='{face_recog}': only ArcFace iresnet50 ('insightface') is built; "
-                                      "the facenet_pytorch variants are a later row of the scope table")
+        if face_recog not in ("insightface", "facenet", "facenet-vggface2"):
+            raise ValueError(f"face_recog='{face_recog}' is not one of the reference's FRS_METHODS (gen_utils.py:31-35)")
+        if face_recog != "insightface" and frm_state is None:
+            # main_attack.py:126-129 downloads the facenet_pytorch weights at run time; there is no file to read here
+            raise ValueError("the FaceNet variants need `frm_state` = an InceptionResnetV1 state dict "
+                             "(facenet_pytorch downloads its weights; nothing is stored in the reference tree)")
         self.device = direction_matrix.device
         if self.device.type != "cuda":
             raise RuntimeError("WrappedModel needs its direction matrix on a CUDA device (no CPU fallback)")
@@ -83,7 +86,8 @@ class WrappedModel(nn.Module):
         else:
             embs = None
         placeholder = embs if embs is not None else torch.zeros(1, EMB_SIZE)
-        self.engine = Engine(generator_state, frm_state, self.dir_mat, placeholder, chunk=chunk, device=self.device)
+        self.engine = Engine(generator_state, frm_state, self.dir_mat, placeholder, chunk=chunk, device=self.device,
+                             frm=face_recog)
         if embs is None:
             print("Generating original embeddings")
             embs = self.engine.embed_latents(self.latents)

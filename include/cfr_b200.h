@@ -33,7 +33,8 @@ typedef struct cfr_matcher cfr_matcher;   /* tensor-core gallery match for large
 
 #define CFR_MAX_PHASES 4
 #define CFR_MAX_TAPS 9
-enum { CFR_ACT_NONE = 0, CFR_ACT_LRELU = 1, CFR_ACT_PRELU = 2 };
+enum { CFR_ACT_NONE = 0, CFR_ACT_LRELU = 1, CFR_ACT_PRELU = 2,
+       CFR_ACT_RELU_POST = 3 /* ReLU applied AFTER the residual add (Inception-ResNet blocks) */ };
 
 /* One implicit-GEMM convolution (tcgen05 / TMEM / TMA).  Replaces the F.conv2d / F.conv_transpose2d calls of
  * stylegan_generator_model.py:667-675,739 and iresnet.py:49,52,55,142,153 together with the element-wise ops
@@ -116,6 +117,13 @@ CFR_API int cfr_program_add_finalize_stats(cfr_program* p, const int64_t* sum, c
 CFR_API int cfr_program_add_affine(cfr_program* p, const void* y_f16, const float* A, const float* B, int n, int hw, int c,
                            void* x_f16);
 /* LastConvBlock :759-762 + postprocess (mod_stylegan_generator.py:303-307) + get_transform (gen_utils.py:77-85) */
+/* facenet_pytorch.InceptionResnetV1 glue (main_attack.py:126-129; no source under /root/reference: parity unpinned):
+ * MaxPool2d(3, stride 2) NHWC fp16 -> channel slice [c_off, c_off + c) of a wider NHWC buffer (torch.cat of the Mixed
+ * blocks); AdaptiveAvgPool2d(1); F.normalize(p=2, dim=1) on fp32 rows. */
+CFR_API int cfr_program_add_maxpool3s2(cfr_program* p, const void* in_f16, int n, int h, int w, int c, void* out_f16,
+                                       int out_c_total, int c_off);
+CFR_API int cfr_program_add_avgpool(cfr_program* p, const void* in_f16, int n, int hw, int c, void* out_f16);
+CFR_API int cfr_program_add_l2norm(cfr_program* p, const float* in, int n, int c, float* out);
 CFR_API int cfr_program_add_torgb_resize(cfr_program* p, const void* x_f16, const float* A, const float* B, int n, int hin,
                                  int c, const float* w_rgb, const float* b_rgb, int rout, float mean, float stdv,
                                  void* out_f16_nhwc16, float* out_planar_f32, const int32_t* out_slot);

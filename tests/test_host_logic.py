@@ -230,3 +230,23 @@ def test_sharded_gallery_key_merge_is_an_unsigned_min():
         b = [shard_bounds(n, w, r) for r in range(w)]
         assert b[0][0] == 0 and b[-1][1] == n and all(b[i][1] == b[i + 1][0] for i in range(w - 1))
         assert max(h - l for l, h in b) - min(h - l for l, h in b) <= 1
+
+
+def test_facenet_tables_and_synthetic_weights_are_consistent():
+    """Config 4 (parity unpinned): the product-side layer table (models/facenet.py) and the oracle's independent one
+    describe the same network, and the synthetic state dict drives the oracle forward to unit-norm embeddings."""
+    from certifyingfacerecognition_b200 import synthetic
+    from certifyingfacerecognition_b200.models import facenet as P
+    from oracle import facenet as O
+    assert [s for _, s in P.STEM] == [tuple(s[1:]) for s in O.STEM]
+    for a, b in ((P.BLOCK35, O.BLOCK35), (P.BLOCK17, O.BLOCK17), (P.BLOCK8, O.BLOCK8), (P.MIXED_6A, O.MIXED_6A),
+                 (P.MIXED_7A, O.MIXED_7A)):
+        assert {k: [tuple(c) for c in v] for k, v in a.items()} == {k: [tuple(c) for c in v] for k, v in b.items()}
+    sd = synthetic.facenet_weights()
+    assert len(P.all_basic_convs()) == 111
+    for p, (cin, cout, (kh, kw), _, _) in P.all_basic_convs():
+        assert sd[p + "conv.weight"].shape == (cout, cin, kh, kw) and sd[p + "bn.running_var"].shape == (cout,)
+        assert float(sd[p + "bn.running_var"].min()) > 0        # calibrated statistics loaded
+    with torch.no_grad():
+        e = O.forward(torch.randn(2, 3, 160, 160, generator=torch.Generator().manual_seed(0)) * 0.5, sd)
+    assert e.shape == (2, 512) and torch.allclose(e.norm(dim=1), torch.ones(2), atol=1e-5)

@@ -32,12 +32,16 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--chunk", type=int, default=50)
     ap.add_argument("--out", default=None)
+    ap.add_argument("--frm", default="insightface", choices=["insightface", "facenet"])
     args = ap.parse_args()
     from certifyingfacerecognition_b200 import synthetic as fixtures
     from certifyingfacerecognition_b200.engine import Engine
     g_sd, f_sd = fixtures.build_models()
     dirs = torch.from_numpy(np.load(os.path.join(ROOT, "tests", "golden", "dirs.npy")))
-    eng = Engine(g_sd, f_sd, dirs, torch.zeros(8, 512), chunk=args.chunk)
+    if args.frm == "facenet":
+        f_sd = fixtures.facenet_weights()
+    eng = Engine(g_sd, f_sd, dirs, torch.zeros(8, 512), chunk=args.chunk,
+                 frm="insightface" if args.frm == "insightface" else "facenet-vggface2")
     eng.embed_latents(torch.from_numpy(fixtures.latents(args.chunk)))
     torch.cuda.synchronize()
     lines = []
