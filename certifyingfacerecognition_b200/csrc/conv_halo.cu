@@ -78,7 +78,8 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
   uint64_t* wdrain = wbar + 1;                             // [1] all MMAs reading the current weights are done
   uint64_t* tfull = wdrain + 1;                            // [16]
   uint64_t* tempty = tfull + 16;                           // [16]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 16);
+  uint64_t* hland = tempty + 16;                           // [3] (+1 pad) non-FOLD tmaBand: band landed (TMA complete_tx)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(hland + 4);
   float* sA = reinterpret_cast<float*>(tmem_slot + 4);     // [64]
   float* sB = sA + 64;                                     // [64]
   // per-(epilogue warp, channel) float partials; each warp owns its slice (64-bit shared atomics are CAS spin loops)
@@ -101,7 +102,8 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
   if (warp == kHaloMmaWarp0) {
     if (lane == 0) {
       for (int i = 0; i < 3; ++i) {
-        mbar_init(&hready[i], 1);
+        mbar_init(&hready[i], (FOLD && p.tmaBand) ? 2 : 1);   // FOLD tmaBand: + the expect_tx arrive of the TMA issuer
+        mbar_init(&hland[i], 1);
         mbar_init(&hempty[i], kMmaWarps);
       }
       mbar_init(wbar, 1);
@@ -323,7 +325,15 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
     auto issue = [&](const Band& bd, int hs) {
       const uint32_t hb_addr = smem_u32(smem + hs * p.haloBytes);
       const __half* img = p.in + static_cast<size_t>(bd.n) * imgStride + lc * 8;
-      if (!(p.dbg & 2)) {
+      if (p.tmaBand) {
+        if (tt == 0) {                        // one 4-D box: (TH + 2) x 130 pixels, out-of-image parts zero-filled
+          // FOLD: nothing touches the band before the MMAs, so the box signals `hready` itself; otherwise the loader
+          // warps wait for it on `hland`, apply the affine in place and then arrive on `hready`
+          uint64_t* bar = FOLD ? &hready[hs] : &hland[hs];
+          mbar_expect_tx(bar, static_cast<uint32_t>((p.TH + 2) * kHaloW * p.rowBytes));
+          tma_load_4d(smem + hs * p.haloBytes, &p.tmIn, bar, 0, bd.x0 - 1, bd.y0 - 1, bd.n);
+        }
+      } else if (!(p.dbg & 2)) {
         // rows of the band that lie inside the image: [r_lo, r_hi) of TH + 2; the others are zero-filled
         const int R = p.TH + 2;
         const int r_lo = bd.y0 == 0 ? 1 : 0;
@@ -431,6 +441,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
       const Band bd = decode_band(p, b);
       const int ahead = min(NS - 1, band1 - b) - 1;      // younger groups still allowed in flight
       if (ahead >= 1) cp_async_wait<1>(); else cp_async_wait<0>();
+      if (!FOLD && p.tmaBand) mbar_wait(&hland[hs], (static_cast<uint32_t>(b - band0) / NS) & 1);   // band landed
       if (!FOLD && affine) {
         if (bd.n != cur_n) {
           cur_n = bd.n;
@@ -931,6 +942,18 @@ int halo_build(const cfr_conv_desc& s, const float* inA, const float* inB, const
                      CU_TENSOR_MAP_INTERLEAVE_NONE, swz(p.rowBytes), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("halo conv: encode(W) failed: %d", (int)r); return 3; }
+    static const bool want_tma = getenv("CFR_HALO_TMA") == nullptr || atoi(getenv("CFR_HALO_TMA")) != 0;
+    p.tmaBand = want_tma;
+    if (p.tmaBand) {
+      cuuint64_t idims[4] = {(cuuint64_t)s.Cin, (cuuint64_t)s.Win, (cuuint64_t)s.Hin, (cuuint64_t)s.N};
+      cuuint64_t istr[3] = {(cuuint64_t)s.Cin * 2, (cuuint64_t)s.Win * s.Cin * 2, (cuuint64_t)s.Hin * s.Win * s.Cin * 2};
+      cuuint32_t ibox[4] = {(cuuint32_t)s.Cin, (cuuint32_t)kHaloW, (cuuint32_t)(p.TH + 2), 1};
+      cuuint32_t iestr[4] = {1, 1, 1, 1};
+      r = enc(&p.tmIn, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(s.in), idims, istr, ibox, iestr,
+              CU_TENSOR_MAP_INTERLEAVE_NONE, swz(p.rowBytes), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) { set_error("halo conv: encode(input band) failed: %d", (int)r); return 3; }
+    }
     if (p.fold) {
       cuuint64_t adims[2] = {16, (cuuint64_t)s.N * p.wsets * s.Cout};
       cuuint64_t astr[1] = {32};

@@ -39,6 +39,8 @@ constexpr int kHaloW = 130;         // 128 output columns + 1 halo column each s
 struct HaloParams {
   const __half* in;                 // NHWC fp16 input [N,H,W,Cin]
   CUtensorMap tmW;                  // weights (Cin, [n *] phases*taps*Cout), box {Cin, wBoxRows}
+  CUtensorMap tmIn;                 // tmaBand: input (Cin, W, H, N), box {Cin, 130, TH+2, 1}, OOB zero fill == conv padding
+  int tmaBand;                      // FOLD: the band is fetched by ONE TMA box instead of ~3.6-7 K cp.async per band
   CUtensorMap tmWa;                 // FOLD: aux weight tiles (16, n*phases*taps*Cout), box {16, wBoxRows}
   int fold;                         // per-sample folded weights + aux band
   int composite;                    // blur o up-conv: 4 phases x 9 taps, 8 weight sets (first/last-row variants), 4 noise slots
