@@ -33,7 +33,12 @@ constexpr int kHaloThreads = (kEpiWarps + kLoaderWarps + kMmaWarps) * 32;
 // Register re-allocation between the roles (setmaxnreg; each role is a whole number of 4-warp groups): the kernel starts
 // with 96 registers per thread (640 threads); the MMA issuers and loaders hand registers to the epilogue warps, whose
 // per-channel accumulators otherwise spill.  8*32*kRegsEpi + 8*32*kRegsLoader + 4*32*kRegsMma <= 640 * 96.
-constexpr int kRegsEpi = 128, kRegsLoader = 72, kRegsMma = 56;
+#ifndef CFR_HALO_REGS_EPI
+#define CFR_HALO_REGS_EPI 128
+#define CFR_HALO_REGS_LOADER 72
+#define CFR_HALO_REGS_MMA 56
+#endif
+constexpr int kRegsEpi = CFR_HALO_REGS_EPI, kRegsLoader = CFR_HALO_REGS_LOADER, kRegsMma = CFR_HALO_REGS_MMA;
 constexpr int kHaloW = 130;         // 128 output columns + 1 halo column each side
 
 struct HaloParams {
