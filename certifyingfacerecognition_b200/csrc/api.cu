@@ -177,9 +177,10 @@ static int add_folded(cfr_program* p, const cfr_conv_desc* d, const float* base_
   const float* bias = d->bias;
   const float* noise_w = d->noise_w;
   cfr_conv_desc keep = *d;                       // tap tables live in the closure
+  const int layout = composite ? 1 : (raw->p.rowmma ? 2 : 0);
   p->add([=](cudaStream_t st) {
     return launch_fold_weights(base_w, inA, inB, bias, noise_w, &keep.tap_dy[0][0], &keep.tap_dx[0][0], n, phases, ntaps,
-                               cout, cin, composite, static_cast<__half*>(w_main_f16), static_cast<__half*>(w_aux_f16), st);
+                               cout, cin, layout, static_cast<__half*>(w_main_f16), static_cast<__half*>(w_aux_f16), st);
   }, "fold_weights");
   if (composite) {
     const __half* yin = static_cast<const __half*>(d->in);

@@ -138,6 +138,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
     const bool leader = elect_one();
     const uint32_t idesc = make_idesc_f16(128, COUT);
     [[maybe_unused]] const uint32_t idesc2 = make_idesc_f16(128, 2 * COUT), idesc4 = make_idesc_f16(128, 4 * COUT);
+    [[maybe_unused]] const uint32_t idesc3 = make_idesc_f16(128, 3 * (COUT > 32 ? 16 : COUT));
     const uint32_t dhi = smem_desc_hi(8 * p.rowBytes, p.rowBytes);
     const int kPer = p.Cin / 16;
     const uint32_t rb16 = p.rowBytes >> 4;                 // row pitch in 16-byte units
@@ -226,6 +227,50 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
       const uint32_t a_band = smem_desc_lo(smem_u32(smem + hs * p.haloBytes));
       const uint32_t x_band = smem_desc_lo(smem_u32(aux + hs * p.auxBytes));
       const int ngroups = p.numPhases == 4 ? bd.rows : (bd.rows + G - 1) / G;
+      if (FOLD && !COMP && COUT <= 32 && p.rowmma == 2) {
+        // Row-stationary order (see the per-group variant below) over the WHOLE band: one warp owns a band (same-thread
+        // MMAs execute in order, which the overlapping accumulate chains need) and walks its input rows once, 3 x kPer
+        // MMAs of N = 3*COUT each; accumulator groups are acquired / handed to the epilogue as the walk reaches them.
+        if (((b - band0) & (kMmaWarps - 1)) == static_cast<int>(mw)) {
+          const int rows = bd.rows;
+          auto tile_d = [&](int o) {
+            const uint32_t gc = gbase + o / G;
+            return tmem_base + ((gc & (AS - 1)) * G + (o % G)) * ACC_COLS;
+          };
+          for (int i = 0; i < rows + 2; ++i) {
+            if (i < rows) {
+              if (i % G == 0) {
+                const uint32_t gc = gbase + i / G;
+                mbar_wait(&tempty[gc & (AS - 1)], ((gc >> asLog) & 1) ^ 1);
+                tc_fence_after();
+              }
+              umma_f16_pred<false>(tile_d(i), x_band + i * aux_row_step, dhi_aux, wa_lo, dhi_aux, idesc, lead);
+            }
+            const int o_hi = min(i, rows - 1);
+            const uint32_t a_row = a_band + i * row_step;
+            for (int o = max(i - 2, 0); o <= o_hi;) {
+              int e = o;                                       // longest run of TMEM-contiguous accumulators (ring wrap)
+              while (e < o_hi && tile_d(e + 1) == tile_d(e) + ACC_COLS) ++e;
+              const int nt = e - o + 1;
+              const uint32_t id = nt == 1 ? idesc : (nt == 2 ? idesc2 : idesc3);
+              const uint32_t d = tile_d(o);
+              const uint32_t bt = static_cast<uint32_t>(2 - i + o);   // first dy tile of the triple: dy = 1 - bt
+#pragma unroll
+              for (int dx = 0; dx < 3; ++dx) {
+                umma_f16_pred<true>(d, a_row + dx * rb16, dhi, w_lo + (dx * 3 + bt) * w_tap, dhi, id, lead);
+                if (kPer > 1)
+                  umma_f16_pred<true>(d, a_row + dx * rb16 + 2, dhi, w_lo + (dx * 3 + bt) * w_tap + 2, dhi, id, lead);
+              }
+              o = e + 1;
+            }
+            const int done = i - 2;                            // output row i-2 has all nine taps now
+            if (done >= 0 && ((done % G) == G - 1 || done == rows - 1)) {
+              if (leader) umma_commit(&tfull[(gbase + done / G) & (AS - 1)]);
+              __syncwarp();
+            }
+          }
+        }
+      } else
       for (int j = 0; j < ngroups; ++j) {
         const uint32_t gc = gbase + j;
         if ((gc & (kMmaWarps - 1)) != mw) continue;
@@ -271,6 +316,49 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
 #pragma unroll
           for (int k = 0; k < 4; ++k)
             issue_tile(d0 + k * ACC_COLS, a_row, x_row, w_lo + k * p.ntaps * w_tap, wa_lo + k * (COUT * 2), toff[k]);
+        } else if (FOLD && !COMP && COUT <= 32 && p.rowmma == 1) {
+          // Row-stationary issue order for 3x3 convs with few output channels.  The MMA stream of these layers is bound
+          // by the issuing warps' instruction overhead and the 128-row A operand read, both per MMA and independent of
+          // N (profiles/ncu_r01_notes.md section 9), so instead of 9 MMAs per OUTPUT row this issues 3 per INPUT row:
+          // input row i times [W(dy=+1,dx) | W(dy=0,dx) | W(dy=-1,dx)] (N = 3*COUT; weights in layout 2) lands in the
+          // accumulators of output rows i-2, i-1, i, which sit side by side in the group's TMEM columns.  The aux MMA
+          // (shift / bias / noise row) of an output row goes first and initialises its accumulator.  A group of 4
+          // output rows reads 6 input rows: 4 + 18 MMAs instead of 40.
+          const int r0 = j * G, gr = min(G, bd.rows - r0);
+          const uint32_t a0 = a_band + r0 * row_step, x0 = x_band + r0 * aux_row_step;
+          auto issue_rows = [&](auto GRc) {
+            constexpr int GR = decltype(GRc)::value, NI = GR + 2, H = (NI + 1) / 2;
+#pragma unroll
+            for (int k = 0; k < GR; ++k)
+              umma_f16_pred<false>(d0 + k * ACC_COLS, x0 + k * aux_row_step, dhi_aux, wa_lo, dhi_aux, idesc, lead);
+            // input rows a and a + H touch disjoint accumulators: alternate them to keep two accumulate chains going
+#pragma unroll
+            for (int a = 0; a < H; ++a) {
+#pragma unroll
+              for (int dx = 0; dx < 3; ++dx) {
+#pragma unroll
+                for (int kk = 0; kk < 2; ++kk) {
+                  if (kk < kPer) {
+#pragma unroll
+                    for (int s2 = 0; s2 < 2; ++s2) {
+                      const int ii = a + s2 * H;
+                      if (ii < NI) {
+                        const int o_lo = ii - 2 > 0 ? ii - 2 : 0, o_hi = ii < GR - 1 ? ii : GR - 1;
+                        const int nt = o_hi - o_lo + 1, bt = 2 - ii + o_lo;       // first dy tile of the triple: dy = 1 - bt
+                        const uint32_t id = nt == 1 ? idesc : (nt == 2 ? idesc2 : idesc3);
+                        umma_f16_pred<true>(d0 + o_lo * ACC_COLS, a0 + ii * row_step + dx * rb16 + 2 * kk, dhi,
+                                            w_lo + (dx * 3 + bt) * w_tap + 2 * kk, dhi, id, lead);
+                      }
+                    }
+                  }
+                }
+              }
+            }
+          };
+          if (gr == 4) issue_rows(integral_constant<int, 4>{});
+          else if (gr == 3) issue_rows(integral_constant<int, 3>{});
+          else if (gr == 2) issue_rows(integral_constant<int, 2>{});
+          else issue_rows(integral_constant<int, 1>{});
         } else if (FOLD && p.ntaps == 9 && kPer == 1 && j * G + G <= bd.rows && !(p.dbg & 16)) {
           // tile k of the group == output row j*G + k.  Tap-major over the G tiles: consecutive MMAs write DIFFERENT
           // accumulators, so the tensor pipe is not serialised on one accumulate chain (N = 16 MMAs are latency-,
@@ -724,6 +812,7 @@ struct FoldTaps {
   int8_t k[8][9];      // aux K index of the "input (y+dy, x+dx) inside?" indicator of (weight set, tap), -1 = unused
   int8_t noise_k[8];   // aux K index of the noise value used by the weight set
   int8_t center_k;     // aux K index of the (0,0) indicator (carries the bias)
+  int8_t tpos[9];      // output tile position of tap t inside a weight set (identity unless row-stationary layout)
 };
 __global__ void k_fold_weights(const float* __restrict__ base_w, const float* __restrict__ inA,
                                const float* __restrict__ inB, const float* __restrict__ bias,
@@ -742,7 +831,8 @@ __global__ void k_fold_weights(const float* __restrict__ base_w, const float* __
   for (int t = 0; t < ntaps; ++t) {
     const size_t widx = ((static_cast<size_t>(ws) * ntaps + t) * cout + co) * cin + ci;
     const float w = base_w[widx];
-    const size_t oidx = composite ? ((static_cast<size_t>(t) * wsets + pos) * cout + co) * cin + ci : widx;
+    const size_t oidx = composite ? ((static_cast<size_t>(t) * wsets + pos) * cout + co) * cin + ci
+                                  : ((static_cast<size_t>(ws) * ntaps + ft.tpos[t]) * cout + co) * cin + ci;
     w_main[static_cast<size_t>(n) * wsets * ntaps * cout * cin + oidx] = __float2half_rn(w * a);
     float sh = w * b;
     for (int o = cin >> 1; o > 0; o >>= 1) sh += __shfl_xor_sync(0xffffffffu, sh, o);
@@ -752,7 +842,8 @@ __global__ void k_fold_weights(const float* __restrict__ base_w, const float* __
 }
 int launch_fold_weights(const float* base_w, const float* inA, const float* inB, const float* bias, const float* noise_w,
                         const int8_t* tap_dy, const int8_t* tap_dx, int n, int phases, int ntaps, int cout, int cin,
-                        int composite, __half* w_main, __half* w_aux, cudaStream_t st) {
+                        int layout, __half* w_main, __half* w_aux, cudaStream_t st) {
+  const int composite = layout == 1 ? 1 : 0;
   if (cout * cin > 1024 || (cin != 16 && cin != 32)) { set_error("fold_weights: Cout*Cin=%d unsupported", cout * cin); return 2; }
   FoldTaps ft;
   const int wsets = composite ? 8 : phases;
@@ -765,6 +856,10 @@ int launch_fold_weights(const float* base_w, const float* inA, const float* inB,
                         ? static_cast<int8_t>(m_off + 3 * (tap_dy[(ph % phases) * 9 + t] + 1) + (tap_dx[(ph % phases) * 9 + t] + 1)) : -1;
   }
   ft.center_k = static_cast<int8_t>(m_off + 4);
+  // layout 2 (row-stationary MMAs, see conv_halo_kernel): tiles ordered dx-major, dy descending, so the three dy
+  // variants of one dx are ONE contiguous N = 3*cout operand [dy=+1 | dy=0 | dy=-1]
+  for (int t = 0; t < 9; ++t)
+    ft.tpos[t] = static_cast<int8_t>(layout == 2 && t < ntaps ? (tap_dx[t] + 1) * 3 + (1 - tap_dy[t]) : t);
   k_fold_weights<<<dim3(wsets, n), cout * cin, 0, st>>>(base_w, inA, inB, bias, noise_w, ft, wsets, ntaps, cout, cin, composite, w_main, w_aux);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { set_error("fold_weights launch: %s", cudaGetErrorString(e)); return 4; }
@@ -887,6 +982,17 @@ int halo_build(const cfr_conv_desc& s, const float* inA, const float* inB, const
   if (composite && (!p.fold || s.numPhases != 4 || s.ntaps != 9 || s.Cout != 16 || s.Cin > 32)) { set_error("halo conv: composite needs fold, 4 phases, 9 taps"); return 2; }
   p.wsets = composite ? 8 : s.numPhases;
   if (const char* e = getenv("CFR_HALO_DBG")) p.dbg = atoi(e);
+  p.rowmma = 0;
+  if (p.fold && !composite && s.numPhases == 1 && s.ntaps == 9 && s.Cout <= 32) {
+    unsigned seen = 0;                   // a full 3x3 stencil, any tap order
+    for (int t = 0; t < 9; ++t)
+      if (s.tap_dy[0][t] >= -1 && s.tap_dy[0][t] <= 1 && s.tap_dx[0][t] >= -1 && s.tap_dx[0][t] <= 1)
+        seen |= 1u << ((s.tap_dy[0][t] + 1) * 3 + s.tap_dx[0][t] + 1);
+    // 1: per accumulator group (4 issuing warps; N = 16 tiles are issue-bound), 2: per band (fewest MMAs; wins once
+    // the MMAs are N = 96 wide).  Measured: profiles/ncu_r01_notes.md section 13.
+    if (seen == 0x1ffu) p.rowmma = s.Cout == 32 ? 2 : 1;
+    if (const char* e = getenv("CFR_HALO_ROWMMA")) p.rowmma = p.rowmma ? atoi(e) : 0;
+  }
   if (p.fold && s.Cin > 32) { set_error("halo conv: folded variant needs Cin <= 32"); return 2; }
   p.rowBytes = s.Cin * 2;
   p.wRows = p.wsets * s.ntaps * s.Cout;

@@ -50,6 +50,7 @@ struct HaloParams {
   int fold;                         // per-sample folded weights + aux band
   int composite;                    // blur o up-conv: 4 phases x 9 taps, 8 weight sets (first/last-row variants), 4 noise slots
   int wsets;                        // weight sets resident in smem (numPhases, or 8 when composite)
+  int rowmma;                       // 3x3 FOLD conv, Cout <= 32: row-stationary MMA order (1 per group, 2 per band), weights in layout 2
   const float* corr;                // composite: border-column correction [N][2 sides][outH][Cout] fp32
   int dbg;                          // ablation bits for profiling only (env CFR_HALO_DBG): 1 skip epilogue math/store,
                                     // 2 skip band cp.async, 4 skip aux rows, 8 skip MMAs (results are then garbage)
@@ -88,7 +89,7 @@ int halo_build(const cfr_conv_desc& s, const float* inA, const float* inB, const
 // per-sample weight folding for the FOLD variant (see conv_halo.cu)
 int launch_fold_weights(const float* base_w, const float* inA, const float* inB, const float* bias, const float* noise_w,
                         const int8_t* tap_dy, const int8_t* tap_dx, int n, int phases, int ntaps, int cout, int cin,
-                        int composite, __half* w_main, __half* w_aux, cudaStream_t st);
+                        int layout, __half* w_main, __half* w_aux, cudaStream_t st);   // 0 plain, 1 composite, 2 row-stationary
 // composite up-conv+blur: exact values for the first / last hi-res column (see engine.composite_upconv_weights)
 int launch_upblur_corr(const __half* y, const float* inA, const float* inB, const float* corr_d, int n, int h, int w,
                        int cin, int cout, float* corr, cudaStream_t st);
