@@ -1072,6 +1072,10 @@ int halo_build(const cfr_conv_desc& s, const float* inA, const float* inB, const
   }
   const int total = p.N * p.bandsX * p.bandsY;
   op->grid = total < num_sms() ? total : num_sms();
+  if (const char* e = getenv("CFR_MAX_CTAS")) {      // tests: few CTAs => many work items per CTA (ring wrap, phase flips)
+    const int m = atoi(e);
+    if (m > 0 && op->grid > m) op->grid = m;
+  }
   op->smemBytes = p.haloStages * (p.haloBytes + p.auxBytes) + p.wBytes + p.wAuxBytes + ctrl + 1024;
   op->flops = 2.0 * s.N * s.Hout * s.Wout * s.numPhases * s.ntaps * static_cast<double>(s.Cin) * s.Cout;
   // algorithmic HBM bytes: every input element read once, every output element written once (fp16)

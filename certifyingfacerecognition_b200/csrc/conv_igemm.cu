@@ -605,6 +605,10 @@ int conv_build(const ConvSpec& s, ConvOp* op) {
 
   const int total = ((p.tilesX * p.tilesY * p.tilesN + p.MT - 1) / p.MT) * p.numPhases * p.numNTiles;
   op->grid = total < num_sms() ? total : num_sms();
+  if (const char* e = getenv("CFR_MAX_CTAS")) {      // tests: few CTAs => many work items per CTA (ring wrap, phase flips)
+    const int m = atoi(e);
+    if (m > 0 && op->grid > m) op->grid = m;
+  }
   // algorithmic FLOPs of this launch: 2 * (valid output-grid pixels) * phases * taps * Cin * Cout
   op->flops = 2.0 * s.N * s.Hout * s.Wout * s.numPhases * s.ntaps * static_cast<double>(s.Cin) * s.Cout;
   return 0;
