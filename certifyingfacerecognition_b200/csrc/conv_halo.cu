@@ -822,29 +822,56 @@ __global__ void k_fold_weights(const float* __restrict__ base_w, const float* __
   // composite: tap-major output with the weight sets ordered [4 5 | 0 1 2 3 | 6 7] inside a tap, so that the four
   // interior phases are ONE contiguous N = 4*cout operand (and the first / last-row variants contiguous pairs)
   const int pos = composite ? (ws < 4 ? ws + 2 : (ws < 6 ? ws - 4 : ws)) : ws;
-  const int co = threadIdx.x / cin, ci = threadIdx.x % cin;          // cin in {16, 32}: a group never straddles a warp
+  // blockDim.x = min(256, cout*cin) threads = co_step whole output channels; cin in {16, 32, 64}
+  __shared__ float part[8][9];                                       // cin == 64: per-warp halves of a channel row, per tap
+  const int ci = threadIdx.x % cin, co_step = blockDim.x / cin;
   const float a = inA != nullptr ? inA[n * cin + ci] : 1.f;
   const float b = inB != nullptr ? inB[n * cin + ci] : 0.f;
+  const int co = blockIdx.z * co_step + threadIdx.x / cin;             // gridDim.z * co_step == cout
   __half* aux_row = w_aux + ((static_cast<size_t>(n) * wsets + pos) * cout + co) * 16;
   if (ci < 16) aux_row[ci] = __float2half_rn((ci == ft.noise_k[ws] && noise_w != nullptr) ? noise_w[co] : 0.f);
-  __syncwarp();
-  for (int t = 0; t < ntaps; ++t) {
-    const size_t widx = ((static_cast<size_t>(ws) * ntaps + t) * cout + co) * cin + ci;
-    const float w = base_w[widx];
-    const size_t oidx = composite ? ((static_cast<size_t>(t) * wsets + pos) * cout + co) * cin + ci
-                                  : ((static_cast<size_t>(ws) * ntaps + ft.tpos[t]) * cout + co) * cin + ci;
-    w_main[static_cast<size_t>(n) * wsets * ntaps * cout * cin + oidx] = __float2half_rn(w * a);
-    float sh = w * b;
-    for (int o = cin >> 1; o > 0; o >>= 1) sh += __shfl_xor_sync(0xffffffffu, sh, o);
-    const int k = ft.k[ws][t];
-    if (ci == 0 && k >= 0) aux_row[k] = __float2half_rn(sh + ((k == ft.center_k && bias != nullptr) ? bias[co] : 0.f));
+  float w[9];
+#pragma unroll
+  for (int t = 0; t < 9; ++t)                                          // all taps in flight before the first use
+    w[t] = t < ntaps ? base_w[((static_cast<size_t>(ws) * ntaps + t) * cout + co) * cin + ci] : 0.f;
+  float sh[9];
+#pragma unroll
+  for (int t = 0; t < 9; ++t) {
+    if (t < ntaps) {
+      const size_t oidx = composite ? ((static_cast<size_t>(t) * wsets + pos) * cout + co) * cin + ci
+                                    : ((static_cast<size_t>(ws) * ntaps + ft.tpos[t]) * cout + co) * cin + ci;
+      w_main[static_cast<size_t>(n) * wsets * ntaps * cout * cin + oidx] = __float2half_rn(w[t] * a);
+    }
+    sh[t] = w[t] * b;
+    for (int o = (cin < 32 ? cin : 32) >> 1; o > 0; o >>= 1) sh[t] += __shfl_xor_sync(0xffffffffu, sh[t], o);
+  }
+  if (cin == 64) {                                                     // channel row = two warps: combine through smem
+    if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+      for (int t = 0; t < 9; ++t) part[threadIdx.x >> 5][t] = sh[t];
+    }
+    __syncthreads();
+    if (ci == 0) {
+#pragma unroll
+      for (int t = 0; t < 9; ++t) sh[t] = part[threadIdx.x >> 5][t] + part[(threadIdx.x >> 5) + 1][t];
+    }
+  }
+  __syncwarp();                                                        // the zero / noise fill of aux_row above
+  if (ci == 0) {
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      const int k = t < ntaps ? ft.k[ws][t] : -1;
+      if (k >= 0) aux_row[k] = __float2half_rn(sh[t] + ((k == ft.center_k && bias != nullptr) ? bias[co] : 0.f));
+    }
   }
 }
+
 int launch_fold_weights(const float* base_w, const float* inA, const float* inB, const float* bias, const float* noise_w,
                         const int8_t* tap_dy, const int8_t* tap_dx, int n, int phases, int ntaps, int cout, int cin,
                         int layout, __half* w_main, __half* w_aux, cudaStream_t st) {
   const int composite = layout == 1 ? 1 : 0;
-  if (cout * cin > 1024 || (cin != 16 && cin != 32)) { set_error("fold_weights: Cout*Cin=%d unsupported", cout * cin); return 2; }
+  const int threads = cout * cin < 256 ? cout * cin : 256;       // small blocks: the kernel is a latency chain, not bandwidth
+  if ((cin != 16 && cin != 32 && cin != 64) || cout % (threads / cin) != 0) { set_error("fold_weights: Cout=%d Cin=%d unsupported", cout, cin); return 2; }
   FoldTaps ft;
   const int wsets = composite ? 8 : phases;
   const int m_off = composite ? 4 : 1;            // indicators follow the noise slots in the aux row
@@ -860,7 +887,7 @@ int launch_fold_weights(const float* base_w, const float* inA, const float* inB,
   // variants of one dx are ONE contiguous N = 3*cout operand [dy=+1 | dy=0 | dy=-1]
   for (int t = 0; t < 9; ++t)
     ft.tpos[t] = static_cast<int8_t>(layout == 2 && t < ntaps ? (tap_dx[t] + 1) * 3 + (1 - tap_dy[t]) : t);
-  k_fold_weights<<<dim3(wsets, n), cout * cin, 0, st>>>(base_w, inA, inB, bias, noise_w, ft, wsets, ntaps, cout, cin, composite, w_main, w_aux);
+  k_fold_weights<<<dim3(wsets, n, cout / (threads / cin)), threads, 0, st>>>(base_w, inA, inB, bias, noise_w, ft, wsets, ntaps, cout, cin, composite, w_main, w_aux);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { set_error("fold_weights launch: %s", cudaGetErrorString(e)); return 4; }
   count_launch();
@@ -993,7 +1020,7 @@ int halo_build(const cfr_conv_desc& s, const float* inA, const float* inB, const
     if (seen == 0x1ffu) p.rowmma = s.Cout == 32 ? 2 : 1;
     if (const char* e = getenv("CFR_HALO_ROWMMA")) p.rowmma = p.rowmma ? atoi(e) : 0;
   }
-  if (p.fold && s.Cin > 32) { set_error("halo conv: folded variant needs Cin <= 32"); return 2; }
+  if (p.fold && s.Cin > 64) { set_error("halo conv: folded variant needs Cin <= 64"); return 2; }
   p.rowBytes = s.Cin * 2;
   p.wRows = p.wsets * s.ntaps * s.Cout;
   p.wAuxBytes = p.fold ? (p.wsets * s.Cout * 32 + 1023) / 1024 * 1024 : 0;
@@ -1089,7 +1116,8 @@ int halo_launch(const HaloOp& op, cudaStream_t stream) {
   std::call_once(once, [] {
     const void* fns[] = {(const void*)conv_halo_kernel<16, false>, (const void*)conv_halo_kernel<32, false>,
                          (const void*)conv_halo_kernel<64, false>, (const void*)conv_halo_kernel<16, true>,
-                         (const void*)conv_halo_kernel<32, true>, (const void*)conv_halo_kernel<16, true, true>};
+                         (const void*)conv_halo_kernel<32, true>, (const void*)conv_halo_kernel<16, true, true>,
+                         (const void*)conv_halo_kernel<64, true>};
     for (const void* f : fns)
       if (attr_err == cudaSuccess)
         attr_err = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
@@ -1110,7 +1138,10 @@ int halo_launch(const HaloOp& op, cudaStream_t stream) {
       if (op.p.fold) conv_halo_kernel<32, true><<<op.grid, kHaloThreads, op.smemBytes, stream>>>(op.p);
       else conv_halo_kernel<32, false><<<op.grid, kHaloThreads, op.smemBytes, stream>>>(op.p);
       break;
-    default: conv_halo_kernel<64, false><<<op.grid, kHaloThreads, op.smemBytes, stream>>>(op.p); break;
+    default:
+      if (op.p.fold) conv_halo_kernel<64, true><<<op.grid, kHaloThreads, op.smemBytes, stream>>>(op.p);
+      else conv_halo_kernel<64, false><<<op.grid, kHaloThreads, op.smemBytes, stream>>>(op.p);
+      break;
   }
   if (profile_on()) {
     cudaEventRecord(e1, stream);

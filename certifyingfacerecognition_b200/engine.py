@@ -289,6 +289,7 @@ class SynthesisProgram(Program):
         import os as _os
         if _os.environ.get("CFR_FUSED_UPBLUR") is not None:          # A/B knob for profiling
             fused_upblur = _os.environ["CFR_FUSED_UPBLUR"] != "0"
+        fold_max_cin = int(_os.environ.get("CFR_FOLD_MAX_CIN", "64"))   # A/B knob: widest layer input that is folded
         sd = {k: v.detach().float().cpu() for k, v in g_sd.items()}
         lib, h = self.lib, self.handle
 
@@ -347,7 +348,7 @@ class SynthesisProgram(Program):
             ssq = self.stats[1, stat_off:stat_off + chunk * cout]
             stat_off += chunk * cout
             hk = use_halo(l)
-            fold = hk and fold_small and cin <= 32
+            fold = hk and fold_small and cin <= fold_max_cin
             assert pending is None or hk
             if l % 2 == 1:
                 w = sd[f"synthesis.layer{l}.conv.weight"] * (math.sqrt(2.0) / math.sqrt(cin * 9))

@@ -331,7 +331,8 @@ def test_match_vote_bit_exact(E):
 @pytest.mark.parametrize("n,cin,cout,h,w,affine,fold", [
     (2, 16, 16, 40, 256, True, False), (1, 32, 32, 24, 128, True, False), (2, 64, 64, 16, 200, True, False),
     (3, 16, 16, 8, 64, False, False), (1, 64, 64, 9, 130, False, False),
-    (3, 16, 16, 40, 256, True, True), (2, 32, 32, 24, 200, True, True), (2, 16, 16, 8, 64, False, True)])
+    (3, 16, 16, 40, 256, True, True), (2, 32, 32, 24, 200, True, True), (2, 16, 16, 8, 64, False, True),
+    (2, 64, 64, 16, 200, True, True), (3, 64, 64, 9, 130, True, True)])
 def test_halo_conv_matches_torch(E, n, cin, cout, h, w, affine, fold):
     g = torch.Generator().manual_seed(cin * 7 + h)
     yprev = torch.randn(n, cin, h, w, generator=g).cuda().half().float()
@@ -383,7 +384,8 @@ def _check_stats(ssum, ssq, got, ref, runs, per_pixel):
 
 
 @pytest.mark.parametrize("n,cin,cout,lo_h,lo_w,fold", [(2, 64, 32, 12, 128, False), (1, 32, 16, 20, 256, False),
-                                                        (2, 64, 32, 5, 96, False), (3, 32, 16, 20, 256, True)])
+                                                        (2, 64, 32, 5, 96, False), (3, 32, 16, 20, 256, True),
+                                                        (2, 64, 32, 12, 128, True)])
 def test_halo_upconv_matches_torch(E, n, cin, cout, lo_h, lo_w, fold):
     g = torch.Generator().manual_seed(cin + lo_h)
     yprev = torch.randn(n, cin, lo_h, lo_w, generator=g).cuda().half().float()
@@ -488,7 +490,8 @@ def test_halo_upconv_blur_composite_matches_torch(E, n, cin, cout, lo_h, lo_w):
     (2, 16, 16, 7, 128, False, True),      # groups of 4 + 3
     (3, 32, 32, 24, 200, True, True),      # row-stationary per band: bands of 7, 7, 7, 3 rows, ring wrap inside a band
     (2, 32, 32, 15, 128, True, True),      # 7, 7, 1
-    (2, 64, 64, 16, 200, True, False), (2, 32, 32, 24, 128, True, False), (3, 16, 16, 40, 256, True, False)])
+    (2, 64, 64, 16, 200, True, False), (2, 32, 32, 24, 128, True, False), (3, 16, 16, 40, 256, True, False),
+    (3, 64, 64, 16, 200, True, True)])
 def test_halo_conv_few_ctas(E, monkeypatch, ctas, n, cin, cout, h, w, affine, fold):
     monkeypatch.setenv("CFR_MAX_CTAS", str(ctas))
     test_halo_conv_matches_torch(E, n, cin, cout, h, w, affine, fold)
