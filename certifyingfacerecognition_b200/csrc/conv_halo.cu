@@ -714,9 +714,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
               __half2* h2 = reinterpret_cast<__half2*>(o);
 #pragma unroll
               for (int i = 0; i < 8; ++i) h2[i] = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
-              uint4* op = reinterpret_cast<uint4*>(p.out + pix * COUT + ch0);
-              op[0] = o[0];
-              op[1] = o[1];
+              st_global_256(p.out + pix * COUT + ch0, o[0], o[1]);     // 16 channels = one 32-byte sector (halo_build checks alignment)
             }
             if (do_stats) {
               if constexpr (REG_STATS) {
@@ -1055,6 +1053,7 @@ int halo_build(const cfr_conv_desc& s, const float* inA, const float* inB, const
   if (s.numPhases != 1 && s.numPhases != 4) { set_error("halo conv: 1 or 4 phases"); return 2; }
   if (s.ntaps != 4 && s.ntaps != 9) { set_error("halo conv: 4 or 9 taps per phase"); return 2; }
   if (s.numPhases == 4 && s.Cout == 64) { set_error("halo conv: 4-phase up-conv needs Cout <= 32"); return 2; }
+  if ((reinterpret_cast<uintptr_t>(s.out) & 31) != 0) { set_error("halo conv: output must be 32-byte aligned"); return 2; }
   p.inA = inA; p.inB = inB;
   p.out = static_cast<__half*>(s.out);
   p.outH = s.outH; p.outW = s.outW; p.outC = s.outC; p.oscale = s.oscale;

@@ -400,9 +400,13 @@ conv_igemm_kernel(const __grid_constant__ ConvParams p) {
             __half2* h2 = reinterpret_cast<__half2*>(o);
 #pragma unroll
             for (int i = 0; i < 8; ++i) h2[i] = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
-            uint4* op = reinterpret_cast<uint4*>(p.out + pix * p.outC + ch0);
-            op[0] = o[0];
-            op[1] = o[1];
+            __half* op = p.out + pix * p.outC + ch0;
+            if (p.out256) {
+              st_global_256(op, o[0], o[1]);                 // 16 channels = one 32-byte sector per lane
+            } else {
+              reinterpret_cast<uint4*>(op)[0] = o[0];
+              reinterpret_cast<uint4*>(op)[1] = o[1];
+            }
           }
         }
         if (do_stats) {
@@ -571,6 +575,7 @@ int conv_build(const ConvSpec& s, ConvOp* op) {
   p.wRowsPerPhase = s.wRowsPerPhase;
   if (s.outIsF32) p.out32 = static_cast<float*>(s.out); else p.out = static_cast<__half*>(s.out);
   p.outH = s.outH; p.outW = s.outW; p.outC = s.outC; p.oscale = s.oscale;
+  p.out256 = (reinterpret_cast<uintptr_t>(s.out) & 31) == 0 && s.outC % 16 == 0;   // every 16-channel chunk is a 32-byte sector
   memcpy(p.ooff_y, s.ooff_y, sizeof(p.ooff_y));
   memcpy(p.ooff_x, s.ooff_x, sizeof(p.ooff_x));
   p.bias = s.bias; p.cbias = s.cbias; p.cbiasPerSample = s.cbiasPerSample;

@@ -55,6 +55,7 @@ struct ConvParams {
   __half* out;
   float* out32;                  // if non-null, fp32 output instead of fp16
   int outH, outW, outC;
+  int out256;                       // fp16 output rows are 32-byte aligned per 16-channel chunk: 256-bit stores
   int oscale;                    // output pixel = grid pixel * oscale + ooff[phase]
   int8_t ooff_y[kMaxPhases], ooff_x[kMaxPhases];
   // epilogue

@@ -241,6 +241,13 @@ __device__ __forceinline__ void umma_f16_lohi_pred(uint32_t d_tmem, uint32_t a_l
 }
 
 // Instruction descriptor: fp16 x fp16 -> fp32, both operands K-major, M x N tile.
+// 256-bit global store (sm_100: STG.256): one 32-byte sector per lane in ONE instruction.  `ptr` must be 32-byte aligned.
+__device__ __forceinline__ void st_global_256(void* ptr, const uint4& a, const uint4& b) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(ptr), "r"(a.x), "r"(a.y), "r"(a.z),
+               "r"(a.w), "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w)
+               : "memory");
+}
+
 __host__ __device__ __forceinline__ uint32_t make_idesc_f16(uint32_t M, uint32_t N) {
   uint32_t d = 0;
   d |= 1u << 4;             // D format: F32
