@@ -896,59 +896,98 @@ int launch_fold_weights(const float* base_w, const float* inA, const float* inB,
 // composite blur o up-conv: exact-value correction for hi-res column 0 (side 0) and 2W-1 (side 1).
 //   corr[n][side][Y][co] = sum_{dy,ci} D[side][a][rc][dy][co][ci] * x(i+dy, col),  Y = 2i+a, col = 0 / W-1,
 //   x = A[n][ci]*y + B[n][ci] inside the image, 0 outside; rc = first / last hi-res row variant.
-// One thread per (Y, co); a few MFLOP per image.
+// One thread per hi-res row Y (all 16 output channels); a few MFLOP per image.
 // ---------------------------------------------------------------------------------------------------------
 constexpr int kCorrRows = 64;       // low-res rows per block
-__global__ void __launch_bounds__(256) k_upblur_corr(const __half* __restrict__ y, const float* __restrict__ inA,
+__global__ void __launch_bounds__(2 * kCorrRows) k_upblur_corr(const __half* __restrict__ y, const float* __restrict__ inA,
                                                      const float* __restrict__ inB, const float* __restrict__ corr_d,
                                                      int h, int w, int cin, int cout, float* __restrict__ corr) {
   extern __shared__ float csm[];
-  float* xcol = csm;                                   // [kCorrRows + 2][cin] transformed border column (0 outside)
-  float* dsm = csm + (kCorrRows + 2) * cin;            // [a][dy][ci][co] interior-row coefficients (co fastest)
+  // row pitch cin + 1: the 16 rows a warp reads at once (lanes = consecutive Y) must not share a bank
+  const int xp = cin + 1;
+  float* xcol = csm;                                   // [kCorrRows + 2][cin + 1] transformed border column (0 outside)
+  float* dsm = csm + (((kCorrRows + 2) * xp + 3) & ~3);  // [a][dy][ci][co] interior-row coefficients (co fastest)
   const int n = blockIdx.z, side = blockIdx.y, i0 = blockIdx.x * kCorrRows;
   const int col = side == 0 ? 0 : w - 1;
-  for (int t = threadIdx.x; t < (kCorrRows + 2) * cin; t += blockDim.x) {
-    const int r = i0 - 1 + t / cin, ci = t % cin;
-    float xv = 0.f;
+  // border column: 8 channels (one 16-byte load) per thread-iteration
+  for (int t = threadIdx.x; t < (kCorrRows + 2) * (cin >> 3); t += blockDim.x) {
+    const int r = i0 - 1 + t / (cin >> 3), c8 = (t % (cin >> 3)) * 8;
+    float xv[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     if (r >= 0 && r < h) {
-      xv = __half2float(y[((static_cast<size_t>(n) * h + r) * w + col) * cin + ci]);
-      if (inA != nullptr) xv = __half2float(__float2half_rn(fmaf(xv, inA[n * cin + ci], inB[n * cin + ci])));
+      const uint4 raw = __ldg(reinterpret_cast<const uint4*>(y + ((static_cast<size_t>(n) * h + r) * w + col) * cin + c8));
+      const __half2* h2 = reinterpret_cast<const __half2*>(&raw);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float2 f = __half22float2(h2[k]);
+        xv[2 * k] = f.x;
+        xv[2 * k + 1] = f.y;
+      }
+      if (inA != nullptr) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          xv[k] = __half2float(__float2half_rn(fmaf(xv[k], inA[n * cin + c8 + k], inB[n * cin + c8 + k])));
+      }
     }
-    xcol[t] = xv;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) xcol[(t / (cin >> 3)) * xp + c8 + k] = xv[k];
   }
+  // interior-row coefficients: read [a][dy][co][ci] contiguously (ci fastest), store transposed (co fastest)
   for (int t = threadIdx.x; t < 2 * 3 * cin * cout; t += blockDim.x) {
-    const int co = t % cout, ci = (t / cout) % cin, dy = (t / (cout * cin)) % 3, a = t / (cout * cin * 3);
-    dsm[t] = corr_d[((((static_cast<size_t>(side) * 2 + a) * 3 + 0) * 3 + dy) * cout + co) * cin + ci];
+    const int ci = t % cin, co = (t / cin) % cout, dy = (t / (cout * cin)) % 3, a = t / (cout * cin * 3);
+    dsm[((a * 3 + dy) * cin + ci) * cout + co] =
+        corr_d[((((static_cast<size_t>(side) * 2 + a) * 3 + 0) * 3 + dy) * cout + co) * cin + ci];
+  }
+  // first / last hi-res row of the image (Y = 0: a = 0, rc = 1; Y = 2h-1: a = 1, rc = 2) use their own coefficient set:
+  // the one block that owns such a row stages it too (a single thread streaming 1.5 K dependent global loads was the
+  // long pole of this kernel: ~170 us per launch)
+  float* dsm2 = dsm + 2 * 3 * cin * cout;              // [which: 0 = first row, 1 = last row][dy][ci][co]
+  const bool has_first = i0 == 0, has_last = 2 * (i0 + kCorrRows) >= 2 * h;
+  for (int t = threadIdx.x; t < 2 * 3 * cin * cout; t += blockDim.x) {
+    const int ci = t % cin, co = (t / cin) % cout, dy = (t / (cout * cin)) % 3, which = t / (cout * cin * 3);
+    if (which == 0 ? has_first : has_last) {
+      const int a = which, rc = which + 1;
+      dsm2[((which * 3 + dy) * cin + ci) * cout + co] =
+          corr_d[((((static_cast<size_t>(side) * 2 + a) * 3 + rc) * 3 + dy) * cout + co) * cin + ci];
+    }
   }
   __syncthreads();
-  for (int idx = threadIdx.x; idx < 2 * kCorrRows * cout; idx += blockDim.x) {
-    const int co = idx % cout, Yl = idx / cout;
+  // one thread per hi-res row Y, all 16 output channels in registers: one broadcast load of x and four 128-bit loads
+  // of D per 16 FMAs (one thread per (Y, co) was shared-memory-load bound: two loads per FMA)
+  for (int Yl = threadIdx.x; Yl < 2 * kCorrRows; Yl += blockDim.x) {
     const int Y = 2 * i0 + Yl, il = Yl >> 1, a = Yl & 1;
     if (Y >= 2 * h) break;
     const int rc = (Y == 0) ? 1 : (Y == 2 * h - 1 ? 2 : 0);
-    float acc = 0.f;
-    if (rc == 0) {
-      for (int dy = 0; dy < 3; ++dy) {
-        const float* xr = xcol + (il + dy) * cin;
-        const float* dd = dsm + ((a * 3 + dy) * cin) * cout + co;
-        for (int ci = 0; ci < cin; ++ci) acc = fmaf(dd[ci * cout], xr[ci], acc);
-      }
-    } else {                                           // first / last hi-res row: two rows per image, read D directly
-      const float* d = corr_d + ((((static_cast<size_t>(side) * 2 + a) * 3 + rc) * 3) * cout + co) * cin;
-      for (int dy = 0; dy < 3; ++dy) {
-        const float* xr = xcol + (il + dy) * cin;
-        for (int ci = 0; ci < cin; ++ci) acc = fmaf(d[dy * cout * cin + ci], xr[ci], acc);
+    float acc[16];
+#pragma unroll
+    for (int c = 0; c < 16; ++c) acc[c] = 0.f;
+    const float* dbase = rc == 0 ? dsm + (a * 3) * cin * 16 : dsm2 + ((rc - 1) * 3) * cin * 16;
+    for (int dy = 0; dy < 3; ++dy) {
+      const float* xr = xcol + (il + dy) * xp;
+      const float4* dd = reinterpret_cast<const float4*>(dbase + dy * cin * 16);
+      for (int ci = 0; ci < cin; ++ci) {
+        const float xv = xr[ci];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float4 d4 = dd[ci * 4 + q];
+          acc[4 * q] = fmaf(d4.x, xv, acc[4 * q]);
+          acc[4 * q + 1] = fmaf(d4.y, xv, acc[4 * q + 1]);
+          acc[4 * q + 2] = fmaf(d4.z, xv, acc[4 * q + 2]);
+          acc[4 * q + 3] = fmaf(d4.w, xv, acc[4 * q + 3]);
+        }
       }
     }
-    corr[((static_cast<size_t>(n) * 2 + side) * (2 * h) + Y) * cout + co] = acc;
+    float4* op = reinterpret_cast<float4*>(corr + ((static_cast<size_t>(n) * 2 + side) * (2 * h) + Y) * 16);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) op[q] = make_float4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]);
   }
 }
+
 int launch_upblur_corr(const __half* y, const float* inA, const float* inB, const float* corr_d, int n, int h, int w,
                        int cin, int cout, float* corr, cudaStream_t st) {
   dim3 grid((h + kCorrRows - 1) / kCorrRows, 2, n);
-  const size_t smem = (static_cast<size_t>(kCorrRows + 2) * cin + 2 * 3 * cin * cout) * sizeof(float);
-  if (smem > 48 * 1024) { set_error("upblur_corr: Cin*Cout too large"); return 2; }
-  k_upblur_corr<<<grid, 256, smem, st>>>(y, inA, inB, corr_d, h, w, cin, cout, corr);
+  const size_t smem = ((static_cast<size_t>(kCorrRows + 2) * (cin + 1) + 3) / 4 * 4 + 2 * 2 * 3 * cin * cout) * sizeof(float);
+  if (smem > 48 * 1024 || cout != 16) { set_error("upblur_corr: needs Cout == 16 and a small Cin"); return 2; }
+  k_upblur_corr<<<grid, 2 * kCorrRows, smem, st>>>(y, inA, inB, corr_d, h, w, cin, cout, corr);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { set_error("upblur_corr launch: %s", cudaGetErrorString(e)); return 4; }
   count_launch();

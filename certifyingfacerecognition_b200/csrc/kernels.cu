@@ -681,14 +681,28 @@ __global__ void k_torgb_resize(const __half* __restrict__ x, const float* __rest
                                int n, int hin, int c, const float* __restrict__ w_rgb, const float* __restrict__ b_rgb,
                                int rout, float mean, float stdv, __half* __restrict__ out,
                                float* __restrict__ out_planar, const int* __restrict__ slot) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n * rout * rout) return;
+  // one sample per blockIdx.y: toRGB weights with the sample's IN/AdaIN folded in live in shared memory
+  //   rgb_k = sum_c w[k][c] * (A_c x_c + B_c) + b_k = sum_c (w[k][c] A_c) x_c + (b_k + sum_c w[k][c] B_c)
+  extern __shared__ float trs[];                 // [3][c] fused weights, then [3] fused bias
+  const int s = blockIdx.y;
+  for (int t = threadIdx.x; t < 3 * c; t += blockDim.x)
+    trs[t] = w_rgb[t] * (A != nullptr ? A[s * c + t % c] : 1.f);
+  if (threadIdx.x < 3) {
+    float bsum = b_rgb[threadIdx.x];
+    if (B != nullptr)
+      for (int cc = 0; cc < c; ++cc) bsum = fmaf(w_rgb[threadIdx.x * c + cc], B[s * c + cc], bsum);
+    trs[3 * c + threadIdx.x] = bsum;
+  }
+  __syncthreads();
+  const int ip = blockIdx.x * blockDim.x + threadIdx.x;      // pixel inside the sample
+  if (ip >= rout * rout) return;
+  const int i = s * rout * rout + ip;
   if (slot != nullptr) {                    // write into the slot-th group of n images of a larger buffer
     const size_t g = static_cast<size_t>(*slot) * n * rout * rout;
     if (out != nullptr) out += g * 16;
     if (out_planar != nullptr) out_planar += g * 3;
   }
-  const int ox = i % rout, oy = (i / rout) % rout, s = i / (rout * rout);
+  const int ox = ip % rout, oy = ip / rout;
   const float scale = static_cast<float>(hin) / static_cast<float>(rout);
   float sy = scale * (oy + 0.5f) - 0.5f;
   float sx = scale * (ox + 0.5f) - 0.5f;
@@ -710,14 +724,12 @@ __global__ void k_torgb_resize(const __half* __restrict__ x, const float* __rest
         load8(src + cc, v);
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-          float t = v[k];
-          if (A != nullptr) t = t * A[s * c + cc + k] + B[s * c + cc + k];
-          r += w_rgb[cc + k] * t;
-          g += w_rgb[c + cc + k] * t;
-          bl += w_rgb[2 * c + cc + k] * t;
+          r = fmaf(trs[cc + k], v[k], r);
+          g = fmaf(trs[c + cc + k], v[k], g);
+          bl = fmaf(trs[2 * c + cc + k], v[k], bl);
         }
       }
-      const float rgb[3] = {r + b_rgb[0], g + b_rgb[1], bl + b_rgb[2]};
+      const float rgb[3] = {r + trs[3 * c], g + trs[3 * c + 1], bl + trs[3 * c + 2]};
 #pragma unroll
       for (int k = 0; k < 3; ++k) {
         float t = (rgb[k] + 1.0f) / 2.0f + 0.5f / 255.f;
@@ -745,8 +757,8 @@ __global__ void k_torgb_resize(const __half* __restrict__ x, const float* __rest
 int launch_torgb_resize(const __half* x, const float* A, const float* B, int n, int hin, int c, const float* w_rgb,
                         const float* b_rgb, int rout, float mean, float stdv, __half* out, float* out_planar,
                         const int* slot, cudaStream_t st) {
-  const int total = n * rout * rout;
-  k_torgb_resize<<<(total + 127) / 128, 128, 0, st>>>(x, A, B, n, hin, c, w_rgb, b_rgb, rout, mean, stdv, out, out_planar, slot);
+  if (c > 2048) { set_error("torgb_resize: c=%d too large", c); return 2; }
+  k_torgb_resize<<<dim3((rout * rout + 127) / 128, n), 128, (3 * c + 3) * sizeof(float), st>>>(x, A, B, n, hin, c, w_rgb, b_rgb, rout, mean, stdv, out, out_planar, slot);
   CFR_LAUNCH_CHECK("torgb_resize");
   return 0;
 }
