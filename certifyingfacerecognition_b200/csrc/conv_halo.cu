@@ -138,7 +138,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
     const bool leader = elect_one();
     const uint32_t idesc = make_idesc_f16(128, COUT);
     [[maybe_unused]] const uint32_t idesc2 = make_idesc_f16(128, 2 * COUT), idesc4 = make_idesc_f16(128, 4 * COUT);
-    [[maybe_unused]] const uint32_t idesc3 = make_idesc_f16(128, 3 * (COUT > 32 ? 16 : COUT));
+    [[maybe_unused]] const uint32_t idesc3 = make_idesc_f16(128, 3 * COUT);
     const uint32_t dhi = smem_desc_hi(8 * p.rowBytes, p.rowBytes);
     const int kPer = p.Cin / 16;
     const uint32_t rb16 = p.rowBytes >> 4;                 // row pitch in 16-byte units
@@ -227,7 +227,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
       const uint32_t a_band = smem_desc_lo(smem_u32(smem + hs * p.haloBytes));
       const uint32_t x_band = smem_desc_lo(smem_u32(aux + hs * p.auxBytes));
       const int ngroups = p.numPhases == 4 ? bd.rows : (bd.rows + G - 1) / G;
-      if (FOLD && !COMP && COUT <= 32 && p.rowmma == 2) {
+      if (FOLD && !COMP && p.rowmma == 2) {
         // Row-stationary order (see the per-group variant below) over the WHOLE band: one warp owns a band (same-thread
         // MMAs execute in order, which the overlapping accumulate chains need) and walks its input rows once, 3 x kPer
         // MMAs of N = 3*COUT each; accumulator groups are acquired / handed to the epilogue as the walk reaches them.
@@ -257,9 +257,10 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
               const uint32_t bt = static_cast<uint32_t>(2 - i + o);   // first dy tile of the triple: dy = 1 - bt
 #pragma unroll
               for (int dx = 0; dx < 3; ++dx) {
-                umma_f16_pred<true>(d, a_row + dx * rb16, dhi, w_lo + (dx * 3 + bt) * w_tap, dhi, id, lead);
-                if (kPer > 1)
-                  umma_f16_pred<true>(d, a_row + dx * rb16 + 2, dhi, w_lo + (dx * 3 + bt) * w_tap + 2, dhi, id, lead);
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                  if (k < kPer)
+                    umma_f16_pred<true>(d, a_row + dx * rb16 + 2 * k, dhi, w_lo + (dx * 3 + bt) * w_tap + 2 * k, dhi, id, lead);
               }
               o = e + 1;
             }
@@ -1047,15 +1048,16 @@ int halo_build(const cfr_conv_desc& s, const float* inA, const float* inB, const
   p.wsets = composite ? 8 : s.numPhases;
   if (const char* e = getenv("CFR_HALO_DBG")) p.dbg = atoi(e);
   p.rowmma = 0;
-  if (p.fold && !composite && s.numPhases == 1 && s.ntaps == 9 && s.Cout <= 32) {
+  if (p.fold && !composite && s.numPhases == 1 && s.ntaps == 9) {
     unsigned seen = 0;                   // a full 3x3 stencil, any tap order
     for (int t = 0; t < 9; ++t)
       if (s.tap_dy[0][t] >= -1 && s.tap_dy[0][t] <= 1 && s.tap_dx[0][t] >= -1 && s.tap_dx[0][t] <= 1)
         seen |= 1u << ((s.tap_dy[0][t] + 1) * 3 + s.tap_dx[0][t] + 1);
     // 1: per accumulator group (4 issuing warps; N = 16 tiles are issue-bound), 2: per band (fewest MMAs; wins once
     // the MMAs are N = 96 wide).  Measured: profiles/ncu_r01_notes.md section 13.
-    if (seen == 0x1ffu) p.rowmma = s.Cout == 32 ? 2 : 1;
+    if (seen == 0x1ffu) p.rowmma = s.Cout >= 32 ? 2 : 1;
     if (const char* e = getenv("CFR_HALO_ROWMMA")) p.rowmma = p.rowmma ? atoi(e) : 0;
+    if (s.Cout > 32 && p.rowmma == 1) p.rowmma = 2;     // (the per-group variant is only instantiated for Cout <= 32)
   }
   if (p.fold && s.Cin > 64) { set_error("halo conv: folded variant needs Cin <= 64"); return 2; }
   p.rowBytes = s.Cin * 2;
