@@ -159,6 +159,17 @@ static int add_folded(cfr_program* p, const cfr_conv_desc* d, const float* base_
   const int wsets = composite ? 8 : d->numPhases;
   dd.wRows = d->N * wsets * d->ntaps * d->Cout;
   dd.Kpad = d->Cin;
+  const bool upshare = !composite && halo_upshare_ok(*d);
+  if (upshare) {                                 // shared-A up-conv: 18 weight tiles per sample (two of them zero) -- the
+    const size_t bytes = static_cast<size_t>(d->N) * kUpShareTiles * d->Cout * d->Cin * 2;   // library owns that buffer
+    void* own = nullptr;
+    if (cudaMalloc(&own, bytes) != cudaSuccess) { set_error("folded conv: cudaMalloc(per-sample weights) failed"); return 5; }
+    p->owned.push_back(own);
+    if (cudaMemset(own, 0, bytes) != cudaSuccess) { set_error("folded conv: cudaMemset failed"); return 5; }
+    w_main_f16 = own;
+    dd.w = own;
+    dd.wRows = d->N * kUpShareTiles * d->Cout;
+  }
   int r = halo_build(dd, nullptr, nullptr, w_aux_f16, composite, composite ? corr_buf : nullptr, op.get());
   if (r != 0) return r;
   HaloOp* raw = op.get();
@@ -177,7 +188,7 @@ static int add_folded(cfr_program* p, const cfr_conv_desc* d, const float* base_
   const float* bias = d->bias;
   const float* noise_w = d->noise_w;
   cfr_conv_desc keep = *d;                       // tap tables live in the closure
-  const int layout = composite ? 1 : (raw->p.rowmma ? 2 : 0);
+  const int layout = composite ? 1 : (raw->p.upshare ? 3 : (raw->p.rowmma ? 2 : 0));
   p->add([=](cudaStream_t st) {
     return launch_fold_weights(base_w, inA, inB, bias, noise_w, &keep.tap_dy[0][0], &keep.tap_dx[0][0], n, phases, ntaps,
                                cout, cin, layout, static_cast<__half*>(w_main_f16), static_cast<__half*>(w_aux_f16), st);

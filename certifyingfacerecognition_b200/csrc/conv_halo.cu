@@ -312,6 +312,24 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
               umma_f16_pred<true>(dd, x_row, dhi_aux, wa_lo + so * (COUT * 2), dhi_aux, idesc2, leader ? 1u : 0u);
             }
           }
+        } else if (FOLD && COUT <= 32 && p.upshare) {
+          // 4-phase up-conv (nearest x2 + 3x3): phase (py,px) reads the low-res taps {py-1,py} x {px-1,px}, so each of the
+          // nine input positions serves 1, 2 or 4 phases.  One MMA per (position, k-step) with the weights of the phases
+          // that use it side by side (layout 3; the (0,+-1) positions span three accumulators with a zero tile in the
+          // middle) and ONE N = 4*COUT aux MMA: 1 + 9*kPer MMAs per low-res row tile instead of 4 + 16*kPer.
+          const uint32_t a_row = a_band + j * row_step, x_row = x_band + j * aux_row_step;
+          umma_f16_pred<false>(d0, x_row, dhi_aux, wa_lo, dhi_aux, idesc4, lead);
+          constexpr int P_DY[9] = {0, -1, 1, 0, 0, -1, -1, 1, 1}, P_DX[9] = {0, 0, 0, -1, 1, -1, 1, -1, 1};
+          constexpr int P_D[9] = {0, 0, 2, 0, 1, 0, 1, 2, 3}, P_N[9] = {4, 2, 2, 3, 3, 1, 1, 1, 1};
+          constexpr int P_B[9] = {0, 4, 6, 8, 11, 14, 15, 16, 17};
+#pragma unroll
+          for (int P = 0; P < 9; ++P) {
+            const uint32_t a_lo = a_row + ((1 + P_DY[P]) * kHaloW + 1 + P_DX[P]) * rb16, b_lo = w_lo + P_B[P] * w_tap;
+            const uint32_t id = P_N[P] == 4 ? idesc4 : (P_N[P] == 3 ? idesc3 : (P_N[P] == 2 ? idesc2 : idesc));
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              if (k < kPer) umma_f16_pred<true>(d0 + P_D[P] * ACC_COLS, a_lo + 2 * k, dhi, b_lo + 2 * k, dhi, id, lead);
+          }
         } else if (p.numPhases == 4) {     // G == 4: tile k of the group == phase k of low-res row j
           const uint32_t a_row = a_band + j * row_step, x_row = x_band + j * aux_row_step;
 #pragma unroll
@@ -811,12 +829,12 @@ struct FoldTaps {
   int8_t k[8][9];      // aux K index of the "input (y+dy, x+dx) inside?" indicator of (weight set, tap), -1 = unused
   int8_t noise_k[8];   // aux K index of the noise value used by the weight set
   int8_t center_k;     // aux K index of the (0,0) indicator (carries the bias)
-  int8_t tpos[9];      // output tile position of tap t inside a weight set (identity unless row-stationary layout)
+  int8_t tile[8][9];   // non-composite layouts: destination weight tile of (weight set, tap)
 };
 __global__ void k_fold_weights(const float* __restrict__ base_w, const float* __restrict__ inA,
                                const float* __restrict__ inB, const float* __restrict__ bias,
-                               const float* __restrict__ noise_w, FoldTaps ft, int wsets, int ntaps, int cout, int cin,
-                               int composite, __half* __restrict__ w_main, __half* __restrict__ w_aux) {
+                               const float* __restrict__ noise_w, FoldTaps ft, int wsets, int ntaps, int ntiles, int cout,
+                               int cin, int composite, __half* __restrict__ w_main, __half* __restrict__ w_aux) {
   const int n = blockIdx.y, ws = blockIdx.x;
   // composite: tap-major output with the weight sets ordered [4 5 | 0 1 2 3 | 6 7] inside a tap, so that the four
   // interior phases are ONE contiguous N = 4*cout operand (and the first / last-row variants contiguous pairs)
@@ -838,8 +856,8 @@ __global__ void k_fold_weights(const float* __restrict__ base_w, const float* __
   for (int t = 0; t < 9; ++t) {
     if (t < ntaps) {
       const size_t oidx = composite ? ((static_cast<size_t>(t) * wsets + pos) * cout + co) * cin + ci
-                                    : ((static_cast<size_t>(ws) * ntaps + ft.tpos[t]) * cout + co) * cin + ci;
-      w_main[static_cast<size_t>(n) * wsets * ntaps * cout * cin + oidx] = __float2half_rn(w[t] * a);
+                                    : (static_cast<size_t>(ft.tile[ws][t]) * cout + co) * cin + ci;
+      w_main[static_cast<size_t>(n) * ntiles * cout * cin + oidx] = __float2half_rn(w[t] * a);
     }
     sh[t] = w[t] * b;
     for (int o = (cin < 32 ? cin : 32) >> 1; o > 0; o >>= 1) sh[t] += __shfl_xor_sync(0xffffffffu, sh[t], o);
@@ -884,9 +902,22 @@ int launch_fold_weights(const float* base_w, const float* inA, const float* inB,
   ft.center_k = static_cast<int8_t>(m_off + 4);
   // layout 2 (row-stationary MMAs, see conv_halo_kernel): tiles ordered dx-major, dy descending, so the three dy
   // variants of one dx are ONE contiguous N = 3*cout operand [dy=+1 | dy=0 | dy=-1]
-  for (int t = 0; t < 9; ++t)
-    ft.tpos[t] = static_cast<int8_t>(layout == 2 && t < ntaps ? (tap_dx[t] + 1) * 3 + (1 - tap_dy[t]) : t);
-  k_fold_weights<<<dim3(wsets, n, cout / (threads / cin)), threads, 0, st>>>(base_w, inA, inB, bias, noise_w, ft, wsets, ntaps, cout, cin, composite, w_main, w_aux);
+  // layout 3 (shared-A up-conv, see conv_halo_kernel): one B operand per input position (dy,dx), holding the phases
+  // that use it side by side in TMEM order
+  static const int8_t up_base[3][3] = {{14, 4, 15}, {8, 0, 11}, {16, 6, 17}};   // first tile of position [dy+1][dx+1]
+  static const int8_t up_doff[3][3] = {{0, 0, 1}, {0, 0, 1}, {2, 2, 3}};        // first phase (accumulator) it writes
+  for (int ws = 0; ws < 8; ++ws)
+    for (int t = 0; t < 9; ++t) {
+      int tile = ws * ntaps + t;
+      if (ws < wsets && t < ntaps) {
+        const int dy = tap_dy[(ws % phases) * 9 + t], dx = tap_dx[(ws % phases) * 9 + t];
+        if (layout == 2) tile = ws * ntaps + (dx + 1) * 3 + (1 - dy);
+        if (layout == 3) tile = up_base[dy + 1][dx + 1] + ws - up_doff[dy + 1][dx + 1];
+      }
+      ft.tile[ws][t] = static_cast<int8_t>(tile);
+    }
+  const int ntiles = layout == 3 ? kUpShareTiles : wsets * ntaps;
+  k_fold_weights<<<dim3(wsets, n, cout / (threads / cin)), threads, 0, st>>>(base_w, inA, inB, bias, noise_w, ft, wsets, ntaps, ntiles, cout, cin, composite, w_main, w_aux);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { set_error("fold_weights launch: %s", cudaGetErrorString(e)); return 4; }
   count_launch();
@@ -1023,6 +1054,23 @@ int launch_pack_noise(const float* noise, int h, int w, int mode, void* out, cud
   return 0;
 }
 
+bool halo_upshare_ok(const cfr_conv_desc& s) {
+  if (const char* e = getenv("CFR_HALO_UPSHARE")) if (atoi(e) == 0) return false;
+  if (s.numPhases != 4 || s.ntaps != 4 || s.Cout > 32 || s.oscale != 2) return false;
+  for (int ph = 0; ph < 4; ++ph) {                     // phase (py,px) = nearest x2 + 3x3: taps {py-1,py} x {px-1,px}
+    const int py = ph >> 1, px = ph & 1;
+    if (s.ooff_y[ph] != py || s.ooff_x[ph] != px) return false;
+    unsigned seen = 0;
+    for (int t = 0; t < 4; ++t) {
+      const int dy = s.tap_dy[ph][t] - (py - 1), dx = s.tap_dx[ph][t] - (px - 1);
+      if (dy < 0 || dy > 1 || dx < 0 || dx > 1) return false;
+      seen |= 1u << (dy * 2 + dx);
+    }
+    if (seen != 0xfu) return false;
+  }
+  return true;
+}
+
 int halo_build(const cfr_conv_desc& s, const float* inA, const float* inB, const void* w_aux, int composite,
                const float* corr, HaloOp* op) {
   EncodeTiledFn enc = reinterpret_cast<EncodeTiledFn>(get_encode_tiled());
@@ -1047,6 +1095,7 @@ int halo_build(const cfr_conv_desc& s, const float* inA, const float* inB, const
   if (composite && (!p.fold || s.numPhases != 4 || s.ntaps != 9 || s.Cout != 16 || s.Cin > 32)) { set_error("halo conv: composite needs fold, 4 phases, 9 taps"); return 2; }
   p.wsets = composite ? 8 : s.numPhases;
   if (const char* e = getenv("CFR_HALO_DBG")) p.dbg = atoi(e);
+  p.upshare = p.fold && !composite && halo_upshare_ok(s);
   p.rowmma = 0;
   if (p.fold && !composite && s.numPhases == 1 && s.ntaps == 9) {
     unsigned seen = 0;                   // a full 3x3 stencil, any tap order
@@ -1061,7 +1110,7 @@ int halo_build(const cfr_conv_desc& s, const float* inA, const float* inB, const
   }
   if (p.fold && s.Cin > 64) { set_error("halo conv: folded variant needs Cin <= 64"); return 2; }
   p.rowBytes = s.Cin * 2;
-  p.wRows = p.wsets * s.ntaps * s.Cout;
+  p.wRows = p.upshare ? kUpShareTiles * s.Cout : p.wsets * s.ntaps * s.Cout;
   p.wAuxBytes = p.fold ? (p.wsets * s.Cout * 32 + 1023) / 1024 * 1024 : 0;
   p.wBytes = (p.wRows * p.rowBytes + 1023) / 1024 * 1024;
   p.wBoxRows = p.wRows;

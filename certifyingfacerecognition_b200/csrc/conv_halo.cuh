@@ -36,7 +36,7 @@ constexpr int kHaloThreads = (kEpiWarps + kLoaderWarps + kMmaWarps) * 32;
 #ifndef CFR_HALO_REGS_EPI
 #define CFR_HALO_REGS_EPI 128
 #define CFR_HALO_REGS_LOADER 72
-#define CFR_HALO_REGS_MMA 56
+#define CFR_HALO_REGS_MMA 64
 #endif
 constexpr int kRegsEpi = CFR_HALO_REGS_EPI, kRegsLoader = CFR_HALO_REGS_LOADER, kRegsMma = CFR_HALO_REGS_MMA;
 constexpr int kHaloW = 130;         // 128 output columns + 1 halo column each side
@@ -50,6 +50,7 @@ struct HaloParams {
   int fold;                         // per-sample folded weights + aux band
   int composite;                    // blur o up-conv: 4 phases x 9 taps, 8 weight sets (first/last-row variants), 4 noise slots
   int wsets;                        // weight sets resident in smem (numPhases, or 8 when composite)
+  int upshare;                      // FOLD 4-phase up-conv: phases share the A operand per input position (weights in layout 3)
   int rowmma;                       // 3x3 FOLD conv, Cout <= 32: row-stationary MMA order (1 per group, 2 per band), weights in layout 2
   const float* corr;                // composite: border-column correction [N][2 sides][outH][Cout] fp32
   int dbg;                          // ablation bits for profiling only (env CFR_HALO_DBG): 1 skip epilogue math/store,
@@ -89,7 +90,7 @@ int halo_build(const cfr_conv_desc& s, const float* inA, const float* inB, const
 // per-sample weight folding for the FOLD variant (see conv_halo.cu)
 int launch_fold_weights(const float* base_w, const float* inA, const float* inB, const float* bias, const float* noise_w,
                         const int8_t* tap_dy, const int8_t* tap_dx, int n, int phases, int ntaps, int cout, int cin,
-                        int layout, __half* w_main, __half* w_aux, cudaStream_t st);   // 0 plain, 1 composite, 2 row-stationary
+                        int layout, __half* w_main, __half* w_aux, cudaStream_t st);   // 0 plain, 1 composite, 2 row-stationary, 3 shared-A up-conv
 // composite up-conv+blur: exact values for the first / last hi-res column (see engine.composite_upconv_weights)
 int launch_upblur_corr(const __half* y, const float* inA, const float* inB, const float* corr_d, int n, int h, int w,
                        int cin, int cout, float* corr, cudaStream_t st);
@@ -97,6 +98,9 @@ int launch_upblur_corr(const __half* y, const float* inA, const float* inB, cons
 // (no register-staged noise loads on its critical path).  mode 0: out[y][x] = {half noise(y,x), half (y>0 && x>0)};
 // mode 1 (composite, low-res grid h x w, noise is 2h x 2w): out[y][x] = 4 halves noise(2y+a, 2x+b), (a,b) row-major.
 int launch_pack_noise(const float* noise, int h, int w, int mode, void* out, cudaStream_t st);
+// FOLD 4-phase (nearest x2 + 3x3) up-conv whose phases can share A operands: 18 weight tiles per sample instead of 16
+constexpr int kUpShareTiles = 18;
+bool halo_upshare_ok(const cfr_conv_desc& s);
 int halo_launch(const HaloOp& op, cudaStream_t stream);
 
 }  // namespace cfr
