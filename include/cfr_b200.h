@@ -81,12 +81,14 @@ CFR_API int cfr_program_add_conv(cfr_program* p, const cfr_conv_desc* d);
  * (Kpad == Cin).  inA/inB (may be NULL): per-(n, cin) affine x = y*A + B applied on load -- the previous layer's
  * InstanceNorm + AdaIN (stylegan_generator_model.py:420-422,:505) -- with the conv's zero padding left at zero. */
 CFR_API int cfr_program_add_conv_halo(cfr_program* p, const cfr_conv_desc* d, const float* inA, const float* inB);
-/* Folded variant (Cin <= 32): records (1) a per-sample weight-folding kernel -- w_main[n] = fp16(base_w * A[n]); one aux
+/* Folded variant (Cin <= 64): records (1) a per-sample weight-folding kernel -- w_main[n] = fp16(base_w * A[n]); one aux
  * tile per phase carrying the noise gain, and per 3x3-neighbourhood position sum_ci base_w*B[n] (+ bias at the centre) --
  * and (2) the halo conv, which feeds one extra 16-channel row per output pixel {noise, inside-image indicators} through
  * ONE more MMA per tile, so IN+AdaIN, noise and bias cost nothing on the CUDA cores and stay exact at the borders.
  * base_w: fp32 [phases*taps][Cout][Cin]; w_main_f16: [N][phases*taps*Cout][Cin]; w_aux_f16: [N][phases*Cout][16] (zeroed).
- * d->bias / d->noise / d->noise_w are consumed by the fold; d->w is ignored. */
+ * d->bias / d->noise / d->noise_w are consumed by the fold; d->w is ignored.  The layout INSIDE w_main is the library's
+ * business (3x3 convs: taps reordered for row-stationary MMAs; nearest-x2 4-phase up-convs: one operand per shared input
+ * position, held in a library-owned buffer of 18 tiles per sample -- w_main_f16 is then left untouched). */
 CFR_API int cfr_program_add_conv_halo_folded(cfr_program* p, const cfr_conv_desc* d, const float* base_w, const float* inA,
                                      const float* inB, void* w_main_f16, void* w_aux_f16);
 /* UpConvBlock INCLUDING its BlurLayer and epilogue (stylegan_generator_model.py:665-678, :463, :559-562) as ONE
