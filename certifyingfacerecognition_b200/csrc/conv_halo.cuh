@@ -7,9 +7,18 @@
 // 32/64/128-byte swizzle is a function of absolute smem address bits, so row-shifted starts stay consistent
 // with what TMA wrote).  Weights for all taps/phases stay resident in smem for the CTA's lifetime.
 //
-// Fused on load: the previous layer's InstanceNorm + AdaIN (x = y*A[n,c] + B[n,c], stylegan_generator_model.py
-// :420-422,:505) is applied to the band in shared memory (in-bounds pixels only, so the conv's zero padding
-// stays zero).  Fused in the epilogue: +noise*w_c + b_c, LeakyReLU(0.2), fp16 store, per-(n,c) sum / sumsq.
+// The previous layer's InstanceNorm + AdaIN (x = y*A[n,c] + B[n,c], stylegan_generator_model.py:420-422,:505) is
+// fused in one of two ways.  FOLD (what the synthesis program uses for all five layers): A goes into per-sample fp16
+// weights, and the shift B, this layer's bias and the noise gain ride on one auxiliary 16-wide row per output pixel
+// {noise, inside-image indicators of the 3x3 input neighbourhood} consumed by ONE extra MMA -- exact at the borders,
+// nothing left for the loaders or the epilogue to do.  Non-FOLD: the loader warps apply the affine to the band in
+// shared memory (in-bounds pixels only, so the conv's zero padding stays zero) and the epilogue adds noise*w_c + b_c.
+// Epilogue in both: LeakyReLU(0.2), fp16 store (one 256-bit store per 16 channels), per-(n,c) sum / sumsq.
+//
+// MMA issue orders (FOLD): 3x3 convs are row-stationary -- input row i times [W(dy=+1,dx)|W(dy=0,dx)|W(dy=-1,dx)]
+// (N = 3*Cout) accumulates into output rows i-2, i-1, i, whose accumulators are adjacent TMEM columns (`rowmma`);
+// the nearest-x2 up-conv issues one MMA per input position for all the sub-pixel phases that read it (`upshare`);
+// the composite blur o up-conv shares the A operand between its four phases (one N = 4*Cout MMA per tap).
 #pragma once
 #include <cuda.h>
 #include <cuda_fp16.h>
