@@ -250,3 +250,19 @@ def test_facenet_tables_and_synthetic_weights_are_consistent():
     with torch.no_grad():
         e = O.forward(torch.randn(2, 3, 160, 160, generator=torch.Generator().manual_seed(0)) * 0.5, sd)
     assert e.shape == (2, 512) and torch.allclose(e.norm(dim=1), torch.ones(2), atol=1e-5)
+
+
+def test_ncu_launch_summary_is_reproducible():
+    """profiles/launches_r01e_summary.tsv is exactly what tools/summarize_ncu.py makes of the committed ncu launch list."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    csv_path = os.path.join(root, "profiles", "launches_r01e.csv")
+    want = open(os.path.join(root, "profiles", "launches_r01e_summary.tsv")).read().splitlines()
+    got = subprocess.run([sys.executable, os.path.join(root, "tools", "summarize_ncu.py"), "launches", csv_path, "x"],
+                         capture_output=True, text=True, check=True).stdout.splitlines()
+    assert got[1:] == want[1:]                       # (line 0 carries the free-text command)
+    shares = {ln.split("\t")[0]: float(ln.split("\t")[3]) for ln in got[2:]}
+    halo = sum(v for k, v in shares.items() if "conv_halo_kernel" in k)
+    igemm = sum(v for k, v in shares.items() if "conv_igemm_kernel" in k)
+    assert 0.3 < halo < 0.5 and 0.3 < igemm < 0.5    # the two conv kernels are ~80 % of the GPU time of the bench process
