@@ -56,6 +56,7 @@ SIGNATURES = {
     "cfr_program_destroy": (None, [_P]),
     "cfr_program_run": (_I, [_P, _P]),
     "cfr_program_num_launches": (_I, [_P]),
+    "cfr_program_run_range": (_I, [_P, _I, _I, _P]),
     "cfr_program_op_label": (C.c_char_p, [_P, _I]),
     "cfr_program_op_flops": (C.c_double, [_P, _I]),
     "cfr_program_run_timed": (_I, [_P, _P, C.POINTER(C.c_float), _I]),

@@ -125,6 +125,19 @@ CFR_API int cfr_program_run(cfr_program* p, cfr_stream_t stream) {
   return 0;
 }
 
+// Replay ops [first, last) only (diagnostics: tools/diag_precision.py compares every layer with the oracle).
+CFR_API int cfr_program_run_range(cfr_program* p, int first, int last, cfr_stream_t stream) {
+  if (first < 0 || last > static_cast<int>(p->ops.size()) || first > last) {
+    set_error("cfr_program_run_range: [%d, %d) outside [0, %d)", first, last, static_cast<int>(p->ops.size()));
+    return 2;
+  }
+  for (int i = first; i < last; ++i) {
+    int r = p->ops[i](S(stream));
+    if (r != 0) return r;
+  }
+  return 0;
+}
+
 CFR_API int cfr_program_add_conv(cfr_program* p, const cfr_conv_desc* d) {
   std::unique_ptr<ConvOp> op(new ConvOp());
   int r = conv_build(*d, op.get());

@@ -308,8 +308,10 @@ conv_igemm_kernel(const __grid_constant__ ConvParams p) {
       if (p.argmax_keys != nullptr) {
         // gallery match: score = acc + bias[j] (= 2 e.g_j - |g_j|^2); keep the best column of this tile per row and
         // fold it into the global per-query key (max score, then lowest index == torch.argmax tie-break)
-        float best = -3.4e38f;
-        int best_j = 0;
+        // -inf start + first column of the tile: a NaN score (fp16 overflow upstream) never wins a comparison, so the
+        // pick stays a real row (padded rows carry bias -inf and tile 0 starts at row 0) instead of a padded one
+        float best = -INFINITY;
+        int best_j = t.ntile * p.BN;
         for (int c0 = 0; c0 < p.BN; c0 += 16) {
           float v[16];
           tmem_ld16(t_row + c0, v);

@@ -822,7 +822,7 @@ __global__ void k_vote(unsigned long long* __restrict__ keys, int b, int* __rest
 // ------------------------------------------------------------------------------------------
 // Tensor-core gallery match (large galleries): fp32 rows are split into fp16 hi + lo parts so that
 //   e.g = e_h.g_h + e_h.g_l + e_l.g_h  (+ O(2^-22)),  one K = 3*512 GEMM:  A = [e_h, e_h, e_l],  B = [g_h, g_l, g_h].
-// mode 0 (gallery): dst = [h, l, h], bias[row] = -|g|^2 (exact fp32; padded rows get -3e38);
+// mode 0 (gallery): dst = [h, l, h], bias[row] = -|g|^2 (exact fp32; padded rows get -inf);
 // mode 1 (queries): dst = [2h, 2h, 2l]  (the factor 2 of 2 e.g - |g|^2 is exact in fp16).
 // ------------------------------------------------------------------------------------------
 __global__ void k_split_hilo(const float* __restrict__ src, int rows, int rows_pad, int mode, __half* __restrict__ dst,
@@ -845,7 +845,7 @@ __global__ void k_split_hilo(const float* __restrict__ src, int rows, int rows_p
   if (bias != nullptr) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) nrm += __shfl_xor_sync(0xffffffffu, nrm, o);
-    if (lane == 0) bias[row] = row < rows ? -nrm : -3.0e38f;
+    if (lane == 0) bias[row] = row < rows ? -nrm : -INFINITY;
   }
 }
 int launch_split_hilo(const float* src, int rows, int rows_pad, int mode, __half* dst, float* bias, cudaStream_t st) {

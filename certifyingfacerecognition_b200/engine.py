@@ -21,6 +21,7 @@ from . import _lib as L
 Tensor = torch.Tensor
 NUM_LAYERS = 18
 PSI, TRUNC_LAYERS = 0.7, 8          # models/model_settings.py:65-66
+N_DIRS = 5                          # attack_utils/proj_utils.py:16-21 (ATTRS): age, eyeglasses, gender, pose, smile
 
 
 def layer_channels(layer: int) -> int:
@@ -192,6 +193,12 @@ class Program:
             stream = torch.cuda.current_stream().cuda_stream
         L.check(self.lib.cfr_program_run(self.handle, C.c_void_p(stream)))
 
+    def run_range(self, first: int, last: int, stream: Optional[int] = None) -> None:
+        """Replay ops [first, last) only (diagnostics)."""
+        if stream is None:
+            stream = torch.cuda.current_stream().cuda_stream
+        L.check(self.lib.cfr_program_run_range(self.handle, first, last, C.c_void_p(stream)))
+
     @property
     def num_launches(self) -> int:
         return self.lib.cfr_program_num_launches(self.handle)
@@ -287,9 +294,11 @@ class SynthesisProgram(Program):
         dev = torch.device(device)
         self.chunk, self.out_res = chunk, out_res
         import os as _os
-        if _os.environ.get("CFR_FUSED_UPBLUR") is not None:          # A/B knob for profiling
-            fused_upblur = _os.environ["CFR_FUSED_UPBLUR"] != "0"
-        fold_max_cin = int(_os.environ.get("CFR_FOLD_MAX_CIN", "64"))   # A/B knob: widest layer input that is folded
+        fold_max_cin = 64                                            # widest layer input that is folded
+        if _os.environ.get("CFR_DEBUG_KNOBS") == "1":                # A/B knobs for profiling runs only: they change
+            if _os.environ.get("CFR_FUSED_UPBLUR") is not None:      # numerics, so a stray variable must not reach the
+                fused_upblur = _os.environ["CFR_FUSED_UPBLUR"] != "0"   # product path
+            fold_max_cin = int(_os.environ.get("CFR_FOLD_MAX_CIN", "64"))
         sd = {k: v.detach().float().cpu() for k, v in g_sd.items()}
         lib, h = self.lib, self.handle
 
@@ -335,6 +344,8 @@ class SynthesisProgram(Program):
         xhat0 = self.hold(_f32(t.permute(1, 2, 0).reshape(16, 512), dev))
         L.check(lib.cfr_program_add_layer0(h, L.ptr(xhat0), L.ptr(self.styles), off, self.style_off[0], chunk, L.ptr(x)))
 
+        # diagnostics: (layer, ops recorded when its output is complete, buffer, res, C, (A, B) still to apply or None)
+        self.layer_marks = [(0, self.num_launches, x, 4, 512, None)]
         stat_off = chunk * 512          # layer 0 uses no statistics slot
         pending = None                  # (A, B) of the previous layer when its IN/AdaIN has not been applied yet
         use_halo = lambda l: halo and layer_channels(l - 1) <= 64 and layer_channels(l) <= 64
@@ -406,6 +417,7 @@ class SynthesisProgram(Program):
                 pending = None
             else:
                 pending = (A, B)            # applied on load by the consumer (halo conv / toRGB)
+            self.layer_marks.append((l, self.num_launches, y, res, cout, pending))
             if l < NUM_LAYERS - 1:
                 x, y = y, x
         # ---- toRGB + postprocess + bilinear + normalise; the last layer's IN/AdaIN is applied on load
@@ -533,6 +545,10 @@ class Engine:
         self.synth = SynthesisProgram(g_sd, chunk, res, device, keep_planar=keep_planar, groups=self.frm_group)
         self.frm = frm_cls(f_sd, chunk, self.synth.img, device)
         self.frm_big = frm_cls(f_sd, chunk * self.frm_group, self.synth.img, device) if self.frm_group > 1 else None
+        if tuple(dir_mat.shape) != (N_DIRS, 512):
+            # the noise kernel (k_noise_project) and the C ABI fix the attribute space at the reference's five
+            # InterFaceGAN directions (proj_utils.py:16-21 ATTRS); fewer / more rows would read out of bounds
+            raise ValueError(f"direction matrix must be [{N_DIRS}, 512] (got {tuple(dir_mat.shape)})")
         self.dir_mat = _f32(dir_mat, self.device)
         self.tc_match = tc_match
         self.matcher = None
@@ -616,6 +632,11 @@ class Engine:
         z = _f32(z.reshape(-1), self.device)
         x = _f32(x.reshape(-1), self.device)
         sigma = _f32(sigma.reshape(-1), self.device)
+        if z.numel() != 512 or x.numel() != N_DIRS or sigma.numel() not in (1, N_DIRS):
+            raise ValueError(f"sample_votes: z must hold ONE latent [1,512], x [1,{N_DIRS}], sigma 1 or {N_DIRS} values "
+                             f"(got {z.numel()}, {x.numel()}, {sigma.numel()})")
+        if noise is not None and noise.numel() != num * N_DIRS:
+            raise ValueError(f"sample_votes: noise must be [num, {N_DIRS}]")
         if counts is None:
             counts = torch.zeros(self.num_classes, dtype=torch.int64, device=self.device)
         noise_d = _f32(noise.reshape(-1, 5), self.device) if noise is not None else None

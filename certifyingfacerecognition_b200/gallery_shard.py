@@ -46,7 +46,7 @@ def allgather_merge(keys: torch.Tensor, group=None) -> torch.Tensor:
 
 class ShardedGallery:
     def __init__(self, rows: torch.Tensor, lo: int, n_total: int, max_b: int, process_group=None,
-                 tc_match: Optional[bool] = None) -> None:
+                 tc_match: Optional[bool] = None, world: Optional[int] = None) -> None:
         if not rows.is_cuda:
             raise RuntimeError("ShardedGallery needs its rows on a CUDA device (no CPU fallback)")
         if rows.shape[0] == 0:
@@ -56,7 +56,21 @@ class ShardedGallery:
         self.lo, self.n_total, self.max_b = int(lo), int(n_total), int(max_b)
         self.group = process_group
         self.device = rows.device
-        use_tc = tc_match if tc_match is not None else self.rows.shape[0] >= TC_MATCH_MIN_ROWS
+        # The two matchers encode their keys differently, so EVERY rank must pick the same one: decide from the
+        # rank-independent floor(n_total / world) (shard sizes differ by at most one row), never from the local count.
+        # (`world`: number of shards when several of them live in one process, as in the single-GPU tests.)
+        if process_group is not None:
+            import torch.distributed as dist
+            world = dist.get_world_size(process_group)
+        world = max(1, int(world or 1))
+        use_tc = bool(tc_match) if tc_match is not None else (self.n_total // world) >= TC_MATCH_MIN_ROWS
+        if process_group is not None:
+            import torch.distributed as dist
+            flag = torch.tensor([int(use_tc), -int(use_tc)], device=self.device)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=process_group)
+            if int(flag[0]) != -int(flag[1]):
+                raise RuntimeError("ShardedGallery: ranks disagree on the matcher (tc_match must be the same everywhere)")
+        self.use_tc = use_tc
         self.matcher = None
         if use_tc:
             m = C.c_void_p()

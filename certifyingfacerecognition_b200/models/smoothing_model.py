@@ -102,8 +102,15 @@ class WrappedModel(nn.Module):
         return F.softmax(-d / np.sqrt(EMB_SIZE), dim=1)
 
     def embed(self, x: torch.Tensor, p: torch.Tensor) -> torch.Tensor:
-        """Embeddings of z + p @ dir_mat (smoothing_model.py:63-69)."""
+        """Embeddings of x + p @ dir_mat (smoothing_model.py:63-69).  x: [1,512] (what Smooth passes) or [b,512] with
+        one latent per row of p, as the reference's broadcast ``x + pert`` allows."""
         p = p.reshape(-1, self.dir_mat.shape[0])
+        x = x.reshape(-1, 512)
+        if x.shape[0] != 1:
+            if x.shape[0] != p.shape[0]:
+                raise ValueError(f"WrappedModel: x has {x.shape[0]} latents for {p.shape[0]} perturbations")
+            w = x.to(self.device, torch.float32) + p.to(self.device, torch.float32) @ self.dir_mat.float()
+            return self.engine.embed_latents(w)                 # lat2embs on the perturbed latents, row by row
         _, extra = self.engine.sample_votes(x, torch.zeros(self.dir_mat.shape[0]), torch.ones(1), p.shape[0],
                                             noise=p, want_emb=True,
                                             counts=torch.zeros(self.engine.num_classes, dtype=torch.int64,

@@ -69,6 +69,8 @@ CFR_API int cfr_program_create(cfr_program** out);
 CFR_API void cfr_program_destroy(cfr_program* p);
 CFR_API int cfr_program_run(cfr_program* p, cfr_stream_t stream);
 CFR_API int cfr_program_num_launches(const cfr_program* p);
+/* replay ops [first, last) only -- diagnostics (per-layer comparison with the oracle, tools/diag_precision.py) */
+CFR_API int cfr_program_run_range(cfr_program* p, int first, int last, cfr_stream_t stream);
 /* per-op introspection / timing (tools/profile_program.py): label, algorithmic FLOPs, and one timed replay with a
  * CUDA event between consecutive ops (synchronises) */
 CFR_API const char* cfr_program_op_label(const cfr_program* p, int i);

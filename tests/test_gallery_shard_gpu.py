@@ -80,3 +80,23 @@ def test_engine_sharded_votes_equal_unsharded(golden, models):
     c2, p2 = eng.sample_votes_sharded(whole, z, x, sigma, 20, seed=3, want_pred=True)
     torch.cuda.synchronize()
     assert torch.equal(c2, full) and torch.equal(p2, ex["pred"])
+
+
+def test_matcher_choice_is_rank_independent_at_the_threshold():
+    """65 535 rows over 2 ranks = shards of 32 767 and 32 768 rows, one below and one at the tensor-core
+    threshold.  The two matchers encode keys differently, so the choice must come from floor(n_total / world) -- the same
+    on every rank -- and the merged result must equal the unsharded exact match."""
+    from certifyingfacerecognition_b200.gallery_shard import (ShardedGallery, TC_MATCH_MIN_ROWS, merge_keys_unsigned_min,
+                                                              rows_of_keys, shard_bounds)
+    g = torch.Generator().manual_seed(6)
+    n = 2 * TC_MATCH_MIN_ROWS - 1
+    gallery = torch.randn(n, 512, generator=g)
+    emb = gallery[torch.randint(0, n, (32,), generator=g)] + 0.2 * torch.randn(32, 512, generator=g)
+    bounds = [shard_bounds(n, 2, r) for r in range(2)]
+    assert sorted(hi - lo for lo, hi in bounds) == [TC_MATCH_MIN_ROWS - 1, TC_MATCH_MIN_ROWS]
+    shards = [ShardedGallery(gallery[lo:hi].cuda(), lo, n, max_b=32, world=2) for lo, hi in bounds]
+    assert shards[0].use_tc == shards[1].use_tc
+    keys = merge_keys_unsigned_min(torch.stack([s.local_keys(emb.cuda()) for s in shards]))
+    torch.cuda.synchronize()
+    ref = (-torch.cdist(emb, gallery, compute_mode="donot_use_mm_for_euclid_dist")).argmax(1)
+    assert torch.equal(rows_of_keys(keys).cpu(), ref)
