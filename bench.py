@@ -98,27 +98,65 @@ def build_fixture(n_ids: int):
     return g_sd, f_sd, dirs, lat, fixtures
 
 
-def cpu_arm(steps: int, warmup: int, sample: int):
-    """The reference's algorithm (oracle/mc_path.py restatement; /root/reference cannot travel to the GPU box) on
-    the host cores: each step classifies ``sample`` MC samples of one identity end to end."""
-    from oracle import mc_path as M
+def cpu_arm(steps: int, warmup: int, sample: int, one_thread_sample: int = 0):
+    """The reference's CPU path on the host cores; each step classifies ``sample`` MC samples of one identity end to end
+    (one batch of BASELINE config 1, whose batch size is 10).
+
+    kind "reference": the UNMODIFIED reference modules -- ``Smooth._sample_noise`` -> ``WrappedModel.forward`` ->
+    ``lat2embs`` -> ``compute_probs`` (smooth.py:109-138) -- imported from ``oracle/_ref`` (collected by
+    oracle/build_ref.py; /root/reference itself when present) through the shims of SURVEY.md section 8c, fixture weights
+    loaded into the reference's own StyleGAN / iresnet50 modules.  kind "port": oracle/mc_path.py, only when the
+    collected reference is missing.  Returns (samples/s, seconds, threads, kind, samples/s on ONE thread or None)."""
     torch.set_num_threads(os.cpu_count())
     g_sd, f_sd, dirs, lat, fixtures = build_fixture(8)
     gallery = fixtures.synthetic_gallery(torch.randn(8, 512, generator=torch.Generator().manual_seed(0)) * 1.5, N_GALLERY)
     x, sigma = torch.zeros(1, 5), torch.tensor([SIGMA])
-    gen = torch.Generator().manual_seed(1234)
+    from oracle import reference_shims as RS
+    if RS.available():
+        import tempfile
+        kind = "reference"
+        cwd = os.getcwd()
+        scratch = tempfile.mkdtemp(prefix="cfr_ref_bench_")
+        RS.make_scratch(scratch, lat.numpy(), gallery, f_sd)
+        os.chdir(scratch)               # the reference reads its files by cwd-relative names
+        try:
+            ref = RS.import_reference("cpu")
+            model = ref.WrappedModel(dirs, "insightface", n_embs=N_GALLERY, load_embs=True)
+        finally:
+            os.chdir(cwd)
+        RS.load_stylegan_into(model.generator.model, g_sd)
+        model.generator.model.eval()
+        model.eval()
+        smooth = ref.Smooth(model, N_GALLERY, sigma, ref.L2Certificate(1, device=ref.device))
+        torch.manual_seed(1234)
 
-    def step(i):
-        z = lat[i % lat.shape[0]:i % lat.shape[0] + 1]
-        classify = lambda p: M.wrapped_forward(z, p, dirs, gallery, g_sd, f_sd, literal=True)
-        return M.sample_noise_counts(classify, x, sigma, sample, sample, N_GALLERY, generator=gen)
+        def step(i, n=sample):
+            z = lat[i % lat.shape[0]:i % lat.shape[0] + 1]
+            return smooth._sample_noise(z, x, n, n, device=ref.device)
+    else:
+        from oracle import mc_path as M
+        kind = "port"
+        gen = torch.Generator().manual_seed(1234)
+
+        def step(i, n=sample):
+            z = lat[i % lat.shape[0]:i % lat.shape[0] + 1]
+            classify = lambda p: M.wrapped_forward(z, p, dirs, gallery, g_sd, f_sd, literal=True)
+            return M.sample_noise_counts(classify, x, sigma, n, n, N_GALLERY, generator=gen)
     for i in range(warmup):
         step(i)
     t0 = time.perf_counter()
     for i in range(steps):
-        step(warmup + i)
+        c = step(warmup + i)
     dt = time.perf_counter() - t0
-    return sample * steps / dt, dt, os.cpu_count()
+    assert int(c.sum()) == sample
+    one = None
+    if one_thread_sample > 0:
+        torch.set_num_threads(1)
+        t1 = time.perf_counter()
+        step(0, one_thread_sample)
+        one = one_thread_sample / (time.perf_counter() - t1)
+        torch.set_num_threads(os.cpu_count())
+    return sample * steps / dt, dt, os.cpu_count(), kind, one
 
 
 def main():
@@ -130,8 +168,12 @@ def main():
     ap.add_argument("--batch", type=int, default=250, help="MC samples per step (BASELINE config 2: 250)")
     ap.add_argument("--chunk", type=int, default=125, help="samples per GAN+FRM program run")
     ap.add_argument("--frm-group", type=int, default=2, help="synthesis chunks per ArcFace program run")
-    ap.add_argument("--shard", default="identities", choices=["identities", "samples"])
-    ap.add_argument("--cpu-sample", type=int, default=4, help="MC samples per CPU-baseline step")
+    ap.add_argument("--shard", default="identities", choices=["identities", "samples"],
+                    help="how the certification-batch loop uses N > 1 ranks (the certify loop always shards samples)")
+    ap.add_argument("--headline-batches", action="store_true",
+                    help="N > 1: keep the certification-batch loop as the headline instead of BASELINE config 3")
+    ap.add_argument("--cpu-sample", type=int, default=10,
+                    help="MC samples per CPU-baseline step (BASELINE config 1 classifies batches of 10)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--frm", default="insightface", choices=["insightface", "facenet"],
                     help="face recognition model: ArcFace iresnet50 (headline, BASELINE config 2) or FaceNet "
@@ -155,15 +197,19 @@ def main():
         if rank != 0:
             return
         steps = max(1, args.steps)
-        val, dt, cores = cpu_arm(steps, args.warmup, args.cpu_sample)
+        val, dt, cores, kind, one = cpu_arm(steps, args.warmup, args.cpu_sample, one_thread_sample=2)
+        what = ("the unmodified reference (oracle/_ref: Smooth._sample_noise -> WrappedModel.forward -> lat2embs, torch fp32)"
+                if kind == "reference" else "oracle/mc_path.py (torch fp32 port)")
         line = {"impl": "reference", "metric": "MC samples/sec (StyleGAN1024->ArcFace vote)", "value": val,
                 "unit": "samples/s", "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup,
                 "ms_per_step": 1e3 * dt / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic",
-                "config": {"workload": workload, "step": f"{args.cpu_sample} MC samples of one identity (bounded sample)"},
-                "cpu_baseline": {"value": val, "unit": "samples/s", "cores": cores, "kind": "port",
-                                 "sample": f"{args.cpu_sample} samples/step x {steps} steps, oracle/mc_path.py (torch fp32, "
-                                           f"{cores} threads)"},
+                "config": {"workload": workload, "step": f"{args.cpu_sample} MC samples of one identity = one batch of "
+                                                         "BASELINE config 1 (n0=10, n=100, batch 10): a bounded sample"},
+                "cpu_baseline": {"value": val, "unit": "samples/s", "cores": cores, "kind": kind,
+                                 "value_1_thread": one,
+                                 "sample": f"{args.cpu_sample} samples/step x {steps} steps, {what}, {cores} threads; "
+                                           "1-thread figure from one batch of 2 samples"},
                 "e2e": {"value": val, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line))
         return
@@ -176,92 +222,166 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     from certifyingfacerecognition_b200 import _lib as L
-    from certifyingfacerecognition_b200.engine import Engine
+    from certifyingfacerecognition_b200.models.smoothing_model import WrappedModel
+    from certifyingfacerecognition_b200.smoothing import L2Certificate, Smooth
     lib = L.load()
     n_ids = 64
     g_sd, f_sd, dirs, lat, fixtures = build_fixture(n_ids)
     if args.frm == "facenet":
         f_sd = fixtures.facenet_weights()
-    eng = Engine(g_sd, f_sd, dirs, torch.zeros(1, 512), chunk=args.chunk, frm_group=args.frm_group,
-                 frm="insightface" if args.frm == "insightface" else "facenet-vggface2")
+    dev = torch.device("cuda", local_rank)
+    # the drop-in classes own the engine (one set of buffers); the gallery is computed by the engine, as
+    # WrappedModel(load_embs=False) does (smoothing_model.py:48-53), then padded to 5000 rows
+    model = WrappedModel(dirs.to(dev), "insightface" if args.frm == "insightface" else "facenet-vggface2",
+                         generator_state=g_sd, frm_state=f_sd, latents=lat, orig_embs=torch.zeros(1, 512),
+                         chunk=args.chunk, frm_group=args.frm_group)
+    eng = model.engine
     true_rows = eng.embed_latents(lat).cpu()
     eng.set_gallery(fixtures.synthetic_gallery(true_rows, N_GALLERY))
-    dev = eng.device
+    model.orig_embs = eng.gallery
     lat_d = lat.to(dev)
     x_d, sigma_d = torch.zeros(5, device=dev), torch.tensor([SIGMA], device=dev)
     counts = torch.zeros(N_GALLERY, dtype=torch.int64, device=dev)
     stream = torch.cuda.current_stream()
-    per_rank = args.batch if args.shard == "identities" else args.batch // world
+    ident_mode = args.shard == "identities"
+    per_rank = args.batch if ident_mode else args.batch // world
     state = {"draws": 0}
-
-    def step(i):
-        ident = (i * world + rank) % n_ids if args.shard == "identities" else i % n_ids
-        off = state["draws"] + (0 if args.shard == "identities" else rank * per_rank)
-        counts.zero_()
-        eng.sample_votes(lat_d[ident], x_d, sigma_d, per_rank, seed=1234, sample_offset=off, counts=counts)
-        if args.shard == "samples" and world > 1:
-            dist.all_reduce(counts)
-        state["draws"] += args.batch
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for i in range(max(3, args.warmup)):
-        step(i)
-    barrier()
-    sampler = ClockSampler(local_rank) if rank == 0 else None
-    if sampler:
-        sampler.start()
-    launches0 = lib.cfr_launch_count()
-    lib.cfr_profile_enable(1)
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    ev0.record(stream)
-    for i in range(args.steps):
-        step(1000 + i)
-    ev1.record(stream)
-    barrier()
-    ms = ev0.elapsed_time(ev1)
-    prof = {}
-    for kind, name in ((0, "igemm"), (1, "halo")):
-        t_ms, work, n_l = C.c_double(), C.c_double(), C.c_int64()
-        L.check(lib.cfr_profile_read(kind, C.byref(t_ms), C.byref(work), C.byref(n_l)))
-        prof[name] = (t_ms.value, work.value, n_l.value)
-    lib.cfr_profile_enable(0)
-    launches = lib.cfr_launch_count() - launches0
-    clocks = sampler.stop() if sampler else None
-    t = torch.tensor([ms, float(launches)], device=dev, dtype=torch.float64)
-    if world > 1:
-        tmax = t.clone()
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-        tsum = t.clone()
-        dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
-        ms, launches = tmax[0].item(), int(tsum[1].item())
-    total_samples = per_rank * world * args.steps
-    value = total_samples / (ms * 1e-3)
+    def timed(fn, steps, warm, on_start=None):
+        """K steps on the launch stream between a barrier + synchronize on both sides; device time, max over ranks."""
+        for i in range(warm):
+            fn(i)
+        barrier()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        if on_start:
+            on_start()
+        barrier()
+        ev0.record(stream)
+        for i in range(steps):
+            fn(1000 + i)
+        ev1.record(stream)
+        barrier()
+        t = torch.tensor([ev0.elapsed_time(ev1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.item()
 
-    # ---- end to end through the C ABI with HOST buffers (H2D of z/x/sigma, D2H of the counts, sync per step)
+    def wall(fn, steps, warm, on_start=None):
+        """The same through host buffers, wall clock (max over ranks)."""
+        for i in range(warm):
+            fn(i)
+        if on_start:
+            on_start()
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(steps):
+            fn(1000 + i)
+        barrier()
+        t = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.item()
+
+    # ---- (A) certification batches (BASELINE config 2): identities sharded over the ranks, no data-path collective
+    #      (--shard samples: every batch split over the ranks + one all-reduce)
+    def batch_step(i):
+        ident = (i * world + rank) % n_ids if ident_mode else i % n_ids
+        off = state["draws"] + (0 if ident_mode else rank * per_rank)
+        counts.zero_()
+        eng.sample_votes(lat_d[ident], x_d, sigma_d, per_rank, seed=1234, sample_offset=off, counts=counts)
+        if not ident_mode and world > 1:
+            dist.all_reduce(counts)
+        state["draws"] += args.batch
+
     z_h = [lat[(i * world + rank) % n_ids].numpy().copy() for i in range(args.steps)]
     x_h, s_h = np.zeros(5, dtype=np.float32), np.array([SIGMA], dtype=np.float32)
     c_h = np.zeros(N_GALLERY, dtype=np.int64)
     sptr = C.c_void_p(stream.cuda_stream)
-    for i in range(2):
-        L.check(lib.cfr_sample_votes_host(eng.sampler, z_h[i % len(z_h)].ctypes.data, x_h.ctypes.data, s_h.ctypes.data, 1,
-                                          per_rank, 99, 0, c_h.ctypes.data, sptr))
-    barrier()
-    t0 = time.perf_counter()
-    for i in range(args.steps):
-        L.check(lib.cfr_sample_votes_host(eng.sampler, z_h[i].ctypes.data, x_h.ctypes.data, s_h.ctypes.data, 1, per_rank,
-                                          99, i * args.batch, c_h.ctypes.data, sptr))
-    barrier()
-    e2e_s = time.perf_counter() - t0
-    te = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+
+    def batch_step_host(i):
+        j = i % len(z_h)
+        L.check(lib.cfr_sample_votes_host(eng.sampler, z_h[j].ctypes.data, x_h.ctypes.data, s_h.ctypes.data, 1, per_rank,
+                                          99, j * args.batch, c_h.ctypes.data, sptr))
+
+    # ---- (B) whole certifications (BASELINE config 3): Smooth.certify through the drop-in API, anisotropic sigma
+    #      (certify.py:85-95: sigma * eps^2), N0 = 100 selection + n = 1000 estimation samples of ONE identity split over the
+    #      ranks by global sample index; both passes end in an NCCL int64 all-reduce of the [5000] vote counts (the first
+    #      one feeds the early-exit decision every rank must agree on, smooth.py:66-68)
+    eps2 = torch.tensor([0.25, 0.25, 0.04, 0.25, 0.64], device=dev)          # red_ellipse_mat_inv (proj_utils.py:16-21)
+    smooth = Smooth(model, N_GALLERY, SIGMA * eps2, L2Certificate(1, device=dev), seed=4321,
+                    process_group=dist.group.WORLD if world > 1 else None)
+    N0, NEST, ALPHA = 100, 1000, 0.001
+    zero5 = torch.zeros(1, 5, device=dev)
+    labels = [torch.tensor([i], device=dev) for i in range(n_ids)]
+    lat_pin = lat.pin_memory()
+    cert_stat = {"certified": 0, "calls": 0}
+
+    def certify_step(i, host=False):
+        ident = i % n_ids
+        z = lat_pin[ident:ident + 1].to(dev, non_blocking=True) if host else lat_d[ident:ident + 1]
+        pred, gap = smooth.certify(z, zero5, labels[ident], N0, NEST, ALPHA, args.batch, device=dev)
+        cert_stat["calls"] += 1
+        cert_stat["certified"] += int(pred == ident and gap > 0)
+
+    headline_certify = world > 1 and ident_mode and not args.headline_batches
+    warm = max(3, args.warmup)
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    results, snap = {}, {}
+
+    def start_headline():
+        if sampler:
+            sampler.start()
+        snap["launches"] = lib.cfr_launch_count()
+        lib.cfr_profile_enable(1)
+
+    def mark_draws():
+        snap["draws"] = smooth._draws
+
+    for name in (("batches", "certify") if headline_certify else ("certify", "batches")):   # headline loop last
+        is_headline = name == ("certify" if headline_certify else "batches")
+        hook = start_headline if is_headline else None
+        if name == "batches":
+            ms = timed(batch_step, args.steps, warm, hook)
+            total = per_rank * world * args.steps
+        else:
+            ms = timed(certify_step, args.steps, warm if is_headline else 1,
+                       (lambda: (mark_draws(), start_headline())) if is_headline else mark_draws)
+            total = smooth._draws - snap["draws"]            # global MC samples classified (N0 + n per certified identity)
+        if is_headline:
+            prof = {}
+            for kind, pname in ((0, "igemm"), (1, "halo")):
+                t_ms, work, n_l = C.c_double(), C.c_double(), C.c_int64()
+                L.check(lib.cfr_profile_read(kind, C.byref(t_ms), C.byref(work), C.byref(n_l)))
+                prof[pname] = (t_ms.value, work.value, n_l.value)
+            lib.cfr_profile_enable(0)
+            launches = lib.cfr_launch_count() - snap["launches"]
+            clocks = sampler.stop() if sampler else None
+        results[name] = {"ms": ms, "samples": total, "value": total / (ms * 1e-3)}
+    # end to end through the public entry with HOST buffers
+    if headline_certify:
+        e2e_s = wall(lambda i: certify_step(i, host=True), args.steps, 1, mark_draws)
+        e2e_total = smooth._draws - snap["draws"]
+        e2e_api = ("Smooth.certify (drop-in Python API): latent from pinned host memory per identity, vote counts read back "
+                   "to the host after each of the two all-reduced passes")
+        h2d, d2h = 512 * 4, 2 * N_GALLERY * 8
+    else:
+        e2e_s = wall(batch_step_host, args.steps, 2)
+        e2e_total = per_rank * world * args.steps
+        e2e_api = "cfr_sample_votes_host (C ABI, host buffers, one call per step)"
+        h2d, d2h = 528 * 4, N_GALLERY * 8
+        assert int(c_h.sum()) == per_rank
+    e2e_value = e2e_total / e2e_s
+    head = results["certify" if headline_certify else "batches"]
+    ms, value = head["ms"], head["value"]
+    lt = torch.tensor([float(launches)], device=dev, dtype=torch.float64)
     if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = total_samples / te.item()
-    assert int(c_h.sum()) == per_rank
+        dist.all_reduce(lt)
+    launches = int(lt.item())
 
     if rank != 0:
         if world > 1:
@@ -296,28 +416,49 @@ def main():
                   "launches_timed": int(ig_n), "avg_launch_ms": ig_ms / max(1, ig_n),
                   "alg_gflop_per_launch": ig_flops / max(1, ig_n) / 1e9, "share_of_step": ig_ms / ms if ms > 0 else None}
     dominant, other = (halo_roof, igemm_roof) if ha_ms >= ig_ms else (igemm_roof, halo_roof)
+    if headline_certify:
+        workload = (f"anisotropic certify (BASELINE config 3): Smooth.certify of one identity per step, N0={N0} + n={NEST} MC "
+                    f"samples split over {world} ranks by global sample index, sigma = {SIGMA} * eps^2 along the five "
+                    f"W-boundaries, NCCL int64 all-reduce of the [{N_GALLERY}] vote counts after each pass; StyleGAN-FFHQ-1024 + "
+                    f"ArcFace iresnet50 random-init, {N_GALLERY}-row synthetic gallery")
+    second = results["batches" if headline_certify else "certify"]
     line = {
         "metric": "MC samples/sec (StyleGAN1024->ArcFace vote)", "value": value, "unit": "samples/s", "n_gpus": world,
-        "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps, "higher_is_better": True,
-        "scaling": "weak" if args.shard == "identities" else "strong", "vs_baseline": None,
-        "dtype": "fp16 operands / fp32 accumulate", "data": "synthetic",
-        "config": {"workload": workload, "chunk": args.chunk, "frm_group": args.frm_group, "shard": args.shard, "gallery": N_GALLERY,
+        "steps": args.steps, "warmup": warm, "ms_per_step": ms / args.steps, "higher_is_better": True,
+        "scaling": "strong" if (headline_certify or not ident_mode) else "weak", "vs_baseline": None,
+        "dtype": "fp16 operands / fp32 accumulate (StyleGAN layers 1-%d: fp16 hi/lo split operands, fp32 activations)"
+                 % eng.hp_layers,
+        "data": "synthetic",
+        "config": {"workload": workload, "chunk": args.chunk, "frm_group": args.frm_group,
+                   "shard": "samples" if headline_certify else args.shard, "gallery": N_GALLERY,
+                   "hp_layers": eng.hp_layers,
                    "l2": "working set per step (activations, GBs) far exceeds the 126 MB L2; no flush needed",
                    "gflop_per_sample_algorithmic": gflop_per_sample,
                    "pipeline_tflops": value * gflop_per_sample / 1e3,
                    "pipeline_frac_of_bf16_sustained": value * gflop_per_sample / 1e3 / (pk["tf_sustained"] * world)},
-        "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": 528 * 4, "d2h_bytes_per_step": N_GALLERY * 8,
-                "api": "cfr_sample_votes_host (C ABI, host buffers, one call per step)"},
+        "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "api": e2e_api},
         "gpu_launches": int(launches),
         "roofline": dominant,
         "roofline_second_kernel": other,
         "clocks": clocks,
+        # both partitions of SURVEY.md section 8e are timed in every run; the headline is (B) for N > 1, (A) for N = 1
+        "samples_sharded": {"what": "BASELINE config 3: whole certifications (N0=100 + n=1000), samples of one identity "
+                                    "split over the ranks, two int64 all-reduces per identity; device-timed",
+                            "value": results["certify"]["value"], "unit": "samples/s",
+                            "ms_per_identity": results["certify"]["ms"] / args.steps,
+                            "identities_certified": cert_stat["certified"], "certify_calls": cert_stat["calls"]},
+        "identities_sharded": {"what": f"BASELINE config 2: batches of {args.batch} samples, one identity per rank and step, "
+                                       "no data-path collective; device-timed",
+                               "value": results["batches"]["value"], "unit": "samples/s",
+                               "ms_per_step": results["batches"]["ms"] / args.steps},
     }
-    if not args.no_cpu_baseline:
-        val, dt, cores = cpu_arm(2, 1, args.cpu_sample)
-        line["cpu_baseline"] = {"value": val, "unit": "samples/s", "cores": cores, "kind": "port",
+    if not args.no_cpu_baseline and world == 1:
+        val, dt, cores, kind, _ = cpu_arm(2, 1, args.cpu_sample)
+        line["cpu_baseline"] = {"value": val, "unit": "samples/s", "cores": cores, "kind": kind,
                                 "sample": f"{args.cpu_sample} samples/step x 2 steps (+1 warm-up) of the same workload, "
-                                          f"oracle/mc_path.py torch fp32 on {cores} threads"}
+                                          + ("the unmodified reference (oracle/_ref) " if kind == "reference" else
+                                             "oracle/mc_path.py ") + f"torch fp32 on {cores} threads"}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

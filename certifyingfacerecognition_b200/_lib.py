@@ -33,6 +33,7 @@ class ConvDesc(C.Structure):
         ("act", C.c_int32), ("slope", C.c_float), ("alpha", C.c_void_p),
         ("resid", C.c_void_p), ("residC", C.c_int32),
         ("stat_sum", C.c_void_p), ("stat_sq", C.c_void_p),
+        ("kSplit", C.c_int32),
     ]
 
 
@@ -67,6 +68,9 @@ SIGNATURES = {
     "cfr_program_add_memset": (_I, [_P, _P, _I, _SZ]),
     "cfr_program_add_styles": (_I, [_P, _P, _P, _P, _I, _I, _I, _P]),
     "cfr_program_add_layer0": (_I, [_P, _P, _P, _I, _I, _I, _P]),
+    "cfr_program_add_layer0_split": (_I, [_P, _P, _P, _I, _I, _I, _P]),
+    "cfr_program_add_blur_act_stats_f32": (_I, [_P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _I]),
+    "cfr_program_add_affine_f32": (_I, [_P, _P, _P, _P, _I, _I, _I, _P, _I]),
     "cfr_program_add_blur_act_stats": (_I, [_P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _I]),
     "cfr_program_add_finalize_stats": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _F, _P, _P]),
     "cfr_program_add_affine": (_I, [_P, _P, _P, _P, _I, _I, _I, _P]),

@@ -145,8 +145,9 @@ CFR_API int cfr_program_add_conv(cfr_program* p, const cfr_conv_desc* d) {
   ConvOp* raw = op.get();
   p->convs.push_back(std::move(op));
   char lab[160];
-  snprintf(lab, sizeof(lab), "conv %dx%d s%d taps%dx%d Cin%d Cout%d grid%dx%d n%d BN%d", d->Hout, d->Wout, d->stride,
-           d->numPhases, d->ntaps, d->Cin, d->Cout, d->Hout, d->Wout, d->N, raw->p.BN);
+  snprintf(lab, sizeof(lab), "conv %dx%d s%d taps%dx%d Cin%d%s Cout%d grid%dx%d n%d BN%d", d->Hout, d->Wout, d->stride,
+           d->numPhases, d->ntaps, d->kSplit == 3 ? d->Cin / 3 : d->Cin, d->kSplit == 3 ? "(x3 hi/lo)" : "", d->Cout,
+           d->Hout, d->Wout, d->N, raw->p.BN);
   p->add([raw](cudaStream_t st) { return conv_launch(*raw, st); }, lab, raw->flops);
   return 0;
 }
@@ -248,6 +249,31 @@ CFR_API int cfr_program_add_layer0(cfr_program* p, const float* xhat0, const flo
   p->add([=](cudaStream_t st) {
     return launch_layer0(xhat0, styles, style_stride, style_off, b, static_cast<__half*>(out_f16), st);
   }, "layer0");
+  return 0;
+}
+
+CFR_API int cfr_program_add_layer0_split(cfr_program* p, const float* xhat0, const float* styles, int style_stride,
+                                 int style_off, int b, void* out_f16_split) {
+  p->add([=](cudaStream_t st) {
+    return launch_layer0_split(xhat0, styles, style_stride, style_off, b, static_cast<__half*>(out_f16_split), st);
+  }, "layer0_split");
+  return 0;
+}
+
+CFR_API int cfr_program_add_blur_act_stats_f32(cfr_program* p, const float* raw, float* y, int n, int h, int w, int c,
+                                       const float* noise, const float* noise_w, const float* bias, int64_t* sum,
+                                       int64_t* sq, int mode) {
+  p->add([=](cudaStream_t st) {
+    return launch_blur_act_stats_f32(raw, y, n, h, w, c, noise, noise_w, bias, sum, sq, mode, st);
+  }, "blur_act_stats_f32");
+  return 0;
+}
+
+CFR_API int cfr_program_add_affine_f32(cfr_program* p, const float* y, const float* A, const float* B, int n, int hw, int c,
+                               void* x_f16, int split) {
+  p->add([=](cudaStream_t st) {
+    return launch_affine_f32(y, A, B, n, hw, c, static_cast<__half*>(x_f16), split, st);
+  }, split == 3 ? "affine_f32_split" : "affine_f32");
   return 0;
 }
 

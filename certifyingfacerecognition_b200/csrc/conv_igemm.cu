@@ -539,7 +539,8 @@ int conv_build(const ConvSpec& s, ConvOp* op) {
   // are faster with 128 (two accumulator sets in flight, twice the work items on the small ArcFace maps), the
   // 4-phase up-convs (short K, Cin >= 256: ingest-bound) with 256.  CFR_IGEMM_BN_MAX overrides for A/B runs.
   static const int bn_env = getenv("CFR_IGEMM_BN_MAX") != nullptr ? atoi(getenv("CFR_IGEMM_BN_MAX")) : 0;
-  const int bn_max = bn_env > 0 ? bn_env : (s.numPhases == 1 ? 128 : 256);
+  // split-precision convs have 3x the K loop (the epilogue share is small) and 3x the A bytes: the wider tile wins
+  const int bn_max = bn_env > 0 ? bn_env : ((s.numPhases == 1 && s.kSplit != 3) ? 128 : 256);
   if (bn > bn_max) {
     bn = bn_max;
     while (s.Cout % bn != 0) bn -= 16;
@@ -617,7 +618,11 @@ int conv_build(const ConvSpec& s, ConvOp* op) {
     if (m > 0 && op->grid > m) op->grid = m;
   }
   // algorithmic FLOPs of this launch: 2 * (valid output-grid pixels) * phases * taps * Cin * Cout
-  op->flops = 2.0 * s.N * s.Hout * s.Wout * s.numPhases * s.ntaps * static_cast<double>(s.Cin) * s.Cout;
+  // (split-precision convs issue 3x the MMAs for the same algorithmic contraction: counted on the logical Cin / 3)
+  if (s.kSplit != 0 && s.kSplit != 1 && s.kSplit != 3) { set_error("conv: kSplit=%d unsupported", s.kSplit); return 2; }
+  if (s.kSplit == 3 && s.Cin % 3 != 0) { set_error("conv: kSplit=3 needs Cin %% 3 == 0"); return 2; }
+  const int cinLogical = s.kSplit == 3 ? s.Cin / 3 : s.Cin;
+  op->flops = 2.0 * s.N * s.Hout * s.Wout * s.numPhases * s.ntaps * static_cast<double>(cinLogical) * s.Cout;
   return 0;
 }
 

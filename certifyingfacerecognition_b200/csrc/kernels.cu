@@ -174,6 +174,29 @@ int launch_layer0(const float* xhat0, const float* styles, int style_stride, int
   CFR_LAUNCH_CHECK("layer0");
   return 0;
 }
+// Split-precision variant: out [b,16,3*512] = [hi | lo | hi] with hi = fp16(x), lo = fp16(x - hi), the operand layout of
+// the hi/lo-split convolutions (cfr_conv_desc.kSplit == 3).
+__global__ void k_layer0_split(const float* __restrict__ xhat0, const float* __restrict__ styles, int style_stride,
+                               int style_off, int b, __half* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;   // over b*16*512
+  if (i >= b * 16 * 512) return;
+  const int c = i % 512, pix = i / 512, s = i / (512 * 16);
+  const float s0 = styles[static_cast<size_t>(s) * style_stride + style_off + c];
+  const float s1 = styles[static_cast<size_t>(s) * style_stride + style_off + 512 + c];
+  const float v = xhat0[(pix % 16) * 512 + c] * (s0 + 1.f) + s1;
+  const __half hi = __float2half_rn(v);
+  const __half lo = __float2half_rn(v - __half2float(hi));
+  __half* o = out + static_cast<size_t>(pix) * 1536 + c;
+  o[0] = hi;
+  o[512] = lo;
+  o[1024] = hi;
+}
+int launch_layer0_split(const float* xhat0, const float* styles, int style_stride, int style_off, int b, __half* out,
+                        cudaStream_t st) {
+  k_layer0_split<<<(b * 16 * 512 + 255) / 256, 256, 0, st>>>(xhat0, styles, style_stride, style_off, b, out);
+  CFR_LAUNCH_CHECK("layer0_split");
+  return 0;
+}
 
 // ------------------------------------------------------------------------------------------
 // Mapping network Z -> W (generate_data.py path).  8 dense 512x512 layers in fp32 on the CUDA cores: 4.2 MFLOP per
@@ -257,6 +280,15 @@ __device__ __forceinline__ void store8(__half* p, const float (&f)[8]) {
   *reinterpret_cast<uint4*>(p) = o;
 }
 
+__device__ __forceinline__ void load8(const float* p, float (&f)[8]) {
+  const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+  f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+}
+__device__ __forceinline__ void store8(float* p, const float (&f)[8]) {
+  reinterpret_cast<float4*>(p)[0] = make_float4(f[0], f[1], f[2], f[3]);
+  reinterpret_cast<float4*>(p)[1] = make_float4(f[4], f[5], f[6], f[7]);
+}
+
 // Block-level reduction of per-thread channel sums for the InstanceNorm statistics.  256 threads; thread t owns the
 // 8 channels starting at (t % c8) * 8.  Warp shuffles, then one float slot per (warp-slice, channel) in `part`
 // ([2][2048] floats), then a fixed-order sum -> Q43.20 -> one global 64-bit RED per channel: deterministic, and no
@@ -295,8 +327,8 @@ __device__ __forceinline__ void block_flush_stats(float (&acc)[8], float (&acc2)
   }
 }
 
-template <int MODE>
-__global__ void __launch_bounds__(256) k_blur_act_stats(const __half* __restrict__ raw, __half* __restrict__ y, int h,
+template <int MODE, typename T = __half>
+__global__ void __launch_bounds__(256) k_blur_act_stats(const T* __restrict__ raw, T* __restrict__ y, int h,
                                                         int w, int c, const float* __restrict__ noise,
                                                         const float* __restrict__ noise_w,
                                                         const float* __restrict__ bias, stat_t* __restrict__ gsum,
@@ -316,7 +348,7 @@ __global__ void __launch_bounds__(256) k_blur_act_stats(const __half* __restrict
     acc2[i] = 0.f;
   }
   const int hw = h * w;
-  const __half* img = raw + static_cast<size_t>(n) * hw * c;
+  const T* img = raw + static_cast<size_t>(n) * hw * c;
   if (pl < ppb) {
     for (int pix = blockIdx.x * ppb + pl; pix < hw; pix += gridDim.x * ppb) {
       float v[8];
@@ -621,6 +653,24 @@ int launch_blur_act_stats(const __half* raw, __half* y, int n, int h, int w, int
   return 0;
 }
 
+// fp32 in / fp32 out (split-precision early layers; at most 64x64 x 256 channels: the simple kernel is enough)
+int launch_blur_act_stats_f32(const float* raw, float* y, int n, int h, int w, int c, const float* noise,
+                              const float* noise_w, const float* bias, void* sum_v, void* sq_v, int mode, cudaStream_t st) {
+  stat_t* sum = static_cast<stat_t*>(sum_v);
+  stat_t* sq = static_cast<stat_t*>(sq_v);
+  if (c < 8 || c > 512 || (c & (c - 1)) != 0) { set_error("blur_act_stats_f32: C=%d unsupported (power of two in 8..512)", c); return 2; }
+  const int ppb = 256 / (c / 8);
+  int bx = (h * w + ppb - 1) / ppb;
+  const int cap = 16 * 148 / (n > 0 ? n : 1) + 1;
+  if (bx > cap) bx = cap;
+  if (bx < 1) bx = 1;
+  dim3 grid(bx, n);
+  if (mode == 0) k_blur_act_stats<0, float><<<grid, 256, 0, st>>>(raw, y, h, w, c, noise, noise_w, bias, sum, sq);
+  else k_blur_act_stats<1, float><<<grid, 256, 0, st>>>(raw, y, h, w, c, noise, noise_w, bias, sum, sq);
+  CFR_LAUNCH_CHECK("blur_act_stats_f32");
+  return 0;
+}
+
 // ------------------------------------------------------------------------------------------
 __global__ void k_finalize_stats(const long long* __restrict__ sum, const long long* __restrict__ sq,
                                  const float* __restrict__ styles, int style_stride, int style_off, int n, int c,
@@ -670,6 +720,52 @@ int launch_affine(const __half* y, const float* A, const float* B, int n, int hw
   if (blocks > 148 * 32) blocks = 148 * 32;
   k_affine<<<static_cast<unsigned>(blocks), 256, 0, st>>>(y, A, B, total8, hw, c, x);
   CFR_LAUNCH_CHECK("affine");
+  return 0;
+}
+
+// fp32 y -> x = y*A + B as fp16: SPLIT == 1 plain [.., c]; SPLIT == 3 [.., 3c] = [hi | lo | hi], lo = fp16(x - hi)
+template <int SPLIT>
+__global__ void k_affine_f32(const float* __restrict__ y, const float* __restrict__ A, const float* __restrict__ B,
+                             size_t total8, int hw, int c, __half* __restrict__ x) {
+  const int c8 = c >> 3;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total8;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int cg = static_cast<int>(i % c8);
+    const size_t pix = i / c8;
+    const int n = static_cast<int>(pix / hw);
+    float v[8];
+    load8(y + i * 8, v);
+    const float4* a4 = reinterpret_cast<const float4*>(A + static_cast<size_t>(n) * c + cg * 8);
+    const float4* b4 = reinterpret_cast<const float4*>(B + static_cast<size_t>(n) * c + cg * 8);
+    const float4 a0 = __ldg(a4), a1 = __ldg(a4 + 1), b0 = __ldg(b4), b1 = __ldg(b4 + 1);
+    v[0] = v[0] * a0.x + b0.x; v[1] = v[1] * a0.y + b0.y; v[2] = v[2] * a0.z + b0.z; v[3] = v[3] * a0.w + b0.w;
+    v[4] = v[4] * a1.x + b1.x; v[5] = v[5] * a1.y + b1.y; v[6] = v[6] * a1.z + b1.z; v[7] = v[7] * a1.w + b1.w;
+    if (SPLIT == 1) {
+      store8(x + i * 8, v);
+    } else {
+      float lo[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float hi = __half2float(__float2half_rn(v[k]));
+        lo[k] = v[k] - hi;
+        v[k] = hi;
+      }
+      __half* o = x + pix * (3 * static_cast<size_t>(c)) + cg * 8;
+      store8(o, v);
+      store8(o + c, lo);
+      store8(o + 2 * c, v);
+    }
+  }
+}
+int launch_affine_f32(const float* y, const float* A, const float* B, int n, int hw, int c, __half* x, int split,
+                      cudaStream_t st) {
+  if (split != 1 && split != 3) { set_error("affine_f32: split must be 1 or 3"); return 2; }
+  const size_t total8 = static_cast<size_t>(n) * hw * c / 8;
+  size_t blocks = (total8 + 255) / 256;
+  if (blocks > 148 * 32) blocks = 148 * 32;
+  if (split == 3) k_affine_f32<3><<<static_cast<unsigned>(blocks), 256, 0, st>>>(y, A, B, total8, hw, c, x);
+  else k_affine_f32<1><<<static_cast<unsigned>(blocks), 256, 0, st>>>(y, A, B, total8, hw, c, x);
+  CFR_LAUNCH_CHECK("affine_f32");
   return 0;
 }
 

@@ -26,6 +26,9 @@ int launch_styles(const float* wp2, const float* w_style, const float* b_style, 
 int launch_layer0(const float* xhat0, const float* styles, int style_stride, int style_off, int b, __half* out,
                   cudaStream_t st);
 
+int launch_layer0_split(const float* xhat0, const float* styles, int style_stride, int style_off, int b, __half* out,
+                        cudaStream_t st);
+
 // BlurLayer :463 + EpilogueBlock :560-562 (+noise*w +bias, lrelu) + per-(n,c) sums for IN.  mode 0: blur+act+write;
 // mode 1: statistics of an existing tensor only.
 int launch_blur_act_stats(const __half* raw, __half* y, int n, int h, int w, int c, const float* noise,
@@ -35,6 +38,11 @@ int launch_blur_act_stats(const __half* raw, __half* y, int n, int h, int w, int
 int launch_finalize_stats(const void* sum, const void* sq, const float* styles, int style_stride, int style_off,
                           int n, int c, float inv_count, float* A, float* B, cudaStream_t st);
 int launch_affine(const __half* y, const float* A, const float* B, int n, int hw, int c, __half* x, cudaStream_t st);
+// split-precision early layers: fp32 activations between kernels, fp16 hi/lo operand pairs into the tensor cores
+int launch_blur_act_stats_f32(const float* raw, float* y, int n, int h, int w, int c, const float* noise,
+                              const float* noise_w, const float* bias, void* sum, void* sq, int mode, cudaStream_t st);
+int launch_affine_f32(const float* y, const float* A, const float* B, int n, int hw, int c, __half* x, int split,
+                      cudaStream_t st);
 
 // LastConvBlock :759-762 + postprocess mod_stylegan_generator.py:303-307 + get_transform gen_utils.py:77-85
 // x [n,H,W,C] fp16 (optionally still un-normalised: per-(n,c) A,B applied on load) -> img [n,R,R,16] fp16 (ch 0..2)

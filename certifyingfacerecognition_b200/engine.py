@@ -72,6 +72,19 @@ def pack_conv_weight(w: Tensor, cin_pad: Optional[int] = None) -> Tensor:
     return out
 
 
+def split3_weight(m: Tensor, ntaps: int, cin: int) -> Tensor:
+    """[rows, >= ntaps*cin] fp32 (K = (tap, cin)) -> fp16 [rows, ntaps*3*cin], per tap [w_hi | w_hi | w_lo] with
+    hi = fp16(w), lo = fp16(w - hi): the weight side of a split-precision conv (cfr_conv_desc.kSplit == 3), matching
+    activations laid out [x_hi | x_lo | x_hi]:  x.w = x_hi.w_hi + x_lo.w_hi + x_hi.w_lo  (+ O(2^-22))."""
+    rows = m.shape[0]
+    w = m[:, :ntaps * cin].reshape(rows, ntaps, cin).float()
+    hi = w.half()
+    lo = (w - hi.float()).half()
+    out = torch.cat([hi, hi, lo], dim=2).reshape(rows, ntaps * 3 * cin)
+    assert out.shape[1] % 64 == 0
+    return out.contiguous()
+
+
 TAPS3 = [(dy, dx) for dy in (-1, 0, 1) for dx in (-1, 0, 1)]
 
 # Sub-pixel decomposition of nearest-x2 + 3x3 conv (pad 1): output (2i+a, 2j+b) reads the low-res rows
@@ -220,7 +233,7 @@ class Program:
              slope: float = 0.2, alpha: Optional[Tensor] = None, resid: Optional[Tensor] = None, resid_c: int = 0,
              stat_sum: Optional[Tensor] = None, stat_sq: Optional[Tensor] = None, halo: bool = False,
              in_affine: Optional[Tuple[Tensor, Tensor]] = None, fold_center_tap: Optional[int] = None,
-             composite_corr: Optional[Tensor] = None) -> None:
+             composite_corr: Optional[Tensor] = None, k_split: int = 0) -> None:
         """Record one convolution.  ``halo``: use the halo-resident kernel (Cin, Cout <= 64); ``in_affine`` (A, B):
         apply x = y*A + B on load; ``fold_center_tap`` (halo, Cin <= 32): fold A into per-sample weights and carry
         B / bias / noise on the auxiliary band -- ``w`` is then the fp32 base weight [phases*taps*Cout, Cin]."""
@@ -248,6 +261,8 @@ class Program:
         d.act, d.slope, d.alpha = act, slope, L.ptr(alpha)
         d.resid, d.residC = L.ptr(resid), resid_c
         d.stat_sum, d.stat_sq = L.ptr(stat_sum), L.ptr(stat_sq)
+        d.kSplit = k_split
+        assert k_split in (0, 1) or not halo, "split-precision convs run on the implicit-GEMM kernel"
         for t in (inp, w, out, bias, cbias, noise, noise_w, alpha, resid, stat_sum, stat_sq):
             if t is not None:
                 self.keep.append(t)
@@ -289,7 +304,7 @@ class SynthesisProgram(Program):
     def __init__(self, g_sd: Dict[str, Tensor], chunk: int, out_res: int = 112, device="cuda",
                  keep_planar: bool = False, mean: float = 0.5, std: float = 0.5, halo: bool = True,
                  fold_small: bool = True, groups: int = 1, blur_on_tensor_cores: bool = True,
-                 fused_upblur: bool = True, nhwc_out: bool = True):
+                 fused_upblur: bool = True, nhwc_out: bool = True, hp_layers: int = 0):
         super().__init__()
         dev = torch.device(device)
         self.chunk, self.out_res = chunk, out_res
@@ -301,6 +316,12 @@ class SynthesisProgram(Program):
             fold_max_cin = int(_os.environ.get("CFR_FOLD_MAX_CIN", "64"))
         sd = {k: v.detach().float().cpu() for k, v in g_sd.items()}
         lib, h = self.lib, self.handle
+        # Split-precision prefix: layers 1..hp_layers take fp16 hi/lo operand pairs (3 MMAs per product, ~2^-21) and keep
+        # fp32 activations between kernels.  Rounding errors of the first (4x4 .. 64x64) layers are spatially coarse, get
+        # amplified by every later InstanceNorm and dominate the embedding error (tests/diag_precision.py).
+        if not 0 <= hp_layers <= 11:
+            raise ValueError("hp_layers must be in 0..11 (layer 12 feeds the halo kernel, which reads fp16)")
+        self.hp_layers = hp_layers
 
         # ---- inputs / small tensors
         self.wp2 = self.hold(torch.zeros(chunk, 2, 512, device=dev))
@@ -342,7 +363,8 @@ class SynthesisProgram(Program):
         t = t - t.mean(dim=[1, 2], keepdim=True)
         t = t / torch.sqrt((t * t).mean(dim=[1, 2], keepdim=True) + 1e-8)
         xhat0 = self.hold(_f32(t.permute(1, 2, 0).reshape(16, 512), dev))
-        L.check(lib.cfr_program_add_layer0(h, L.ptr(xhat0), L.ptr(self.styles), off, self.style_off[0], chunk, L.ptr(x)))
+        add_l0 = lib.cfr_program_add_layer0_split if hp_layers >= 1 else lib.cfr_program_add_layer0
+        L.check(add_l0(h, L.ptr(xhat0), L.ptr(self.styles), off, self.style_off[0], chunk, L.ptr(x)))
 
         # diagnostics: (layer, ops recorded when its output is complete, buffer, res, C, (A, B) still to apply or None)
         self.layer_marks = [(0, self.num_launches, x, 4, 512, None)]
@@ -361,6 +383,38 @@ class SynthesisProgram(Program):
             hk = use_halo(l)
             fold = hk and fold_small and cin <= fold_max_cin
             assert pending is None or hk
+            if l <= hp_layers:
+                # ---- split-precision layer: x [.., 3*cin] = [hi|lo|hi] fp16 -> y fp32 -> x' fp16 (split again or plain)
+                y32, raw32 = y.view(torch.float32), raw.view(torch.float32)
+                if l % 2 == 1:
+                    w = sd[f"synthesis.layer{l}.conv.weight"] * (math.sqrt(2.0) / math.sqrt(cin * 9))
+                    fused_stats = res >= 16
+                    self.conv(inp=x, n=chunk, hin=res, win=res, cin=3 * cin, w=self.hold(split3_weight(
+                                  pack_conv_weight(w), 9, cin).to(dev)), cout=cout, hout=res, wout=res,
+                              tile=tile_for(res), out=y32, out_hwc=(res, res, cout), taps=[TAPS3], noise=noise,
+                              noise_w=noise_w, bias=bias, act=L.ACT_LRELU, slope=0.2,
+                              stat_sum=ssum if fused_stats else None, stat_sq=ssq if fused_stats else None, k_split=3)
+                    if not fused_stats:
+                        L.check(lib.cfr_program_add_blur_act_stats_f32(h, L.ptr(y32), None, chunk, res, res, cout, None,
+                                                                       None, None, L.ptr(ssum), L.ptr(ssq), 1))
+                else:
+                    lo = res // 2
+                    wp, taps = pack_upconv_phases(upconv_equiv_weight(sd, l))
+                    self.conv(inp=x, n=chunk, hin=lo, win=lo, cin=3 * cin, w=self.hold(split3_weight(wp, 4, cin).to(dev)),
+                              cout=cout, hout=lo, wout=lo, tile=tile_for(lo), out=raw32, out_hwc=(res, res, cout),
+                              taps=taps, oscale=2, ooff=[(0, 0), (0, 1), (1, 0), (1, 1)], w_rows_per_phase=cout, k_split=3)
+                    L.check(lib.cfr_program_add_blur_act_stats_f32(h, L.ptr(raw32), L.ptr(y32), chunk, res, res, cout,
+                                                                   L.ptr(noise), L.ptr(noise_w), L.ptr(bias), L.ptr(ssum),
+                                                                   L.ptr(ssq), 0))
+                A, B = self.AB[l % 2]
+                L.check(lib.cfr_program_add_finalize_stats(h, L.ptr(ssum), L.ptr(ssq), L.ptr(self.styles), off,
+                                                           self.style_off[l], chunk, cout, 1.0 / (res * res),
+                                                           L.ptr(A), L.ptr(B)))
+                # the conv's input buffer is free now: the next layer's operands go there
+                L.check(lib.cfr_program_add_affine_f32(h, L.ptr(y32), L.ptr(A), L.ptr(B), chunk, res * res, cout, L.ptr(x),
+                                                       3 if l + 1 <= hp_layers else 1))
+                self.layer_marks.append((l, self.num_launches, y32, res, cout, (A, B)))
+                continue
             if l % 2 == 1:
                 w = sd[f"synthesis.layer{l}.conv.weight"] * (math.sqrt(2.0) / math.sqrt(cin * 9))
                 fused_stats = res >= 16
@@ -523,9 +577,11 @@ class Engine:
 
     TC_MATCH_MIN_ROWS = 32768      # galleries at least this large use the tensor-core matcher (cfr_matcher_*)
 
+    HP_LAYERS = 8                  # StyleGAN layers 1..8 (4x4 .. 64x64) run split-precision (SynthesisProgram.hp_layers)
+
     def __init__(self, g_sd, f_sd, dir_mat: Tensor, gallery: Tensor, chunk: int = 32, device="cuda",
                  keep_planar: bool = False, frm_group: int = 1, tc_match: Optional[bool] = None,
-                 frm: str = "insightface"):
+                 frm: str = "insightface", hp_layers: Optional[int] = None):
         if not torch.cuda.is_available():
             raise RuntimeError("certifyingfacerecognition_b200 needs a CUDA device (no CPU fallback)")
         self.lib = L.load()
@@ -542,7 +598,14 @@ class Engine:
             frm_cls, res = FaceNetProgram, INPUT_RES
         else:
             raise ValueError(f"unknown face recognition model '{frm}'")
-        self.synth = SynthesisProgram(g_sd, chunk, res, device, keep_planar=keep_planar, groups=self.frm_group)
+        if hp_layers is None:
+            import os as _os
+            hp_layers = self.HP_LAYERS
+            if _os.environ.get("CFR_DEBUG_KNOBS") == "1" and _os.environ.get("CFR_HP_LAYERS") is not None:
+                hp_layers = int(_os.environ["CFR_HP_LAYERS"])       # A/B runs (precision vs throughput)
+        self.hp_layers = hp_layers
+        self.synth = SynthesisProgram(g_sd, chunk, res, device, keep_planar=keep_planar, groups=self.frm_group,
+                                      hp_layers=hp_layers)
         self.frm = frm_cls(f_sd, chunk, self.synth.img, device)
         self.frm_big = frm_cls(f_sd, chunk * self.frm_group, self.synth.img, device) if self.frm_group > 1 else None
         if tuple(dir_mat.shape) != (N_DIRS, 512):

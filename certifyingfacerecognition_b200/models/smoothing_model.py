@@ -52,7 +52,7 @@ class WrappedModel(nn.Module):
                  generator_state: Optional[Dict[str, torch.Tensor]] = None,
                  frm_state: Optional[Dict[str, torch.Tensor]] = None,
                  latents: Optional[torch.Tensor] = None, orig_embs: Optional[torch.Tensor] = None,
-                 chunk: int = 32) -> None:
+                 chunk: int = 32, frm_group: int = 1) -> None:
         super().__init__()
         if face_recog not in ("insightface", "facenet", "facenet-vggface2"):
             raise ValueError(f"face_recog='{face_recog}' is not one of the reference's FRS_METHODS (gen_utils.py:31-35)")
@@ -86,7 +86,8 @@ class WrappedModel(nn.Module):
         else:
             embs = None
         placeholder = embs if embs is not None else torch.zeros(1, EMB_SIZE)
-        self.engine = Engine(generator_state, frm_state, self.dir_mat, placeholder, chunk=chunk, device=self.device,
+        self.engine = Engine(generator_state, frm_state, self.dir_mat, placeholder, chunk=chunk, frm_group=frm_group,
+                             device=self.device,
                              frm=face_recog)
         if embs is None:
             print("Generating original embeddings")
@@ -123,8 +124,10 @@ class WrappedModel(nn.Module):
         traffic the fused match+vote kernel avoids."""
         return self.compute_probs(self.embed(x, p))
 
-    def sample_votes(self, z, x, sigma, num: int, seed: int = 0, sample_offset: int = 0) -> torch.Tensor:
+    def sample_votes(self, z, x, sigma, num: int, seed: int = 0, sample_offset: int = 0,
+                     noise: Optional[torch.Tensor] = None) -> torch.Tensor:
         """Per-identity int64 vote counts of ``num`` MC samples around (z, x) -- the body of
-        Smooth._sample_noise (smooth.py:126-137) as one call."""
-        counts, _ = self.engine.sample_votes(z, x, sigma, num, seed=seed, sample_offset=sample_offset)
+        Smooth._sample_noise (smooth.py:126-137) as one call.  ``noise`` [num, 5]: injected (already scaled) noise
+        instead of the Philox stream."""
+        counts, _ = self.engine.sample_votes(z, x, sigma, num, seed=seed, sample_offset=sample_offset, noise=noise)
         return counts

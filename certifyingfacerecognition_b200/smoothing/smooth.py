@@ -42,6 +42,7 @@ class Smooth:
         self.seed = seed                    # Philox key of the device noise stream
         self.process_group = process_group  # torch.distributed group: MC samples are sharded across its ranks
         self._draws = 0                     # global sample counter -> Philox subsequence offset
+        self._replay = None                 # injected noise rows still to be consumed (parity runs), see inject_noise
         self.samples_classified = 0         # bookkeeping for throughput reports
 
     # ------------------------------------------------------------------------------------------ certify
@@ -72,6 +73,12 @@ class Smooth:
         if _binomtest(int(count1), int(count1 + count2), p=0.5).pvalue > alpha:
             return Smooth.ABSTAIN
         return top2[0]
+
+    def inject_noise(self, noise: Optional[torch.Tensor]) -> None:
+        """Parity runs on identical noise tensors: the next ``_sample_noise`` calls consume the rows of ``noise``
+        ([total, 5], already scaled by sigma -- what ``certificate.sample_noise`` returned in the run being replayed)
+        in order instead of drawing from the device Philox stream.  ``None`` switches back."""
+        self._replay = None if noise is None else noise.reshape(-1, noise.shape[-1]).clone()
 
     # ------------------------------------------------------------------------------------------ MC loop
     def _fused(self) -> bool:
@@ -105,8 +112,14 @@ class Smooth:
             rank, world = dist.get_rank(self.process_group), dist.get_world_size(self.process_group)
         lo = (num * rank) // world
         hi = (num * (rank + 1)) // world
-        counts = self.base_classifier.sample_votes(z, x, self.sigma, hi - lo, seed=self.seed,
-                                                   sample_offset=self._draws + lo)
+        if self._replay is not None:
+            if self._replay.shape[0] < num:
+                raise ValueError(f"inject_noise: {self._replay.shape[0]} rows left, {num} needed")
+            rows, self._replay = self._replay[:num], self._replay[num:]
+            counts = self.base_classifier.sample_votes(z, x, self.sigma, hi - lo, noise=rows[lo:hi])
+        else:
+            counts = self.base_classifier.sample_votes(z, x, self.sigma, hi - lo, seed=self.seed,
+                                                       sample_offset=self._draws + lo)
         if world > 1:
             import torch.distributed as dist
             dist.all_reduce(counts, op=dist.ReduceOp.SUM, group=self.process_group)

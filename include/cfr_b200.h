@@ -58,6 +58,12 @@ typedef struct cfr_conv_desc {
   const void* resid; int32_t residC;          /* fp16 [N,outH,outW,residC] or NULL */
   int64_t* stat_sum; int64_t* stat_sq;        /* [N,Cout] per-(n,c) sum / sum of squares, Q43.20 fixed point
                                                  (integer atomics: bit-reproducible), or NULL */
+  int32_t kSplit;                             /* 0 / 1: plain fp16 operands.  3: split-precision conv -- the Cin input
+                                                 channels are [x_hi | x_lo | x_hi] of Cin/3 logical channels and the
+                                                 weights [w_hi | w_hi | w_lo] per tap (hi = fp16(v), lo = fp16(v - hi)),
+                                                 so the fp32 accumulator holds x.w to ~2^-21 (the x_lo.w_lo term is
+                                                 dropped); algorithmic FLOPs are counted on Cin/3.  Used for the early
+                                                 StyleGAN layers, whose rounding errors dominate the embedding error. */
 } cfr_conv_desc;
 
 CFR_API const char* cfr_last_error(void);
@@ -110,6 +116,9 @@ CFR_API int cfr_program_add_styles(cfr_program* p, const float* wp2, const float
 /* FirstConvBlock + epilogue, :581-584 */
 CFR_API int cfr_program_add_layer0(cfr_program* p, const float* xhat0, const float* styles, int style_stride,
                            int style_off, int b, void* out_f16);
+/* split-precision variant: out [b,4,4,3*512] = [hi | lo | hi] (see cfr_conv_desc.kSplit) */
+CFR_API int cfr_program_add_layer0_split(cfr_program* p, const float* xhat0, const float* styles, int style_stride,
+                                 int style_off, int b, void* out_f16_split);
 /* BlurLayer :463 + noise/bias/LeakyReLU :560-562 + InstanceNorm sums :420-422.  mode 1 = sums only */
 CFR_API int cfr_program_add_blur_act_stats(cfr_program* p, const void* raw_f16, void* y_f16, int n, int h, int w, int c,
                                    const float* noise, const float* noise_w, const float* bias, int64_t* sum,
@@ -120,7 +129,13 @@ CFR_API int cfr_program_add_finalize_stats(cfr_program* p, const int64_t* sum, c
                                    float* B);
 CFR_API int cfr_program_add_affine(cfr_program* p, const void* y_f16, const float* A, const float* B, int n, int hw, int c,
                            void* x_f16);
-/* LastConvBlock :759-762 + postprocess (mod_stylegan_generator.py:303-307) + get_transform (gen_utils.py:77-85) */
+/* fp32 activations of the split-precision layers: blur/act/stats fp32 -> fp32, and x = y*A + B written as fp16
+ * operands, split == 3: [.., 3c] = [hi | lo | hi] for the next split conv; split == 1: plain [.., c] */
+CFR_API int cfr_program_add_blur_act_stats_f32(cfr_program* p, const float* raw, float* y, int n, int h, int w, int c,
+                                       const float* noise, const float* noise_w, const float* bias, int64_t* sum,
+                                       int64_t* sq, int mode);
+CFR_API int cfr_program_add_affine_f32(cfr_program* p, const float* y, const float* A, const float* B, int n, int hw, int c,
+                               void* x_f16, int split);
 /* facenet_pytorch.InceptionResnetV1 glue (main_attack.py:126-129; no source under /root/reference: parity unpinned):
  * MaxPool2d(3, stride 2) NHWC fp16 -> channel slice [c_off, c_off + c) of a wider NHWC buffer (torch.cat of the Mixed
  * blocks); AdaptiveAvgPool2d(1); F.normalize(p=2, dim=1) on fp32 rows. */

@@ -1,8 +1,8 @@
 """Import the UNMODIFIED reference from /root/reference on a CPU-only host.
 
-TEST INFRASTRUCTURE ONLY; usable only in the build container (``/root/reference`` does not exist
-on the GPU box).  Used by ``oracle/make_golden.py`` (golden vectors) and by ``bench.py --impl
-reference`` when the reference tree is present.
+TEST INFRASTRUCTURE ONLY.  Used by ``oracle/make_golden*.py`` (golden vectors, build container) and by ``bench.py``'s
+CPU legs, which on the GPU box import the unmodified files collected under ``oracle/_ref`` by ``oracle/build_ref.py``
+(``/root/reference`` does not exist there).
 
 Shims (none of them touches the arithmetic on the path):
   1. stub modules ``matplotlib``, ``matplotlib.pyplot``, ``matplotlib.image``, ``facenet_pytorch``;
@@ -24,11 +24,22 @@ import types
 import numpy as np
 import torch
 
-REFERENCE_ROOT = "/root/reference"
+def _reference_root() -> str:
+    """/root/reference in the build container; on the GPU box the collected copy ``oracle/_ref`` (oracle/build_ref.py,
+    git-ignored, unmodified files).  CFR_REFERENCE_ROOT overrides (testing the collected copy here)."""
+    env = os.environ.get("CFR_REFERENCE_ROOT")
+    if env:
+        return env
+    if os.path.isdir("/root/reference/smoothing"):
+        return "/root/reference"
+    return os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
+
+
+REFERENCE_ROOT = _reference_root()
 
 
 def available() -> bool:
-    return os.path.isdir(os.path.join(REFERENCE_ROOT, "smoothing"))
+    return os.path.isfile(os.path.join(REFERENCE_ROOT, "smoothing", "smooth.py"))
 
 
 def install_shims() -> None:

@@ -23,6 +23,8 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--n", type=int, default=2)
     ap.add_argument("--out", default=None)
+    ap.add_argument("--hp", type=int, nargs="+", default=[-1],
+                    help="split-precision prefix lengths to try (Engine hp_layers); -1 = the engine's default")
     args = ap.parse_args()
     from certifyingfacerecognition_b200.engine import Engine
     from oracle import fixtures
@@ -39,8 +41,6 @@ def main():
     dirs = torch.from_numpy(np.load(os.path.join(ROOT, "tests", "golden", "dirs.npy")))
     n = args.n
     w = torch.from_numpy(fixtures.latents(64)[32:32 + n])
-    eng = Engine(g_sd, f_sd, dirs, torch.zeros(4, 512), chunk=n, keep_planar=True)
-
     # ---- oracle, every layer kept
     ref_layers = {}
     with torch.no_grad():
@@ -49,9 +49,21 @@ def main():
         ref_img = M.transform(M.postprocess(raw))
         ref_emb = M.iresnet50(ref_img, f_sd)
 
+    for hp in args.hp:
+        eng = Engine(g_sd, f_sd, dirs, torch.zeros(4, 512), chunk=n, keep_planar=True, hp_layers=None if hp < 0 else hp)
+        say(f"==== hp_layers = {eng.hp_layers}")
+        one_engine(eng, n, w, ref_layers, ref_img, ref_emb, f_sd, say)
+    if args.out:
+        os.makedirs(os.path.dirname(args.out) or ".", exist_ok=True)
+        with open(args.out, "w") as fh:
+            fh.write("\n".join(lines) + "\n")
+
+
+def one_engine(eng, n, w, ref_layers, ref_img, ref_emb, f_sd, say):
     # ---- engine, layer by layer
     from certifyingfacerecognition_b200 import _lib as L
     from certifyingfacerecognition_b200.engine import PSI
+    from oracle import mc_path as M
     syn = eng.synth
     syn.out_slot.zero_()
     L.check(eng.lib.cfr_truncate(L.ptr(w.cuda()), L.ptr(syn.w_avg), PSI, n, L.ptr(syn.wp2), eng._stream()))
@@ -93,10 +105,6 @@ def main():
     torch.cuda.synchronize()
     rep("oracle image -> our ArcFace", eng.frm.emb[:n].cpu())
     say("ref emb norms", [round(v, 2) for v in ref_emb.norm(dim=1).tolist()])
-    if args.out:
-        os.makedirs(os.path.dirname(args.out) or ".", exist_ok=True)
-        with open(args.out, "w") as fh:
-            fh.write("\n".join(lines) + "\n")
 
 
 if __name__ == "__main__":

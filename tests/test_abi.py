@@ -32,14 +32,24 @@ def test_version_and_error_string_without_gpu():
     assert lib.cfr_launch_count() == 0 or lib.cfr_launch_count() > 0
 
 
-def test_conv_desc_layout_matches_header():
-    """ctypes mirror of cfr_conv_desc must have the C struct's size (checked against a tiny C program's sizeof
-    would need a compiler at test time; here: field order / count sanity + natural alignment)."""
-    from certifyingfacerecognition_b200._lib import ConvDesc
+def test_conv_desc_layout_matches_header(tmp_path):
+    """ctypes mirrors of cfr_conv_desc / cfr_sampler_desc have the C structs' size and field offsets (a tiny C program
+    compiled against include/cfr_b200.h prints them)."""
+    import subprocess
+    from certifyingfacerecognition_b200._lib import ConvDesc, SamplerDesc
     names = [f[0] for f in ConvDesc._fields_]
     assert names[:5] == ["inp", "N", "Hin", "Win", "Cin"]
-    assert names[-2:] == ["stat_sum", "stat_sq"]
-    assert ctypes.sizeof(ConvDesc) % 8 == 0
+    assert names[-3:] == ["stat_sum", "stat_sq", "kSplit"]
+    src = tmp_path / "layout.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "cfr_b200.h"\n'
+                   'int main(void) { printf("%zu %zu %zu %zu %zu %zu\\n", sizeof(cfr_conv_desc), '
+                   'offsetof(cfr_conv_desc, out), offsetof(cfr_conv_desc, stat_sum), offsetof(cfr_conv_desc, kSplit), '
+                   'sizeof(cfr_sampler_desc), offsetof(cfr_sampler_desc, matcher)); return 0; }\n')
+    exe = tmp_path / "layout"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    got = [int(v) for v in subprocess.check_output([str(exe)]).split()]
+    assert got == [ctypes.sizeof(ConvDesc), ConvDesc.out.offset, ConvDesc.stat_sum.offset, ConvDesc.kSplit.offset,
+                   ctypes.sizeof(SamplerDesc), SamplerDesc.matcher.offset]
 
 
 def test_no_cpu_fallback():

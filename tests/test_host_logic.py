@@ -13,6 +13,8 @@ from certifyingfacerecognition_b200.smoothing import L2Certificate, Smooth
 from certifyingfacerecognition_b200.smoothing.smooth import lower_confidence_bound
 from oracle import mc_path as M
 
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
 CPU = torch.device("cpu")
 
 
@@ -266,3 +268,51 @@ def test_ncu_launch_summary_is_reproducible():
     halo = sum(v for k, v in shares.items() if "conv_halo_kernel" in k)
     igemm = sum(v for k, v in shares.items() if "conv_igemm_kernel" in k)
     assert 0.3 < halo < 0.5 and 0.3 < igemm < 0.5    # the two conv kernels are ~80 % of the GPU time of the bench process
+
+
+def test_injected_noise_is_consumed_in_order_by_the_fused_path():
+    """Parity runs replay the reference's own noise tensors: Smooth.inject_noise feeds the fused path row by row, first
+    the selection pass, then the estimation pass; without injection the Philox offsets keep advancing."""
+    class FakeFused:
+        supports_fused_votes = True
+
+        def __init__(self):
+            self.calls = []
+
+        def eval(self):
+            return self
+
+        def sample_votes(self, z, x, sigma, num, seed=0, sample_offset=0, noise=None):
+            self.calls.append((num, sample_offset, None if noise is None else noise.clone()))
+            c = torch.zeros(3, dtype=torch.int64)
+            c[0] = num
+            return c
+
+    fake = FakeFused()
+    s = Smooth(fake, 3, torch.tensor([0.1]), L2Certificate(1, device=CPU))
+    noise = torch.arange(30 * 5, dtype=torch.float32).view(30, 5)
+    s.inject_noise(noise)
+    pred, gap = s.certify(torch.zeros(1, 512), torch.zeros(1, 5), torch.tensor([0]), 10, 20, 0.001, 8, device=CPU)
+    assert pred == 0 and gap > 0
+    assert [c[0] for c in fake.calls] == [10, 20]
+    assert torch.equal(fake.calls[0][2], noise[:10]) and torch.equal(fake.calls[1][2], noise[10:30])
+    with pytest.raises(ValueError):
+        s._sample_noise(torch.zeros(1, 512), torch.zeros(1, 5), 1, 1, device=CPU)      # nothing left to replay
+    s.inject_noise(None)
+    s._sample_noise(torch.zeros(1, 512), torch.zeros(1, 5), 7, 7, device=CPU)
+    assert fake.calls[-1][2] is None and fake.calls[-1][1] == 30                       # Philox offset after 30 draws
+
+
+def test_reference_collection_recipe_lists_only_path_modules():
+    """oracle/build_ref.py collects the certify path's modules only (no vendored TF trees) and never writes outside
+    oracle/_ref (which is git-ignored)."""
+    from oracle import build_ref
+    assert build_ref.DST.endswith(os.path.join("oracle", "_ref"))
+    assert all("tf_official" not in g and "examples" not in g for g in build_ref.GLOBS)
+    ignore = open(os.path.join(ROOT, ".gitignore")).read()
+    assert "oracle/_ref/" in ignore
+    if os.path.isdir(build_ref.SRC):
+        dst = build_ref.build()
+        assert os.path.isfile(os.path.join(dst, "smoothing", "smooth.py"))
+        assert open(os.path.join(dst, "smoothing", "smooth.py")).read() == \
+            open(os.path.join(build_ref.SRC, "smoothing", "smooth.py")).read()

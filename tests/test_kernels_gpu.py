@@ -515,3 +515,112 @@ def test_halo_upconv_few_ctas(E, monkeypatch, n, cin, cout, lo_h, lo_w, fold):
 def test_conv_few_ctas(E, monkeypatch, n, cin, cout, res, stride, ks):
     monkeypatch.setenv("CFR_MAX_CTAS", "3")
     test_conv_matches_torch(E, n, cin, cout, res, stride, ks)
+
+
+# ---- split-precision (fp16 hi/lo operand pairs) early StyleGAN layers -----------------------------------------------
+def _split3_nhwc(x):
+    """[n,c,h,w] fp32 -> NHWC fp16 [n,h,w,3c] = [hi | lo | hi]"""
+    v = x.permute(0, 2, 3, 1).contiguous()
+    hi = v.half()
+    lo = (v - hi.float()).half()
+    return torch.cat([hi, lo, hi], dim=3).contiguous()
+
+
+@pytest.mark.parametrize("n,cin,cout,res", [(3, 512, 512, 4), (2, 512, 512, 16), (2, 256, 256, 64), (5, 64, 128, 32)])
+def test_split_precision_conv_is_fp32_class(E, n, cin, cout, res):
+    """kSplit == 3: un-rounded fp32 operands, x.w = x_hi.w_hi + x_lo.w_hi + x_hi.w_lo in the fp32 accumulator.  Against an
+    fp64 torch conv the error must be >= 15x below what fp16-rounded operands give (2^-11 per operand); what is left
+    (~1e-5 at K = 4608) is the tensor core's own fp32 accumulation."""
+    g = torch.Generator().manual_seed(res * 7 + cin)
+    x = torch.randn(n, cin, res, res, generator=g).cuda()
+    w = (torch.randn(cout, cin, 3, 3, generator=g) / math.sqrt(cin * 9)).cuda()
+    bias = torch.randn(cout, generator=g).cuda()
+    ref = F.conv2d(x.double(), w.double(), bias.double(), padding=1)
+    out = torch.full((n * res * res * cout,), float("nan"), dtype=torch.float32, device="cuda")
+    prog = E.Program()
+    prog.conv(inp=_split3_nhwc(x), n=n, hin=res, win=res, cin=3 * cin, w=E.split3_weight(E.pack_conv_weight(w.cpu()), 9, cin).cuda(),
+              cout=cout, hout=res, wout=res, tile=E.tile_for(res), out=out, out_hwc=(res, res, cout), taps=[E.TAPS3],
+              bias=bias, k_split=3)
+    prog.run()
+    _sync()
+    got = out.view(n, res, res, cout).permute(0, 3, 1, 2).double()
+    rel = ((got - ref).norm() / ref.norm()).item()
+    rel16 = ((F.conv2d(x.half().double(), w.half().double(), bias.double(), padding=1) - ref).norm() / ref.norm()).item()
+    assert rel < 2e-5 and rel < rel16 / 15, (rel, rel16)
+    # FLOPs are accounted on the logical Cin, not on the 3x wider operand
+    assert prog.lib.cfr_program_op_flops(prog.handle, 0) == pytest.approx(2.0 * n * res * res * 9 * cin * cout)
+
+
+def test_split_precision_upconv_blur_affine_chain(E):
+    """One split-precision up-conv layer end to end: 4-phase conv (fp32 out) -> blur/noise/bias/LeakyReLU/statistics in
+    fp32 -> IN + AdaIN coefficients -> x = y*A + B written as [hi|lo|hi]; compared with torch fp64."""
+    n, cin, cout, lo = 2, 64, 128, 16
+    res = 2 * lo
+    g = torch.Generator().manual_seed(31)
+    x = torch.randn(n, cin, lo, lo, generator=g).cuda()
+    weq = (torch.randn(cout, cin, 3, 3, generator=g) / math.sqrt(cin * 9))
+    noise = torch.randn(res, res, generator=g).cuda()
+    nw, bias = torch.randn(cout, generator=g).cuda(), torch.randn(cout, generator=g).cuda()
+    styles = torch.randn(n, 2 * cout, generator=g).cuda()
+    k = torch.tensor([1.0, 2.0, 1.0], dtype=torch.float64)
+    kb = ((k[:, None] * k[None, :]) / 16).view(1, 1, 3, 3).repeat(cout, 1, 1, 1).cuda()
+    raw_ref = F.conv2d(F.interpolate(x.double(), scale_factor=2, mode="nearest"), weq.cuda().double(), padding=1)
+    y_ref = F.leaky_relu(F.conv2d(raw_ref, kb, padding=1, groups=cout) + noise.double().view(1, 1, res, res)
+                         * nw.double().view(1, -1, 1, 1) + bias.double().view(1, -1, 1, 1), 0.2)
+    mean = y_ref.mean(dim=[2, 3], keepdim=True)
+    xhat = (y_ref - mean) / torch.sqrt(((y_ref - mean) ** 2).mean(dim=[2, 3], keepdim=True) + 1e-8)
+    x_ref = xhat * (styles[:, :cout].double().view(n, cout, 1, 1) + 1) + styles[:, cout:].double().view(n, cout, 1, 1)
+
+    wp, taps = E.pack_upconv_phases(weq)
+    raw = torch.zeros(n * res * res * cout, device="cuda")
+    y = torch.zeros(n * res * res * cout, device="cuda")
+    xs = torch.zeros(n * res * res * 3 * cout, dtype=torch.float16, device="cuda")
+    ssum, ssq = _stats(n, cout)
+    A, B = torch.zeros(n * cout, device="cuda"), torch.zeros(n * cout, device="cuda")
+    prog = E.Program()
+    L = E.L
+    prog.conv(inp=_split3_nhwc(x), n=n, hin=lo, win=lo, cin=3 * cin, w=E.split3_weight(wp, 4, cin).cuda(), cout=cout,
+              hout=lo, wout=lo, tile=E.tile_for(lo), out=raw, out_hwc=(res, res, cout), taps=taps, oscale=2,
+              ooff=[(0, 0), (0, 1), (1, 0), (1, 1)], w_rows_per_phase=cout, k_split=3)
+    L.check(prog.lib.cfr_program_add_blur_act_stats_f32(prog.handle, L.ptr(raw), L.ptr(y), n, res, res, cout,
+                                                        L.ptr(noise.reshape(-1).contiguous()), L.ptr(nw), L.ptr(bias),
+                                                        L.ptr(ssum), L.ptr(ssq), 0))
+    L.check(prog.lib.cfr_program_add_finalize_stats(prog.handle, L.ptr(ssum), L.ptr(ssq), L.ptr(styles), 2 * cout, 0, n,
+                                                    cout, 1.0 / (res * res), L.ptr(A), L.ptr(B)))
+    L.check(prog.lib.cfr_program_add_affine_f32(prog.handle, L.ptr(y), L.ptr(A), L.ptr(B), n, res * res, cout,
+                                                L.ptr(xs), 3))
+    prog.keep += [noise, nw, bias, styles, raw, y, xs, ssum, ssq, A, B]
+    prog.run()
+    _sync()
+    y_got = y.view(n, res, res, cout).permute(0, 3, 1, 2).double()
+    assert ((y_got - y_ref).norm() / y_ref.norm()).item() < 2e-5
+    v = xs.view(n, res, res, 3, cout).double()
+    assert torch.equal(v[:, :, :, 0], v[:, :, :, 2])                       # hi stored twice
+    x_got = (v[:, :, :, 0] + v[:, :, :, 1]).permute(0, 3, 1, 2)
+    assert ((x_got - x_ref).norm() / x_ref.norm()).item() < 5e-5
+    # plain fp16 output (the hand-over to the first ordinary layer)
+    xp = torch.zeros(n * res * res * cout, dtype=torch.float16, device="cuda")
+    p2 = E.Program()
+    L.check(p2.lib.cfr_program_add_affine_f32(p2.handle, L.ptr(y), L.ptr(A), L.ptr(B), n, res * res, cout, L.ptr(xp), 1))
+    p2.run()
+    _sync()
+    assert torch.equal(xp.view(n, res, res, cout), xs.view(n, res, res, 3, cout)[:, :, :, 0])
+
+
+def test_layer0_split_equals_plain_layer0(E):
+    n = 3
+    g = torch.Generator().manual_seed(8)
+    xhat0 = torch.randn(16, 512, generator=g).cuda()
+    styles = torch.randn(n, 1024, generator=g).cuda()
+    plain = torch.zeros(n * 16 * 512, dtype=torch.float16, device="cuda")
+    split = torch.zeros(n * 16 * 1536, dtype=torch.float16, device="cuda")
+    L = E.L
+    prog = E.Program()
+    L.check(prog.lib.cfr_program_add_layer0(prog.handle, L.ptr(xhat0), L.ptr(styles), 1024, 0, n, L.ptr(plain)))
+    L.check(prog.lib.cfr_program_add_layer0_split(prog.handle, L.ptr(xhat0), L.ptr(styles), 1024, 0, n, L.ptr(split)))
+    prog.run()
+    _sync()
+    v = split.view(n, 16, 3, 512)
+    assert torch.equal(v[:, :, 0], plain.view(n, 16, 512)) and torch.equal(v[:, :, 0], v[:, :, 2])
+    ref = xhat0.view(1, 16, 512).double() * (styles[:, :512].double().view(n, 1, 512) + 1) + styles[:, 512:].double().view(n, 1, 512)
+    assert ((v[:, :, 0].double() + v[:, :, 1].double() - ref).abs().max() / ref.abs().max()).item() < 1e-6

@@ -74,40 +74,28 @@ def _run_both(setup, sigma, n, seed):
 
 
 def test_votes_match_oracle_on_identical_noise(setup):
-    """certify.py's two regimes (isotropic sigma, anisotropic sigma * eps^2) with decoy rows 2 sigma away along every
-    direction so that the votes are mixed (i.e. many samples sit close to a decision boundary on purpose).
-    Pooled top-1 agreement with the fp32 oracle >= 99.5 %, not counting disagreements that are inside the embedding
-    tolerance itself: by the triangle inequality two rows can legitimately swap when the oracle's margin between them is
-    at most 2 * ||e_ours - e_oracle|| (and that error is what the cosine >= 0.999 bar bounds).  Strict agreement must
-    still be >= 97 %; counts are bit-exact whenever all predictions of a regime agree."""
-    from oracle import mc_path as M
-    gallery = setup[4]
-    agree_n, tie_n, total = 0, 0, 0
+    """Small cross-check against the CPU oracle port on identical injected noise (certify.py's two regimes, decoy rows
+    2 sigma away so that the votes are mixed): embedding cosine >= 0.999, every sample votes once, and the tallies differ
+    from the oracle's only by the samples whose prediction differs.  The top-1 >= 99.5 % gate itself needs a sample size
+    that resolves 0.5 %: it is asserted strictly on the 2 x 1100 reference-classified samples of
+    tests/test_votes_golden_gpu.py, not here."""
     for seed, sigma in ((4321, torch.tensor([SIGMA])),
-                        (4322, 0.4 * torch.from_numpy(M.red_ellipse_mat_inv()).float())):
+                        (4322, 0.4 * torch.from_numpy(__import__("oracle.mc_path", fromlist=["x"]).red_ellipse_mat_inv()).float())):
         n = 32
         counts, pred, emb, counts_ref, pref, eref = _run_both(setup, sigma, n, seed)
         assert F.cosine_similarity(emb, eref).min().item() >= 0.999
         assert counts.sum().item() == n
         assert len(np.nonzero(counts_ref)[0]) >= 2          # the decoys do draw votes: not a trivial tally
         same = pred == pref
-        agree_n += int(same.sum())
-        total += n
-        for i in torch.nonzero(~same).flatten().tolist():
-            d_ref = (eref[i] - gallery[pref[i]]).norm().item()
-            d_our = (eref[i] - gallery[pred[i]]).norm().item()
-            tie_n += int(d_our - d_ref <= 2.0 * (emb[i] - eref[i]).norm().item())
-        if bool(same.all()):
-            assert np.array_equal(counts.numpy().astype(np.float64), counts_ref)
-    assert agree_n / total >= 0.97, (agree_n, total)
-    assert (agree_n + tie_n) / total >= 0.995, (agree_n, tie_n, total)
+        moved = torch.bincount(pred[~same], minlength=N_GALLERY) - torch.bincount(pref[~same], minlength=N_GALLERY)
+        assert np.array_equal((counts - moved).numpy().astype(np.float64), counts_ref)
+        assert int((~same).sum()) <= 2, (int((~same).sum()), n)
 
 
 def test_far_regime_disagreements_are_near_ties(setup):
     """Stress case (2x the anisotropic budget: the sample lands far from every gallery row, and the 5000 synthetic
-    rows are nearly equidistant).  Any top-1 disagreement with the fp32 oracle must be a near tie: the oracle's
-    distance to our pick within 0.5 % of its distance to its own pick, or inside the embedding error (margin at most
-    2 * ||e_ours - e_oracle||, see test_votes_match_oracle_on_identical_noise)."""
+    rows are nearly equidistant).  Any top-1 disagreement with the fp32 oracle must be a near tie OF THE ORACLE ITSELF:
+    its distance to our pick within 0.5 % of its distance to its own pick."""
     from oracle import mc_path as M
     gallery = setup[4]
     sigma = 2.0 * torch.from_numpy(M.red_ellipse_mat_inv()).float()
@@ -116,7 +104,7 @@ def test_far_regime_disagreements_are_near_ties(setup):
     for i in torch.nonzero(pred != pref).flatten().tolist():
         d_ref = (eref[i] - gallery[pref[i]]).norm().item()
         d_our = (eref[i] - gallery[pred[i]]).norm().item()
-        assert d_our <= d_ref * 1.005 or d_our - d_ref <= 2.0 * (emb[i] - eref[i]).norm().item(), (i, d_ref, d_our)
+        assert d_our <= d_ref * 1.005, (i, d_ref, d_our)
 
 
 def test_bit_reproducible_run_to_run(setup):

@@ -32,6 +32,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--chunk", type=int, default=50)
     ap.add_argument("--out", default=None)
+    ap.add_argument("--hp", type=int, default=-1, help="split-precision prefix (Engine hp_layers); -1 = default")
     ap.add_argument("--frm", default="insightface", choices=["insightface", "facenet"])
     args = ap.parse_args()
     from certifyingfacerecognition_b200 import synthetic as fixtures
@@ -41,7 +42,8 @@ def main():
     if args.frm == "facenet":
         f_sd = fixtures.facenet_weights()
     eng = Engine(g_sd, f_sd, dirs, torch.zeros(8, 512), chunk=args.chunk,
-                 frm="insightface" if args.frm == "insightface" else "facenet-vggface2")
+                 frm="insightface" if args.frm == "insightface" else "facenet-vggface2",
+                 hp_layers=None if args.hp < 0 else args.hp)
     eng.embed_latents(torch.from_numpy(fixtures.latents(args.chunk)))
     torch.cuda.synchronize()
     lines = []
