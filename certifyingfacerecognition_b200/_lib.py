@@ -43,7 +43,7 @@ class SamplerDesc(C.Structure):
         ("wp2", C.c_void_p), ("emb", C.c_void_p), ("dir_mat", C.c_void_p), ("w_avg", C.c_void_p),
         ("psi", C.c_float), ("gallery", C.c_void_p), ("n_gallery", C.c_int32),
         ("frm_group", C.c_int32), ("frm_big", C.c_void_p), ("emb_big", C.c_void_p), ("out_slot", C.c_void_p),
-        ("matcher", C.c_void_p),
+        ("matcher", C.c_void_p), ("tail", C.c_void_p),
     ]
 
 
@@ -75,6 +75,7 @@ SIGNATURES = {
     "cfr_program_add_finalize_stats": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _F, _P, _P]),
     "cfr_program_add_affine": (_I, [_P, _P, _P, _P, _I, _I, _I, _P]),
     "cfr_program_add_torgb_resize": (_I, [_P, _P, _P, _P, _I, _I, _I, _P, _P, _I, _F, _F, _P, _P, _P]),
+    "cfr_program_add_sum_partials": (_I, [_P, _P, _P, _I, _I, _I, _P]),
     "cfr_program_add_maxpool3s2": (_I, [_P, _P, _I, _I, _I, _I, _P, _I, _I]),
     "cfr_program_add_avgpool": (_I, [_P, _P, _I, _I, _I, _P]),
     "cfr_program_add_l2norm": (_I, [_P, _P, _I, _I, _P]),

@@ -303,6 +303,12 @@ CFR_API int cfr_program_add_affine(cfr_program* p, const void* y_f16, const floa
   return 0;
 }
 
+CFR_API int cfr_program_add_sum_partials(cfr_program* p, const float* in, const float* bias, int n, int parts, int c,
+                                 float* out) {
+  p->add([=](cudaStream_t st) { return launch_sum_partials(in, bias, n, parts, c, out, st); }, "sum_partials");
+  return 0;
+}
+
 CFR_API int cfr_program_add_maxpool3s2(cfr_program* p, const void* in_f16, int n, int h, int w, int c, void* out_f16,
                                        int out_c_total, int c_off) {
   p->add([=](cudaStream_t st) {
@@ -455,6 +461,17 @@ CFR_API int cfr_sample_votes(cfr_sampler* s, const float* z, const float* x, con
   const int K = (d.frm_group > 1 && d.frm_big != nullptr && d.out_slot != nullptr) ? d.frm_group : 1;
   int64_t done = 0;
   while (done < num) {
+    const int64_t rem = num - done;
+    if (rem < d.chunk && d.tail != nullptr) {
+      // remainder: hand it to the smallest sampler down the chain whose chunk still holds it
+      cfr_sampler* best = nullptr;
+      for (cfr_sampler* t = d.tail; t != nullptr; t = t->d.tail)
+        if (t->d.chunk >= rem && (best == nullptr || t->d.chunk < best->d.chunk)) best = t;
+      if (best != nullptr)
+        return cfr_sample_votes(best, z, x, sigma, sigma_len, noise_in ? noise_in + done * 5 : nullptr, rem, seed,
+                                sample_offset + done, counts, pred_out ? pred_out + done : nullptr,
+                                emb_out ? emb_out + done * 512 : nullptr, noise_out ? noise_out + done * 5 : nullptr, stream);
+    }
     // a full group of K chunks goes through the big ArcFace program (better SM fill); the tail chunk by chunk
     const int g = (num - done >= static_cast<int64_t>(K) * d.chunk) ? K : 1;
     const int b = static_cast<int>(num - done < static_cast<int64_t>(g) * d.chunk ? num - done : static_cast<int64_t>(g) * d.chunk);

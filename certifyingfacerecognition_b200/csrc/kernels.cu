@@ -983,6 +983,23 @@ int launch_match_vote(const float* emb, int b, const float* gallery, int n, unsi
   return 0;
 }
 
+// out[n][c] = bias[c] + sum_p in[n][p][c] in a fixed order (split-K partial sums of the ArcFace FC)
+__global__ void k_sum_partials(const float* __restrict__ in, const float* __restrict__ bias, int n, int parts, int c,
+                               float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * c) return;
+  const int s = i / c, ch = i - s * c;
+  float a = in[(static_cast<size_t>(s) * parts) * c + ch];
+  for (int p = 1; p < parts; ++p) a += in[(static_cast<size_t>(s) * parts + p) * c + ch];
+  out[i] = a + (bias != nullptr ? bias[ch] : 0.f);
+}
+int launch_sum_partials(const float* in, const float* bias, int n, int parts, int c, float* out, cudaStream_t st) {
+  if (n <= 0) return 0;
+  k_sum_partials<<<(n * c + 255) / 256, 256, 0, st>>>(in, bias, n, parts, c, out);
+  CFR_LAUNCH_CHECK("sum_partials");
+  return 0;
+}
+
 // ---- InceptionResnetV1 glue kernels (tiny, HBM-trivial) ------------------------------------------------------
 __global__ void k_maxpool3s2(const __half* __restrict__ in, int n, int h, int w, int c, __half* __restrict__ out,
                              int out_c_total, int c_off) {

@@ -58,6 +58,8 @@ int launch_vote_argmax(unsigned long long* keys, int b, int* pred, long long* co
 int launch_match_vote(const float* emb, int b, const float* gallery, int n, unsigned long long* keys, int* pred,
                       long long* counts, cudaStream_t st);
 
+// split-K partial sums [n][parts][c] (+ bias) -> [n][c], fixed summation order
+int launch_sum_partials(const float* in, const float* bias, int n, int parts, int c, float* out, cudaStream_t st);
 // InceptionResnetV1 glue: MaxPool2d(3,2) into a channel slice, global average pool, row-wise L2 normalisation
 int launch_maxpool3s2(const __half* in, int n, int h, int w, int c, __half* out, int out_c_total, int c_off, cudaStream_t st);
 int launch_avgpool(const __half* in, int n, int hw, int c, __half* out, cudaStream_t st);

@@ -501,6 +501,7 @@ def _bn_affine(sd, p, eps=1e-5):
 class ArcFaceProgram(Program):
     LAYERS = (3, 4, 14, 3)
     PLANES = (64, 128, 256, 512)
+    FC_SPLIT = 4                   # K-slices of the final FC (<= CFR_MAX_PHASES)
 
     def __init__(self, f_sd: Dict[str, Tensor], chunk: int, img: Tensor, device="cuda"):
         super().__init__()
@@ -565,23 +566,47 @@ class ArcFaceProgram(Program):
         bias = (sd["fc.bias"] + torch.einsum("ochw,c->o", wfc, tb2)) * sf + tf
         wfold = (wfc * sb.view(1, -1, 1, 1) * sf.view(-1, 1, 1, 1)).permute(0, 2, 3, 1).reshape(512, 49 * 512)
         self.emb = self.hold(torch.zeros(n, 512, device=dev))
-        self.conv(inp=xs, n=n, hin=1, win=1, cin=49 * 512, w=self.hold(_f16(wfold.contiguous(), dev)), cout=512,
-                  hout=1, wout=1, tile=(1, 1, 128), out=self.emb, out_hwc=(1, 1, 512), taps=[[(0, 0)]],
-                  bias=self.hold(_f32(bias, dev)))
+        # split-K: the 25088-long contraction as FC_SPLIT "phases" of one conv -- phase p reads K-slice p (the input viewed
+        # as [n, 1, FC_SPLIT, 25088 / FC_SPLIT], tap dx = p) against weight rows [p*512, (p+1)*512) and writes its fp32
+        # partial sums to column p of [n, FC_SPLIT, 512]; k_sum_partials adds them in a fixed order (+ bias).  One K-slice
+        # per work item: 4x the CTAs of the 8 (M tile, N tile) pairs a plain GEMM of this shape has.
+        P = self.FC_SPLIT
+        kp = 49 * 512 // P
+        assert 49 * 512 % P == 0 and kp % 64 == 0
+        wsplit = wfold.reshape(512, P, kp).permute(1, 0, 2).reshape(P * 512, kp).contiguous()
+        partial = self.hold(torch.zeros(n * P * 512, device=dev))
+        self.conv(inp=xs, n=n, hin=1, win=P, cin=kp, w=self.hold(_f16(wsplit, dev)), cout=512, hout=1, wout=1,
+                  tile=(1, 1, 128), out=partial, out_hwc=(1, P, 512), taps=[[(0, p)] for p in range(P)],
+                  ooff=[(0, p) for p in range(P)], w_rows_per_phase=512)
+        L.check(self.lib.cfr_program_add_sum_partials(self.handle, L.ptr(partial), L.ptr(self.hold(_f32(bias, dev))), n, P,
+                                                      512, L.ptr(self.emb)))
         self.final_features = xs
 
 
 # ------------------------------------------------------------------------------------------------------
+class _Pipeline:
+    """One recorded (synthesis, FRM[, grouped FRM]) program set for a fixed chunk size, plus its C sampler."""
+
+    def __init__(self, g_sd, f_sd, frm_cls, res, chunk, frm_group, device, keep_planar, hp_layers):
+        self.chunk, self.frm_group = chunk, max(1, int(frm_group))
+        self.synth = SynthesisProgram(g_sd, chunk, res, device, keep_planar=keep_planar, groups=self.frm_group,
+                                      hp_layers=hp_layers)
+        self.frm = frm_cls(f_sd, chunk, self.synth.img, device)
+        self.frm_big = frm_cls(f_sd, chunk * self.frm_group, self.synth.img, device) if self.frm_group > 1 else None
+        self.sampler = None
+
+
 class Engine:
     """StyleGAN -> resize -> iresnet50 -> gallery vote, for one GPU."""
 
     TC_MATCH_MIN_ROWS = 32768      # galleries at least this large use the tensor-core matcher (cfr_matcher_*)
-
-    HP_LAYERS = 8                  # StyleGAN layers 1..8 (4x4 .. 64x64) run split-precision (SynthesisProgram.hp_layers)
+    HP_LAYERS = 6                  # StyleGAN layers 1..6 (4x4 .. 32x32) run split-precision (SynthesisProgram.hp_layers)
 
     def __init__(self, g_sd, f_sd, dir_mat: Tensor, gallery: Tensor, chunk: int = 32, device="cuda",
                  keep_planar: bool = False, frm_group: int = 1, tc_match: Optional[bool] = None,
-                 frm: str = "insightface", hp_layers: Optional[int] = None):
+                 frm: str = "insightface", hp_layers: Optional[int] = None, tail_chunks=()):
+        """``tail_chunks``: extra, smaller chunk sizes recorded as their own program sets (descending, all < chunk); the
+        remainder of a ``sample_votes`` call runs on the smallest one that holds it instead of a whole chunk."""
         if not torch.cuda.is_available():
             raise RuntimeError("certifyingfacerecognition_b200 needs a CUDA device (no CPU fallback)")
         self.lib = L.load()
@@ -604,10 +629,10 @@ class Engine:
             if _os.environ.get("CFR_DEBUG_KNOBS") == "1" and _os.environ.get("CFR_HP_LAYERS") is not None:
                 hp_layers = int(_os.environ["CFR_HP_LAYERS"])       # A/B runs (precision vs throughput)
         self.hp_layers = hp_layers
-        self.synth = SynthesisProgram(g_sd, chunk, res, device, keep_planar=keep_planar, groups=self.frm_group,
-                                      hp_layers=hp_layers)
-        self.frm = frm_cls(f_sd, chunk, self.synth.img, device)
-        self.frm_big = frm_cls(f_sd, chunk * self.frm_group, self.synth.img, device) if self.frm_group > 1 else None
+        tail_chunks = sorted({int(c) for c in tail_chunks if 0 < int(c) < chunk}, reverse=True)
+        self.pipes = [_Pipeline(g_sd, f_sd, frm_cls, res, chunk, self.frm_group, device, keep_planar, hp_layers)]
+        self.pipes += [_Pipeline(g_sd, f_sd, frm_cls, res, c, 1, device, False, hp_layers) for c in tail_chunks]
+        self.synth, self.frm, self.frm_big = self.pipes[0].synth, self.pipes[0].frm, self.pipes[0].frm_big
         if tuple(dir_mat.shape) != (N_DIRS, 512):
             # the noise kernel (k_noise_project) and the C ABI fix the attribute space at the reference's five
             # InterFaceGAN directions (proj_utils.py:16-21 ATTRS); fewer / more rows would read out of bounds
@@ -619,15 +644,6 @@ class Engine:
 
     def set_gallery(self, gallery: Tensor) -> None:
         self.gallery = _f32(gallery, self.device)
-        d = L.SamplerDesc()
-        d.synth, d.frm, d.chunk = self.synth.handle, self.frm.handle, self.chunk
-        d.wp2, d.emb = L.ptr(self.synth.wp2), L.ptr(self.frm.emb)
-        d.dir_mat, d.w_avg, d.psi = L.ptr(self.dir_mat), L.ptr(self.synth.w_avg), PSI
-        d.gallery, d.n_gallery = L.ptr(self.gallery), self.gallery.shape[0]
-        d.frm_group = self.frm_group
-        d.frm_big = self.frm_big.handle if self.frm_big is not None else None
-        d.emb_big = L.ptr(self.frm_big.emb) if self.frm_big is not None else None
-        d.out_slot = L.ptr(self.synth.out_slot)
         if getattr(self, "matcher", None):
             self.lib.cfr_matcher_destroy(self.matcher)
             self.matcher = None
@@ -637,18 +653,34 @@ class Engine:
             L.check(self.lib.cfr_matcher_create(L.ptr(self.gallery), self.gallery.shape[0], self.chunk * self.frm_group,
                                                 self._stream(), C.byref(m)))
             self.matcher = m
-        d.matcher = self.matcher
-        if getattr(self, "sampler", None):
-            self.lib.cfr_sampler_destroy(self.sampler)
-        h = C.c_void_p()
-        L.check(self.lib.cfr_sampler_create(C.byref(d), C.byref(h)))
-        self.sampler = h
+        tail = None
+        for pipe in reversed(self.pipes):              # smallest chunk first: each sampler points at the next smaller one
+            d = L.SamplerDesc()
+            d.synth, d.frm, d.chunk = pipe.synth.handle, pipe.frm.handle, pipe.chunk
+            d.wp2, d.emb = L.ptr(pipe.synth.wp2), L.ptr(pipe.frm.emb)
+            d.dir_mat, d.w_avg, d.psi = L.ptr(self.dir_mat), L.ptr(pipe.synth.w_avg), PSI
+            d.gallery, d.n_gallery = L.ptr(self.gallery), self.gallery.shape[0]
+            d.frm_group = pipe.frm_group
+            d.frm_big = pipe.frm_big.handle if pipe.frm_big is not None else None
+            d.emb_big = L.ptr(pipe.frm_big.emb) if pipe.frm_big is not None else None
+            d.out_slot = L.ptr(pipe.synth.out_slot)
+            d.matcher = self.matcher
+            d.tail = tail
+            if pipe.sampler:
+                self.lib.cfr_sampler_destroy(pipe.sampler)
+            h = C.c_void_p()
+            L.check(self.lib.cfr_sampler_create(C.byref(d), C.byref(h)))
+            pipe.sampler = h
+            tail = h
+        self.sampler = self.pipes[0].sampler
 
     def __del__(self):
         try:
-            if getattr(self, "sampler", None):
-                self.lib.cfr_sampler_destroy(self.sampler)
-                self.sampler = None
+            for pipe in getattr(self, "pipes", []):
+                if pipe.sampler:
+                    self.lib.cfr_sampler_destroy(pipe.sampler)
+                    pipe.sampler = None
+            self.sampler = None
             if getattr(self, "matcher", None):
                 self.lib.cfr_matcher_destroy(self.matcher)
                 self.matcher = None

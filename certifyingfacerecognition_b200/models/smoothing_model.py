@@ -52,7 +52,7 @@ class WrappedModel(nn.Module):
                  generator_state: Optional[Dict[str, torch.Tensor]] = None,
                  frm_state: Optional[Dict[str, torch.Tensor]] = None,
                  latents: Optional[torch.Tensor] = None, orig_embs: Optional[torch.Tensor] = None,
-                 chunk: int = 32, frm_group: int = 1) -> None:
+                 chunk: int = 32, frm_group: int = 1, tail_chunks="auto") -> None:
         super().__init__()
         if face_recog not in ("insightface", "facenet", "facenet-vggface2"):
             raise ValueError(f"face_recog='{face_recog}' is not one of the reference's FRS_METHODS (gen_utils.py:31-35)")
@@ -87,6 +87,7 @@ class WrappedModel(nn.Module):
             embs = None
         placeholder = embs if embs is not None else torch.zeros(1, EMB_SIZE)
         self.engine = Engine(generator_state, frm_state, self.dir_mat, placeholder, chunk=chunk, frm_group=frm_group,
+                             tail_chunks=tuple(c for c in (64, 32, 16) if c < chunk) if tail_chunks == "auto" else tail_chunks,
                              device=self.device,
                              frm=face_recog)
         if embs is None:

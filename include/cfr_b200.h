@@ -136,6 +136,10 @@ CFR_API int cfr_program_add_blur_act_stats_f32(cfr_program* p, const float* raw,
                                        int64_t* sq, int mode);
 CFR_API int cfr_program_add_affine_f32(cfr_program* p, const float* y, const float* A, const float* B, int n, int hw, int c,
                                void* x_f16, int split);
+/* out[n][c] = bias[c] + sum_p in[n][p][c], fixed order: the reduction of a split-K GEMM recorded as a multi-phase conv
+ * (the ArcFace FC 25088 -> 512, iresnet.py:153, runs as 4 K-slices so that it fills more than 8 SMs) */
+CFR_API int cfr_program_add_sum_partials(cfr_program* p, const float* in, const float* bias, int n, int parts, int c,
+                                 float* out);
 /* facenet_pytorch.InceptionResnetV1 glue (main_attack.py:126-129; no source under /root/reference: parity unpinned):
  * MaxPool2d(3, stride 2) NHWC fp16 -> channel slice [c_off, c_off + c) of a wider NHWC buffer (torch.cat of the Mixed
  * blocks); AdaptiveAvgPool2d(1); F.normalize(p=2, dim=1) on fp32 rows. */
@@ -202,6 +206,10 @@ typedef struct cfr_sampler_desc {
   const float* emb_big;   /* [K*chunk,512] */
   int32_t* out_slot;      /* device int read by the synthesis program's torgb_resize op */
   cfr_matcher* matcher;   /* optional: tensor-core match (max_b >= frm_group*chunk) instead of the exact SIMT kernel */
+  cfr_sampler* tail;      /* optional: a sampler recorded for a SMALLER chunk (it may have a tail of its own: a chain in
+                             descending chunk size).  A program run always costs a whole chunk, so the remainder of a call
+                             (num % chunk samples) goes to the smallest sampler of the chain that still holds it -- what
+                             keeps 13-sample selection passes (N0 = 100 split over 8 ranks) from costing 125 samples */
 } cfr_sampler_desc;
 CFR_API int cfr_sampler_create(const cfr_sampler_desc* d, cfr_sampler** out);
 CFR_API void cfr_sampler_destroy(cfr_sampler* s);

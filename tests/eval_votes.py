@@ -44,6 +44,8 @@ def main():
         eng = Engine(g_sd, f_sd, dirs, gallery, chunk=args.chunk, frm_group=2 if args.chunk >= 100 else 1,
                      hp_layers=None if hp < 0 else hp)
         for tag in ("iso", "aniso"):
+            if not os.path.isfile(os.path.join(GOLDEN, f"votes_{tag}.npz")):
+                continue
             v = np.load(os.path.join(GOLDEN, f"votes_{tag}.npz"))
             noise = torch.from_numpy(v["noise"])
             n, n0 = noise.shape[0], int(v["n0"])

@@ -44,12 +44,12 @@ def test_conv_desc_layout_matches_header(tmp_path):
     src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "cfr_b200.h"\n'
                    'int main(void) { printf("%zu %zu %zu %zu %zu %zu\\n", sizeof(cfr_conv_desc), '
                    'offsetof(cfr_conv_desc, out), offsetof(cfr_conv_desc, stat_sum), offsetof(cfr_conv_desc, kSplit), '
-                   'sizeof(cfr_sampler_desc), offsetof(cfr_sampler_desc, matcher)); return 0; }\n')
+                   'sizeof(cfr_sampler_desc), offsetof(cfr_sampler_desc, tail)); return 0; }\n')
     exe = tmp_path / "layout"
     subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
     got = [int(v) for v in subprocess.check_output([str(exe)]).split()]
     assert got == [ctypes.sizeof(ConvDesc), ConvDesc.out.offset, ConvDesc.stat_sum.offset, ConvDesc.kSplit.offset,
-                   ctypes.sizeof(SamplerDesc), SamplerDesc.matcher.offset]
+                   ctypes.sizeof(SamplerDesc), SamplerDesc.tail.offset]
 
 
 def test_no_cpu_fallback():

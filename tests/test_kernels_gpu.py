@@ -181,6 +181,20 @@ def test_fc_as_conv(E):
     _sync()
     ref = x @ w.t() + bias
     assert (out - ref).abs().max().item() < 2e-3
+    # split-K form used by ArcFaceProgram: 4 K-slices as conv phases + a fixed-order sum of the partials
+    P, kp = 4, k // 4
+    wsplit = w.reshape(cout, P, kp).permute(1, 0, 2).reshape(P * cout, kp).half().contiguous()
+    partial = torch.full((n * P * cout,), float("nan"), device="cuda")
+    out2 = torch.zeros(n, cout, device="cuda")
+    p2 = E.Program()
+    p2.conv(inp=x.half().contiguous(), n=n, hin=1, win=P, cin=kp, w=wsplit, cout=cout, hout=1, wout=1, tile=(1, 1, 128),
+            out=partial, out_hwc=(1, P, cout), taps=[[(0, q)] for q in range(P)], ooff=[(0, q) for q in range(P)],
+            w_rows_per_phase=cout)
+    E.L.check(p2.lib.cfr_program_add_sum_partials(p2.handle, E.L.ptr(partial), E.L.ptr(bias), n, P, cout, E.L.ptr(out2)))
+    p2.run()
+    _sync()
+    assert (out2 - ref).abs().max().item() < 2e-3
+    assert (out2 - out).abs().max().item() < 1e-4          # same products, another summation order
 
 
 @pytest.mark.parametrize("n,c,res", [(2, 32, 64), (1, 64, 128), (2, 128, 40), (1, 256, 16), (1, 512, 8), (1, 32, 256)])
@@ -624,3 +638,142 @@ def test_layer0_split_equals_plain_layer0(E):
     assert torch.equal(v[:, :, 0], plain.view(n, 16, 512)) and torch.equal(v[:, :, 0], v[:, :, 2])
     ref = xhat0.view(1, 16, 512).double() * (styles[:, :512].double().view(n, 1, 512) + 1) + styles[:, 512:].double().view(n, 1, 512)
     assert ((v[:, :, 0].double() + v[:, :, 1].double() - ref).abs().max() / ref.abs().max()).item() < 1e-6
+
+
+# ---- stand-ins for compute-sanitizer (closed on this GPU pool, profiles/sanitizer_r02.md) ---------------------------
+class _Guarded:
+    """Tensors carved out of larger allocations whose guard bands (1 KiB before and after) hold a sentinel."""
+    GUARD = 1024
+
+    def __init__(self):
+        self.blocks = []
+
+    def make(self, numel, dtype, fill=0):
+        es = torch.empty((), dtype=dtype).element_size()
+        g = self.GUARD // es
+        base = torch.empty(numel + 2 * g, dtype=dtype, device="cuda")
+        raw = base.view(torch.uint8)
+        raw.fill_(0xA5)
+        view = base[g:g + numel]
+        view.fill_(fill)
+        self.blocks.append((base, g, numel))
+        return view
+
+    def check(self):
+        for base, g, numel in self.blocks:
+            raw = base.view(torch.uint8)
+            es = base.element_size()
+            assert bool((raw[:g * es] == 0xA5).all()) and bool((raw[(g + numel) * es:] == 0xA5).all()), \
+                f"guard band of a {base.dtype} buffer of {numel} elements was written"
+
+
+def test_kernels_do_not_write_outside_their_buffers(E, monkeypatch):
+    """Every output / statistics / per-sample weight buffer sits between sentinel guard bands; after the launches (full grid
+    and 3-CTA grid: ring wraps, dummy tiles, partial tiles at image borders) the bands must be untouched."""
+    L = E.L
+    for ctas in (None, "3"):
+        if ctas:
+            monkeypatch.setenv("CFR_MAX_CTAS", ctas)
+        G = _Guarded()
+        g = torch.Generator().manual_seed(17)
+        prog = E.Program()
+        # (1) igemm: odd tile count (paired-tile path with a dummy tile), fused stats, partial tiles (res 20 on 16x8 boxes)
+        n, cin, cout, res = 3, 64, 64, 20
+        x = torch.randn(n, cin, res, res, generator=g).cuda()
+        w = torch.randn(cout, cin, 3, 3, generator=g) / math.sqrt(cin * 9)
+        out = G.make(n * res * res * cout, torch.float16)
+        ssum, ssq = G.make(n * cout, torch.int64), G.make(n * cout, torch.int64)
+        prog.conv(inp=_nhwc16(x), n=n, hin=res, win=res, cin=cin, w=E.pack_conv_weight(w).cuda().half(), cout=cout,
+                  hout=res, wout=res, tile=(16, 8, 1), out=out, out_hwc=(res, res, cout), taps=[E.TAPS3],
+                  stat_sum=ssum, stat_sq=ssq)
+        # (2) split-precision 4-phase up-conv, fp32 output, then the fp32 blur / affine chain
+        lo, ci2, co2 = 6, 64, 64
+        x2 = torch.randn(n, ci2, lo, lo, generator=g).cuda()
+        wp, taps = E.pack_upconv_phases(torch.randn(co2, ci2, 3, 3, generator=g) / math.sqrt(ci2 * 9))
+        raw = G.make(n * 4 * lo * lo * co2, torch.float32)
+        y = G.make(n * 4 * lo * lo * co2, torch.float32)
+        xs = G.make(n * 4 * lo * lo * 3 * co2, torch.float16)
+        s2, q2 = G.make(n * co2, torch.int64), G.make(n * co2, torch.int64)
+        A, B = G.make(n * co2, torch.float32, 1.0), G.make(n * co2, torch.float32)
+        noise = torch.randn(4 * lo * lo, generator=g).cuda()
+        nw, bias = torch.randn(co2, generator=g).cuda(), torch.randn(co2, generator=g).cuda()
+        styles = torch.randn(n, 2 * co2, generator=g).cuda()
+        prog.conv(inp=_split3_nhwc(x2), n=n, hin=lo, win=lo, cin=3 * ci2, w=E.split3_weight(wp, 4, ci2).cuda(), cout=co2,
+                  hout=lo, wout=lo, tile=E.tile_for(lo), out=raw, out_hwc=(2 * lo, 2 * lo, co2), taps=taps, oscale=2,
+                  ooff=[(0, 0), (0, 1), (1, 0), (1, 1)], w_rows_per_phase=co2, k_split=3)
+        L.check(prog.lib.cfr_program_add_blur_act_stats_f32(prog.handle, L.ptr(raw), L.ptr(y), n, 2 * lo, 2 * lo, co2,
+                                                            L.ptr(noise), L.ptr(nw), L.ptr(bias), L.ptr(s2), L.ptr(q2), 0))
+        L.check(prog.lib.cfr_program_add_finalize_stats(prog.handle, L.ptr(s2), L.ptr(q2), L.ptr(styles), 2 * co2, 0, n,
+                                                        co2, 1.0 / (4 * lo * lo), L.ptr(A), L.ptr(B)))
+        L.check(prog.lib.cfr_program_add_affine_f32(prog.handle, L.ptr(y), L.ptr(A), L.ptr(B), n, 4 * lo * lo, co2,
+                                                    L.ptr(xs), 3))
+        # (3) halo conv, folded (per-sample weights written by the fold kernel), odd width, 9 rows
+        h3, w3, c3 = 9, 130, 32
+        y3 = torch.randn(n, c3, h3, w3, generator=g).cuda()
+        out3 = G.make(n * h3 * w3 * c3, torch.float16)
+        s3, q3 = G.make(n * c3, torch.int64), G.make(n * c3, torch.int64)
+        A3 = (torch.rand(n, c3, generator=g) + 0.5).cuda().contiguous()
+        B3 = torch.randn(n, c3, generator=g).cuda().contiguous()
+        nz3 = torch.randn(h3 * w3, generator=g).cuda()
+        nw3, b3 = torch.randn(c3, generator=g).cuda(), torch.randn(c3, generator=g).cuda()
+        prog.conv(inp=_nhwc16(y3), n=n, hin=h3, win=w3, cin=c3, w=E.pack_halo_weight(
+                      torch.randn(c3, c3, 3, 3, generator=g) / math.sqrt(c3 * 9)).cuda().float().contiguous(), cout=c3,
+                  hout=h3, wout=w3, tile=(16, 8, 1), out=out3, out_hwc=(h3, w3, c3), taps=[E.TAPS3], bias=b3, noise=nz3,
+                  noise_w=nw3, act=L.ACT_LRELU, slope=0.2, stat_sum=s3, stat_sq=q3, halo=True, in_affine=(A3, B3),
+                  fold_center_tap=4)
+        # (4) toRGB + resize into a guarded image buffer
+        img = G.make(n * 16 * 16 * 16, torch.float16)
+        x4 = torch.randn(n, 16, 64, 64, generator=g).cuda()
+        A4, B4 = torch.ones(n * 16, device="cuda"), torch.zeros(n * 16, device="cuda")
+        wr, br = torch.randn(3, 16, generator=g).cuda(), torch.randn(3, generator=g).cuda()
+        L.check(prog.lib.cfr_program_add_torgb_resize(prog.handle, L.ptr(_nhwc16(x4)), L.ptr(A4), L.ptr(B4), n, 64, 16,
+                                                      L.ptr(wr), L.ptr(br), 16, 0.5, 0.5, L.ptr(img), None, None))
+        prog.keep += [noise, nw, bias, styles, nz3, nw3, b3, A4, B4, wr, br, x4]
+        prog.run()
+        prog.run()
+        _sync()
+        G.check()
+        assert torch.isfinite(out.float()).all() and torch.isfinite(y).all() and torch.isfinite(out3.float()).all()
+        monkeypatch.delenv("CFR_MAX_CTAS", raising=False)
+
+
+@pytest.mark.parametrize("ctas", [None, "3"])
+def test_conv_kernels_are_run_to_run_deterministic(E, monkeypatch, ctas):
+    """A missing barrier / fence in the TMA -> mbarrier -> tcgen05 -> TMEM -> epilogue pipelines shows up as run-to-run
+    differences: 20 replays of the same igemm (paired tiles, fused statistics) and halo (folded) launches must be
+    bit-identical in outputs and (integer) statistics."""
+    if ctas:
+        monkeypatch.setenv("CFR_MAX_CTAS", ctas)
+    L = E.L
+    g = torch.Generator().manual_seed(23)
+    n, c, res = 5, 64, 24
+    x = torch.randn(n, c, res, res, generator=g).cuda()
+    w = torch.randn(c, c, 3, 3, generator=g) / math.sqrt(c * 9)
+    out = torch.zeros(n * res * res * c, dtype=torch.float16, device="cuda")
+    ssum, ssq = _stats(n, c)
+    h3, w3, c3 = 20, 136, 32
+    y3 = torch.randn(n, c3, h3, w3, generator=g).cuda()
+    out3 = torch.zeros(n * h3 * w3 * c3, dtype=torch.float16, device="cuda")
+    s3, q3 = _stats(n, c3)
+    A3 = (torch.rand(n, c3, generator=g) + 0.5).cuda().contiguous()
+    B3 = torch.randn(n, c3, generator=g).cuda().contiguous()
+    nz3 = torch.randn(h3 * w3, generator=g).cuda()
+    nw3, b3 = torch.randn(c3, generator=g).cuda(), torch.randn(c3, generator=g).cuda()
+    prog = E.Program()
+    prog.memset(ssum), prog.memset(ssq), prog.memset(s3), prog.memset(q3)
+    prog.conv(inp=_nhwc16(x), n=n, hin=res, win=res, cin=c, w=E.pack_conv_weight(w).cuda().half(), cout=c, hout=res,
+              wout=res, tile=(16, 8, 1), out=out, out_hwc=(res, res, c), taps=[E.TAPS3], stat_sum=ssum, stat_sq=ssq)
+    prog.conv(inp=_nhwc16(y3), n=n, hin=h3, win=w3, cin=c3, w=E.pack_halo_weight(
+                  torch.randn(c3, c3, 3, 3, generator=g) / math.sqrt(c3 * 9)).cuda().float().contiguous(), cout=c3,
+              hout=h3, wout=w3, tile=(16, 8, 1), out=out3, out_hwc=(h3, w3, c3), taps=[E.TAPS3], bias=b3, noise=nz3,
+              noise_w=nw3, act=L.ACT_LRELU, slope=0.2, stat_sum=s3, stat_sq=q3, halo=True, in_affine=(A3, B3),
+              fold_center_tap=4)
+    first = None
+    for _ in range(20):
+        prog.run()
+        _sync()
+        snap = [t.clone() for t in (out, ssum, ssq, out3, s3, q3)]
+        if first is None:
+            first = snap
+        else:
+            assert all(torch.equal(a, b) for a, b in zip(first, snap))

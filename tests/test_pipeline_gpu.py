@@ -261,3 +261,26 @@ def test_full_size_certification_step_properties(setup, golden, models):
     torch.cuda.synchronize()
     agree = (ex8["pred"] == ex["pred"]).float().mean().item()
     assert agree >= 0.995, agree
+
+
+def test_tail_samplers_take_the_remainder(setup):
+    """A program run always costs a whole chunk; with ``tail_chunks`` the remainder of a call runs on the smallest
+    recorded chunk that holds it.  Same samples (Philox counter = global sample index), same votes; embeddings agree to
+    the fp16 pipeline's own noise level (a different chunk size means different tile shapes, i.e. another rounding
+    realisation of the same arithmetic)."""
+    from certifyingfacerecognition_b200.engine import Engine
+    eng8, g_sd, f_sd, dirs, gallery, z = setup
+    eng = Engine(g_sd, f_sd, dirs, gallery, chunk=16, tail_chunks=(8, 4))
+    assert [p.chunk for p in eng.pipes] == [16, 8, 4]
+    x, sigma = torch.zeros(1, 5), torch.tensor([2.0 * SIGMA])
+    for num in (23, 3, 16, 21, 37):              # 16+7 -> 8 | 3 -> 4 | exact | 16+5 -> 8 | 32+5 -> 8
+        l0 = eng.lib.cfr_launch_count()
+        c, ex = eng.sample_votes(z, x, sigma, num, seed=13, sample_offset=5, want_pred=True, want_emb=True, want_noise=True)
+        launches = eng.lib.cfr_launch_count() - l0
+        c8, ex8 = eng8.sample_votes(z, x, sigma, num, seed=13, sample_offset=5, want_pred=True, want_emb=True,
+                                    want_noise=True)
+        torch.cuda.synchronize()
+        assert torch.equal(ex["noise"], ex8["noise"])
+        assert F.cosine_similarity(ex["emb"], ex8["emb"]).min().item() > 0.9999
+        assert torch.equal(ex["pred"], ex8["pred"]) and torch.equal(c, c8) and int(c.sum()) == num
+        assert launches > 0
