@@ -92,6 +92,7 @@ SIGNATURES = {
     "cfr_sampler_create": (_I, [C.POINTER(SamplerDesc), C.POINTER(_P)]),
     "cfr_sampler_destroy": (None, [_P]),
     "cfr_sample_votes": (_I, [_P, _P, _P, _P, _I, _P, _I64, _U64, _U64, _P, _P, _P, _P, _P]),
+    "cfr_sample_votes_multi": (_I, [_P, _I, _P, _P, _P, _I, _P, _U64, _P, _P, _P]),
     "cfr_sample_votes_host": (_I, [_P, _P, _P, _P, _I, _I64, _U64, _U64, _P, _P]),
     "cfr_launch_count": (_U64, []),
     "cfr_profile_enable": (_I, [_I]),

@@ -503,6 +503,60 @@ CFR_API int cfr_sample_votes(cfr_sampler* s, const float* z, const float* x, con
   return 0;
 }
 
+CFR_API int cfr_sample_votes_multi(cfr_sampler* s, int n_ids, const float* z, const float* x, const float* sigma,
+                           int sigma_len, const int64_t* num_host, uint64_t seed, const uint64_t* sample_offset_host,
+                           int64_t* counts, cfr_stream_t stream) {
+  if (sigma_len != 1 && sigma_len != 5) { set_error("sigma_len must be 1 or 5"); return 2; }
+  if (n_ids < 0) { set_error("sample_votes_multi: n_ids < 0"); return 2; }
+  int64_t total = 0;
+  for (int g = 0; g < n_ids; ++g) {
+    if (num_host[g] < 0) { set_error("sample_votes_multi: negative sample count"); return 2; }
+    total += num_host[g];
+  }
+  int g = 0;                 // current identity and how many of its samples are done
+  int64_t g_done = 0;
+  int64_t left = total;
+  while (left > 0) {
+    // the sampler whose chunk this run uses: the main one while a whole chunk is left, else the smallest that fits
+    cfr_sampler* cur = s;
+    if (left < s->d.chunk)
+      for (cfr_sampler* t = s->d.tail; t != nullptr; t = t->d.tail)
+        if (t->d.chunk >= left && t->d.chunk < cur->d.chunk) cur = t;
+    const cfr_sampler_desc& d = cur->d;
+    const int cap = d.chunk;
+    struct Piece { int id, slot, b; };
+    Piece pieces[512];
+    int np = 0, slot = 0;
+    int r = 0;
+    if (d.out_slot != nullptr && (r = launch_set_int(d.out_slot, 0, S(stream))) != 0) return r;
+    while (slot < cap && g < n_ids) {
+      const int64_t rem = num_host[g] - g_done;
+      if (rem == 0) { ++g; g_done = 0; continue; }
+      const int b = static_cast<int>(rem < cap - slot ? rem : cap - slot);
+      r = launch_noise_project(z + static_cast<size_t>(g) * 512, x + static_cast<size_t>(g) * 5, sigma, sigma_len, nullptr,
+                               d.dir_mat, d.w_avg, d.psi, seed, sample_offset_host[g] + g_done, b, nullptr,
+                               d.wp2 + static_cast<size_t>(slot) * 2 * 512, S(stream));
+      if (r) return r;
+      if (np == 512) { set_error("sample_votes_multi: more than 512 identities in one chunk"); return 2; }
+      pieces[np++] = Piece{g, slot, b};
+      slot += b;
+      g_done += b;
+    }
+    if ((r = cfr_program_run(d.synth, stream)) != 0) return r;
+    if ((r = cfr_program_run(d.frm, stream)) != 0) return r;
+    for (int i = 0; i < np; ++i) {
+      const float* emb = d.emb + static_cast<size_t>(pieces[i].slot) * 512;
+      int64_t* cnt = counts + static_cast<size_t>(pieces[i].id) * d.n_gallery;
+      if (d.matcher != nullptr) r = cfr_matcher_run(d.matcher, emb, pieces[i].b, nullptr, cnt, stream);
+      else r = launch_match_vote(emb, pieces[i].b, d.gallery, d.n_gallery, cur->keys, nullptr,
+                                 reinterpret_cast<long long*>(cnt), S(stream));
+      if (r) return r;
+    }
+    left -= slot;
+  }
+  return 0;
+}
+
 CFR_API int cfr_sample_votes_host(cfr_sampler* s, const float* z_host, const float* x_host, const float* sigma_host,
                           int sigma_len, int64_t num, uint64_t seed, uint64_t sample_offset, int64_t* counts_host,
                           cfr_stream_t stream) {

@@ -720,6 +720,28 @@ class Engine:
         pred = shard.match_vote(ex["emb"], counts, want_pred=want_pred)
         return counts, pred
 
+    def sample_votes_multi(self, z: Tensor, x: Tensor, sigma: Tensor, nums, seed: int = 0, sample_offsets=None,
+                           counts: Optional[Tensor] = None) -> Tensor:
+        """Several identities in one call (cfr_sample_votes_multi): identity g draws nums[g] samples around (z[g], x[g])
+        at Philox offsets sample_offsets[g]..; consecutive identities share program runs.  Returns counts [G, N] int64."""
+        z = _f32(z.reshape(-1, 512), self.device)
+        g = z.shape[0]
+        x = _f32(x.reshape(-1, N_DIRS), self.device)
+        if x.shape[0] == 1 and g > 1:
+            x = x.expand(g, N_DIRS).contiguous()
+        sigma = _f32(sigma.reshape(-1), self.device)
+        nums = [int(v) for v in nums]
+        offs = [int(v) for v in (sample_offsets if sample_offsets is not None else [0] * g)]
+        if x.shape[0] != g or len(nums) != g or len(offs) != g or sigma.numel() not in (1, N_DIRS):
+            raise ValueError("sample_votes_multi: z [G,512], x [G,5] (or [1,5]), nums / sample_offsets of length G")
+        if counts is None:
+            counts = torch.zeros(g, self.num_classes, dtype=torch.int64, device=self.device)
+        num_arr = (C.c_int64 * g)(*nums)
+        off_arr = (C.c_uint64 * g)(*offs)
+        L.check(self.lib.cfr_sample_votes_multi(self.sampler, g, L.ptr(z), L.ptr(x), L.ptr(sigma), sigma.numel(), num_arr,
+                                                seed, off_arr, L.ptr(counts), self._stream()))
+        return counts
+
     def sample_votes(self, z: Tensor, x: Tensor, sigma: Tensor, num: int, seed: int = 0, sample_offset: int = 0,
                      noise: Optional[Tensor] = None, counts: Optional[Tensor] = None, want_pred: bool = False,
                      want_emb: bool = False, want_noise: bool = False):

@@ -132,3 +132,7 @@ class WrappedModel(nn.Module):
         instead of the Philox stream."""
         counts, _ = self.engine.sample_votes(z, x, sigma, num, seed=seed, sample_offset=sample_offset, noise=noise)
         return counts
+
+    def sample_votes_multi(self, z, x, sigma, nums, seed: int = 0, sample_offsets=None) -> torch.Tensor:
+        """``sample_votes`` for several identities at once (z [G,512]); their samples share program runs.  -> [G, N] int64."""
+        return self.engine.sample_votes_multi(z, x, sigma, nums, seed=seed, sample_offsets=sample_offsets)

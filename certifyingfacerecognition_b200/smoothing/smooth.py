@@ -74,6 +74,57 @@ class Smooth:
             return Smooth.ABSTAIN
         return top2[0]
 
+    def certify_many(self, z: torch.Tensor, x: torch.Tensor, labels: torch.Tensor, n0: int, n: int, alpha: float,
+                     batch_size: int = 0, device: torch.device = torch.device("cuda:0")):
+        """``certify`` (smooth.py:39-77) for G identities at once: z [G,512], x [1,5] or [G,5], labels [G] -> list of G
+        (prediction | ABSTAIN, gap) tuples, each what ``certify`` returns for that identity.
+
+        Not in the reference (its loop, certify.py:120-141, is strictly one identity at a time).  With the MC samples of
+        an identity split over R ranks a selection pass is only N0 / R samples per rank (12-13 for N0 = 100, R = 8) while a
+        program run costs a whole chunk; here the selection passes of all G identities share program runs and ONE
+        all-reduce of the [G, num_classes] counts, then the estimation passes of the identities whose selection matched
+        their label do the same.  Identity g owns the Philox block [D + g (n0 + n), D + (g + 1)(n0 + n)): its draws do not
+        depend on which other identities take the early exit."""
+        if not self._fused() or self._replay is not None:
+            z = z.reshape(-1, 1, z.shape[-1])
+            xs = x.reshape(-1, 1, x.shape[-1])
+            return [self.certify(z[g], xs[g if xs.shape[0] > 1 else 0], labels.reshape(-1)[g:g + 1], n0, n, alpha,
+                                 batch_size, device=device) for g in range(z.shape[0])]
+        self.base_classifier.eval()
+        z = z.reshape(-1, z.shape[-1])
+        G = z.shape[0]
+        labels = [int(v) for v in labels.reshape(-1).tolist()]
+        rank, world = 0, 1
+        if self.process_group is not None:
+            import torch.distributed as dist
+            rank, world = dist.get_rank(self.process_group), dist.get_world_size(self.process_group)
+        base = [self._draws + g * (n0 + n) for g in range(G)]
+        self._draws += G * (n0 + n)
+        xs = x.reshape(-1, x.shape[-1])
+
+        def run(ids, num, extra):
+            lo, hi = (num * rank) // world, (num * (rank + 1)) // world
+            counts = self.base_classifier.sample_votes_multi(z[ids], xs if xs.shape[0] == 1 else xs[ids], self.sigma,
+                                                             [hi - lo] * len(ids), seed=self.seed,
+                                                             sample_offsets=[base[g] + extra + lo for g in ids])
+            if world > 1:
+                import torch.distributed as dist
+                dist.all_reduce(counts, op=dist.ReduceOp.SUM, group=self.process_group)
+            self.samples_classified += (hi - lo) * len(ids)
+            return counts.cpu().numpy()
+
+        with torch.no_grad():
+            c0 = run(list(range(G)), n0, 0)
+            chat = c0.argmax(axis=1)
+            out = [(int(chat[g]), 0.0) for g in range(G)]
+            alive = [g for g in range(G) if int(chat[g]) == labels[g]]
+            if alive:
+                c1 = run(alive, n, n0)
+                for row, g in zip(c1, alive):
+                    pABar = self._lower_confidence_bound(int(row[chat[g]]), n, alpha)
+                    out[g] = (Smooth.ABSTAIN, 0.0) if pABar < 0.5 else (int(chat[g]), self.certificate.compute_gap(pABar))
+        return out
+
     def inject_noise(self, noise: Optional[torch.Tensor]) -> None:
         """Parity runs on identical noise tensors: the next ``_sample_noise`` calls consume the rows of ``noise``
         ([total, 5], already scaled by sigma -- what ``certificate.sample_noise`` returned in the run being replayed)

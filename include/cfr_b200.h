@@ -218,6 +218,15 @@ CFR_API void cfr_sampler_destroy(cfr_sampler* s);
 CFR_API int cfr_sample_votes(cfr_sampler* s, const float* z, const float* x, const float* sigma, int sigma_len,
                      const float* noise_in, int64_t num, uint64_t seed, uint64_t sample_offset, int64_t* counts,
                      int32_t* pred_out, float* emb_out, float* noise_out, cfr_stream_t stream);
+/* Several identities in ONE call: identity g draws num_host[g] samples around (z[g], x[g]) with Philox offsets
+ * sample_offset_host[g] .. and tallies them into counts[g][n_gallery] (ACCUMULATED).  The samples of consecutive
+ * identities share program runs (a chunk is filled across identity boundaries), so the 12-13 samples per rank of a
+ * selection pass split over 8 ranks (N0 = 100, smooth.py:64) cost 1/8 of a chunk instead of a whole one when 8 identities
+ * are certified together (Smooth.certify_many).  z: [n_ids,512], x: [n_ids,5] device; num_host / sample_offset_host: HOST
+ * arrays [n_ids].  Per-sample results are those of cfr_sample_votes with the same (seed, offset). */
+CFR_API int cfr_sample_votes_multi(cfr_sampler* s, int n_ids, const float* z, const float* x, const float* sigma,
+                           int sigma_len, const int64_t* num_host, uint64_t seed, const uint64_t* sample_offset_host,
+                           int64_t* counts, cfr_stream_t stream);
 /* Same with HOST buffers (z[512], x[5], sigma[sigma_len] in, counts_host[n_gallery] out, overwritten):
  * H2D copies, the MC loop, the D2H copy of the counts and a stream sync all inside the call. */
 CFR_API int cfr_sample_votes_host(cfr_sampler* s, const float* z_host, const float* x_host, const float* sigma_host,

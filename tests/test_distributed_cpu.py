@@ -27,6 +27,19 @@ class FakeFused:
         return torch.bincount(votes, minlength=self.n).to(torch.int64)
 
 
+class FakeFusedMulti(FakeFused):
+    """adds the several-identities entry: identity g's votes depend on its latent's first coordinate"""
+
+    def sample_votes_multi(self, z, x, sigma, nums, seed=0, sample_offsets=None):
+        rows = []
+        for g, (num, off) in enumerate(zip(nums, sample_offsets)):
+            idx = torch.arange(off, off + num, dtype=torch.int64)
+            votes = (idx * 2654435761 + seed * 40503 + int(z[g, 0]) * 7) % 5 % self.n
+            votes = torch.where(idx % 3 == 0, votes, torch.full_like(votes, int(z[g, 0]) % self.n))   # a clear winner
+            rows.append(torch.bincount(votes, minlength=self.n).to(torch.int64))
+        return torch.stack(rows)
+
+
 def _free_port():
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
@@ -57,6 +70,31 @@ def test_sample_sharding_two_ranks_equals_single_rank(tmp_path):
     assert np.array_equal(got["c2"], c2) and c2.sum() == 1000
     pred = ref.certify(None, None, torch.tensor([int(c2.argmax())]), 101, 1000, 0.001, 10, device=torch.device("cpu"))
     assert np.allclose(got["pred"], np.array(pred, dtype=np.float64))
+
+
+def _many_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    s = Smooth(FakeFusedMulti(), 16, torch.tensor([0.1]), L2Certificate(1, device="cpu"), seed=5,
+               process_group=dist.group.WORLD)
+    z = torch.arange(6, dtype=torch.float32).view(6, 1).repeat(1, 512)
+    res = s.certify_many(z, torch.zeros(1, 5), torch.tensor([0, 1, 9, 3, 4, 5]), 101, 1000, 0.001)
+    if rank == 0:
+        np.save(out, np.array(res, dtype=np.float64))
+    dist.destroy_process_group()
+
+
+def test_certify_many_two_ranks_equals_single_rank(tmp_path):
+    """Group certification: selection passes of all identities in one sharded call + one all-reduce, estimation passes
+    only for the identities whose selection matched the label (identity 2 is mislabelled: early exit).  (The single-rank
+    run happens in a forked worker as well: torch compute in the pytest process would leave threads behind that the next
+    test's fork() cannot survive.)"""
+    out2, out1 = str(tmp_path / "many2.npy"), str(tmp_path / "many1.npy")
+    mp.start_processes(_many_worker, args=(2, _free_port(), out2), nprocs=2, join=True, start_method="fork")
+    mp.start_processes(_many_worker, args=(1, _free_port(), out1), nprocs=1, join=True, start_method="fork")
+    got, want = np.load(out2), np.load(out1)
+    assert np.allclose(got, want)
+    assert tuple(want[2]) == (2.0, 0.0) and all(w[0] == g and w[1] > 0 for g, w in enumerate(want) if g != 2)
 
 
 # ---- partition C: gallery rows sharded over ranks, 8-byte keys all-gathered and merged -------------------------------

@@ -41,8 +41,10 @@ z, x = lat[0:1].to(dev), torch.zeros(1, 5, device=dev)
 c1 = sm._sample_noise(z, x, 37, 16, device=dev)
 c2 = sm._sample_noise(z, x, 101, 16, device=dev)
 res = sm.certify(z, x, torch.tensor([int(c2.argmax())], device=dev), 24, 88, 0.001, 16, device=dev)
+# several identities certified together: selection / estimation passes share program runs and all-reduces
+many = sm.certify_many(lat.to(dev), x, torch.tensor([0, 1, 3, 3], device=dev), 21, 45, 0.001)
 if rank == 0:
-    np.savez(os.environ["CFR_OUT"], c1=c1, c2=c2, res=np.array(res, dtype=np.float64))
+    np.savez(os.environ["CFR_OUT"], c1=c1, c2=c2, res=np.array(res, dtype=np.float64), many=np.array(many, dtype=np.float64))
 if world > 1:
     dist.destroy_process_group()
 '''
@@ -69,6 +71,7 @@ def test_sample_sharding_over_nccl_ranks_is_exact(tmp_path):
         pytest.skip("needs at least 2 GPUs (run with gpurun --gpus 2)")
     ref = _run(1, str(tmp_path / "w1.npz"), tmp_path)
     assert ref["c1"].sum() == 37 and ref["c2"].sum() == 101 and len(np.nonzero(ref["c2"])[0]) >= 2
+    assert ref["many"].shape == (4, 2) and ref["many"][2, 1] == 0.0          # identity 2 labelled 3: early exit
     for world in (2, 4, 8):
         if world > n:
             break
@@ -76,3 +79,4 @@ def test_sample_sharding_over_nccl_ranks_is_exact(tmp_path):
         assert np.array_equal(got["c1"], ref["c1"]), world
         assert np.array_equal(got["c2"], ref["c2"]), world
         assert np.array_equal(got["res"], ref["res"]), world
+        assert np.array_equal(got["many"], ref["many"]), world

@@ -110,3 +110,40 @@ def test_mapping_network_against_reference():
     assert torch.allclose(z, torch.from_numpy(g["z"]), atol=1e-5)
     w = M.mapping(torch.from_numpy(g["z"]), sd)
     assert torch.allclose(w, torch.from_numpy(g["w"]), atol=2e-5, rtol=1e-5)
+
+
+def test_port_reproduces_the_reference_vote_fixtures(golden, models):
+    """tests/golden/votes_*.npz (2 x 1100 samples classified by the unmodified reference, oracle/make_golden_votes.py):
+    the recorded certify results follow from the recorded predictions through the restated statistics, and the port's
+    embeddings / predictions on a few of the recorded noise rows equal the reference's."""
+    from oracle import fixtures
+    g_sd, f_sd = models
+    dirs = torch.from_numpy(golden["dirs"])
+    z = torch.from_numpy(golden["w_all"][0:1])
+    rows = torch.from_numpy(np.load(os.path.join(ROOT, "tests", "golden", "votes_gallery.npz"))["rows"])
+    assert rows.shape == (72, 512) and np.allclose(rows[:8].numpy(), golden["gallery"])
+    gallery = fixtures.synthetic_gallery(rows, 5000)
+    for tag in ("iso", "aniso"):
+        v = np.load(os.path.join(ROOT, "tests", "golden", f"votes_{tag}.npz"))
+        n0, alpha = int(v["n0"]), float(v["alpha"])
+        pred = v["pred"]
+        assert pred.shape[0] == n0 + 1000 and v["noise"].shape == (n0 + 1000, 5)
+        # Smooth.certify (smooth.py:39-77) restated on the recorded predictions
+        c0 = np.bincount(pred[:n0], minlength=5000)
+        c1 = np.bincount(pred[n0:], minlength=5000)
+        assert int(c0.argmax()) == 0 == int(v["cert_pred"])
+        assert np.array_equal(c1.astype(np.float64), v["counts"])
+        pbar = M.lower_confidence_bound(int(c1[0]), 1000, alpha)
+        assert pbar >= 0.5 and M.compute_gap(pbar) == pytest.approx(float(v["cert_gap"]), rel=1e-9)
+        assert float(v["cert_radius"]) == pytest.approx(float(v["sigma"].min()) * float(v["cert_gap"]), rel=1e-6)
+        assert len(np.nonzero(c1)[0]) >= 10                        # mixed votes
+        # the port on three recorded noise rows (the smallest-margin sample among them)
+        idx = [0, 1, int(np.argmin(v["d2"] - v["d1"]))]
+        p = torch.from_numpy(v["noise"][idx]).view(-1, 1, 1, 5)
+        emb = M.lat2embs(M.perturb_latent(z, p, dirs), g_sd, f_sd, literal=True)
+        ref = torch.from_numpy(v["emb"][idx])
+        assert F.cosine_similarity(emb, ref).min().item() > 0.999999
+        assert (emb - ref).norm(dim=1).max().item() < 2e-3
+        d = torch.cdist(emb, gallery, compute_mode="donot_use_mm_for_euclid_dist")
+        assert np.allclose(d.topk(2, dim=1, largest=False).values[:, 0].numpy(), v["d1"][idx], atol=2e-3)
+        assert np.array_equal(M.compute_probs(emb[:2], gallery).argmax(1).numpy(), pred[idx[:2]])

@@ -284,3 +284,42 @@ def test_tail_samplers_take_the_remainder(setup):
         assert F.cosine_similarity(ex["emb"], ex8["emb"]).min().item() > 0.9999
         assert torch.equal(ex["pred"], ex8["pred"]) and torch.equal(c, c8) and int(c.sum()) == num
         assert launches > 0
+
+
+def test_several_identities_share_program_runs(setup, golden, models):
+    """cfr_sample_votes_multi / Smooth.certify_many: the samples of consecutive identities fill chunks across identity
+    boundaries; per identity the tallies equal those of separate cfr_sample_votes calls with the same Philox offsets, and
+    certify_many returns what certify returns for each identity on its Philox block."""
+    from certifyingfacerecognition_b200.models.smoothing_model import WrappedModel
+    from certifyingfacerecognition_b200.smoothing import L2Certificate, Smooth
+    eng8, g_sd, f_sd, dirs, gallery, z0 = setup
+    dev = torch.device("cuda")
+    lat = torch.from_numpy(golden["w_all"][:5])
+    model = WrappedModel(dirs.to(dev), "insightface", generator_state=g_sd, frm_state=f_sd, latents=lat,
+                         orig_embs=gallery, chunk=16, tail_chunks=(8, 4))
+    eng = model.engine
+    sigma = torch.tensor([2.0 * SIGMA])
+    nums, offs = [5, 0, 13, 16, 3], [100, 7, 0, 50, 999]
+    l0 = eng.lib.cfr_launch_count()
+    multi = eng.sample_votes_multi(lat, torch.zeros(1, 5), sigma, nums, seed=9, sample_offsets=offs)
+    l_multi = eng.lib.cfr_launch_count() - l0
+    l0 = eng.lib.cfr_launch_count()
+    for g in range(5):
+        c, _ = eng.sample_votes(lat[g:g + 1], torch.zeros(1, 5), sigma, nums[g], seed=9, sample_offset=offs[g])
+        assert torch.equal(c, multi[g]), g
+    l_single = eng.lib.cfr_launch_count() - l0
+    torch.cuda.synchronize()
+    assert multi.sum(dim=1).tolist() == nums
+    assert l_multi < l_single                       # 37 samples = 2 x 16 + one 8-chunk instead of 4 separate program runs
+    # certify_many == certify on the same Philox blocks (identity 3 is mislabelled: early exit after the selection pass)
+    n0, n, alpha = 6, 21, 0.001
+    labels = torch.tensor([0, 1, 2, 7, 4], device=dev)
+    sm = Smooth(model, N_GALLERY, sigma.to(dev), L2Certificate(1, device=dev), seed=31)
+    many = sm.certify_many(lat.to(dev), torch.zeros(1, 5, device=dev), labels, n0, n, alpha)
+    assert sm._draws == 5 * (n0 + n)
+    for g in range(5):
+        one = Smooth(model, N_GALLERY, sigma.to(dev), L2Certificate(1, device=dev), seed=31)
+        one._draws = g * (n0 + n)
+        want = one.certify(lat[g:g + 1].to(dev), torch.zeros(1, 5, device=dev), labels[g:g + 1], n0, n, alpha, 16, device=dev)
+        assert many[g][0] == want[0] and many[g][1] == pytest.approx(want[1], rel=1e-12, abs=0), (g, many[g], want)
+    assert many[3][1] == 0.0
