@@ -34,6 +34,7 @@ class ConvDesc(C.Structure):
         ("resid", C.c_void_p), ("residC", C.c_int32),
         ("stat_sum", C.c_void_p), ("stat_sq", C.c_void_p),
         ("kSplit", C.c_int32),
+        ("keepMap", C.c_void_p), ("keepDim", C.c_int32),
     ]
 
 
@@ -75,6 +76,7 @@ SIGNATURES = {
     "cfr_program_add_finalize_stats": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _F, _P, _P]),
     "cfr_program_add_affine": (_I, [_P, _P, _P, _P, _I, _I, _I, _P]),
     "cfr_program_add_torgb_resize": (_I, [_P, _P, _P, _P, _I, _I, _I, _P, _P, _I, _F, _F, _P, _P, _P]),
+    "cfr_program_add_torgb_resize_sparse": (_I, [_P, _P, _P, _P, _I, _I, _I, _P, _P, _I, _F, _F, _P, _P, _P, _P, _I]),
     "cfr_program_add_sum_partials": (_I, [_P, _P, _P, _I, _I, _I, _P]),
     "cfr_program_add_maxpool3s2": (_I, [_P, _P, _I, _I, _I, _I, _P, _I, _I]),
     "cfr_program_add_avgpool": (_I, [_P, _P, _I, _I, _I, _P]),

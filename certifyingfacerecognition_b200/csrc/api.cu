@@ -214,8 +214,8 @@ static int add_folded(cfr_program* p, const cfr_conv_desc* d, const float* base_
            "upblur_corr");
   }
   char lab[160];
-  snprintf(lab, sizeof(lab), "halo-%s %dx%d taps%dx%d Cin%d Cout%d n%d TH%d", composite ? "upblur" : "folded", d->Hout,
-           d->Wout, d->numPhases, d->ntaps, d->Cin, d->Cout, d->N, raw->p.TH);
+  snprintf(lab, sizeof(lab), "halo-%s %dx%d taps%dx%d Cin%d Cout%d n%d TH%d%s", composite ? "upblur" : "folded", d->Hout,
+           d->Wout, d->numPhases, d->ntaps, d->Cin, d->Cout, d->N, raw->p.TH, d->keepMap ? " sparse-store" : "");
   p->add([raw](cudaStream_t st) { return halo_launch(*raw, st); }, lab, raw->flops);
   return 0;
 }
@@ -334,6 +334,18 @@ CFR_API int cfr_program_add_torgb_resize(cfr_program* p, const void* x_f16, cons
     return launch_torgb_resize(static_cast<const __half*>(x_f16), A, B, n, hin, c, w_rgb, b_rgb, rout, mean, stdv,
                                static_cast<__half*>(out_f16_nhwc16), out_planar_f32, out_slot, st);
   }, "torgb_resize");
+  return 0;
+}
+
+CFR_API int cfr_program_add_torgb_resize_sparse(cfr_program* p, const void* x_f16, const float* A, const float* B, int n,
+                                        int hin, int c, const float* w_rgb, const float* b_rgb, int rout, float mean,
+                                        float stdv, void* out_f16_nhwc16, float* out_planar_f32, const int32_t* out_slot,
+                                        const int32_t* keep_map, int keep_dim) {
+  if (keep_map == nullptr || keep_dim <= 0) { set_error("torgb_resize_sparse: keep_map / keep_dim missing"); return 2; }
+  p->add([=](cudaStream_t st) {
+    return launch_torgb_resize(static_cast<const __half*>(x_f16), A, B, n, hin, c, w_rgb, b_rgb, rout, mean, stdv,
+                               static_cast<__half*>(out_f16_nhwc16), out_planar_f32, out_slot, st, keep_map, keep_dim);
+  }, "torgb_resize_sparse");
   return 0;
 }
 

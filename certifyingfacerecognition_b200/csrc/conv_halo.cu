@@ -65,6 +65,11 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
   constexpr int G = COUT == 64 ? 2 : 4;          // tiles per accumulator group (one mbarrier handshake per group)
   constexpr int AS = 512 / (G * COUT);           // accumulator groups resident in TMEM (8 / 4 / 4)
   constexpr int asLog = AS == 8 ? 3 : 2;
+#ifndef CFR_HALO_KB16
+#define CFR_HALO_KB16 2
+#endif
+  constexpr int KB = (COUT == 16 && !COMP) ? CFR_HALO_KB16 : 1;   // tiles / 16-column chunks per tile whose TMEM loads the epilogue
+  constexpr int CBN = 1;                               // keeps in flight together (registers: KB * CBN * 16)
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int NS = p.haloStages;                                   // 2 or 3 halo band buffers
@@ -615,13 +620,23 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
     const int et = threadIdx.x;            // 0..255
     const bool do_stats = p.stat_sum != nullptr;
     const bool has_noise = !FOLD && p.noise != nullptr, has_bias = !FOLD && p.bias != nullptr;
-    const bool lrelu = p.act == CFR_ACT_LRELU;
-    const float slope = p.slope;
+    // LeakyReLU as max(v, v * slope) (slope < 1); no activation: slope 1.  All epilogue math is plain scalar fp32: the
+    // packed .f32x2 forms saved a third of the arithmetic but cost ~50 register moves per 16-channel chunk (the pairs
+    // never coalesced with the tcgen05.ld destinations / the FMNMX results), 160 SASS per chunk instead of ~85
+    float slope = p.act == CFR_ACT_LRELU ? p.slope : 1.0f;
+    asm volatile("" : "+f"(slope));                // (pinned: not re-derived from the parameters per tile)
     const int ci0 = SPLIT ? grp * NCH_T : 0;       // first chunk this thread handles
-    f2_t racc[NCH_T * 8], racc2[NCH_T * 8];          // per-thread channel sums, packed fp32 pairs (FADD2 / FFMA2)
+    float racc[NCH_T * 16], racc2[NCH_T * 16];      // per-thread channel sums
 #pragma unroll
-    for (int i = 0; i < NCH_T * 8; ++i) { racc[i] = f2_pack(0.f, 0.f); racc2[i] = racc[i]; }
-    const f2_t slope2 = f2_pack(p.slope, p.slope);
+    for (int i = 0; i < NCH_T * 16; ++i) { racc[i] = 0.f; racc2[i] = 0.f; }
+    // element offset of phase ph inside the output row pair (compile-time phase index after unrolling)
+    int ph_off[4];
+#pragma unroll
+    for (int ph = 0; ph < 4; ++ph)
+      ph_off[ph] = ph < p.numPhases ? (static_cast<int>(p.ooff_y[ph]) * p.outW + p.ooff_x[ph]) * COUT : 0;
+    int row_el = p.oscale * p.outW * COUT;         // elements between consecutive band rows in the output
+    int kd_el = p.keepDim * COUT;                  // ... between consecutive rows of the compact (sparse-store) output
+    asm volatile("" : "+r"(row_el), "+r"(kd_el));
     float hnw[HOIST ? COUT : 1], hbs[HOIST ? COUT : 1];
     if constexpr (HOIST) {
 #pragma unroll
@@ -658,8 +673,20 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
       const bool colok = gx < p.W;
       const int ngroups = p.numPhases == 4 ? bd.rows : (bd.rows + G - 1) / G;
       // output pixel of (row r, phase ph): band origin + r * row pitch + per-phase offset (all precomputed)
-      const size_t pix_band = (static_cast<size_t>(bd.n) * p.outH + bd.y0 * p.oscale) * p.outW + gx * p.oscale;
-      const size_t pix_row = static_cast<size_t>(p.oscale) * p.outW;
+      __half* const out_band =
+          p.out + ((static_cast<size_t>(bd.n) * p.outH + bd.y0 * p.oscale) * p.outW + gx * p.oscale) * COUT;
+      constexpr bool SPARSE_OK = COUT == 16 && FOLD && !COMP;      // (only instantiated where it is used: registers)
+      const bool sparse = SPARSE_OK && p.keep_map != nullptr;
+      // sparse store: compact column of this lane's pixel; the compact rows of the band's (<= 16) output rows are fetched
+      // once per band, one per lane, and broadcast by shuffle (a dependent global load per row stalls the warp)
+      const int kcol = (sparse && colok) ? __ldg(p.keep_map + gx) : -1;
+      const int krow_l = (sparse && static_cast<int>(lane) < bd.rows) ? __ldg(p.keep_map + bd.y0 + lane) : -1;
+      __half* const sp_base = p.out + (static_cast<size_t>(bd.n) * p.keepDim * p.keepDim + (kcol < 0 ? 0 : kcol)) * COUT;
+      // (pinned: under register pressure ptxas otherwise re-derives these 64-bit bases from the kernel parameters for
+      //  every tile, ~40 instructions per 16-channel chunk)
+      unsigned long long out_band_u = reinterpret_cast<unsigned long long>(out_band);
+      unsigned long long sp_base_u = reinterpret_cast<unsigned long long>(sp_base);
+      asm volatile("" : "+l"(out_band_u), "+l"(sp_base_u));
       // this warp group's accumulator groups of the band: index gbase + j with (gbase + j) % kEpiGroups == grp
       for (int j = SPLIT ? 0 : ((grp - static_cast<int>(gbase)) & (kEpiGroups - 1)); j < ngroups;
            j += SPLIT ? 1 : kEpiGroups) {
@@ -667,25 +694,55 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
         const uint32_t slot = gc & (AS - 1);
         mbar_wait(&tfull[slot], (gc >> asLog) & 1);
         tc_fence_after();
+        // TMEM -> registers: the loads of KB tiles (of CBN chunks each) are issued back to back and waited for once (with
+        // a wait per 16-column load the two epilogue warps of an SM sub-partition spend most of their time on that latency)
 #pragma unroll
-        for (int k = 0; k < G; ++k) {
+        for (int kb = 0; kb < G; kb += KB) {
+#pragma unroll
+        for (int cb = 0; cb < NCH_T; cb += CBN) {
+        uint32_t vraw[KB][CBN][16];
+        if (!(p.dbg & 1)) {
+#pragma unroll
+          for (int kk = 0; kk < KB; ++kk)
+#pragma unroll
+            for (int cc = 0; cc < CBN; ++cc)
+              tmem_ld16_issue(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + (slot * G + kb + kk) * ACC_COLS +
+                              (ci0 + cb + cc) * 16, vraw[kk][cc]);
+          tmem_ld_wait();
+#pragma unroll
+          for (int kk = 0; kk < KB; ++kk)
+#pragma unroll
+            for (int cc = 0; cc < CBN; ++cc) tmem_ld16_fence(vraw[kk][cc]);
+        }
+#pragma unroll
+        for (int kk = 0; kk < KB; ++kk) {
+          const int k = kb + kk;
           const int r = p.numPhases == 4 ? j : j * G + k;
           const int ph = p.numPhases == 4 ? k : 0;
           if (r >= bd.rows) break;
-          const size_t pix = pix_band + r * pix_row + static_cast<size_t>(p.ooff_y[ph]) * p.outW + p.ooff_x[ph];
+          __half* optr;
+          bool st_ok = colok;
+          if (sparse) {                      // warp-uniform row lookup: most rows skip the pack + store altogether
+            const int krow = __shfl_sync(0xffffffffu, krow_l, r);
+            st_ok = krow >= 0 && kcol >= 0;
+            optr = reinterpret_cast<__half*>(sp_base_u) + (krow < 0 ? 0 : krow) * kd_el;
+          } else {
+            optr = reinterpret_cast<__half*>(out_band_u) + r * row_el + (p.numPhases == 4 ? ph_off[k] : ph_off[0]);
+          }
           float nz = 0.f;
           if (has_noise && colok) {
             const int oy = (bd.y0 + r) * p.oscale + p.ooff_y[ph];
             const int ox = gx * p.oscale + p.ooff_x[ph];
             nz = __ldg(&p.noise[oy * p.outW + ox]);
           }
-          const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + (slot * G + k) * ACC_COLS;
           if (!(p.dbg & 1))
 #pragma unroll
-          for (int cl = 0; cl < NCH_T; ++cl) {
+          for (int cc = 0; cc < CBN; ++cc) {
+            const int cl = cb + cc;
             const int ci = ci0 + cl;
             float v[16];
-            tmem_ld16(t_row + ci * 16, v);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(vraw[kk][cc][i]);
             const int ch0 = ci * 16;
             if constexpr (HOIST) {
 #pragma unroll
@@ -711,37 +768,31 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
               const bool left = gx == 0 && (ph & 1) == 0, right = gx == p.W - 1 && (ph & 1) == 1;
               if (left || right) {
                 const int oy = (bd.y0 + r) * p.oscale + p.ooff_y[ph];
-                const float* cp = p.corr + ((static_cast<size_t>(bd.n) * 2 + (right ? 1 : 0)) * p.outH + oy) * COUT + ch0;
+                const float4* cp = reinterpret_cast<const float4*>(
+                    p.corr + ((static_cast<size_t>(bd.n) * 2 + (right ? 1 : 0)) * p.outH + oy) * COUT + ch0);
 #pragma unroll
-                for (int i = 0; i < 16; ++i) v[i] += cp[i];
+                for (int i = 0; i < 4; ++i) {
+                  const float4 c4 = __ldg(cp + i);
+                  v[4 * i] += c4.x; v[4 * i + 1] += c4.y; v[4 * i + 2] += c4.z; v[4 * i + 3] += c4.w;
+                }
               }
             }
-            f2_t vp[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) vp[i] = f2_pack(v[2 * i], v[2 * i + 1]);
-            if (lrelu) {
-#pragma unroll
-              for (int i = 0; i < 8; ++i) {                                          // max(v, v * slope), slope < 1
-                const float2 sv = f2_unpack(f2_mul(vp[i], slope2));
-                v[2 * i] = fmaxf(v[2 * i], sv.x);
-                v[2 * i + 1] = fmaxf(v[2 * i + 1], sv.y);
-                vp[i] = f2_pack(v[2 * i], v[2 * i + 1]);
-              }
-            }
-            if (colok) {
+            for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], v[i] * slope);
+            if (st_ok) {
               uint4 o[2];
               __half2* h2 = reinterpret_cast<__half2*>(o);
 #pragma unroll
               for (int i = 0; i < 8; ++i) h2[i] = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
-              st_global_256(p.out + pix * COUT + ch0, o[0], o[1]);     // 16 channels = one 32-byte sector (halo_build checks alignment)
+              st_global_256(optr + ch0, o[0], o[1]);     // 16 channels = one 32-byte sector (halo_build checks alignment)
             }
             if (do_stats) {
               if constexpr (REG_STATS) {
                 if (colok) {
 #pragma unroll
-                  for (int i = 0; i < 8; ++i) {
-                    racc[cl * 8 + i] = f2_add(racc[cl * 8 + i], vp[i]);
-                    racc2[cl * 8 + i] = f2_fma(vp[i], vp[i], racc2[cl * 8 + i]);
+                  for (int i = 0; i < 16; ++i) {
+                    racc[cl * 16 + i] += v[i];
+                    racc2[cl * 16 + i] = fmaf(v[i], v[i], racc2[cl * 16 + i]);
                   }
                 }
               } else {
@@ -762,6 +813,8 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
             }
           }
         }
+        }
+        }
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&tempty[slot]);
@@ -773,12 +826,11 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
           for (int cl = 0; cl < NCH_T; ++cl) {
             float a[16], a2[16];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const float2 s1 = f2_unpack(racc[cl * 8 + i]), s2 = f2_unpack(racc2[cl * 8 + i]);
-              a[2 * i] = s1.x; a[2 * i + 1] = s1.y;
-              a2[2 * i] = s2.x; a2[2 * i + 1] = s2.y;
-              racc[cl * 8 + i] = f2_pack(0.f, 0.f);
-              racc2[cl * 8 + i] = racc[cl * 8 + i];
+            for (int i = 0; i < 16; ++i) {
+              a[i] = racc[cl * 16 + i];
+              a2[i] = racc2[cl * 16 + i];
+              racc[cl * 16 + i] = 0.f;
+              racc2[cl * 16 + i] = 0.f;
             }
             const float ssum = warp_reduce16h(a, lane);
             const float ssq = warp_reduce16h(a2, lane);
@@ -1152,6 +1204,16 @@ int halo_build(const cfr_conv_desc& s, const float* inA, const float* inB, const
   p.bias = s.bias; p.noise = s.noise; p.noise_w = s.noise_w; p.act = s.act; p.slope = s.slope;
   p.stat_sum = reinterpret_cast<unsigned long long*>(s.stat_sum); p.stat_sq = reinterpret_cast<unsigned long long*>(s.stat_sq);
   if (s.outC != s.Cout) { set_error("halo conv: outC must equal Cout"); return 2; }
+  if (s.keepMap != nullptr) {
+    if (s.numPhases != 1 || s.oscale != 1 || s.outH != s.outW || s.outH != s.Hout || s.keepDim <= 0 || s.keepDim > s.outH ||
+        s.Cout != 16 || !p.fold || composite) {
+      set_error("halo conv: sparse store needs the folded Cout = 16 variant, one phase, oscale 1, a square output and "
+                "0 < keepDim <= outH");
+      return 2;
+    }
+    p.keep_map = s.keepMap;
+    p.keepDim = s.keepDim;
+  }
   p.in = static_cast<const __half*>(s.in);
   {
     const int totalRows = p.fold ? s.N * p.wRows : p.wRows;
@@ -1195,7 +1257,9 @@ int halo_build(const cfr_conv_desc& s, const float* inA, const float* inB, const
   op->smemBytes = p.haloStages * (p.haloBytes + p.auxBytes) + p.wBytes + p.wAuxBytes + ctrl + 1024;
   op->flops = 2.0 * s.N * s.Hout * s.Wout * s.numPhases * s.ntaps * static_cast<double>(s.Cin) * s.Cout;
   // algorithmic HBM bytes: every input element read once, every output element written once (fp16)
-  op->bytes = 2.0 * s.N * (static_cast<double>(s.Hin) * s.Win * s.Cin + static_cast<double>(s.outH) * s.outW * s.Cout);
+  // (sparse store: only the kept keepDim^2 pixels are written)
+  const double outPix = s.keepMap != nullptr ? static_cast<double>(s.keepDim) * s.keepDim : static_cast<double>(s.outH) * s.outW;
+  op->bytes = 2.0 * s.N * (static_cast<double>(s.Hin) * s.Win * s.Cin + outPix * s.Cout);
   return 0;
 }
 

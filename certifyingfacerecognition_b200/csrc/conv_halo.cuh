@@ -85,6 +85,9 @@ struct HaloParams {
   const void* noise_tab;            // FOLD: packed per-pixel aux-row head (see launch_pack_noise), filled by cp.async
   int act; float slope;
   unsigned long long* stat_sum; unsigned long long* stat_sq;  // [N, Cout] Q43.20 fixed point, or null
+  // sparse store (one phase, oscale 1, square output): only pixels whose row AND column have keep_map[.] >= 0 are written,
+  // into a compact [N][keepDim][keepDim][Cout] buffer; statistics still cover every pixel (cfr_conv_desc.keepMap)
+  const int* keep_map; int keepDim;
 };
 
 struct HaloOp {

@@ -776,7 +776,10 @@ int launch_affine_f32(const float* y, const float* A, const float* B, int n, int
 __global__ void k_torgb_resize(const __half* __restrict__ x, const float* __restrict__ A, const float* __restrict__ B,
                                int n, int hin, int c, const float* __restrict__ w_rgb, const float* __restrict__ b_rgb,
                                int rout, float mean, float stdv, __half* __restrict__ out,
-                               float* __restrict__ out_planar, const int* __restrict__ slot) {
+                               float* __restrict__ out_planar, const int* __restrict__ slot,
+                               const int* __restrict__ keep_map, int keep_dim) {
+  // keep_map != nullptr: x is the compact [n][keep_dim][keep_dim][c] output of a sparse-store conv; source row / column
+  // y lives at index keep_map[y] (the conv kept exactly the rows / columns this resize reads; engine.resize_keep_map)
   // one sample per blockIdx.y: toRGB weights with the sample's IN/AdaIN folded in live in shared memory
   //   rgb_k = sum_c w[k][c] * (A_c x_c + B_c) + b_k = sum_c (w[k][c] A_c) x_c + (b_k + sum_c w[k][c] B_c)
   extern __shared__ float trs[];                 // [3][c] fused weights, then [3] fused bias
@@ -814,7 +817,9 @@ __global__ void k_torgb_resize(const __half* __restrict__ x, const float* __rest
 #pragma unroll
     for (int bq = 0; bq < 2; ++bq) {
       float r = 0.f, g = 0.f, bl = 0.f;
-      const __half* src = x + ((static_cast<size_t>(s) * hin + ys[a]) * hin + xs[bq]) * c;
+      const __half* src = keep_map != nullptr
+          ? x + ((static_cast<size_t>(s) * keep_dim + __ldg(keep_map + ys[a])) * keep_dim + __ldg(keep_map + xs[bq])) * c
+          : x + ((static_cast<size_t>(s) * hin + ys[a]) * hin + xs[bq]) * c;
       for (int cc = 0; cc < c; cc += 8) {
         float v[8];
         load8(src + cc, v);
@@ -852,9 +857,9 @@ __global__ void k_torgb_resize(const __half* __restrict__ x, const float* __rest
 }
 int launch_torgb_resize(const __half* x, const float* A, const float* B, int n, int hin, int c, const float* w_rgb,
                         const float* b_rgb, int rout, float mean, float stdv, __half* out, float* out_planar,
-                        const int* slot, cudaStream_t st) {
+                        const int* slot, cudaStream_t st, const int* keep_map, int keep_dim) {
   if (c > 2048) { set_error("torgb_resize: c=%d too large", c); return 2; }
-  k_torgb_resize<<<dim3((rout * rout + 127) / 128, n), 128, (3 * c + 3) * sizeof(float), st>>>(x, A, B, n, hin, c, w_rgb, b_rgb, rout, mean, stdv, out, out_planar, slot);
+  k_torgb_resize<<<dim3((rout * rout + 127) / 128, n), 128, (3 * c + 3) * sizeof(float), st>>>(x, A, B, n, hin, c, w_rgb, b_rgb, rout, mean, stdv, out, out_planar, slot, keep_map, keep_dim);
   CFR_LAUNCH_CHECK("torgb_resize");
   return 0;
 }

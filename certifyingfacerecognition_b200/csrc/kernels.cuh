@@ -48,7 +48,7 @@ int launch_affine_f32(const float* y, const float* A, const float* B, int n, int
 // x [n,H,W,C] fp16 (optionally still un-normalised: per-(n,c) A,B applied on load) -> img [n,R,R,16] fp16 (ch 0..2)
 int launch_torgb_resize(const __half* x, const float* A, const float* B, int n, int hin, int c, const float* w_rgb,
                         const float* b_rgb, int rout, float mean, float stdv, __half* out, float* out_planar,
-                        const int* slot, cudaStream_t st);
+                        const int* slot, cudaStream_t st, const int* keep_map = nullptr, int keep_dim = 0);
 int launch_set_int(int* p, int v, cudaStream_t st);
 // tensor-core gallery match helpers (see kernels.cu)
 int launch_split_hilo(const float* src, int rows, int rows_pad, int mode, __half* dst, float* bias, cudaStream_t st);

@@ -187,6 +187,23 @@ def composite_upconv_weights(weq: Tensor) -> Tuple[Tensor, Tensor]:
     return base.float().contiguous(), corr.float().contiguous()
 
 
+def resize_keep_map(hin: int, rout: int) -> Tuple[Tensor, int]:
+    """Rows (== columns) of an hin x hin image that F.interpolate(bilinear, align_corners=False) to rout x rout reads
+    (gen_utils.py:77-85; same arithmetic as k_torgb_resize): -> (int32 [hin] map: compact index or -1, count)."""
+    import numpy as np
+    scale = np.float32(hin) / np.float32(rout)
+    keep = set()
+    for o in range(rout):
+        sy = max(np.float32(scale * np.float32(o + 0.5)) - np.float32(0.5), np.float32(0.0))
+        for y0 in {int(sy), int(max(sy - 1e-3, 0.0)), int(sy + 1e-3)}:     # (fused vs separate multiply-add: keep both
+            keep.add(min(y0, hin - 1))                                      #  candidates if sy sits on an integer)
+            keep.add(min(y0 + 1, hin - 1))
+    rows = sorted(keep)
+    m = torch.full((hin,), -1, dtype=torch.int32)
+    m[torch.tensor(rows)] = torch.arange(len(rows), dtype=torch.int32)
+    return m, len(rows)
+
+
 class Program:
     """Owns a cfr_program handle plus every tensor its launches reference."""
 
@@ -233,7 +250,8 @@ class Program:
              slope: float = 0.2, alpha: Optional[Tensor] = None, resid: Optional[Tensor] = None, resid_c: int = 0,
              stat_sum: Optional[Tensor] = None, stat_sq: Optional[Tensor] = None, halo: bool = False,
              in_affine: Optional[Tuple[Tensor, Tensor]] = None, fold_center_tap: Optional[int] = None,
-             composite_corr: Optional[Tensor] = None, k_split: int = 0) -> None:
+             composite_corr: Optional[Tensor] = None, k_split: int = 0,
+             keep_map: Optional[Tensor] = None, keep_dim: int = 0) -> None:
         """Record one convolution.  ``halo``: use the halo-resident kernel (Cin, Cout <= 64); ``in_affine`` (A, B):
         apply x = y*A + B on load; ``fold_center_tap`` (halo, Cin <= 32): fold A into per-sample weights and carry
         B / bias / noise on the auxiliary band -- ``w`` is then the fp32 base weight [phases*taps*Cout, Cin]."""
@@ -262,6 +280,10 @@ class Program:
         d.resid, d.residC = L.ptr(resid), resid_c
         d.stat_sum, d.stat_sq = L.ptr(stat_sum), L.ptr(stat_sq)
         d.kSplit = k_split
+        d.keepMap, d.keepDim = L.ptr(keep_map), keep_dim
+        if keep_map is not None:
+            assert halo, "sparse store is a halo-kernel feature"
+            self.keep.append(keep_map)
         assert k_split in (0, 1) or not halo, "split-precision convs run on the implicit-GEMM kernel"
         for t in (inp, w, out, bias, cbias, noise, noise_w, alpha, resid, stat_sum, stat_sq):
             if t is not None:
@@ -304,7 +326,7 @@ class SynthesisProgram(Program):
     def __init__(self, g_sd: Dict[str, Tensor], chunk: int, out_res: int = 112, device="cuda",
                  keep_planar: bool = False, mean: float = 0.5, std: float = 0.5, halo: bool = True,
                  fold_small: bool = True, groups: int = 1, blur_on_tensor_cores: bool = True,
-                 fused_upblur: bool = True, nhwc_out: bool = True, hp_layers: int = 0):
+                 fused_upblur: bool = True, nhwc_out: bool = True, hp_layers: int = 0, sparse_last: bool = True):
         super().__init__()
         dev = torch.device(device)
         self.chunk, self.out_res = chunk, out_res
@@ -322,6 +344,12 @@ class SynthesisProgram(Program):
         if not 0 <= hp_layers <= 11:
             raise ValueError("hp_layers must be in 0..11 (layer 12 feeds the halo kernel, which reads fp16)")
         self.hp_layers = hp_layers
+        # Sparse store of the last layer: bilinear-resizing 1024^2 to 112^2 (160^2) reads only 224 (320) distinct rows and
+        # columns, so layer 17 writes just those pixels into a compact buffer (its statistics still cover every pixel)
+        kmap, kdim = resize_keep_map(1024, out_res)
+        self.sparse_last = bool(sparse_last and halo and fold_small and kdim <= 512)
+        self.keep_map = self.hold(kmap.to(dev)) if self.sparse_last else None
+        self.keep_dim = kdim if self.sparse_last else 0
 
         # ---- inputs / small tensors
         self.wp2 = self.hold(torch.zeros(chunk, 2, 512, device=dev))
@@ -426,7 +454,9 @@ class SynthesisProgram(Program):
                           tile=tile_for(res), out=y, out_hwc=(res, res, cout), taps=[TAPS3], noise=noise,
                           noise_w=noise_w, bias=bias, act=L.ACT_LRELU, slope=0.2,
                           stat_sum=ssum if fused_stats else None, stat_sq=ssq if fused_stats else None,
-                          halo=hk, in_affine=pending, fold_center_tap=4 if fold else None)
+                          halo=hk, in_affine=pending, fold_center_tap=4 if fold else None,
+                          keep_map=self.keep_map if (l == NUM_LAYERS - 1 and fold) else None,
+                          keep_dim=self.keep_dim if (l == NUM_LAYERS - 1 and fold) else 0)
                 if not fused_stats:
                     L.check(lib.cfr_program_add_blur_act_stats(h, L.ptr(y), None, chunk, res, res, cout, None, None,
                                                                None, L.ptr(ssum), L.ptr(ssq), 1))
@@ -484,9 +514,15 @@ class SynthesisProgram(Program):
         self.img = (self.hold(torch.zeros(groups * chunk, out_res, out_res, 16, dtype=torch.float16, device=dev))
                     if nhwc_out else None)
         self.img_planar = self.hold(torch.zeros(groups * chunk, 3, out_res, out_res, device=dev)) if keep_planar else None
-        L.check(lib.cfr_program_add_torgb_resize(h, L.ptr(y), L.ptr(pending[0]), L.ptr(pending[1]), chunk, 1024, 16,
-                                                 L.ptr(w_rgb), L.ptr(b_rgb), out_res, mean, std, L.ptr(self.img),
-                                                 L.ptr(self.img_planar), L.ptr(self.out_slot)))
+        if self.sparse_last:
+            L.check(lib.cfr_program_add_torgb_resize_sparse(h, L.ptr(y), L.ptr(pending[0]), L.ptr(pending[1]), chunk, 1024, 16,
+                                                            L.ptr(w_rgb), L.ptr(b_rgb), out_res, mean, std, L.ptr(self.img),
+                                                            L.ptr(self.img_planar), L.ptr(self.out_slot),
+                                                            L.ptr(self.keep_map), self.keep_dim))
+        else:
+            L.check(lib.cfr_program_add_torgb_resize(h, L.ptr(y), L.ptr(pending[0]), L.ptr(pending[1]), chunk, 1024, 16,
+                                                     L.ptr(w_rgb), L.ptr(b_rgb), out_res, mean, std, L.ptr(self.img),
+                                                     L.ptr(self.img_planar), L.ptr(self.out_slot)))
         self.last_y = y
 
 
@@ -587,10 +623,10 @@ class ArcFaceProgram(Program):
 class _Pipeline:
     """One recorded (synthesis, FRM[, grouped FRM]) program set for a fixed chunk size, plus its C sampler."""
 
-    def __init__(self, g_sd, f_sd, frm_cls, res, chunk, frm_group, device, keep_planar, hp_layers):
+    def __init__(self, g_sd, f_sd, frm_cls, res, chunk, frm_group, device, keep_planar, hp_layers, sparse_last=True):
         self.chunk, self.frm_group = chunk, max(1, int(frm_group))
         self.synth = SynthesisProgram(g_sd, chunk, res, device, keep_planar=keep_planar, groups=self.frm_group,
-                                      hp_layers=hp_layers)
+                                      hp_layers=hp_layers, sparse_last=sparse_last)
         self.frm = frm_cls(f_sd, chunk, self.synth.img, device)
         self.frm_big = frm_cls(f_sd, chunk * self.frm_group, self.synth.img, device) if self.frm_group > 1 else None
         self.sampler = None
@@ -604,9 +640,10 @@ class Engine:
 
     def __init__(self, g_sd, f_sd, dir_mat: Tensor, gallery: Tensor, chunk: int = 32, device="cuda",
                  keep_planar: bool = False, frm_group: int = 1, tc_match: Optional[bool] = None,
-                 frm: str = "insightface", hp_layers: Optional[int] = None, tail_chunks=()):
+                 frm: str = "insightface", hp_layers: Optional[int] = None, tail_chunks=(), sparse_last: bool = True):
         """``tail_chunks``: extra, smaller chunk sizes recorded as their own program sets (descending, all < chunk); the
-        remainder of a ``sample_votes`` call runs on the smallest one that holds it instead of a whole chunk."""
+        remainder of a ``sample_votes`` call runs on the smallest one that holds it instead of a whole chunk.
+        ``sparse_last=False`` keeps the dense 1024^2 output of the last StyleGAN layer (diagnostics only)."""
         if not torch.cuda.is_available():
             raise RuntimeError("certifyingfacerecognition_b200 needs a CUDA device (no CPU fallback)")
         self.lib = L.load()
@@ -630,8 +667,10 @@ class Engine:
                 hp_layers = int(_os.environ["CFR_HP_LAYERS"])       # A/B runs (precision vs throughput)
         self.hp_layers = hp_layers
         tail_chunks = sorted({int(c) for c in tail_chunks if 0 < int(c) < chunk}, reverse=True)
-        self.pipes = [_Pipeline(g_sd, f_sd, frm_cls, res, chunk, self.frm_group, device, keep_planar, hp_layers)]
-        self.pipes += [_Pipeline(g_sd, f_sd, frm_cls, res, c, 1, device, False, hp_layers) for c in tail_chunks]
+        self.pipes = [_Pipeline(g_sd, f_sd, frm_cls, res, chunk, self.frm_group, device, keep_planar, hp_layers,
+                                sparse_last)]
+        self.pipes += [_Pipeline(g_sd, f_sd, frm_cls, res, c, 1, device, False, hp_layers, sparse_last)
+                       for c in tail_chunks]
         self.synth, self.frm, self.frm_big = self.pipes[0].synth, self.pipes[0].frm, self.pipes[0].frm_big
         if tuple(dir_mat.shape) != (N_DIRS, 512):
             # the noise kernel (k_noise_project) and the C ABI fix the attribute space at the reference's five

@@ -64,6 +64,13 @@ typedef struct cfr_conv_desc {
                                                  so the fp32 accumulator holds x.w to ~2^-21 (the x_lo.w_lo term is
                                                  dropped); algorithmic FLOPs are counted on Cin/3.  Used for the early
                                                  StyleGAN layers, whose rounding errors dominate the embedding error. */
+  const int32_t* keepMap;                     /* halo convs, one phase, square output (may be NULL): sparse store.
+                                                 keepMap[y] (device, outH entries) = index of output row / column y in a
+                                                 COMPACT [N][keepDim][keepDim][Cout] output, or -1: pixel (y, x) is stored
+                                                 only when both keepMap[y] and keepMap[x] are >= 0.  The statistics still
+                                                 cover every pixel.  Used for the last StyleGAN layer, of whose 1024^2
+                                                 pixels the bilinear resize (gen_utils.py:77-85) reads 224^2. */
+  int32_t keepDim;
 } cfr_conv_desc;
 
 CFR_API const char* cfr_last_error(void);
@@ -151,6 +158,11 @@ CFR_API int cfr_program_add_torgb_resize(cfr_program* p, const void* x_f16, cons
                                  int c, const float* w_rgb, const float* b_rgb, int rout, float mean, float stdv,
                                  void* out_f16_nhwc16, float* out_planar_f32, const int32_t* out_slot);
 /* out_slot (device int, may be NULL): the n images are written at group *out_slot of a [groups*n, R, R, 16] buffer */
+/* the same reading a COMPACT source [n][keep_dim][keep_dim][c] written by a sparse-store conv (cfr_conv_desc.keepMap) */
+CFR_API int cfr_program_add_torgb_resize_sparse(cfr_program* p, const void* x_f16, const float* A, const float* B, int n,
+                                        int hin, int c, const float* w_rgb, const float* b_rgb, int rout, float mean,
+                                        float stdv, void* out_f16_nhwc16, float* out_planar_f32, const int32_t* out_slot,
+                                        const int32_t* keep_map, int keep_dim);
 
 /* ---- immediate ops ------------------------------------------------------------------------------------ */
 /* L2Certificate.sample_noise (certificate.py:64-67) + WrappedModel.forward latent perturbation

@@ -50,7 +50,8 @@ def main():
         ref_emb = M.iresnet50(ref_img, f_sd)
 
     for hp in args.hp:
-        eng = Engine(g_sd, f_sd, dirs, torch.zeros(4, 512), chunk=n, keep_planar=True, hp_layers=None if hp < 0 else hp)
+        eng = Engine(g_sd, f_sd, dirs, torch.zeros(4, 512), chunk=n, keep_planar=True, hp_layers=None if hp < 0 else hp,
+                     sparse_last=False)
         say(f"==== hp_layers = {eng.hp_layers}")
         one_engine(eng, n, w, ref_layers, ref_img, ref_emb, f_sd, say)
     if args.out:

@@ -379,6 +379,71 @@ def test_halo_conv_matches_torch(E, n, cin, cout, h, w, affine, fold):
     _check_stats(ssum, ssq, got, ref, runs=2, per_pixel=1e-3 if fold else 0.0)
 
 
+@pytest.mark.parametrize("n,cin,cout,res,rout,ctas", [(2, 16, 16, 256, 28, None), (3, 16, 16, 128, 16, "3"),
+                                                      (1, 32, 16, 256, 40, None)])
+def test_halo_sparse_store_and_compact_resize(E, monkeypatch, n, cin, cout, res, rout, ctas):
+    """Sparse store (cfr_conv_desc.keepMap): only the rows / columns the bilinear resize reads are written, into a compact
+    buffer, bit-identical to the dense kernel's values at those pixels; the statistics are those of the dense run; the
+    resize reading the compact buffer equals the resize reading the dense one (the last StyleGAN layer + toRGB path)."""
+    if ctas:
+        monkeypatch.setenv("CFR_MAX_CTAS", ctas)
+    L = E.L
+    g = torch.Generator().manual_seed(res + rout)
+    yprev = torch.randn(n, cin, res, res, generator=g).cuda().half().float()
+    wt = (torch.randn(cout, cin, 3, 3, generator=g) / math.sqrt(cin * 9)).cuda().half().float()
+    bias, nw = torch.randn(cout, generator=g).cuda(), torch.randn(cout, generator=g).cuda()
+    noise = torch.randn(res, res, generator=g).cuda()
+    A, B = (torch.rand(n, cin, generator=g) + 0.5).cuda(), torch.randn(n, cin, generator=g).cuda()
+    kmap, kdim = E.resize_keep_map(res, rout)
+    assert kdim == 2 * rout and int((kmap >= 0).sum()) == kdim
+    kmap_d = kmap.cuda()
+    wpk = E.pack_halo_weight(wt.cpu()).cuda().float().contiguous()
+    outs, stats = [], []
+    for sparse in (False, True):
+        out = torch.full((n * (kdim * kdim if sparse else res * res) * cout + 64,), float("nan"), dtype=torch.float16,
+                         device="cuda")
+        ssum, ssq = _stats(n, cout)
+        prog = E.Program()
+        prog.conv(inp=_nhwc16(yprev), n=n, hin=res, win=res, cin=cin, w=wpk, cout=cout, hout=res, wout=res, tile=(16, 8, 1),
+                  out=out, out_hwc=(res, res, cout), taps=[E.TAPS3], bias=bias, noise=noise.reshape(-1).contiguous(),
+                  noise_w=nw, act=L.ACT_LRELU, slope=0.2, stat_sum=ssum, stat_sq=ssq, halo=True,
+                  in_affine=(A.contiguous(), B.contiguous()), fold_center_tap=4,
+                  keep_map=kmap_d if sparse else None, keep_dim=kdim if sparse else 0)
+        prog.run()
+        _sync()
+        outs.append(out)
+        stats.append((ssum.clone(), ssq.clone()))
+    dense = outs[0][:n * res * res * cout].view(n, res, res, cout)
+    compact = outs[1][:n * kdim * kdim * cout].view(n, kdim, kdim, cout)
+    assert torch.isnan(outs[1][n * kdim * kdim * cout:]).all()           # nothing written past the compact buffer
+    rows = torch.nonzero(kmap_d >= 0).flatten()
+    assert torch.equal(compact, dense[:, rows][:, :, rows])              # same values, bit for bit
+    assert torch.equal(stats[0][0], stats[1][0]) and torch.equal(stats[0][1], stats[1][1])
+    if cout != 16:
+        return
+    # toRGB + resize from the compact buffer == from the dense buffer
+    lib = L.load()
+    wr, br = torch.randn(3, cout, generator=g).cuda() * 0.3, torch.randn(3, generator=g).cuda() * 0.1
+    A2, B2 = (torch.rand(n, cout, generator=g) + 0.5).cuda(), torch.randn(n, cout, generator=g).cuda() * 0.1
+    res_out = []
+    for sparse in (False, True):
+        planar = torch.zeros(n, 3, rout, rout, device="cuda")
+        img = torch.zeros(n, rout, rout, 16, dtype=torch.float16, device="cuda")
+        prog = E.Program()
+        if sparse:
+            L.check(lib.cfr_program_add_torgb_resize_sparse(prog.handle, L.ptr(outs[1]), L.ptr(A2), L.ptr(B2), n, res, cout,
+                                                            L.ptr(wr.contiguous()), L.ptr(br), rout, 0.5, 0.5, L.ptr(img),
+                                                            L.ptr(planar), None, L.ptr(kmap_d), kdim))
+        else:
+            L.check(lib.cfr_program_add_torgb_resize(prog.handle, L.ptr(outs[0]), L.ptr(A2), L.ptr(B2), n, res, cout,
+                                                     L.ptr(wr.contiguous()), L.ptr(br), rout, 0.5, 0.5, L.ptr(img),
+                                                     L.ptr(planar), None))
+        prog.run()
+        _sync()
+        res_out.append((planar, img))
+    assert torch.equal(res_out[0][0], res_out[1][0]) and torch.equal(res_out[0][1], res_out[1][1])
+
+
 def _check_stats(ssum, ssq, got, ref, runs, per_pixel):
     """Fused per-(n,c) sum / sum of squares.  (1) Against the kernel's OWN fp16 output, tightly: the statistics are taken
     on the fp32 values before the store, so the only difference is the fp16 output rounding (random sign) -- a pixel
