@@ -35,11 +35,14 @@ struct Band {
   int n, y0, x0, rows;
 };
 __device__ __forceinline__ Band decode_band(const HaloParams& p, int b) {
+  // divisions by the (runtime) band counts as multiply-high with precomputed reciprocals (exact: halo_build checks
+  // b < 2^21, divisors <= 2^10); every role decodes every band, and two integer divisions cost ~60 instructions each time
   Band r;
-  const int bx = b % p.bandsX;
-  const int t = b / p.bandsX;
-  const int by = t % p.bandsY;
-  r.n = t / p.bandsY;
+  // (a divisor of 1 has no 32-bit reciprocal: magic == 0 marks it)
+  const int t = p.magicX ? static_cast<int>(__umulhi(static_cast<uint32_t>(b), p.magicX)) : b;
+  const int bx = b - t * p.bandsX;
+  r.n = p.magicY ? static_cast<int>(__umulhi(static_cast<uint32_t>(t), p.magicY)) : t;
+  const int by = t - r.n * p.bandsY;
   r.x0 = bx * 128;
   r.y0 = by * p.TH;
   r.rows = min(p.TH, p.H - r.y0);
@@ -657,11 +660,35 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
       atomicAdd(&p.stat_sum[img * COUT + et], stat_fx(a));
       atomicAdd(&p.stat_sq[img * COUT + et], stat_fx(b));
     };
+    // per-thread channel sums -> this warp's shared-memory slice: once per IMAGE (not per band: the two 16-value
+    // transpose-reduces were a third of the epilogue's instructions on the 16-channel layers); fp32 partials of at
+    // most a few thousand O(1) values per thread, fixed order => still bit-reproducible
+    auto regs_to_smem = [&]() {
+#pragma unroll
+      for (int cl = 0; cl < NCH_T; ++cl) {
+        float a[16], a2[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          a[i] = racc[cl * 16 + i];
+          a2[i] = racc2[cl * 16 + i];
+          racc[cl * 16 + i] = 0.f;
+          racc2[cl * 16 + i] = 0.f;
+        }
+        const float ssum = warp_reduce16h(a, lane);
+        const float ssq = warp_reduce16h(a2, lane);
+        if ((lane & 1) == 0) {
+          const int ch = (ci0 + cl) * 16 + reduce16_channel_h(lane);
+          s_sum[warp * COUT + ch] += ssum;
+          s_sq[warp * COUT + ch] += ssq;
+        }
+      }
+    };
     uint32_t gbase = 0;                     // accumulator-group counter at the start of the band
     int cur_n = -1;
     for (int b = band0; b < band1; ++b) {
       const Band bd = decode_band(p, b);
       if (do_stats && cur_n >= 0 && bd.n != cur_n) {
+        regs_to_smem();
         named_bar_sync(1, kEpiWarps * 32);
         if (et < COUT) {
           flush_channel(cur_n);
@@ -820,30 +847,9 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
         if (lane == 0) mbar_arrive(&tempty[slot]);
       }
       gbase += ngroups;
-      if constexpr (REG_STATS) {
-        if (do_stats) {                      // once per band: registers -> shared
-#pragma unroll
-          for (int cl = 0; cl < NCH_T; ++cl) {
-            float a[16], a2[16];
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              a[i] = racc[cl * 16 + i];
-              a2[i] = racc2[cl * 16 + i];
-              racc[cl * 16 + i] = 0.f;
-              racc2[cl * 16 + i] = 0.f;
-            }
-            const float ssum = warp_reduce16h(a, lane);
-            const float ssq = warp_reduce16h(a2, lane);
-            if ((lane & 1) == 0) {
-              const int ch = (ci0 + cl) * 16 + reduce16_channel_h(lane);
-              s_sum[warp * COUT + ch] += ssum;
-              s_sq[warp * COUT + ch] += ssq;
-            }
-          }
-        }
-      }
     }
     if (do_stats && cur_n >= 0) {
+      regs_to_smem();
       named_bar_sync(1, kEpiWarps * 32);
       if (et < COUT) {
         flush_channel(cur_n);
@@ -1191,6 +1197,12 @@ int halo_build(const cfr_conv_desc& s, const float* inA, const float* inB, const
   p.haloBytes = halo_bytes(th) - p.auxBytes;
   p.bandsX = (s.Wout + 127) / 128;
   p.bandsY = (s.Hout + th - 1) / th;
+  p.magicX = p.bandsX > 1 ? static_cast<uint32_t>((1ull << 32) / p.bandsX + 1) : 0u;   // decode_band: b / bandsX == umulhi(b, magicX)
+  p.magicY = p.bandsY > 1 ? static_cast<uint32_t>((1ull << 32) / p.bandsY + 1) : 0u;
+  if (static_cast<long long>(s.N) * p.bandsX * p.bandsY >= (1ll << 21) || p.bandsX > 1024 || p.bandsY > 1024) {
+    set_error("halo conv: too many bands for the reciprocal band decode");
+    return 2;
+  }
   p.accStages = 0;   // (fixed per template: 512 / (G * Cout) groups of G accumulators)
   if (s.numPhases != 1 && s.numPhases != 4) { set_error("halo conv: 1 or 4 phases"); return 2; }
   if (s.ntaps != 4 && s.ntaps != 9) { set_error("halo conv: 4 or 9 taps per phase"); return 2; }

@@ -69,6 +69,7 @@ struct HaloParams {
   int Cin, Cout;
   int TH;                           // output rows per band
   int bandsX, bandsY;               // per image
+  uint32_t magicX, magicY;          // floor(2^32 / bands) + 1: divisions in decode_band as multiply-high
   int numPhases, ntaps;
   int8_t tap_dy[4][9], tap_dx[4][9];
   int rowBytes;                     // Cin*2 == swizzle width of the halo band and of the weight rows

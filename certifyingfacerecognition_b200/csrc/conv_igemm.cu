@@ -67,6 +67,7 @@ __device__ __forceinline__ int reduce16_channel(uint32_t lane) {
 // channel c of image img: the four epilogue warps' partial sums (fixed order) -> Q43.20 fixed point -> global accumulate
 // (s_sum / s_sq point at the four slices of ONE epilogue group; slices are CoutTotal floats apart)
 __device__ __forceinline__ void flush_stats(const ConvParams& p, float* s_sum, float* s_sq, int img, int c) {
+  // (both column halves of a tile write disjoint channels of the same four lane-quarter slices)
   const int C = p.CoutTotal;
   const float a = (s_sum[c] + s_sum[C + c]) + (s_sum[2 * C + c] + s_sum[3 * C + c]);
   const float b = (s_sq[c] + s_sq[C + c]) + (s_sq[2 * C + c] + s_sq[3 * C + c]);
@@ -128,7 +129,7 @@ conv_igemm_kernel(const __grid_constant__ ConvParams p) {
       }
       for (int i = 0; i < 2; ++i) {
         mbar_init(&tfull_bar[i], 1);
-        mbar_init(&tempty_bar[i], 4 * MT);
+        mbar_init(&tempty_bar[i], 8 * MT);               // every warp of the 2 * MT epilogue groups arrives
       }
       fence_barrier_init();
     }
@@ -252,15 +253,19 @@ conv_igemm_kernel(const __grid_constant__ ConvParams p) {
       }
     }
   } else {
-    // ===================================================================== epilogue (warps 0..3; MT == 2: + warps 6..9)
-    const int sub = warp >= 6 ? 1 : 0;           // which tile of the pair this group drains
-    const int q = warp & 3;                      // TMEM lane quarter this warp may read
+    // ===================================================================== epilogue (warps 0..3 and 6..)
+    const int egrp = warp < 4 ? 0 : (warp - 2) >> 2;             // epilogue group 0 .. 2 * MT - 1
+    const int sub = MT == 2 ? (egrp & 1) : 0;    // which tile of the pair this group drains
+    const int half = MT == 2 ? (egrp >> 1) : egrp;               // which half of the tile's BN columns
+    const int hcols = (p.BN % 32 == 0) ? p.BN / 2 : (half == 0 ? p.BN : 0);   // columns of this half (BN = 16 / 48 / ..: half 0 takes all)
+    const int col_lo = half * (p.BN / 2);
+    const int q = warp & 3;                      // TMEM lane quarter this warp may read (== warp id % 4)
     const int row = q * 32 + lane;               // M row == pixel index inside the tile box
     const int tx = row % p.TW;
     const int ty = (row / p.TW) % p.TH;
     const int tn = row / (p.TW * p.TH);
-    const int et = sub ? threadIdx.x - 192 : threadIdx.x;       // 0..127 inside the group
-    const int gbar = 1 + sub;                    // named barrier of this group
+    const int et = half * 128 + q * 32 + static_cast<int>(lane); // 0..255 among the threads draining this tile
+    const int gbar = 1 + sub;                    // named barrier of this tile's two groups
     s_sum += sub * 4 * p.CoutTotal;              // this group's four slices
     s_sq += sub * 4 * p.CoutTotal;
     int as = 0;
@@ -282,11 +287,11 @@ conv_igemm_kernel(const __grid_constant__ ConvParams p) {
         continue;
       }
       if (do_stats && cur_img >= 0 && t.n0 != cur_img) {
-        named_bar_sync(gbar, 128);
-        for (int c = et; c < p.CoutTotal; c += 128) {
+        named_bar_sync(gbar, 256);
+        for (int c = et; c < p.CoutTotal; c += 256) {
           flush_stats(p, s_sum, s_sq, cur_img, c);
         }
-        named_bar_sync(gbar, 128);
+        named_bar_sync(gbar, 256);
       }
       cur_img = t.n0;
       const int gx = t.x0 + tx, gy = t.y0 + ty, n = t.n0 + tn;
@@ -311,8 +316,8 @@ conv_igemm_kernel(const __grid_constant__ ConvParams p) {
         // -inf start + first column of the tile: a NaN score (fp16 overflow upstream) never wins a comparison, so the
         // pick stays a real row (padded rows carry bias -inf and tile 0 starts at row 0) instead of a padded one
         float best = -INFINITY;
-        int best_j = t.ntile * p.BN;
-        for (int c0 = 0; c0 < p.BN; c0 += 16) {
+        int best_j = t.ntile * p.BN + col_lo;
+        for (int c0 = col_lo; c0 < col_lo + hcols; c0 += 16) {
           float v[16];
           tmem_ld16(t_row + c0, v);
           const int ch0 = t.ntile * p.BN + c0;
@@ -329,14 +334,14 @@ conv_igemm_kernel(const __grid_constant__ ConvParams p) {
             }
           }
         }
-        if (valid) {
+        if (valid && hcols > 0) {
           uint32_t u = __float_as_uint(best);
           u ^= (u >> 31) ? 0xFFFFFFFFu : 0x80000000u;                      // order-preserving float -> uint
           const unsigned long long key = (static_cast<unsigned long long>(u) << 32) | (0xFFFFFFFFu - static_cast<uint32_t>(best_j));
           atomicMax(&p.argmax_keys[n], key);
         }
       } else
-      for (int c0 = 0; c0 < p.BN; c0 += 16) {
+      for (int c0 = col_lo; c0 < col_lo + hcols; c0 += 16) {
         float v[16];
         tmem_ld16(t_row + c0, v);
         const int ch0 = t.ntile * p.BN + c0;
@@ -436,8 +441,8 @@ conv_igemm_kernel(const __grid_constant__ ConvParams p) {
       }
     }
     if (do_stats && cur_img >= 0) {
-      named_bar_sync(gbar, 128);
-      for (int c = et; c < p.CoutTotal; c += 128) {
+      named_bar_sync(gbar, 256);
+      for (int c = et; c < p.CoutTotal; c += 256) {
         flush_stats(p, s_sum, s_sq, cur_img, c);
       }
     }

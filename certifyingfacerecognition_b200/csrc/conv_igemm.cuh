@@ -22,8 +22,13 @@
 
 namespace cfr {
 
-constexpr int kConvThreads = 192;   // warps0-3: epilogue, warp4: TMA producer, warp5: MMA issuer + TMEM owner
-constexpr int kConvThreadsMT2 = 320;  // + warps 6-9: epilogue of the second M tile (MT == 2)
+// warps 0-3: epilogue, warp 4: TMA producer, warp 5: MMA issuer + TMEM owner, warps 6..: more epilogue groups of four
+// warps (one per TMEM lane quarter).  Every M tile is drained by TWO groups, each taking half of the tile's BN columns:
+// the epilogue is latency-bound (tcgen05.ld, __ldg of the per-channel vectors, shuffle reduces: ncu shows its warps
+// issuing 12 % of the time and never waiting on the fused-statistics layers), so twice the warps is twice its rate.
+// MT == 1: groups {0: half 0, 1: half 1};  MT == 2: groups {0: tile 0 half 0, 1: tile 1 half 0, 2: tile 0 half 1, 3: tile 1 half 1}
+constexpr int kConvThreads = 320;
+constexpr int kConvThreadsMT2 = 576;
 constexpr int kBM = 128;
 constexpr int kMaxPhases = 4;
 constexpr int kMaxTaps = 9;
