@@ -62,7 +62,12 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([f.strip() for f in line.split(",")])
+            self.rows.append((time.perf_counter(), [f.strip() for f in line.split(",")]))
+
+    def mark(self):
+        """Start of the timed region: only samples taken from here on count (nvidia-smi itself needs a few hundred ms to
+        deliver its first line, so it is started before the warm-up steps)."""
+        self.t_mark = time.perf_counter()
 
     def stop(self):
         if self.proc is None:
@@ -74,7 +79,11 @@ class ClockSampler:
             self.proc.kill()
         sm, smax, reasons = [], None, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        t_mark = getattr(self, "t_mark", 0.0)
+        inside = [r for t, r in self.rows if t >= t_mark]
+        if not inside:                      # region shorter than one sampling period: the nearest sample
+            inside = [r for _, r in self.rows[-1:]]
+        for r in inside:
             if len(r) < 9:
                 continue
             try:
@@ -99,6 +108,13 @@ def build_fixture(n_ids: int):
 
 
 def cpu_arm(steps: int, warmup: int, sample: int, one_thread_sample: int = 0):
+    # the reference prints progress lines on stdout; the bench's stdout carries exactly ONE JSON line
+    import contextlib
+    with contextlib.redirect_stdout(sys.stderr):
+        return _cpu_arm(steps, warmup, sample, one_thread_sample)
+
+
+def _cpu_arm(steps: int, warmup: int, sample: int, one_thread_sample: int = 0):
     """The reference's CPU path on the host cores; each step classifies ``sample`` MC samples of one identity end to end
     (one batch of BASELINE config 1, whose batch size is 10).
 
@@ -166,8 +182,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=250, help="MC samples per step (BASELINE config 2: 250)")
-    ap.add_argument("--chunk", type=int, default=125, help="samples per GAN+FRM program run")
-    ap.add_argument("--frm-group", type=int, default=2, help="synthesis chunks per ArcFace program run")
+    ap.add_argument("--chunk", type=int, default=250, help="samples per GAN+FRM program run")
+    ap.add_argument("--frm-group", type=int, default=1, help="synthesis chunks per ArcFace program run")
     ap.add_argument("--shard", default="identities", choices=["identities", "samples"],
                     help="how the certification-batch loop uses N > 1 ranks (the certify loop always shards samples)")
     ap.add_argument("--group", type=int, default=8,
@@ -342,21 +358,24 @@ def main():
         cert_stat["certified"] += sum(int(p == j and gap > 0) for (p, gap), j in zip(res, ids))
 
     headline_certify = world > 1 and ident_mode and not args.headline_batches
-    warm = max(3, args.warmup)
+    # at least 10 untimed steps (~0.35 s): the SM clock is still settling under the power cap during the first few, and the
+    # timed region would otherwise read 3-4 % low (the number actually used is what the JSON line reports as "warmup")
+    warm = max(10, args.warmup)
     sampler = ClockSampler(local_rank) if rank == 0 else None
     results, snap = {}, {}
 
     def start_headline():
         if sampler:
-            sampler.start()
+            sampler.mark()
         snap["launches"] = lib.cfr_launch_count()
-        lib.cfr_profile_enable(1)
 
     def mark_draws():
         snap["draws"] = smooth._draws
 
     for name in (("batches", "certify") if headline_certify else ("certify", "batches")):   # headline loop last
         is_headline = name == ("certify" if headline_certify else "batches")
+        if is_headline and sampler:
+            sampler.start()                 # before the warm-up steps; samples count from start_headline() on
         hook = start_headline if is_headline else None
         if name == "batches":
             ms = timed(batch_step, args.steps, warm, hook)
@@ -366,14 +385,21 @@ def main():
                        (lambda: (mark_draws(), start_headline())) if is_headline else mark_draws)
             total = smooth._draws - snap["draws"]            # global MC samples classified (N0 + n per certified identity)
         if is_headline:
+            launches = lib.cfr_launch_count() - snap["launches"]
+            clocks = sampler.stop() if sampler else None
+            # per-kernel roofline pass: the same K steps once more with the two-stream overlap OFF and a CUDA-event pair
+            # around every conv launch (with the FRM side running concurrently on its own stream an event pair would
+            # also time the wait for free SMs); the kernel's share is taken against THIS pass's step time
+            eng.set_overlap(False)
+            lib.cfr_profile_enable(1)
+            ms_serial = timed(batch_step if name == "batches" else certify_step, args.steps, 1)
             prof = {}
             for kind, pname in ((0, "igemm"), (1, "halo")):
                 t_ms, work, n_l = C.c_double(), C.c_double(), C.c_int64()
                 L.check(lib.cfr_profile_read(kind, C.byref(t_ms), C.byref(work), C.byref(n_l)))
                 prof[pname] = (t_ms.value, work.value, n_l.value)
             lib.cfr_profile_enable(0)
-            launches = lib.cfr_launch_count() - snap["launches"]
-            clocks = sampler.stop() if sampler else None
+            eng.set_overlap(True)
         results[name] = {"ms": ms, "samples": total, "value": total / (ms * 1e-3)}
     # end to end through the public entry with HOST buffers
     if headline_certify:
@@ -422,12 +448,14 @@ def main():
                  "frac": ha_gbs / pk["hbm_gbs"], "traffic": halo_traffic, "traffic_unit": "MB per launch (dram read+write, ncu)",
                  "peak_source": pk["source"],
                  "launches_timed": int(ha_n), "avg_launch_ms": ha_ms / max(1, ha_n),
-                 "alg_mbytes_per_launch": ha_bytes / max(1, ha_n) / 1e6, "share_of_step": ha_ms / ms if ms > 0 else None}
+                 "alg_mbytes_per_launch": ha_bytes / max(1, ha_n) / 1e6,
+                 "share_of_step": ha_ms / ms_serial if ms_serial > 0 else None}
     igemm_roof = {"kernel": "conv_igemm_kernel (tcgen05 implicit GEMM: StyleGAN layers 1-12 + every iresnet50 conv / FC)",
                   "bound": "tensor", "achieved": ig_tf, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
                   "frac": ig_tf / pk["tf_sustained"], "traffic": None, "peak_source": pk["source"] + " (sustained)",
                   "launches_timed": int(ig_n), "avg_launch_ms": ig_ms / max(1, ig_n),
-                  "alg_gflop_per_launch": ig_flops / max(1, ig_n) / 1e9, "share_of_step": ig_ms / ms if ms > 0 else None}
+                  "alg_gflop_per_launch": ig_flops / max(1, ig_n) / 1e9,
+                  "share_of_step": ig_ms / ms_serial if ms_serial > 0 else None}
     dominant, other = (halo_roof, igemm_roof) if ha_ms >= ig_ms else (igemm_roof, halo_roof)
     if headline_certify:
         workload = (f"anisotropic certify (BASELINE config 3): {G} identities per step (Smooth.certify_many), each N0={N0} + "
@@ -445,6 +473,7 @@ def main():
         "config": {"workload": workload, "chunk": args.chunk, "frm_group": args.frm_group,
                    "shard": "samples" if headline_certify else args.shard, "gallery": N_GALLERY,
                    "hp_layers": eng.hp_layers,
+                   "overlap": "FRM + match + vote of group i run on a second stream under the synthesis of group i+1",
                    "l2": "working set per step (activations, GBs) far exceeds the 126 MB L2; no flush needed",
                    "gflop_per_sample_algorithmic": gflop_per_sample,
                    "pipeline_tflops": value * gflop_per_sample / 1e3,
@@ -454,6 +483,9 @@ def main():
         "gpu_launches": int(launches),
         "roofline": dominant,
         "roofline_second_kernel": other,
+        "roofline_pass": {"what": "per-launch CUDA-event times of the two conv kernels, taken in a second pass of the same K "
+                                  "steps with the two-stream overlap off (serial launches); share_of_step is against this pass",
+                          "ms_per_step_serial": ms_serial / args.steps},
         "clocks": clocks,
         # both partitions of SURVEY.md section 8e are timed in every run; the headline is (B) for N > 1, (A) for N = 1
         "samples_sharded": {"what": "BASELINE config 3: whole certifications (N0=100 + n=1000), samples of one identity "

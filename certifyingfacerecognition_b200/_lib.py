@@ -45,6 +45,7 @@ class SamplerDesc(C.Structure):
         ("psi", C.c_float), ("gallery", C.c_void_p), ("n_gallery", C.c_int32),
         ("frm_group", C.c_int32), ("frm_big", C.c_void_p), ("emb_big", C.c_void_p), ("out_slot", C.c_void_p),
         ("matcher", C.c_void_p), ("tail", C.c_void_p),
+        ("img_src", C.c_void_p), ("img_frm", C.c_void_p), ("img_chunk_bytes", C.c_uint64),
     ]
 
 
@@ -92,6 +93,7 @@ SIGNATURES = {
     "cfr_matcher_keys": (_I, [_P, _P, _I, C.c_uint32, _P, _P]),
     "cfr_vote_keys": (_I, [_P, _I, _P, _P, _P]),
     "cfr_sampler_create": (_I, [C.POINTER(SamplerDesc), C.POINTER(_P)]),
+    "cfr_sampler_set_overlap": (_I, [_P, _I]),
     "cfr_sampler_destroy": (None, [_P]),
     "cfr_sample_votes": (_I, [_P, _P, _P, _P, _I, _P, _I64, _U64, _U64, _P, _P, _P, _P, _P]),
     "cfr_sample_votes_multi": (_I, [_P, _I, _P, _P, _P, _I, _P, _U64, _P, _P, _P]),

@@ -48,7 +48,48 @@ struct cfr_sampler {
   long long* dev_counts = nullptr;      // [n_gallery]
   float* pin_in = nullptr;              // pinned mirror of dev_in
   long long* pin_counts = nullptr;      // pinned [n_gallery]
+  // two-stream overlap (cfr_sampler_desc.img_frm): FRM + match + vote of group i on `s2` under the synthesis of group i+1
+  cudaStream_t s2 = nullptr;
+  cudaEvent_t ev_start = nullptr, ev_synth = nullptr, ev_copied = nullptr, ev_done = nullptr;
+  bool overlap = false;                 // enabled (cfr_sampler_set_overlap)
+  bool active = false;                  // ... and in use by the current call (calls of a single group stay serial)
+  bool copied_pending = false;          // an img_src -> img_frm copy the caller's stream has not waited for yet
 };
+
+// ---- the FRM side of one group: serial on `stream`, or on the sampler's second stream behind an image copy ----------
+static cudaStream_t frm_stream_begin(cfr_sampler* s, cudaStream_t stream, int chunks) {
+  if (!s->active) {
+    if (s->d.img_frm != nullptr)        // programs are recorded on img_frm: serial mode still needs the copy
+      cudaMemcpyAsync(s->d.img_frm, s->d.img_src, s->d.img_chunk_bytes * chunks, cudaMemcpyDeviceToDevice, stream);
+    return stream;
+  }
+  cudaEventRecord(s->ev_synth, stream);
+  cudaStreamWaitEvent(s->s2, s->ev_synth, 0);
+  cudaMemcpyAsync(s->d.img_frm, s->d.img_src, s->d.img_chunk_bytes * chunks, cudaMemcpyDeviceToDevice, s->s2);
+  cudaEventRecord(s->ev_copied, s->s2);
+  s->copied_pending = true;
+  return s->s2;
+}
+// before the caller's stream overwrites img_src again
+static void synth_may_overwrite(cfr_sampler* s, cudaStream_t stream) {
+  if (s->active && s->copied_pending) {
+    cudaStreamWaitEvent(stream, s->ev_copied, 0);
+    s->copied_pending = false;
+  }
+}
+static void overlap_begin(cfr_sampler* s, cudaStream_t stream, bool several_groups) {
+  s->active = s->overlap && several_groups;
+  if (!s->active) return;
+  cudaEventRecord(s->ev_start, stream);          // e.g. the caller's zeroing of `counts` precedes the votes
+  cudaStreamWaitEvent(s->s2, s->ev_start, 0);
+}
+static void overlap_join(cfr_sampler* s, cudaStream_t stream) {
+  if (!s->active) return;
+  cudaEventRecord(s->ev_done, s->s2);
+  cudaStreamWaitEvent(stream, s->ev_done, 0);
+  s->copied_pending = false;
+  s->active = false;
+}
 
 static inline cudaStream_t S(cfr_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 
@@ -452,7 +493,25 @@ CFR_API int cfr_sampler_create(const cfr_sampler_desc* d, cfr_sampler** out) {
   CFR_CUDA(cudaMalloc(&s->dev_counts, sizeof(long long) * d->n_gallery));
   CFR_CUDA(cudaMallocHost(&s->pin_in, sizeof(float) * 528));
   CFR_CUDA(cudaMallocHost(&s->pin_counts, sizeof(long long) * d->n_gallery));
+  if (d->img_frm != nullptr) {
+    if (d->img_src == nullptr || d->img_chunk_bytes == 0) { set_error("sampler: img_frm needs img_src and img_chunk_bytes"); return 2; }
+    int lo = 0, hi = 0;
+    CFR_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));            // hi = numerically lowest = highest priority
+    // the FRM stream gets the higher priority: its (shorter) kernels take SMs as they free up, synthesis fills the rest
+    CFR_CUDA(cudaStreamCreateWithPriority(&s->s2, cudaStreamNonBlocking, hi));
+    for (cudaEvent_t* e : {&s->ev_start, &s->ev_synth, &s->ev_copied, &s->ev_done})
+      CFR_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+    s->overlap = true;
+  }
   *out = s.release();
+  return 0;
+}
+CFR_API int cfr_sampler_set_overlap(cfr_sampler* s, int on) {
+  if (on && s->s2 == nullptr) { set_error("sampler: created without img_frm, no overlap available"); return 2; }
+  if (s->s2 != nullptr) CFR_CUDA(cudaStreamSynchronize(s->s2));
+  s->overlap = on != 0;
+  s->copied_pending = false;
+  if (s->d.tail != nullptr && s->d.tail->s2 != nullptr) return cfr_sampler_set_overlap(s->d.tail, on);
   return 0;
 }
 CFR_API void cfr_sampler_destroy(cfr_sampler* s) {
@@ -462,6 +521,12 @@ CFR_API void cfr_sampler_destroy(cfr_sampler* s) {
   cudaFree(s->dev_counts);
   cudaFreeHost(s->pin_in);
   cudaFreeHost(s->pin_counts);
+  if (s->s2 != nullptr) {
+    cudaStreamSynchronize(s->s2);
+    cudaStreamDestroy(s->s2);
+    for (cudaEvent_t e : {s->ev_start, s->ev_synth, s->ev_copied, s->ev_done})
+      if (e != nullptr) cudaEventDestroy(e);
+  }
   delete s;
 }
 
@@ -472,6 +537,7 @@ CFR_API int cfr_sample_votes(cfr_sampler* s, const float* z, const float* x, con
   if (sigma_len != 1 && sigma_len != 5) { set_error("sigma_len must be 1 or 5"); return 2; }
   const int K = (d.frm_group > 1 && d.frm_big != nullptr && d.out_slot != nullptr) ? d.frm_group : 1;
   int64_t done = 0;
+  overlap_begin(s, S(stream), num > static_cast<int64_t>(K) * d.chunk);
   while (done < num) {
     const int64_t rem = num - done;
     if (rem < d.chunk && d.tail != nullptr) {
@@ -479,14 +545,17 @@ CFR_API int cfr_sample_votes(cfr_sampler* s, const float* z, const float* x, con
       cfr_sampler* best = nullptr;
       for (cfr_sampler* t = d.tail; t != nullptr; t = t->d.tail)
         if (t->d.chunk >= rem && (best == nullptr || t->d.chunk < best->d.chunk)) best = t;
-      if (best != nullptr)
+      if (best != nullptr) {
+        overlap_join(s, S(stream));
         return cfr_sample_votes(best, z, x, sigma, sigma_len, noise_in ? noise_in + done * 5 : nullptr, rem, seed,
                                 sample_offset + done, counts, pred_out ? pred_out + done : nullptr,
                                 emb_out ? emb_out + done * 512 : nullptr, noise_out ? noise_out + done * 5 : nullptr, stream);
+      }
     }
     // a full group of K chunks goes through the big ArcFace program (better SM fill); the tail chunk by chunk
     const int g = (num - done >= static_cast<int64_t>(K) * d.chunk) ? K : 1;
     const int b = static_cast<int>(num - done < static_cast<int64_t>(g) * d.chunk ? num - done : static_cast<int64_t>(g) * d.chunk);
+    synth_may_overwrite(s, S(stream));
     for (int k = 0; k < g; ++k) {
       const int64_t off = done + static_cast<int64_t>(k) * d.chunk;
       const int bk = static_cast<int>(num - off < d.chunk ? num - off : d.chunk);
@@ -497,21 +566,24 @@ CFR_API int cfr_sample_votes(cfr_sampler* s, const float* z, const float* x, con
       if (r) return r;
       if ((r = cfr_program_run(d.synth, stream)) != 0) return r;
     }
-    int r = cfr_program_run(g == K && K > 1 ? d.frm_big : d.frm, stream);
+    cudaStream_t fs = frm_stream_begin(s, S(stream), g);
+    cfr_stream_t fst = reinterpret_cast<cfr_stream_t>(fs);
+    int r = cfr_program_run(g == K && K > 1 ? d.frm_big : d.frm, fst);
     if (r) return r;
     const float* emb = (g == K && K > 1) ? d.emb_big : d.emb;
     if (emb_out) {
-      CFR_CUDA(cudaMemcpyAsync(emb_out + done * 512, emb, sizeof(float) * 512 * b, cudaMemcpyDeviceToDevice, S(stream)));
+      CFR_CUDA(cudaMemcpyAsync(emb_out + done * 512, emb, sizeof(float) * 512 * b, cudaMemcpyDeviceToDevice, fs));
     }
     if (d.matcher != nullptr) {
-      r = cfr_matcher_run(d.matcher, emb, b, pred_out ? pred_out + done : nullptr, counts, stream);
+      r = cfr_matcher_run(d.matcher, emb, b, pred_out ? pred_out + done : nullptr, counts, fst);
     } else {
       r = launch_match_vote(emb, b, d.gallery, d.n_gallery, s->keys, pred_out ? pred_out + done : nullptr,
-                            reinterpret_cast<long long*>(counts), S(stream));
+                            reinterpret_cast<long long*>(counts), fs);
     }
     if (r) return r;
     done += b;
   }
+  overlap_join(s, S(stream));
   return 0;
 }
 
@@ -528,6 +600,9 @@ CFR_API int cfr_sample_votes_multi(cfr_sampler* s, int n_ids, const float* z, co
   int g = 0;                 // current identity and how many of its samples are done
   int64_t g_done = 0;
   int64_t left = total;
+  // (the sampler in use runs its FRM side on its own second stream; it is joined before another sampler of the tail chain
+  //  takes over -- they may share the matcher's scratch buffers -- and at the end)
+  cfr_sampler* last = nullptr;
   while (left > 0) {
     // the sampler whose chunk this run uses: the main one while a whole chunk is left, else the smallest that fits
     cfr_sampler* cur = s;
@@ -540,6 +615,12 @@ CFR_API int cfr_sample_votes_multi(cfr_sampler* s, int n_ids, const float* z, co
     Piece pieces[512];
     int np = 0, slot = 0;
     int r = 0;
+    if (cur != last) {
+      if (last != nullptr) overlap_join(last, S(stream));
+      overlap_begin(cur, S(stream), left > cur->d.chunk);
+      last = cur;
+    }
+    synth_may_overwrite(cur, S(stream));
     if (d.out_slot != nullptr && (r = launch_set_int(d.out_slot, 0, S(stream))) != 0) return r;
     while (slot < cap && g < n_ids) {
       const int64_t rem = num_host[g] - g_done;
@@ -555,17 +636,20 @@ CFR_API int cfr_sample_votes_multi(cfr_sampler* s, int n_ids, const float* z, co
       g_done += b;
     }
     if ((r = cfr_program_run(d.synth, stream)) != 0) return r;
-    if ((r = cfr_program_run(d.frm, stream)) != 0) return r;
+    cudaStream_t fs = frm_stream_begin(cur, S(stream), 1);
+    cfr_stream_t fst = reinterpret_cast<cfr_stream_t>(fs);
+    if ((r = cfr_program_run(d.frm, fst)) != 0) return r;
     for (int i = 0; i < np; ++i) {
       const float* emb = d.emb + static_cast<size_t>(pieces[i].slot) * 512;
       int64_t* cnt = counts + static_cast<size_t>(pieces[i].id) * d.n_gallery;
-      if (d.matcher != nullptr) r = cfr_matcher_run(d.matcher, emb, pieces[i].b, nullptr, cnt, stream);
+      if (d.matcher != nullptr) r = cfr_matcher_run(d.matcher, emb, pieces[i].b, nullptr, cnt, fst);
       else r = launch_match_vote(emb, pieces[i].b, d.gallery, d.n_gallery, cur->keys, nullptr,
-                                 reinterpret_cast<long long*>(cnt), S(stream));
+                                 reinterpret_cast<long long*>(cnt), fs);
       if (r) return r;
     }
     left -= slot;
   }
+  if (last != nullptr) overlap_join(last, S(stream));
   return 0;
 }
 

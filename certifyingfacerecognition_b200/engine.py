@@ -625,10 +625,21 @@ class _Pipeline:
 
     def __init__(self, g_sd, f_sd, frm_cls, res, chunk, frm_group, device, keep_planar, hp_layers, sparse_last=True):
         self.chunk, self.frm_group = chunk, max(1, int(frm_group))
+        import os as _os
+        split = _os.environ.get("CFR_SPLIT_SMS") if _os.environ.get("CFR_DEBUG_KNOBS") == "1" else None
+        if split:                      # experiment: "S,F" = persistent-grid caps of the synthesis / FRM programs
+            _os.environ["CFR_MAX_CTAS"] = split.split(",")[0]
         self.synth = SynthesisProgram(g_sd, chunk, res, device, keep_planar=keep_planar, groups=self.frm_group,
                                       hp_layers=hp_layers, sparse_last=sparse_last)
-        self.frm = frm_cls(f_sd, chunk, self.synth.img, device)
-        self.frm_big = frm_cls(f_sd, chunk * self.frm_group, self.synth.img, device) if self.frm_group > 1 else None
+        # the FRM programs read their own copy of the images: the sampler runs them (+ match + vote) on a second stream
+        # while the caller's stream already synthesises the next group into synth.img (cfr_sampler_desc.img_frm)
+        self.img_frm = torch.zeros_like(self.synth.img)
+        if split:
+            _os.environ["CFR_MAX_CTAS"] = split.split(",")[1]
+        self.frm = frm_cls(f_sd, chunk, self.img_frm, device)
+        self.frm_big = frm_cls(f_sd, chunk * self.frm_group, self.img_frm, device) if self.frm_group > 1 else None
+        if split:
+            del _os.environ["CFR_MAX_CTAS"]
         self.sampler = None
 
 
@@ -636,7 +647,11 @@ class Engine:
     """StyleGAN -> resize -> iresnet50 -> gallery vote, for one GPU."""
 
     TC_MATCH_MIN_ROWS = 32768      # galleries at least this large use the tensor-core matcher (cfr_matcher_*)
-    HP_LAYERS = 6                  # StyleGAN layers 1..6 (4x4 .. 32x32) run split-precision (SynthesisProgram.hp_layers)
+    # StyleGAN layers 1..5 (4x4 .. 16x16) run split-precision (SynthesisProgram.hp_layers).  Measured on the reference's
+    # golden votes (profiles/votes_r02_hp_sweep.txt, 2 x 1100 samples): strict top-1 agreement iso / aniso 99.00 / 99.55 %
+    # at 0, 99.45 / 99.73 % at 4, 99.64 / 99.82 % at 5, 99.64 / 100 % at 6, 99.73 / 99.82 % at 8 (the remaining flips are
+    # near-ties of the reference itself, margins 0.004-0.03); 5 is the shortest prefix above the 99.5 % bar in both regimes
+    HP_LAYERS = 5
 
     def __init__(self, g_sd, f_sd, dir_mat: Tensor, gallery: Tensor, chunk: int = 32, device="cuda",
                  keep_planar: bool = False, frm_group: int = 1, tc_match: Optional[bool] = None,
@@ -705,6 +720,8 @@ class Engine:
             d.out_slot = L.ptr(pipe.synth.out_slot)
             d.matcher = self.matcher
             d.tail = tail
+            d.img_src, d.img_frm = L.ptr(pipe.synth.img), L.ptr(pipe.img_frm)
+            d.img_chunk_bytes = pipe.synth.img[:pipe.chunk].numel() * pipe.synth.img.element_size()
             if pipe.sampler:
                 self.lib.cfr_sampler_destroy(pipe.sampler)
             h = C.c_void_p()
@@ -712,6 +729,11 @@ class Engine:
             pipe.sampler = h
             tail = h
         self.sampler = self.pipes[0].sampler
+
+    def set_overlap(self, on: bool) -> None:
+        """Two-stream overlap of the FRM side with the next group's synthesis (default on); off = strictly serial launches
+        (what per-kernel CUDA-event timing needs)."""
+        L.check(self.lib.cfr_sampler_set_overlap(self.sampler, int(bool(on))))
 
     def __del__(self):
         try:
@@ -743,6 +765,7 @@ class Engine:
             L.check(self.lib.cfr_truncate(L.ptr(w[i:i + b]), L.ptr(self.synth.w_avg), PSI, b, L.ptr(self.synth.wp2),
                                           self._stream()))
             self.synth.run()
+            self.pipes[0].img_frm[:self.chunk].copy_(self.synth.img[:self.chunk])
             self.frm.run()
             out[i:i + b] = self.frm.emb[:b]
         return out

@@ -222,9 +222,20 @@ typedef struct cfr_sampler_desc {
                              descending chunk size).  A program run always costs a whole chunk, so the remainder of a call
                              (num % chunk samples) goes to the smallest sampler of the chain that still holds it -- what
                              keeps 13-sample selection passes (N0 = 100 split over 8 ranks) from costing 125 samples */
+  /* optional: overlap.  When img_frm != NULL the FRM programs were recorded on img_frm (a second image buffer) and the
+   * sampler runs them, the gallery match and the vote on an internal second stream while the caller's stream already
+   * synthesises the next group: after a group's synthesis the images are copied img_src -> img_frm (img_chunk_bytes per
+   * chunk, device to device), which is all the two streams share.  The persistent conv kernels of the two programs then
+   * fill each other's tail waves and launch gaps.  Results are identical to the serial order (same kernels, same data);
+   * on return everything the call enqueued is ordered before later work on `stream`. */
+  const void* img_src;
+  void* img_frm;
+  uint64_t img_chunk_bytes;
 } cfr_sampler_desc;
 CFR_API int cfr_sampler_create(const cfr_sampler_desc* d, cfr_sampler** out);
 CFR_API void cfr_sampler_destroy(cfr_sampler* s);
+/* switch the two-stream overlap off / on again (per-kernel CUDA-event timing is only meaningful without it) */
+CFR_API int cfr_sampler_set_overlap(cfr_sampler* s, int on);
 /* counts[n_gallery] (int64) is ACCUMULATED into.  noise_in: NULL or [num,5] already-scaled noise.
  * pred_out / emb_out / noise_out: optional per-sample outputs ([num], [num,512], [num,5]). */
 CFR_API int cfr_sample_votes(cfr_sampler* s, const float* z, const float* x, const float* sigma, int sigma_len,

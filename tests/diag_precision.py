@@ -89,6 +89,7 @@ def one_engine(eng, n, w, ref_layers, ref_img, ref_emb, f_sd, say):
     img = syn.img_planar[:n].cpu()
     say(f"img112: mean|d| {(img - ref_img).abs().mean().item():.3e}  max|d| {(img - ref_img).abs().max().item():.3e}"
         f"  (emulated: 1.7e-3)")
+    eng.pipes[0].img_frm[:n].copy_(syn.img[:n])
     eng.frm.run()
     torch.cuda.synchronize()
     emb = eng.frm.emb[:n].cpu()
@@ -100,8 +101,9 @@ def one_engine(eng, n, w, ref_layers, ref_img, ref_emb, f_sd, say):
     with torch.no_grad():
         rep("our image -> oracle ArcFace", M.iresnet50(img, f_sd))
     # oracle image -> our ArcFace: write the oracle's 112^2 image into the program's NHWC fp16 input
-    syn.img[:n].zero_()
-    syn.img[:n, :, :, :3] = ref_img.permute(0, 2, 3, 1).to(syn.img.dtype).cuda()
+    fimg = eng.pipes[0].img_frm                      # the FRM programs read their own copy of the images
+    fimg[:n].zero_()
+    fimg[:n, :, :, :3] = ref_img.permute(0, 2, 3, 1).to(fimg.dtype).cuda()
     eng.frm.run()
     torch.cuda.synchronize()
     rep("oracle image -> our ArcFace", eng.frm.emb[:n].cpu())

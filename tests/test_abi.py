@@ -39,17 +39,19 @@ def test_conv_desc_layout_matches_header(tmp_path):
     from certifyingfacerecognition_b200._lib import ConvDesc, SamplerDesc
     names = [f[0] for f in ConvDesc._fields_]
     assert names[:5] == ["inp", "N", "Hin", "Win", "Cin"]
-    assert names[-3:] == ["stat_sum", "stat_sq", "kSplit"]
+    assert names[-5:] == ["stat_sum", "stat_sq", "kSplit", "keepMap", "keepDim"]
     src = tmp_path / "layout.c"
     src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "cfr_b200.h"\n'
-                   'int main(void) { printf("%zu %zu %zu %zu %zu %zu\\n", sizeof(cfr_conv_desc), '
+                   'int main(void) { printf("%zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(cfr_conv_desc), '
                    'offsetof(cfr_conv_desc, out), offsetof(cfr_conv_desc, stat_sum), offsetof(cfr_conv_desc, kSplit), '
-                   'sizeof(cfr_sampler_desc), offsetof(cfr_sampler_desc, tail)); return 0; }\n')
+                   'sizeof(cfr_sampler_desc), offsetof(cfr_sampler_desc, tail), offsetof(cfr_conv_desc, keepMap), '
+                   'offsetof(cfr_sampler_desc, img_chunk_bytes)); return 0; }\n')
     exe = tmp_path / "layout"
     subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
     got = [int(v) for v in subprocess.check_output([str(exe)]).split()]
     assert got == [ctypes.sizeof(ConvDesc), ConvDesc.out.offset, ConvDesc.stat_sum.offset, ConvDesc.kSplit.offset,
-                   ctypes.sizeof(SamplerDesc), SamplerDesc.tail.offset]
+                   ctypes.sizeof(SamplerDesc), SamplerDesc.tail.offset, ConvDesc.keepMap.offset,
+                   SamplerDesc.img_chunk_bytes.offset]
 
 
 def test_no_cpu_fallback():

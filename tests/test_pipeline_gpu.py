@@ -323,3 +323,36 @@ def test_several_identities_share_program_runs(setup, golden, models):
         want = one.certify(lat[g:g + 1].to(dev), torch.zeros(1, 5, device=dev), labels[g:g + 1], n0, n, alpha, 16, device=dev)
         assert many[g][0] == want[0] and many[g][1] == pytest.approx(want[1], rel=1e-12, abs=0), (g, many[g], want)
     assert many[3][1] == 0.0
+
+
+def test_two_stream_overlap_equals_serial_order(setup):
+    """The sampler runs FRM + match + vote of group i on its own stream while the caller's stream synthesises group i+1
+    (cfr_sampler_desc.img_frm).  Same kernels on the same data: counts, predictions and embeddings are bit-identical to
+    the serial order, for full groups, ragged remainders, tail samplers and the multi-identity entry, and work enqueued
+    on the caller's stream after the call sees the finished tallies."""
+    from certifyingfacerecognition_b200.engine import Engine
+    eng8, g_sd, f_sd, dirs, gallery, z = setup
+    eng = Engine(g_sd, f_sd, dirs, gallery, chunk=8, frm_group=2, tail_chunks=(4,))
+    x, sigma = torch.zeros(1, 5), torch.tensor([2.0 * SIGMA])
+    lat = torch.cat([z, z * 0.9, z * 1.1])
+    for num in (16, 37, 3, 51):
+        out = []
+        for on in (True, False, True):
+            eng.set_overlap(on)
+            counts = torch.zeros(N_GALLERY, dtype=torch.int64, device="cuda")
+            c, ex = eng.sample_votes(z, x, sigma, num, seed=17, sample_offset=3, counts=counts, want_pred=True, want_emb=True)
+            total = c.sum()                               # enqueued on the caller's stream right after the call
+            torch.cuda.synchronize()
+            assert int(total) == num
+            out.append((c.clone(), ex["pred"].clone(), ex["emb"].clone()))
+        for a, b in zip(out[0], out[1]):
+            assert torch.equal(a, b)
+        for a, b in zip(out[0], out[2]):
+            assert torch.equal(a, b)
+    multi = []
+    for on in (True, False):
+        eng.set_overlap(on)
+        multi.append(eng.sample_votes_multi(lat, torch.zeros(1, 5), sigma, [5, 22, 9], seed=3, sample_offsets=[0, 100, 7]))
+        torch.cuda.synchronize()
+    assert torch.equal(multi[0], multi[1]) and multi[0].sum(dim=1).tolist() == [5, 22, 9]
+    eng.set_overlap(True)
