@@ -237,7 +237,10 @@ static int add_folded(cfr_program* p, const cfr_conv_desc* d, const float* base_
     raw->p.noise_tab = tab;
     const float* nz = d->noise;
     const int h = d->Hout, w = d->Wout;
-    p->add([=](cudaStream_t st) { return launch_pack_noise(nz, h, w, composite, tab, st); }, "pack_noise");
+    // the noise maps are weights (fixed per program): packed ONCE, now, instead of on every run
+    int pr = launch_pack_noise(nz, h, w, composite, tab, nullptr);
+    if (pr != 0) return pr;
+    if (cudaDeviceSynchronize() != cudaSuccess) { set_error("folded conv: packing the noise table failed"); return 5; }
   }
   const int n = d->N, cout = d->Cout, cin = d->Cin, phases = d->numPhases, ntaps = d->ntaps;
   const float* bias = d->bias;

@@ -71,7 +71,10 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
 #ifndef CFR_HALO_KB16
 #define CFR_HALO_KB16 2
 #endif
-  constexpr int KB = (COUT == 16 && !COMP) ? CFR_HALO_KB16 : 1;   // tiles / 16-column chunks per tile whose TMEM loads the epilogue
+#ifndef CFR_HALO_KBC
+#define CFR_HALO_KBC 1
+#endif
+  constexpr int KB = COUT == 16 ? (COMP ? CFR_HALO_KBC : CFR_HALO_KB16) : 1;   // tiles / 16-column chunks per tile whose TMEM loads the epilogue
   constexpr int CBN = 1;                               // keeps in flight together (registers: KB * CBN * 16)
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -686,7 +689,8 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
     uint32_t gbase = 0;                     // accumulator-group counter at the start of the band
     int cur_n = -1;
     for (int b = band0; b < band1; ++b) {
-      const Band bd = decode_band(p, b);
+      Band bd = decode_band(p, b);
+      asm volatile("" : "+r"(bd.n), "+r"(bd.y0), "+r"(bd.x0), "+r"(bd.rows));   // (pinned: not re-decoded per tile)
       if (do_stats && cur_n >= 0 && bd.n != cur_n) {
         regs_to_smem();
         named_bar_sync(1, kEpiWarps * 32);
@@ -714,6 +718,19 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
       unsigned long long out_band_u = reinterpret_cast<unsigned long long>(out_band);
       unsigned long long sp_base_u = reinterpret_cast<unsigned long long>(sp_base);
       asm volatile("" : "+l"(out_band_u), "+l"(sp_base_u));
+      // composite: this lane's border-column correction rows of the band (null unless it sits on hi-res column 0 /
+      // 2W-1: the left border corrects the phases with b == 0, the right border those with b == 1)
+      [[maybe_unused]] unsigned long long corr_u = 0;
+      [[maybe_unused]] int corr_par = -1;
+      if constexpr (COMP) {
+        const bool cleft = gx == 0, cright = gx == p.W - 1;
+        if (cleft || cright) {
+          corr_par = cright ? 1 : 0;
+          corr_u = reinterpret_cast<unsigned long long>(
+              p.corr + ((static_cast<size_t>(bd.n) * 2 + corr_par) * p.outH + bd.y0 * p.oscale) * COUT);
+        }
+        asm volatile("" : "+l"(corr_u), "+r"(corr_par));
+      }
       // this warp group's accumulator groups of the band: index gbase + j with (gbase + j) % kEpiGroups == grp
       for (int j = SPLIT ? 0 : ((grp - static_cast<int>(gbase)) & (kEpiGroups - 1)); j < ngroups;
            j += SPLIT ? 1 : kEpiGroups) {
@@ -792,11 +809,9 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
               }
             }
             if constexpr (COMP) {             // composite: exact first / last hi-res column
-              const bool left = gx == 0 && (ph & 1) == 0, right = gx == p.W - 1 && (ph & 1) == 1;
-              if (left || right) {
-                const int oy = (bd.y0 + r) * p.oscale + p.ooff_y[ph];
+              if (corr_par == (k & 1)) {      // (composite phases are (a, b) row-major: k & 1 == b, k >> 1 == a)
                 const float4* cp = reinterpret_cast<const float4*>(
-                    p.corr + ((static_cast<size_t>(bd.n) * 2 + (right ? 1 : 0)) * p.outH + oy) * COUT + ch0);
+                    reinterpret_cast<const float*>(corr_u) + (r * 2 + (k >> 1)) * COUT + ch0);
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                   const float4 c4 = __ldg(cp + i);

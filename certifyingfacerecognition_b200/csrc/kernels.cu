@@ -115,17 +115,22 @@ int launch_truncate(const float* w, const float* w_avg, float psi, int b, float*
 // (k-chunks of 64), thread (sample, row group) accumulates 4 rows in registers -- no shuffles, every weight element is
 // read once per 32 samples.  (The first version used one warp per row with a shuffle reduction per sample: 1.6 us/sample.)
 // ------------------------------------------------------------------------------------------
-constexpr int kStRows = 32, kStSamples = 32, kStK = 64;
+constexpr int kStRows = 64, kStSamples = 64, kStK = 32;
 __global__ void __launch_bounds__(256) k_styles(const float* __restrict__ wp2, const float* __restrict__ w_style,
                                                 const float* __restrict__ b_style, int rows, int rows_trunc, int b,
                                                 float* __restrict__ styles) {
+  // 64 rows x 64 samples per block, 4 x 4 per thread (8 shared loads per 16 FMAs; the 4 x 1 version was LDS-bound)
   __shared__ float ws[kStRows][kStK + 1];
   __shared__ float xs[kStSamples][kStK + 1];
   const int row0 = blockIdx.x * kStRows, s0 = blockIdx.y * kStSamples;
-  // rows_trunc is a multiple of 32 (it is a sum of 2*C with C >= 16), so a block never mixes the two w variants
+  // rows_trunc is a multiple of 64 (launch_styles checks), so a block never mixes the two w variants
   const int variant = row0 < rows_trunc ? 0 : 1;
-  const int ts = threadIdx.x & 31, tr = threadIdx.x >> 5;        // sample lane, row group (4 rows each)
-  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;        // samples tx + 16 i, rows ty * 4 + j
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
   for (int k0 = 0; k0 < 512; k0 += kStK) {
     for (int i = threadIdx.x; i < kStRows * kStK; i += 256) {
       const int r = i / kStK, k = i % kStK;
@@ -135,17 +140,26 @@ __global__ void __launch_bounds__(256) k_styles(const float* __restrict__ wp2, c
     __syncthreads();
 #pragma unroll 8
     for (int k = 0; k < kStK; ++k) {
-      const float x = xs[ts][k];
+      float x[4], w[4];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) acc[j] = fmaf(x, ws[tr * 4 + j][k], acc[j]);
+      for (int i = 0; i < 4; ++i) x[i] = xs[tx + 16 * i][k];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) w[j] = ws[ty * 4 + j][k];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(x[i], w[j], acc[i][j]);
     }
     __syncthreads();
   }
-  if (s0 + ts < b) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int smp = s0 + tx + 16 * i;
+    if (smp >= b) continue;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const int row = row0 + tr * 4 + j;
-      if (row < rows) styles[static_cast<size_t>(s0 + ts) * rows + row] = acc[j] * 0.044194173824159216f + b_style[row];
+      const int row = row0 + ty * 4 + j;
+      if (row < rows) styles[static_cast<size_t>(smp) * rows + row] = acc[i][j] * 0.044194173824159216f + b_style[row];
     }
   }
 }
