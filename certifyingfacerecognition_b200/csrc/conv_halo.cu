@@ -139,6 +139,8 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_trigger();
+  pdl_wait();
 
   if (warp >= kHaloMmaWarp0) {
     // ================================================================ MMA issuers (kMmaWarps warps, alternate tiles)
@@ -1308,19 +1310,29 @@ int halo_launch(const HaloOp& op, cudaStream_t stream) {
     cudaEventRecord(profile_event(1), stream);
     e1 = profile_event(1);
   }
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;      // see pdl_trigger() / pdl_wait() in ptx.cuh
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(op.grid);
+  cfg.blockDim = dim3(kHaloThreads);
+  cfg.dynamicSmemBytes = op.smemBytes;
+  cfg.stream = stream;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
   switch (op.p.Cout) {
     case 16:
-      if (op.p.composite) conv_halo_kernel<16, true, true><<<op.grid, kHaloThreads, op.smemBytes, stream>>>(op.p);
-      else if (op.p.fold) conv_halo_kernel<16, true><<<op.grid, kHaloThreads, op.smemBytes, stream>>>(op.p);
-      else conv_halo_kernel<16, false><<<op.grid, kHaloThreads, op.smemBytes, stream>>>(op.p);
+      if (op.p.composite) cudaLaunchKernelEx(&cfg, conv_halo_kernel<16, true, true>, op.p);
+      else if (op.p.fold) cudaLaunchKernelEx(&cfg, conv_halo_kernel<16, true, false>, op.p);
+      else cudaLaunchKernelEx(&cfg, conv_halo_kernel<16, false, false>, op.p);
       break;
     case 32:
-      if (op.p.fold) conv_halo_kernel<32, true><<<op.grid, kHaloThreads, op.smemBytes, stream>>>(op.p);
-      else conv_halo_kernel<32, false><<<op.grid, kHaloThreads, op.smemBytes, stream>>>(op.p);
+      if (op.p.fold) cudaLaunchKernelEx(&cfg, conv_halo_kernel<32, true, false>, op.p);
+      else cudaLaunchKernelEx(&cfg, conv_halo_kernel<32, false, false>, op.p);
       break;
     default:
-      if (op.p.fold) conv_halo_kernel<64, true><<<op.grid, kHaloThreads, op.smemBytes, stream>>>(op.p);
-      else conv_halo_kernel<64, false><<<op.grid, kHaloThreads, op.smemBytes, stream>>>(op.p);
+      if (op.p.fold) cudaLaunchKernelEx(&cfg, conv_halo_kernel<64, true, false>, op.p);
+      else cudaLaunchKernelEx(&cfg, conv_halo_kernel<64, false, false>, op.p);
       break;
   }
   if (profile_on()) {

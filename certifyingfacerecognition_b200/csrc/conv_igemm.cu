@@ -144,6 +144,8 @@ conv_igemm_kernel(const __grid_constant__ ConvParams p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_trigger();
+  pdl_wait();
 
   if (warp == kProducerWarp) {
     // ===================================================================== TMA producer
@@ -342,24 +344,36 @@ conv_igemm_kernel(const __grid_constant__ ConvParams p) {
         }
       } else
       for (int c0 = col_lo; c0 < col_lo + hcols; c0 += 16) {
+        const int ch0 = t.ntile * p.BN + c0;
+        // the chunk's residual (the one per-pixel global read) is requested BEFORE the TMEM load is waited for: the epilogue
+        // is latency-bound, and behind the (asm volatile) tcgen05.ld / wait it would start only afterwards.  (Doing the
+        // same for the per-channel vectors costs 48 more registers: the 18-warp kernel is capped at 96 and spills;
+        // they are L1-resident after the first tile.)
+        const bool has_cb = cb_row != nullptr, has_bias = p.bias != nullptr, has_nz = p.noise != nullptr;
+        const bool has_alpha = p.act == ACT_PRELU, has_res = p.resid != nullptr && valid;
+        uint4 rv[2];
+        if (has_res) {
+          const uint4* rp = reinterpret_cast<const uint4*>(p.resid + pix * p.residC + ch0);
+          rv[0] = __ldg(rp);
+          rv[1] = __ldg(rp + 1);
+        }
         float v[16];
         tmem_ld16(t_row + c0, v);
-        const int ch0 = t.ntile * p.BN + c0;
-        if (cb_row != nullptr) {
+        if (has_cb) {
 #pragma unroll
           for (int i = 0; i < 16; i += 4) {
             const float4 b4 = __ldg(reinterpret_cast<const float4*>(cb_row + ch0 + i));
             v[i] += b4.x; v[i + 1] += b4.y; v[i + 2] += b4.z; v[i + 3] += b4.w;
           }
         }
-        if (p.bias != nullptr) {
+        if (has_bias) {
 #pragma unroll
           for (int i = 0; i < 16; i += 4) {
             const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + ch0 + i));
             v[i] += b4.x; v[i + 1] += b4.y; v[i + 2] += b4.z; v[i + 3] += b4.w;
           }
         }
-        if (p.noise != nullptr) {
+        if (has_nz) {
 #pragma unroll
           for (int i = 0; i < 16; i += 4) {
             const float4 w4 = __ldg(reinterpret_cast<const float4*>(p.noise_w + ch0 + i));
@@ -369,7 +383,7 @@ conv_igemm_kernel(const __grid_constant__ ConvParams p) {
         if (p.act == ACT_LRELU) {
 #pragma unroll
           for (int i = 0; i < 16; ++i) v[i] = v[i] >= 0.f ? v[i] : v[i] * p.slope;
-        } else if (p.act == ACT_PRELU) {
+        } else if (has_alpha) {
 #pragma unroll
           for (int i = 0; i < 16; i += 4) {
             const float4 a4 = __ldg(reinterpret_cast<const float4*>(p.alpha + ch0 + i));
@@ -379,12 +393,10 @@ conv_igemm_kernel(const __grid_constant__ ConvParams p) {
             v[i + 3] = v[i + 3] >= 0.f ? v[i + 3] : v[i + 3] * a4.w;
           }
         }
-        if (p.resid != nullptr && valid) {
-          const uint4* rp = reinterpret_cast<const uint4*>(p.resid + pix * p.residC + ch0);
+        if (has_res) {
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
-            const uint4 r4 = __ldg(rp + h);
-            const __half2* h2 = reinterpret_cast<const __half2*>(&r4);
+            const __half2* h2 = reinterpret_cast<const __half2*>(&rv[h]);
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
               const float2 f = __half22float2(h2[i]);
@@ -680,6 +692,11 @@ void profile_account(int kind, double work) {
   g_prof[kind & 1].launches += 1;
 }
 
+bool pdl_enabled() {
+  static const bool on = getenv("CFR_PDL") == nullptr || atoi(getenv("CFR_PDL")) != 0;     // CFR_PDL=0: A/B runs
+  return on;
+}
+
 int conv_launch(const ConvOp& op, cudaStream_t stream) {
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
@@ -694,8 +711,18 @@ int conv_launch(const ConvOp& op, cudaStream_t stream) {
     cudaEventRecord(profile_event(0), stream);
     e1 = profile_event(0);
   }
-  if (op.p.MT == 2) conv_igemm_kernel<2><<<op.grid, kConvThreadsMT2, op.smemBytes, stream>>>(op.p);
-  else conv_igemm_kernel<1><<<op.grid, kConvThreads, op.smemBytes, stream>>>(op.p);
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;      // see pdl_trigger() / pdl_wait() in ptx.cuh
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(op.grid);
+  cfg.blockDim = dim3(op.p.MT == 2 ? kConvThreadsMT2 : kConvThreads);
+  cfg.dynamicSmemBytes = op.smemBytes;
+  cfg.stream = stream;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  if (op.p.MT == 2) cudaLaunchKernelEx(&cfg, conv_igemm_kernel<2>, op.p);
+  else cudaLaunchKernelEx(&cfg, conv_igemm_kernel<1>, op.p);
   if (profile_on()) {
     cudaEventRecord(e1, stream);
     profile_account(0, op.flops);

@@ -98,6 +98,7 @@ int conv_launch(const ConvOp& op, cudaStream_t stream);
 void set_error(const char* fmt, ...);
 const char* last_error();
 int num_sms();
+bool pdl_enabled();   // programmatic dependent launch of the conv kernels (env CFR_PDL=0 switches it off)
 void count_launch(int n = 1);
 unsigned long long launch_count();
 void profile_enable(int on);

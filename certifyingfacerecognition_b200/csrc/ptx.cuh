@@ -65,6 +65,13 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 __device__ __forceinline__ void fence_barrier_init() {
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
+// Programmatic dependent launch (the conv kernels are launched with cudaLaunchAttributeProgrammaticStreamSerialization):
+// pdl_trigger() lets the NEXT kernel of the stream start its CTAs as SMs free up, so its prologue (barrier init, TMEM
+// allocation, descriptor prefetch) hides under this kernel's tail; pdl_wait() blocks until every kernel this one depends
+// on has completed and flushed its memory -- nothing produced by a predecessor may be read or overwritten before it.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 __device__ __forceinline__ void fence_proxy_async() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }

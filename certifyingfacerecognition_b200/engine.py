@@ -577,9 +577,10 @@ class ArcFaceProgram(Program):
                                  and not (cc == 0 and dx < 0) and not (cc == 2 and dx > 0)]
                         cb[rc * 3 + cc] = tb[:, valid].sum(dim=1)
                 w1p = pack_conv_weight(w1 * s1.view(1, -1, 1, 1))
+                cb = cb + t2.view(1, -1)                # bn2's shift rides on the class bias: one vector less to fetch
                 self.conv(inp=xs, n=n, hin=res, win=res, cin=inplanes, w=self.hold(_f16(w1p, dev)), cout=planes,
                           hout=res, wout=res, tile=tile_for(res, n), out=hbuf, out_hwc=(res, res, planes), taps=[TAPS3],
-                          bias=self.hold(_f32(t2, dev)), cbias=self.hold(_f32(cb, dev)), act=L.ACT_PRELU,
+                          cbias=self.hold(_f32(cb, dev)), act=L.ACT_PRELU,
                           alpha=self.hold(_f32(sd[p + "prelu.weight"], dev)))
                 identity = xs
                 if bi == 0:
