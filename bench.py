@@ -186,7 +186,7 @@ def main():
     ap.add_argument("--frm-group", type=int, default=1, help="synthesis chunks per ArcFace program run")
     ap.add_argument("--shard", default="identities", choices=["identities", "samples"],
                     help="how the certification-batch loop uses N > 1 ranks (the certify loop always shards samples)")
-    ap.add_argument("--group", type=int, default=8,
+    ap.add_argument("--group", type=int, default=20,
                     help="identities certified together per step of the certify loop (Smooth.certify_many); 1 = one at a time")
     ap.add_argument("--headline-batches", action="store_true",
                     help="N > 1: keep the certification-batch loop as the headline instead of BASELINE config 3")
@@ -427,14 +427,16 @@ def main():
             dist.destroy_process_group()
         return
     pk = peaks()
-    # DRAM bytes per launch of the halo kernel from the committed `ncu --set full` capture of this very command
-    # (profiles/traffic_r01_halo.json; only meaningful for the chunk size it was captured at)
-    halo_traffic = None
+    # DRAM bytes per launch of the halo kernel from the committed `ncu --set full` capture of this command (it cannot be
+    # measured in-process; the file names the command, chunk size and build it was taken at, and is only used for that
+    # chunk size -- a kernel change makes it stale, which `traffic_source` lets a reader check)
+    halo_traffic, traffic_source = None, None
     try:
-        with open(os.path.join(ROOT, "profiles", "traffic_r01_halo.json")) as fh:
+        with open(os.path.join(ROOT, "profiles", "traffic_r02_halo.json")) as fh:
             tj = json.load(fh)
-        if args.chunk == 125:
+        if tj.get("chunk") == args.chunk:
             halo_traffic = tj["avg_dram_bytes_per_launch"] / 1e6
+            traffic_source = "profiles/traffic_r02_halo.json: " + tj.get("source", "")
     except (OSError, KeyError, ValueError):
         pass
     ig_ms, ig_flops, ig_n = prof["igemm"]
@@ -446,6 +448,7 @@ def main():
                            "by arithmetic intensity, SURVEY.md section 8d)",
                  "bound": "hbm", "achieved": ha_gbs, "peak": pk["hbm_gbs"], "unit": "GB/s",
                  "frac": ha_gbs / pk["hbm_gbs"], "traffic": halo_traffic, "traffic_unit": "MB per launch (dram read+write, ncu)",
+                 "traffic_source": traffic_source,
                  "peak_source": pk["source"],
                  "launches_timed": int(ha_n), "avg_launch_ms": ha_ms / max(1, ha_n),
                  "alg_mbytes_per_launch": ha_bytes / max(1, ha_n) / 1e6,

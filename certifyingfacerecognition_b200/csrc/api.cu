@@ -39,6 +39,14 @@ struct cfr_matcher {
   __half* q_split = nullptr;            // [max_b][1536]  = [2e_h, 2e_h, 2e_l]
   unsigned long long* keys = nullptr;   // [max_b]
   ConvOp op;
+  // owns its device buffers: an early return from cfr_matcher_create (e.g. out of memory on a 1 M-row gallery) frees
+  // whatever had been allocated through the unique_ptr
+  ~cfr_matcher() {
+    cudaFree(g_split);
+    cudaFree(g_bias);
+    cudaFree(q_split);
+    cudaFree(keys);
+  }
 };
 
 struct cfr_sampler {
@@ -54,6 +62,20 @@ struct cfr_sampler {
   bool overlap = false;                 // enabled (cfr_sampler_set_overlap)
   bool active = false;                  // ... and in use by the current call (calls of a single group stay serial)
   bool copied_pending = false;          // an img_src -> img_frm copy the caller's stream has not waited for yet
+  // owns its buffers / stream / events (early returns from cfr_sampler_create free what had been created)
+  ~cfr_sampler() {
+    cudaFree(keys);
+    cudaFree(dev_in);
+    cudaFree(dev_counts);
+    cudaFreeHost(pin_in);
+    cudaFreeHost(pin_counts);
+    if (s2 != nullptr) {
+      cudaStreamSynchronize(s2);
+      cudaStreamDestroy(s2);
+    }
+    for (cudaEvent_t e : {ev_start, ev_synth, ev_copied, ev_done})
+      if (e != nullptr) cudaEventDestroy(e);
+  }
 };
 
 // ---- the FRM side of one group: serial on `stream`, or on the sampler's second stream behind an image copy ----------
@@ -441,14 +463,7 @@ CFR_API int cfr_matcher_create(const float* gallery, int n_gallery, int max_b, c
   *out = m.release();
   return 0;
 }
-CFR_API void cfr_matcher_destroy(cfr_matcher* m) {
-  if (!m) return;
-  cudaFree(m->g_split);
-  cudaFree(m->g_bias);
-  cudaFree(m->q_split);
-  cudaFree(m->keys);
-  delete m;
-}
+CFR_API void cfr_matcher_destroy(cfr_matcher* m) { delete m; }
 CFR_API int cfr_matcher_run(cfr_matcher* m, const float* emb, int b, int32_t* pred, int64_t* counts, cfr_stream_t stream) {
   if (b > m->max_b) { set_error("matcher: b=%d exceeds max_b=%d", b, m->max_b); return 2; }
   if (b <= 0) return 0;
@@ -517,21 +532,7 @@ CFR_API int cfr_sampler_set_overlap(cfr_sampler* s, int on) {
   if (s->d.tail != nullptr && s->d.tail->s2 != nullptr) return cfr_sampler_set_overlap(s->d.tail, on);
   return 0;
 }
-CFR_API void cfr_sampler_destroy(cfr_sampler* s) {
-  if (!s) return;
-  cudaFree(s->keys);
-  cudaFree(s->dev_in);
-  cudaFree(s->dev_counts);
-  cudaFreeHost(s->pin_in);
-  cudaFreeHost(s->pin_counts);
-  if (s->s2 != nullptr) {
-    cudaStreamSynchronize(s->s2);
-    cudaStreamDestroy(s->s2);
-    for (cudaEvent_t e : {s->ev_start, s->ev_synth, s->ev_copied, s->ev_done})
-      if (e != nullptr) cudaEventDestroy(e);
-  }
-  delete s;
-}
+CFR_API void cfr_sampler_destroy(cfr_sampler* s) { delete s; }
 
 CFR_API int cfr_sample_votes(cfr_sampler* s, const float* z, const float* x, const float* sigma, int sigma_len,
                      const float* noise_in, int64_t num, uint64_t seed, uint64_t sample_offset, int64_t* counts,

@@ -87,7 +87,7 @@ class WrappedModel(nn.Module):
             embs = None
         placeholder = embs if embs is not None else torch.zeros(1, EMB_SIZE)
         self.engine = Engine(generator_state, frm_state, self.dir_mat, placeholder, chunk=chunk, frm_group=frm_group,
-                             tail_chunks=tuple(c for c in (64, 32, 16) if c < chunk) if tail_chunks == "auto" else tail_chunks,
+                             tail_chunks=tuple(c for c in (128, 64, 32, 16) if c < chunk) if tail_chunks == "auto" else tail_chunks,
                              device=self.device,
                              frm=face_recog)
         if embs is None:

@@ -77,7 +77,10 @@ def traffic(path: str, cmd: str) -> None:
         out.append({"kernel": d["kernel"], "dram_read_bytes": rd * scale.get(ru, 1.0),
                     "dram_write_bytes": wr * scale.get(wu, 1.0), "ncu_time_ms": t * scale.get(tu, 1.0)})
     avg = sum(o["dram_read_bytes"] + o["dram_write_bytes"] for o in out) / max(1, len(out))
-    json.dump({"source": cmd, "launches": out, "avg_dram_bytes_per_launch": avg}, sys.stdout, indent=1)
+    import re as _re
+    m = _re.search(r"--chunk (\d+)", cmd)
+    json.dump({"source": cmd, "chunk": int(m.group(1)) if m else None, "launches": out,
+               "avg_dram_bytes_per_launch": avg}, sys.stdout, indent=1)
     print()
 
 
