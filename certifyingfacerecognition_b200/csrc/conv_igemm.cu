@@ -29,7 +29,7 @@ __device__ __forceinline__ TileCoord decode_item(const ConvParams& p, int item, 
   t.ntile = item % p.numNTiles;
   int r = item / p.numNTiles;
   t.phase = r % p.numPhases;
-  int m = (r / p.numPhases) * p.MT + sub;
+  int m = (r / p.numPhases) * p.tilesPerItem + sub;
   int tx = m % p.tilesX;
   m /= p.tilesX;
   int ty = m % p.tilesY;
@@ -84,9 +84,20 @@ __device__ __forceinline__ void flush_stats(const ConvParams& p, float* s_sum, f
 // stage, and every K step issues two MMAs (one per accumulator) against the same B operand: the bytes the SM pulls from
 // L2 per FLOP drop by 1/4 - 1/3.  These layers are bound by the chip-wide L2 -> SM feed (ncu: ~12 TB/s delivered,
 // tensor pipe 17-55 % busy), not by the tensor cores.  A second group of four epilogue warps drains the second tile.
-template <int MT>
+//
+// CG == 2 (with MT == 1): the two CTAs of a 2-CTA cluster (two SMs of a TPC) work on two adjacent M tiles -- one each --
+// against ONE 256-wide N tile.  Each CTA stages its own A tile and HALF of the weight rows; the even CTA issues
+// tcgen05.mma.cta_group::2 (M = 256: rows 0..127 from its shared memory / into its TMEM, rows 128..255 the peer's), every
+// TMA load signals the even CTA's `full` barrier, tcgen05.commit multicasts `empty` / `tfull` to both CTAs, and both
+// CTAs' epilogue warps arrive on the even CTA's `tempty`.  Bytes pulled from L2 per FLOP: 32 KB per 128 x 256 x 64 per SM
+// instead of 48 KB (MT == 2, BN == 128) -- these layers sit on the chip-wide L2 -> SM cap -- with both accumulator sets
+// (2 x 256 columns) still in flight.
+template <int MT, int CG = 1>
 __global__ void __launch_bounds__(MT == 2 ? kConvThreadsMT2 : kConvThreads, 1)
 conv_igemm_kernel(const __grid_constant__ ConvParams p) {
+  static_assert(CG == 1 || MT == 1, "a CTA pair works on one M tile per CTA");
+  constexpr int TPI = CG == 2 ? 2 : MT;           // M tiles per work item
+  const uint32_t crank = CG == 2 ? cluster_ctarank() : 0u;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int S = p.numStages;
@@ -106,9 +117,10 @@ conv_igemm_kernel(const __grid_constant__ ConvParams p) {
 
   // (an odd tile count leaves the last pair with a dummy second tile: its sample index is >= N, so TMA zero-fills its
   //  A box and the epilogue only keeps the barriers in step)
-  const int totalItems = ((p.tilesX * p.tilesY * p.tilesN + MT - 1) / MT) * p.numPhases * p.numNTiles;
-  const int per = (totalItems + gridDim.x - 1) / gridDim.x;
-  const int item0 = blockIdx.x * per;
+  const int totalItems = ((p.tilesX * p.tilesY * p.tilesN + TPI - 1) / TPI) * p.numPhases * p.numNTiles;
+  const int nWorkers = CG == 2 ? gridDim.x / 2 : gridDim.x;       // a CTA pair walks one item list together
+  const int per = (totalItems + nWorkers - 1) / nWorkers;
+  const int item0 = (CG == 2 ? blockIdx.x / 2 : blockIdx.x) * per;
   const int item1 = min(totalItems, item0 + per);
 
   const int chunksTotal = p.ntaps * p.nCB;
@@ -129,19 +141,25 @@ conv_igemm_kernel(const __grid_constant__ ConvParams p) {
       }
       for (int i = 0; i < 2; ++i) {
         mbar_init(&tfull_bar[i], 1);
-        mbar_init(&tempty_bar[i], 8 * MT);               // every warp of the 2 * MT epilogue groups arrives
+        mbar_init(&tempty_bar[i], 8 * MT * CG);          // every warp of the 2 * MT epilogue groups (of both CTAs) arrives
       }
       fence_barrier_init();
     }
     __syncwarp();
-    tmem_alloc(tmem_slot, tmemCols);
-    tmem_relinquish();
+    if constexpr (CG == 2) {
+      tmem_alloc_pair(tmem_slot, tmemCols);
+      tmem_relinquish_pair();
+    } else {
+      tmem_alloc(tmem_slot, tmemCols);
+      tmem_relinquish();
+    }
   }
   if (p.stat_sum != nullptr) {
     for (int i = threadIdx.x; i < MT * 8 * p.CoutTotal; i += blockDim.x) s_sum[i] = 0.f;
   }
   tc_fence_before();
   __syncthreads();
+  if constexpr (CG == 2) cluster_sync_all();      // the peer's barriers are initialised before anything signals them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   pdl_trigger();
@@ -154,9 +172,11 @@ conv_igemm_kernel(const __grid_constant__ ConvParams p) {
     int stage = 0;
     uint32_t phase = 0;
     for (int item = item0; item < item1; ++item) {
-      const TileCoord t = decode_item(p, item, 0);
+      const TileCoord t = decode_item(p, item, CG == 2 ? static_cast<int>(crank) : 0);
       const TileCoord t1 = decode_item(p, item, MT - 1);          // second tile of the pair (== t when MT == 1)
-      const int wrow = t.n0 * p.wRowsPerSample + t.phase * p.wRowsPerPhase + t.ntile * p.BN;
+      // (CTA pair: this CTA's half of the N tile's weight rows)
+      const int wrow = t.n0 * p.wRowsPerSample + t.phase * p.wRowsPerPhase + t.ntile * p.BN +
+                       (CG == 2 ? static_cast<int>(crank) * (p.BN / 2) : 0);
       const int xb = t.x0 * p.stride, yb = t.y0 * p.stride;
       const int xb1 = t1.x0 * p.stride, yb1 = t1.y0 * p.stride;
       int chunk = 0;
@@ -165,6 +185,18 @@ conv_igemm_kernel(const __grid_constant__ ConvParams p) {
         const int nch = min(p.G, chunksTotal - chunk);
         uint8_t* a_dst = smem + static_cast<size_t>(stage) * p.stageBytes;
         if (leader) {
+          if constexpr (CG == 2) {
+            // both CTAs' boxes complete on the EVEN CTA's barrier, which expects the bytes of both
+            if (crank == 0) mbar_expect_tx(&full_bar[stage], 2 * (nch * subBytes + (p.BN / 2) * 128));
+            for (int g = 0; g < nch; ++g) {
+              const int c = chunk + g;
+              const int tap = c / p.nCB;
+              const int cb = c - tap * p.nCB;
+              tma_load_4d_pair(a_dst + g * subBytes, &p.tmA, &full_bar[stage], cb * p.CB, xb + p.tap_dx[t.phase][tap],
+                               yb + p.tap_dy[t.phase][tap], t.n0);
+            }
+            tma_load_2d_pair(a_dst + kBM * 128, &p.tmB, &full_bar[stage], s * 64, wrow);
+          } else {
           mbar_expect_tx(&full_bar[stage], MT * nch * subBytes + p.BN * 128);
           for (int g = 0; g < nch; ++g) {
             const int c = chunk + g;
@@ -177,6 +209,7 @@ conv_igemm_kernel(const __grid_constant__ ConvParams p) {
                           xb1 + p.tap_dx[t.phase][tap], yb1 + p.tap_dy[t.phase][tap], t1.n0);
           }
           tma_load_2d(a_dst + MT * kBM * 128, &p.tmB, &full_bar[stage], s * 64, wrow);
+          }
         }
         __syncwarp();
         chunk += nch;
@@ -187,9 +220,9 @@ conv_igemm_kernel(const __grid_constant__ ConvParams p) {
       }
     }
   } else if (warp == kMmaWarp) {
-    // ===================================================================== MMA issuer
-    const bool leader = elect_one();
-    const uint32_t idesc = make_idesc_f16(kBM, p.BN);
+    // ===================================================================== MMA issuer (CTA pair: the even CTA's only)
+    const bool leader = elect_one() && crank == 0;
+    const uint32_t idesc = make_idesc_f16(CG == 2 ? 2 * kBM : kBM, p.BN);
     const uint32_t a_hi = smem_desc_hi(8 * p.swizzleA, p.swizzleA);
     const uint32_t b_hi = smem_desc_hi(1024, 128);
     const int kPer = p.CB / 16;
@@ -200,7 +233,7 @@ conv_igemm_kernel(const __grid_constant__ ConvParams p) {
     uint32_t phase = 0;
     int as = 0;
     uint32_t aphase = 0;
-    for (int item = item0; item < item1; ++item) {
+    for (int item = (CG == 2 && crank != 0) ? item1 : item0; item < item1; ++item) {
       mbar_wait(&tempty_bar[as], aphase ^ 1);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + as * MT * p.BN;
@@ -216,7 +249,12 @@ conv_igemm_kernel(const __grid_constant__ ConvParams p) {
         const uint32_t a0 = smem_lo + stage * stage16;
         const uint32_t b0 = a0 + MT * (kBM * 128 >> 4);
         if (leader) {
-          if (kPer == 4) {                 // one 64-channel chunk per stage: 4 K-steps inside the 128B swizzle row
+          if constexpr (CG == 2) {         // (conv_build: CB == 64 only) one M = 256 MMA per K step across the pair
+            umma_f16_lohi_pair(d_tmem, a0, a_hi, b0, b_hi, idesc, acc);
+            umma_f16_lohi_pair(d_tmem, a0 + 2, a_hi, b0 + 2, b_hi, idesc, 1u);
+            umma_f16_lohi_pair(d_tmem, a0 + 4, a_hi, b0 + 4, b_hi, idesc, 1u);
+            umma_f16_lohi_pair(d_tmem, a0 + 6, a_hi, b0 + 6, b_hi, idesc, 1u);
+          } else if (kPer == 4) {          // one 64-channel chunk per stage: 4 K-steps inside the 128B swizzle row
             umma_f16_lohi(d_tmem, a0, a_hi, b0, b_hi, idesc, acc);
             if (MT == 2) umma_f16_lohi(d_tmem1, a0 + a1off, a_hi, b0, b_hi, idesc, acc);
             umma_f16_lohi(d_tmem, a0 + 2, a_hi, b0 + 2, b_hi, idesc, 1u);
@@ -238,7 +276,8 @@ conv_igemm_kernel(const __grid_constant__ ConvParams p) {
               }
             }
           }
-          umma_commit(&empty_bar[stage]);   // frees this smem stage once the MMAs above have read it
+          // frees this smem stage (in both CTAs of a pair) once the MMAs above have read it
+          if constexpr (CG == 2) umma_commit_pair(&empty_bar[stage]); else umma_commit(&empty_bar[stage]);
         }
         acc = 1;
         __syncwarp();
@@ -247,7 +286,9 @@ conv_igemm_kernel(const __grid_constant__ ConvParams p) {
           phase ^= 1;
         }
       }
-      if (leader) umma_commit(&tfull_bar[as]);        // accumulator(s) complete -> epilogue
+      if (leader) {                                   // accumulator(s) complete -> epilogue (of both CTAs of a pair)
+        if constexpr (CG == 2) umma_commit_pair(&tfull_bar[as]); else umma_commit(&tfull_bar[as]);
+      }
       __syncwarp();
       if (++as == p.nAcc) {
         as = 0;
@@ -257,7 +298,8 @@ conv_igemm_kernel(const __grid_constant__ ConvParams p) {
   } else {
     // ===================================================================== epilogue (warps 0..3 and 6..)
     const int egrp = warp < 4 ? 0 : (warp - 2) >> 2;             // epilogue group 0 .. 2 * MT - 1
-    const int sub = MT == 2 ? (egrp & 1) : 0;    // which tile of the pair this group drains
+    const int slice = MT == 2 ? (egrp & 1) : 0;  // which tile of this CTA's (MT) tiles this group drains
+    const int sub = CG == 2 ? static_cast<int>(crank) : slice;     // ... = which tile of the work item
     const int half = MT == 2 ? (egrp >> 1) : egrp;               // which half of the tile's BN columns
     const int hcols = (p.BN % 32 == 0) ? p.BN / 2 : (half == 0 ? p.BN : 0);   // columns of this half (BN = 16 / 48 / ..: half 0 takes all)
     const int col_lo = half * (p.BN / 2);
@@ -267,21 +309,23 @@ conv_igemm_kernel(const __grid_constant__ ConvParams p) {
     const int ty = (row / p.TW) % p.TH;
     const int tn = row / (p.TW * p.TH);
     const int et = half * 128 + q * 32 + static_cast<int>(lane); // 0..255 among the threads draining this tile
-    const int gbar = 1 + sub;                    // named barrier of this tile's two groups
-    s_sum += sub * 4 * p.CoutTotal;              // this group's four slices
-    s_sq += sub * 4 * p.CoutTotal;
+    const int gbar = 1 + slice;                  // named barrier of this tile's two groups
+    s_sum += slice * 4 * p.CoutTotal;            // this group's four slices
+    s_sq += slice * 4 * p.CoutTotal;
     int as = 0;
     uint32_t aphase = 0;
     int cur_img = -1;
     const bool do_stats = p.stat_sum != nullptr;
     for (int item = item0; item < item1; ++item) {
       const TileCoord t = decode_item(p, item, sub);
-      if (MT == 2 && t.n0 >= p.N) {              // dummy tile of an odd tile count
+      if (TPI == 2 && t.n0 >= p.N) {             // dummy tile of an odd tile count
         mbar_wait(&tfull_bar[as], aphase);
         tc_fence_after();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&tempty_bar[as]);
+        if (lane == 0) {
+          if constexpr (CG == 2) mbar_arrive_remote(&tempty_bar[as], 0); else mbar_arrive(&tempty_bar[as]);
+        }
         if (++as == p.nAcc) {
           as = 0;
           aphase ^= 1;
@@ -311,7 +355,7 @@ conv_igemm_kernel(const __grid_constant__ ConvParams p) {
 
       mbar_wait(&tfull_bar[as], aphase);
       tc_fence_after();
-      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + (as * MT + sub) * p.BN;
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + (as * MT + slice) * p.BN;
       if (p.argmax_keys != nullptr) {
         // gallery match: score = acc + bias[j] (= 2 e.g_j - |g_j|^2); keep the best column of this tile per row and
         // fold it into the global per-query key (max score, then lowest index == torch.argmax tie-break)
@@ -446,7 +490,9 @@ conv_igemm_kernel(const __grid_constant__ ConvParams p) {
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[as]);
+      if (lane == 0) {
+        if constexpr (CG == 2) mbar_arrive_remote(&tempty_bar[as], 0); else mbar_arrive(&tempty_bar[as]);
+      }
       if (++as == p.nAcc) {
         as = 0;
         aphase ^= 1;
@@ -462,9 +508,10 @@ conv_igemm_kernel(const __grid_constant__ ConvParams p) {
 
   tc_fence_before();
   __syncthreads();
+  if constexpr (CG == 2) cluster_sync_all();      // no CTA leaves while its peer may still read its shared memory / TMEM
   if (warp == kMmaWarp) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, tmemCols);
+    if constexpr (CG == 2) tmem_dealloc_pair(tmem_base, tmemCols); else tmem_dealloc(tmem_base, tmemCols);
   }
 }
 
@@ -575,8 +622,26 @@ int conv_build(const ConvSpec& s, ConvOp* op) {
     if (force == 1) mt2 = false;
     p.MT = mt2 ? 2 : 1;
     p.nAcc = (2 * p.MT * bn <= 512) ? 2 : 1;
+    p.CG = 1;
+    // CTA pair (tcgen05 cta_group::2) for plain convs with Cout % 256 == 0: N tile 256 split over the pair's two SMs, one
+    // M tile per CTA, both accumulator sets in flight.  Not for 1x1-grid GEMMs (FC, gallery matcher: few M tiles), not
+    // for the split-precision convs (their 3x K loop already hides the epilogue at BN = 256).  CFR_IGEMM_CG2=0: A/B runs.
+    static const int cg_env = getenv("CFR_IGEMM_CG2") != nullptr ? atoi(getenv("CFR_IGEMM_CG2")) : 1;
+    const long long pairItems256 = static_cast<long long>(mTiles / 2) * s.numPhases * (s.Cout / 256);
+    // Measured (profiles/ncu_r02_notes.md section 9): L7 3.87 -> 3.56 us, L9 4.10 -> 3.85 us; short-K layers (1x1
+    // down-samples, 28x28 Cin 128) lose 10 % to the coarser work items, hence K >= 2304.
+    if (cg_env != 0 && s.numPhases == 1 && s.kSplit != 3 && s.Cout % 256 == 0 && s.Cin % 64 == 0 && mTiles >= 2 &&
+        same_rows && s.Hout * s.Wout > 1 && pairItems256 >= num_sms() / 4 && (cg_env == 2 || s.ntaps * s.Cin >= 2304)) {
+      p.CG = 2;
+      p.MT = 1;
+      p.nAcc = 2;
+      bn = 256;
+      p.BN = bn;
+      p.numNTiles = s.Cout / bn;
+    }
+    p.tilesPerItem = p.CG == 2 ? 2 : p.MT;
   }
-  p.stageBytes = p.MT * kBM * 128 + bn * 128;
+  p.stageBytes = p.MT * kBM * 128 + (p.CG == 2 ? bn / 2 : bn) * 128;
   const int statBytes = s.stat_sum != nullptr ? p.MT * 8 * s.Cout * 4 : 0;
   const int ctrlBytes = 8 * (2 * 8 + 4) + 16 + statBytes;
   const int budget = 227 * 1024 - 1024 - ctrlBytes;
@@ -584,6 +649,7 @@ int conv_build(const ConvSpec& s, ConvOp* op) {
   if (p.numStages > 8) p.numStages = 8;
   if (p.numStages < 3 && p.MT == 2) {                   // not enough stages to pipeline: fall back to one tile per step
     p.MT = 1;
+    p.tilesPerItem = 1;
     p.nAcc = 2;
     p.stageBytes = kBM * 128 + bn * 128;
     p.numStages = (227 * 1024 - 1024 - (8 * (2 * 8 + 4) + 16 + (s.stat_sum != nullptr ? 8 * s.Cout * 4 : 0))) / p.stageBytes;
@@ -619,7 +685,7 @@ int conv_build(const ConvSpec& s, ConvOp* op) {
   {
     cuuint64_t dims[2] = {(cuuint64_t)s.Kpad, (cuuint64_t)s.wRows};
     cuuint64_t strides[1] = {(cuuint64_t)s.Kpad * 2};
-    cuuint32_t box[2] = {64, (cuuint32_t)bn};
+    cuuint32_t box[2] = {64, (cuuint32_t)(p.CG == 2 ? bn / 2 : bn)};     // CTA pair: each CTA stages half of the N tile
     cuuint32_t estr[2] = {1, 1};
     CUresult r = enc(&p.tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(s.w), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -628,11 +694,13 @@ int conv_build(const ConvSpec& s, ConvOp* op) {
   }
   if (s.Kpad % 64 != 0 || s.Kpad < s.ntaps * s.Cin) { set_error("conv: Kpad=%d must be a multiple of 64 and >= taps*Cin", s.Kpad); return 2; }
 
-  const int total = ((p.tilesX * p.tilesY * p.tilesN + p.MT - 1) / p.MT) * p.numPhases * p.numNTiles;
+  const int total = ((p.tilesX * p.tilesY * p.tilesN + p.tilesPerItem - 1) / p.tilesPerItem) * p.numPhases * p.numNTiles;
   op->grid = total < num_sms() ? total : num_sms();
+  if (p.CG == 2) op->grid = 2 * (total < num_sms() / 2 ? total : num_sms() / 2);      // whole CTA pairs
   if (const char* e = getenv("CFR_MAX_CTAS")) {      // tests: few CTAs => many work items per CTA (ring wrap, phase flips)
     const int m = atoi(e);
     if (m > 0 && op->grid > m) op->grid = m;
+    if (p.CG == 2) op->grid = op->grid < 2 ? 2 : (op->grid & ~1);
   }
   // algorithmic FLOPs of this launch: 2 * (valid output-grid pixels) * phases * taps * Cin * Cout
   // (split-precision convs issue 3x the MMAs for the same algorithmic contraction: counted on the logical Cin / 3)
@@ -704,6 +772,8 @@ int conv_launch(const ConvOp& op, cudaStream_t stream) {
     attr_err = cudaFuncSetAttribute(conv_igemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (attr_err == cudaSuccess)
       attr_err = cudaFuncSetAttribute(conv_igemm_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (attr_err == cudaSuccess)
+      attr_err = cudaFuncSetAttribute(conv_igemm_kernel<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   });
   if (attr_err != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(attr_err)); return 4; }
   cudaEvent_t e1 = nullptr;
@@ -711,17 +781,29 @@ int conv_launch(const ConvOp& op, cudaStream_t stream) {
     cudaEventRecord(profile_event(0), stream);
     e1 = profile_event(0);
   }
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;      // see pdl_trigger() / pdl_wait() in ptx.cuh
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (op.p.CG == 2) {                                                   // the CTA pair is a 2-CTA cluster
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = 2;
+    attr[na].val.clusterDim.y = 1;
+    attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
+  if (pdl_enabled()) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // see pdl_trigger() / pdl_wait() in ptx.cuh
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(op.grid);
   cfg.blockDim = dim3(op.p.MT == 2 ? kConvThreadsMT2 : kConvThreads);
   cfg.dynamicSmemBytes = op.smemBytes;
   cfg.stream = stream;
   cfg.attrs = attr;
-  cfg.numAttrs = pdl_enabled() ? 1 : 0;
-  if (op.p.MT == 2) cudaLaunchKernelEx(&cfg, conv_igemm_kernel<2>, op.p);
+  cfg.numAttrs = na;
+  if (op.p.CG == 2) cudaLaunchKernelEx(&cfg, conv_igemm_kernel<1, 2>, op.p);
+  else if (op.p.MT == 2) cudaLaunchKernelEx(&cfg, conv_igemm_kernel<2>, op.p);
   else cudaLaunchKernelEx(&cfg, conv_igemm_kernel<1>, op.p);
   if (profile_on()) {
     cudaEventRecord(e1, stream);

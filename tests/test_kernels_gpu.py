@@ -60,7 +60,10 @@ CONV_CASES = [
     (2, 64, 320, 16, 1, 3),
     (297, 16, 32, 8, 1, 3),      # 149 M tiles (odd): paired-tile (MT=2) path with a dummy last tile
     (150, 64, 128, 16, 1, 3),    # 300 M tiles: paired-tile path, two accumulator sets in flight
-    (160, 128, 256, 16, 1, 3),   # paired tiles with BN=256 (single accumulator set)
+    (160, 256, 256, 16, 1, 3),   # 160 tile pairs, Cout 256, K 2304: CTA-pair kernel (cta_group::2, N tile 256 over two SMs)
+    (75, 256, 256, 14, 1, 3),    # CTA pairs, 115 M tiles (odd): the peer CTA's last tile is a dummy; tiles span images
+    (40, 256, 512, 16, 1, 3),    # CTA pairs, two 256-wide N tiles
+    (64, 256, 256, 28, 2, 3),    # CTA pairs, stride 2
 ]
 
 
@@ -108,6 +111,38 @@ def test_conv_epilogue_noise_lrelu_stats(E):
     assert (got - ref).abs().max().item() < 2e-2
     assert torch.allclose(_fx(ssum), ref.double().sum(dim=[2, 3]), rtol=1e-4, atol=1e-2)
     assert torch.allclose(_fx(ssq), (ref * ref).double().sum(dim=[2, 3]), rtol=1e-4, atol=1e-2)
+
+
+def test_conv_cta_pair_epilogue_noise_lrelu_stats(E):
+    """The CTA-pair kernel (Cout % 256 == 0, >= 37 tile pairs) with the StyleGAN epilogue: noise, bias, LeakyReLU and the
+    fused per-(n,c) statistics, each CTA of a pair flushing the sums of its own M tile; replayed for determinism."""
+    n, cin, c, res = 6, 256, 256, 64
+    g = torch.Generator().manual_seed(55)
+    x = torch.randn(n, cin, res, res, generator=g).cuda().half().float()
+    w = (torch.randn(c, cin, 3, 3, generator=g) / math.sqrt(cin * 9)).cuda().half().float()
+    bias, nw = torch.randn(c, generator=g).cuda(), torch.randn(c, generator=g).cuda()
+    noise = torch.randn(res, res, generator=g).cuda()
+    ref = F.leaky_relu(F.conv2d(x, w, padding=1) + noise.view(1, 1, res, res) * nw.view(1, -1, 1, 1)
+                       + bias.view(1, -1, 1, 1), 0.2)
+    outs = []
+    for _ in range(2):
+        out = torch.zeros(n * res * res * c, dtype=torch.float16, device="cuda")
+        ssum, ssq = _stats(n, c)
+        prog = E.Program()
+        prog.conv(inp=_nhwc16(x), n=n, hin=res, win=res, cin=cin, w=E.pack_conv_weight(w.cpu()).cuda().half(), cout=c,
+                  hout=res, wout=res, tile=E.tile_for(res), out=out, out_hwc=(res, res, c), taps=[E.TAPS3], bias=bias,
+                  noise=noise.reshape(-1).contiguous(), noise_w=nw, act=E.L.ACT_LRELU, slope=0.2, stat_sum=ssum,
+                  stat_sq=ssq)
+        assert "BN256" in prog.lib.cfr_program_op_label(prog.handle, 0).decode()
+        prog.run()
+        _sync()
+        outs.append((out, ssum.clone(), ssq.clone()))
+    got = _from_nhwc(outs[0][0], n, res, res, c)
+    assert (got - ref).abs().max().item() < 2e-2
+    assert torch.allclose(_fx(outs[0][1]), ref.double().sum(dim=[2, 3]), rtol=1e-4, atol=2e-2)
+    assert torch.allclose(_fx(outs[0][2]), (ref * ref).double().sum(dim=[2, 3]), rtol=1e-4, atol=2e-2)
+    for a, b in zip(outs[0], outs[1]):
+        assert torch.equal(a, b)
 
 
 def test_conv_prelu_residual_classbias(E):
@@ -588,7 +623,7 @@ def test_halo_upconv_few_ctas(E, monkeypatch, n, cin, cout, lo_h, lo_w, fold):
     test_halo_upconv_matches_torch(E, n, cin, cout, lo_h, lo_w, fold)
 
 
-@pytest.mark.parametrize("n,cin,cout,res,stride,ks", [(8, 128, 128, 28, 1, 3), (297, 16, 32, 8, 1, 3),
+@pytest.mark.parametrize("n,cin,cout,res,stride,ks", [(8, 128, 128, 28, 1, 3), (297, 16, 32, 8, 1, 3), (75, 256, 256, 14, 1, 3),
                                                        (150, 64, 128, 16, 1, 3), (160, 128, 256, 16, 1, 3),
                                                        (3, 256, 512, 14, 2, 3)])
 def test_conv_few_ctas(E, monkeypatch, n, cin, cout, res, stride, ks):
