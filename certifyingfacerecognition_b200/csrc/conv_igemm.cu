@@ -187,8 +187,9 @@ conv_igemm_kernel(const __grid_constant__ ConvParams p) {
         if (leader) {
           if constexpr (CG == 2) {
             // both CTAs' boxes complete on the EVEN CTA's barrier, which expects the bytes of both
-            if (crank == 0) mbar_expect_tx(&full_bar[stage], 2 * (nch * subBytes + (p.BN / 2) * 128));
-            for (int g = 0; g < nch; ++g) {
+            const int na = (p.dbg & 4) ? 0 : nch;
+            if (crank == 0) mbar_expect_tx(&full_bar[stage], 2 * (na * subBytes + (p.BN / 2) * 128));
+            for (int g = 0; g < na; ++g) {
               const int c = chunk + g;
               const int tap = c / p.nCB;
               const int cb = c - tap * p.nCB;
@@ -197,8 +198,9 @@ conv_igemm_kernel(const __grid_constant__ ConvParams p) {
             }
             tma_load_2d_pair(a_dst + kBM * 128, &p.tmB, &full_bar[stage], s * 64, wrow);
           } else {
-          mbar_expect_tx(&full_bar[stage], MT * nch * subBytes + p.BN * 128);
-          for (int g = 0; g < nch; ++g) {
+          const int na = (p.dbg & 4) ? 0 : nch;
+          mbar_expect_tx(&full_bar[stage], MT * na * subBytes + p.BN * 128);
+          for (int g = 0; g < na; ++g) {
             const int c = chunk + g;
             const int tap = c / p.nCB;
             const int cb = c - tap * p.nCB;
@@ -249,7 +251,8 @@ conv_igemm_kernel(const __grid_constant__ ConvParams p) {
         const uint32_t a0 = smem_lo + stage * stage16;
         const uint32_t b0 = a0 + MT * (kBM * 128 >> 4);
         if (leader) {
-          if constexpr (CG == 2) {         // (conv_build: CB == 64 only) one M = 256 MMA per K step across the pair
+          if (p.dbg & 2) {
+          } else if constexpr (CG == 2) {  // (conv_build: CB == 64 only) one M = 256 MMA per K step across the pair
             umma_f16_lohi_pair(d_tmem, a0, a_hi, b0, b_hi, idesc, acc);
             umma_f16_lohi_pair(d_tmem, a0 + 2, a_hi, b0 + 2, b_hi, idesc, 1u);
             umma_f16_lohi_pair(d_tmem, a0 + 4, a_hi, b0 + 4, b_hi, idesc, 1u);
@@ -387,7 +390,7 @@ conv_igemm_kernel(const __grid_constant__ ConvParams p) {
           atomicMax(&p.argmax_keys[n], key);
         }
       } else
-      for (int c0 = col_lo; c0 < col_lo + hcols; c0 += 16) {
+      for (int c0 = col_lo; c0 < ((p.dbg & 1) ? col_lo : col_lo + hcols); c0 += 16) {
         const int ch0 = t.ntile * p.BN + c0;
         // the chunk's residual (the one per-pixel global read) is requested BEFORE the TMEM load is waited for: the epilogue
         // is latency-bound, and behind the (asm volatile) tcgen05.ld / wait it would start only afterwards.  (Doing the
@@ -641,6 +644,7 @@ int conv_build(const ConvSpec& s, ConvOp* op) {
     }
     p.tilesPerItem = p.CG == 2 ? 2 : p.MT;
   }
+  if (const char* e = getenv("CFR_IGEMM_DBG")) p.dbg = atoi(e);
   p.stageBytes = p.MT * kBM * 128 + (p.CG == 2 ? bn / 2 : bn) * 128;
   const int statBytes = s.stat_sum != nullptr ? p.MT * 8 * s.Cout * 4 : 0;
   const int ctrlBytes = 8 * (2 * 8 + 4) + 16 + statBytes;

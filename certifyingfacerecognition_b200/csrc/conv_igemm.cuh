@@ -54,6 +54,8 @@ struct ConvParams {
   int numStages, stageBytes;
   int MT;                        // M tiles per CTA step (1 or 2): two adjacent tiles share every weight stage
   int nAcc;                      // TMEM accumulator sets (of MT x BN columns) in flight: 2, or 1 when MT*BN == 512
+  int dbg;                       // ablation bits for profiling only (env CFR_IGEMM_DBG; results are then garbage): 1 skip the
+                                 // epilogue's loads / math / stores, 2 skip the MMAs, 4 skip the A-tile loads
   int CG;                        // 1, or 2: a CTA PAIR (2-CTA cluster, tcgen05 cta_group::2) works on two adjacent M tiles
                                  // (one per CTA) against a 256-wide N tile of which each CTA stages half the weight rows
   int tilesPerItem;              // M tiles per work item: MT, or 2 for a CTA pair
