@@ -77,3 +77,46 @@ def test_gallery_builder_tool_roundtrip(tmp_path):
     # the gallery rows are the embeddings of the unperturbed latents: identity i must match row i
     probs = m(m.latents[2:3], torch.zeros(1, 1, 1, 5, device="cuda"))
     assert int(probs.argmax(1)) == 2
+
+
+def test_main_attack_cli_writes_reference_result_files(tmp_path, golden, models):
+    """main_attack.py --attack-type manual on the reference's cwd-relative layout: result / log files with the reference's
+    names and keys (gen_utils.py:413-437); identity 0 (decoy rows 4-7 sigma away in the gallery) is broken, as in the
+    unmodified reference's own run (tests/golden/attack_vectors.npz), and the stored delta re-verifies."""
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    from conftest import GOLDEN
+    g_sd, f_sd = models
+    from certifyingfacerecognition_b200.attack_utils import proj_utils
+    dirs = golden["dirs"]
+    os.makedirs(tmp_path / "boundaries")
+    for k, attr in enumerate(proj_utils.ATTRS):
+        np.save(tmp_path / "boundaries" / f"stylegan_ffhq_{attr}_w_boundary.npy", dirs[k:k + 1].astype(np.float64))
+    os.makedirs(tmp_path / "data" / "stylegan_ffhq_1M")
+    np.save(tmp_path / "data" / "stylegan_ffhq_1M" / "w.npy", golden["w_all"])
+    os.makedirs(tmp_path / "embeddings")
+    rows = torch.from_numpy(np.load(os.path.join(GOLDEN, "votes_gallery.npz"))["rows"])        # 8 true + 64 decoy rows
+    torch.save(rows, tmp_path / "embeddings" / "embs.pth")
+    os.makedirs(tmp_path / "weights" / "ms1mv3_arcface_r50")
+    torch.save(f_sd, tmp_path / "weights" / "ms1mv3_arcface_r50" / "backbone.pth")
+    os.makedirs(tmp_path / "models" / "pretrain")
+    torch.save(g_sd, tmp_path / "models" / "pretrain" / "stylegan_ffhq.pth")
+    env = dict(os.environ, PYTHONPATH=ROOT)
+    cmd = [sys.executable, os.path.join(ROOT, "main_attack.py"), "--output-dir", "demo", "--load-embs", "--embs-file",
+           "embeddings/embs.pth", "--load-n-embs", "72", "--chunks", "2", "--iters", "4", "--restarts", "6", "--seed", "3"]
+    r = subprocess.run(cmd, cwd=tmp_path, env=env, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stderr[-2000:]
+    out = tmp_path / "exp_results" / "demo"
+    logs = sorted(os.listdir(out / "logs"))
+    assert logs == ["results_chunk0of2.txt", "results_chunk1of2.txt"]
+    vals = dict(l.strip().split(":") for l in open(out / "logs" / logs[0]))
+    assert int(vals["instances"]) == 4 and int(vals["successes"]) >= 1 and 0 < float(vals["avg_mags"]) <= 1.001
+    data = torch.load(out / "results" / "results_chunk0of2.pth")
+    assert set(data) == {"deltas", "successes", "magnitudes"}
+    assert 0 in data["successes"].flatten().tolist()                       # identity 0 falls to one of its decoys
+    assert data["deltas"].shape[1] == 5 and (data["magnitudes"] <= 1 + 1e-3).all()
+    total = dict(l.strip().split(":") for l in open(out / "results.txt"))
+    assert int(total["instances"]) == 8 and int(total["successes"]) >= 1
+    # the variants that need a backward pass say so instead of silently doing something else
+    r2 = subprocess.run(cmd + ["--attack-type", "apgd-ce"], cwd=tmp_path, env=env, capture_output=True, text=True, timeout=300)
+    assert r2.returncode != 0 and "not" in (r2.stderr + r2.stdout)
