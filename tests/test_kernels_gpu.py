@@ -64,6 +64,8 @@ CONV_CASES = [
     (75, 256, 256, 14, 1, 3),    # CTA pairs, 115 M tiles (odd): the peer CTA's last tile is a dummy; tiles span images
     (40, 256, 512, 16, 1, 3),    # CTA pairs, two 256-wide N tiles
     (64, 256, 256, 28, 2, 3),    # CTA pairs, stride 2
+    (3, 128, 128, 128, 1, 3),    # 128-wide grid (one image row per M tile), two K chunks
+    (2, 64, 256, 128, 1, 3),     # ... two N tiles
 ]
 
 
@@ -111,6 +113,38 @@ def test_conv_epilogue_noise_lrelu_stats(E):
     assert (got - ref).abs().max().item() < 2e-2
     assert torch.allclose(_fx(ssum), ref.double().sum(dim=[2, 3]), rtol=1e-4, atol=1e-2)
     assert torch.allclose(_fx(ssq), (ref * ref).double().sum(dim=[2, 3]), rtol=1e-4, atol=1e-2)
+
+
+def test_conv_128_wide_epilogue_noise_lrelu_stats(E, monkeypatch):
+    """StyleGAN layer 11's shape (128-pixel-wide grid, one image row per M tile) with the StyleGAN epilogue and fused
+    statistics, on 3 CTAs so that every CTA walks many tile pairs / ring wraps; replayed for bit identity."""
+    monkeypatch.setenv("CFR_MAX_CTAS", "3")
+    n, cin, c, res = 2, 128, 128, 128
+    g = torch.Generator().manual_seed(56)
+    x = torch.randn(n, cin, res, res, generator=g).cuda().half().float()
+    w = (torch.randn(c, cin, 3, 3, generator=g) / math.sqrt(cin * 9)).cuda().half().float()
+    bias, nw = torch.randn(c, generator=g).cuda(), torch.randn(c, generator=g).cuda()
+    noise = torch.randn(res, res, generator=g).cuda()
+    ref = F.leaky_relu(F.conv2d(x, w, padding=1) + noise.view(1, 1, res, res) * nw.view(1, -1, 1, 1)
+                       + bias.view(1, -1, 1, 1), 0.2)
+    outs = []
+    for _ in range(2):
+        out = torch.zeros(n * res * res * c, dtype=torch.float16, device="cuda")
+        ssum, ssq = _stats(n, c)
+        prog = E.Program()
+        prog.conv(inp=_nhwc16(x), n=n, hin=res, win=res, cin=cin, w=E.pack_conv_weight(w.cpu()).cuda().half(), cout=c,
+                  hout=res, wout=res, tile=E.tile_for(res), out=out, out_hwc=(res, res, c), taps=[E.TAPS3], bias=bias,
+                  noise=noise.reshape(-1).contiguous(), noise_w=nw, act=E.L.ACT_LRELU, slope=0.2, stat_sum=ssum,
+                  stat_sq=ssq)
+        prog.run()
+        _sync()
+        outs.append((out, ssum.clone(), ssq.clone()))
+    got = _from_nhwc(outs[0][0], n, res, res, c)
+    assert (got - ref).abs().max().item() < 2e-2
+    assert torch.allclose(_fx(outs[0][1]), ref.double().sum(dim=[2, 3]), rtol=1e-4, atol=5e-2)
+    assert torch.allclose(_fx(outs[0][2]), (ref * ref).double().sum(dim=[2, 3]), rtol=1e-4, atol=5e-2)
+    for a, b in zip(outs[0], outs[1]):
+        assert torch.equal(a, b)
 
 
 def test_conv_cta_pair_epilogue_noise_lrelu_stats(E):
@@ -179,7 +213,9 @@ def test_conv_prelu_residual_classbias(E):
 
 
 @pytest.mark.parametrize("cin,cout,lo,fused", [(512, 512, 4, False), (64, 32, 16, True), (32, 16, 32, True),
-                                                 (128, 64, 8, False)])
+                                                 (128, 64, 8, False),
+                                                 # 128-wide grids (StyleGAN layer 12's shape): one image row per M tile
+                                                 (128, 64, 128, False), (64, 128, 128, False)])
 def test_upconv_phases_match_upsample_conv(E, cin, cout, lo, fused):
     n = 2
     g = torch.Generator().manual_seed(cin + lo)
