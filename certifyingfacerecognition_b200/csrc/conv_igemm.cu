@@ -92,16 +92,26 @@ __device__ __forceinline__ void flush_stats(const ConvParams& p, float* s_sum, f
 // CTAs' epilogue warps arrive on the even CTA's `tempty`.  Bytes pulled from L2 per FLOP: 32 KB per 128 x 256 x 64 per SM
 // instead of 48 KB (MT == 2, BN == 128) -- these layers sit on the chip-wide L2 -> SM cap -- with both accumulator sets
 // (2 x 256 columns) still in flight.
-template <int MT, int CG = 1>
+//
+// ROWS (with MT == 2, CG == 1; layers whose output grid is exactly 128 pixels wide: StyleGAN L11 / L12): a work item is two
+// consecutive image rows (x one or two column phases of an up-conv's row phase).  Per 64-channel K chunk ONE TMA box of
+// aRows input rows x 130 pixels lands in a two-deep A ring; every tap of both rows is that box read through a shifted
+// UMMA descriptor ((row, pixel) offset in units of the 128-byte swizzled rows -- the swizzle is a function of the
+// absolute shared-memory address, so shifted starts stay consistent with what TMA wrote, as in conv_halo.cu).  Weight
+// tiles stream through their own ring, one per (phase, tap, K chunk).  A bytes per K chunk: 66 KB instead of 18 x 16 KB
+// (3x3) and 50 KB instead of 16 x 16 KB for both column phases of an up-conv row phase: these layers sit on the
+// chip-wide L2 -> SM cap (profiles/ncu_r02_notes.md sections 4, 10).
+template <int MT, int CG = 1, bool ROWS = false>
 __global__ void __launch_bounds__(MT == 2 ? kConvThreadsMT2 : kConvThreads, 1)
 conv_igemm_kernel(const __grid_constant__ ConvParams p) {
   static_assert(CG == 1 || MT == 1, "a CTA pair works on one M tile per CTA");
+  static_assert(!ROWS || (MT == 2 && CG == 1), "ROWS: two image rows per CTA step");
   constexpr int TPI = CG == 2 ? 2 : MT;           // M tiles per work item
   const uint32_t crank = CG == 2 ? cluster_ctarank() : 0u;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const int S = p.numStages;
-  uint8_t* ctrl = smem + static_cast<size_t>(S) * p.stageBytes;
+  const int S = p.numStages;                      // (ROWS: bStages + 2 -- the last two barrier pairs belong to the A ring)
+  uint8_t* ctrl = smem + p.ctrlOffset;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(ctrl);
   uint64_t* empty_bar = full_bar + S;
   uint64_t* tfull_bar = empty_bar + S;
@@ -117,7 +127,9 @@ conv_igemm_kernel(const __grid_constant__ ConvParams p) {
 
   // (an odd tile count leaves the last pair with a dummy second tile: its sample index is >= N, so TMA zero-fills its
   //  A box and the epilogue only keeps the barriers in step)
-  const int totalItems = ((p.tilesX * p.tilesY * p.tilesN + TPI - 1) / TPI) * p.numPhases * p.numNTiles;
+  const int totalItems = ROWS ? p.N * (p.Hout / 2) * p.rowsNPG * p.numNTiles
+                              : ((p.tilesX * p.tilesY * p.tilesN + TPI - 1) / TPI) * p.numPhases * p.numNTiles;
+  const int accW = ROWS ? 128 : p.BN;             // TMEM columns per M tile (ROWS: rowsPG phases x BN)
   const int nWorkers = CG == 2 ? gridDim.x / 2 : gridDim.x;       // a CTA pair walks one item list together
   const int per = (totalItems + nWorkers - 1) / nWorkers;
   const int item0 = (CG == 2 ? blockIdx.x / 2 : blockIdx.x) * per;
@@ -127,12 +139,22 @@ conv_igemm_kernel(const __grid_constant__ ConvParams p) {
   const int stagesPerTile = (chunksTotal + p.G - 1) / p.G;
   const uint32_t subBytes = kBM * p.CB * 2;
   uint32_t tmemCols = 32;
-  while (tmemCols < static_cast<uint32_t>(p.nAcc * MT * p.BN)) tmemCols <<= 1;
+  while (tmemCols < static_cast<uint32_t>(p.nAcc * MT * accW)) tmemCols <<= 1;
 
   if (warp == kProducerWarp && lane == 0) {
-    tma_prefetch_desc(&p.tmA);
+    tma_prefetch_desc(ROWS ? &p.tmA2 : &p.tmA);
     tma_prefetch_desc(&p.tmB);
   }
+  // ROWS work item -> (image, first output row, phase group, N tile)
+  auto rows_item = [&](int item, int& n, int& y0, int& pg, int& ntile) {
+    ntile = item % p.numNTiles;
+    int r = item / p.numNTiles;
+    pg = r % p.rowsNPG;
+    r /= p.rowsNPG;
+    const int hp = p.Hout / 2;
+    y0 = 2 * (r % hp);
+    n = r / hp;
+  };
   if (warp == kMmaWarp) {
     if (lane == 0) {
       for (int i = 0; i < S; ++i) {
@@ -171,6 +193,49 @@ conv_igemm_kernel(const __grid_constant__ ConvParams p) {
     const bool leader = elect_one();
     int stage = 0;
     uint32_t phase = 0;
+    if constexpr (ROWS) {
+      const int SB = p.bStages;
+      uint8_t* bring = smem + 2 * p.aBoxBytes;
+      const uint32_t bBytes = static_cast<uint32_t>(p.BN) * 128u;
+      int ab = 0;
+      uint32_t abphase = 0;
+      for (int item = item0; item < item1; ++item) {
+        int n, y0, pg, ntile;
+        rows_item(item, n, y0, pg, ntile);
+        for (int cb = 0; cb < p.nCB; ++cb) {
+          mbar_wait(&empty_bar[SB + ab], abphase ^ 1);
+          if (leader) {
+            const bool skip = (p.dbg & 4) != 0;
+            mbar_expect_tx(&full_bar[SB + ab], skip ? 0u : static_cast<uint32_t>(p.aRows) * 130u * 128u);
+            if (!skip)
+              tma_load_4d(smem + ab * p.aBoxBytes, &p.tmA2, &full_bar[SB + ab], cb * 64, -1, y0 + p.rowsDyMin[pg], n);
+          }
+          __syncwarp();
+          if (++ab == 2) {
+            ab = 0;
+            abphase ^= 1;
+          }
+          for (int j = 0; j < p.rowsPG; ++j) {
+            const int ph = pg * p.rowsPG + j;
+            const int wrow = ph * p.wRowsPerPhase + ntile * p.BN;
+            for (int t = 0; t < p.ntaps; t += p.tapsPerStage) {
+              mbar_wait(&empty_bar[stage], phase ^ 1);
+              if (leader) {
+                mbar_expect_tx(&full_bar[stage], bBytes * p.tapsPerStage);
+                for (int u = 0; u < p.tapsPerStage; ++u)
+                  tma_load_2d(bring + (stage * p.tapsPerStage + u) * bBytes, &p.tmB, &full_bar[stage],
+                              ((t + u) * p.nCB + cb) * 64, wrow);
+              }
+              __syncwarp();
+              if (++stage == SB) {
+                stage = 0;
+                phase ^= 1;
+              }
+            }
+          }
+        }
+      }
+    } else
     for (int item = item0; item < item1; ++item) {
       const TileCoord t = decode_item(p, item, CG == 2 ? static_cast<int>(crank) : 0);
       const TileCoord t1 = decode_item(p, item, MT - 1);          // second tile of the pair (== t when MT == 1)
@@ -235,6 +300,71 @@ conv_igemm_kernel(const __grid_constant__ ConvParams p) {
     uint32_t phase = 0;
     int as = 0;
     uint32_t aphase = 0;
+    if constexpr (ROWS) {
+      const int SB = p.bStages;
+      const uint32_t bring16 = smem_lo + ((2u * static_cast<uint32_t>(p.aBoxBytes)) >> 4);
+      const uint32_t b16 = (static_cast<uint32_t>(p.BN) * 128u) >> 4;
+      const uint32_t abox16 = static_cast<uint32_t>(p.aBoxBytes) >> 4;
+      int ab = 0;
+      uint32_t abphase = 0;
+      for (int item = item0; item < item1; ++item) {
+        int n, y0, pg, ntile;
+        rows_item(item, n, y0, pg, ntile);
+        mbar_wait(&tempty_bar[as], aphase ^ 1);
+        tc_fence_after();
+        const uint32_t d_base = tmem_base + as * MT * 128;
+        for (int cb = 0; cb < p.nCB; ++cb) {
+          mbar_wait(&full_bar[SB + ab], abphase);
+          tc_fence_after();
+          const uint32_t a_base = smem_lo + ab * abox16;
+          for (int j = 0; j < p.rowsPG; ++j) {
+            const int ph = pg * p.rowsPG + j;
+            for (int t0 = 0; t0 < p.ntaps; t0 += p.tapsPerStage) {
+              mbar_wait(&full_bar[stage], phase);
+              tc_fence_after();
+              for (int u = 0; u < p.tapsPerStage; ++u)
+              if (leader && !(p.dbg & 2)) {
+                const int t = t0 + u;
+                // input (row, pixel) of output pixel 0 of tile 0 inside the box, in 128-byte rows (16-byte units: x 8)
+                const int r0 = p.tap_dy[ph][t] - p.rowsDyMin[pg];
+                const int c0 = p.tap_dx[ph][t] + 1;
+                const uint32_t a0 = a_base + static_cast<uint32_t>(r0 * 130 + c0) * 8u;
+                const uint32_t a1 = a0 + 130u * 8u;                        // second output row
+                const uint32_t b0 = bring16 + (stage * p.tapsPerStage + u) * b16;
+                const uint32_t d0 = d_base + j * p.BN, d1 = d0 + 128;
+                const uint32_t acc = (cb == 0 && t == 0) ? 0u : 1u;
+                umma_f16_lohi(d0, a0, a_hi, b0, b_hi, idesc, acc);
+                umma_f16_lohi(d1, a1, a_hi, b0, b_hi, idesc, acc);
+                umma_f16_lohi(d0, a0 + 2, a_hi, b0 + 2, b_hi, idesc, 1u);
+                umma_f16_lohi(d1, a1 + 2, a_hi, b0 + 2, b_hi, idesc, 1u);
+                umma_f16_lohi(d0, a0 + 4, a_hi, b0 + 4, b_hi, idesc, 1u);
+                umma_f16_lohi(d1, a1 + 4, a_hi, b0 + 4, b_hi, idesc, 1u);
+                umma_f16_lohi(d0, a0 + 6, a_hi, b0 + 6, b_hi, idesc, 1u);
+                umma_f16_lohi(d1, a1 + 6, a_hi, b0 + 6, b_hi, idesc, 1u);
+              }
+              if (leader) umma_commit(&empty_bar[stage]);
+              __syncwarp();
+              if (++stage == SB) {
+                stage = 0;
+                phase ^= 1;
+              }
+            }
+          }
+          if (leader) umma_commit(&empty_bar[SB + ab]);                   // this K chunk's input rows are free again
+          __syncwarp();
+          if (++ab == 2) {
+            ab = 0;
+            abphase ^= 1;
+          }
+        }
+        if (leader) umma_commit(&tfull_bar[as]);
+        __syncwarp();
+        if (++as == p.nAcc) {
+          as = 0;
+          aphase ^= 1;
+        }
+      }
+    } else
     for (int item = (CG == 2 && crank != 0) ? item1 : item0; item < item1; ++item) {
       mbar_wait(&tempty_bar[as], aphase ^ 1);
       tc_fence_after();
@@ -304,8 +434,10 @@ conv_igemm_kernel(const __grid_constant__ ConvParams p) {
     const int slice = MT == 2 ? (egrp & 1) : 0;  // which tile of this CTA's (MT) tiles this group drains
     const int sub = CG == 2 ? static_cast<int>(crank) : slice;     // ... = which tile of the work item
     const int half = MT == 2 ? (egrp >> 1) : egrp;               // which half of the tile's BN columns
-    const int hcols = (p.BN % 32 == 0) ? p.BN / 2 : (half == 0 ? p.BN : 0);   // columns of this half (BN = 16 / 48 / ..: half 0 takes all)
-    const int col_lo = half * (p.BN / 2);
+    const int hcols = (accW % 32 == 0) ? accW / 2 : (half == 0 ? accW : 0);   // columns of this half (BN = 16 / 48 / ..: half 0 takes all)
+    const int col_lo = half * (accW / 2);
+    // ROWS with two phases per item: the column halves ARE the two phases (BN = 64 each)
+    const int chan_off = (ROWS && p.rowsPG == 2) ? col_lo : 0;
     const int q = warp & 3;                      // TMEM lane quarter this warp may read (== warp id % 4)
     const int row = q * 32 + lane;               // M row == pixel index inside the tile box
     const int tx = row % p.TW;
@@ -320,8 +452,16 @@ conv_igemm_kernel(const __grid_constant__ ConvParams p) {
     int cur_img = -1;
     const bool do_stats = p.stat_sum != nullptr;
     for (int item = item0; item < item1; ++item) {
-      const TileCoord t = decode_item(p, item, sub);
-      if (TPI == 2 && t.n0 >= p.N) {             // dummy tile of an odd tile count
+      TileCoord t;
+      if constexpr (ROWS) {
+        int n, y0, pg, ntile;
+        rows_item(item, n, y0, pg, ntile);
+        t.n0 = n; t.y0 = y0 + sub; t.x0 = 0; t.ntile = ntile;
+        t.phase = pg * p.rowsPG + (p.rowsPG == 2 ? half : 0);
+      } else {
+        t = decode_item(p, item, sub);
+      }
+      if (!ROWS && TPI == 2 && t.n0 >= p.N) {    // dummy tile of an odd tile count
         mbar_wait(&tfull_bar[as], aphase);
         tc_fence_after();
         tc_fence_before();
@@ -358,7 +498,7 @@ conv_igemm_kernel(const __grid_constant__ ConvParams p) {
 
       mbar_wait(&tfull_bar[as], aphase);
       tc_fence_after();
-      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + (as * MT + slice) * p.BN;
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + (as * MT + slice) * accW;
       if (p.argmax_keys != nullptr) {
         // gallery match: score = acc + bias[j] (= 2 e.g_j - |g_j|^2); keep the best column of this tile per row and
         // fold it into the global per-query key (max score, then lowest index == torch.argmax tie-break)
@@ -369,7 +509,7 @@ conv_igemm_kernel(const __grid_constant__ ConvParams p) {
         for (int c0 = col_lo; c0 < col_lo + hcols; c0 += 16) {
           float v[16];
           tmem_ld16(t_row + c0, v);
-          const int ch0 = t.ntile * p.BN + c0;
+          const int ch0 = t.ntile * p.BN + c0 - chan_off;
 #pragma unroll
           for (int i = 0; i < 16; i += 4) {
             const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + ch0 + i));
@@ -391,7 +531,7 @@ conv_igemm_kernel(const __grid_constant__ ConvParams p) {
         }
       } else
       for (int c0 = col_lo; c0 < ((p.dbg & 1) ? col_lo : col_lo + hcols); c0 += 16) {
-        const int ch0 = t.ntile * p.BN + c0;
+        const int ch0 = t.ntile * p.BN + c0 - chan_off;
         // the chunk's residual (the one per-pixel global read) is requested BEFORE the TMEM load is waited for: the epilogue
         // is latency-bound, and behind the (asm volatile) tcgen05.ld / wait it would start only afterwards.  (Doing the
         // same for the per-channel vectors costs 48 more registers: the 18-warp kernel is capped at 96 and spills;
@@ -643,6 +783,38 @@ int conv_build(const ConvSpec& s, ConvOp* op) {
       p.numNTiles = s.Cout / bn;
     }
     p.tilesPerItem = p.CG == 2 ? 2 : p.MT;
+    // ROWS mode (see the kernel comment): exactly 128 output pixels per row, stride 1, 64-channel K chunks, shared weights
+    static const int rows_env = getenv("CFR_IGEMM_ROWS") != nullptr ? atoi(getenv("CFR_IGEMM_ROWS")) : 1;
+    p.rows = 0;
+    if (rows_env != 0 && p.CG == 1 && s.Wout == 128 && s.Win == 128 && s.Hin == s.Hout && s.stride == 1 && s.TW == 128 &&
+        s.TH == 1 && s.TN == 1 && s.Hout % 2 == 0 && s.Cin % 64 == 0 && s.kSplit != 3 && s.wRowsPerSample == 0) {
+      bool ok = false;
+      if (s.numPhases == 1 && s.ntaps == 9 && s.Cout % 128 == 0) {          // 3x3: rows y-1 .. y+2 serve two output rows
+        ok = true;
+        for (int t = 0; t < 9; ++t)
+          ok = ok && s.tap_dy[0][t] >= -1 && s.tap_dy[0][t] <= 1 && s.tap_dx[0][t] >= -1 && s.tap_dx[0][t] <= 1;
+        p.aRows = 4; p.rowsPG = 1; p.rowsNPG = 1; p.rowsDyMin[0] = -1; p.rowsDyMin[1] = -1;
+        bn = 128;
+      } else if (s.numPhases == 4 && s.ntaps == 4 && s.Cout % 64 == 0 && s.wRowsPerPhase == s.Cout) {
+        // nearest-x2 up-conv: phases (a, b) = 2a + b; both column phases of row phase a read input rows {a-1, a}
+        ok = true;
+        for (int ph = 0; ph < 4; ++ph)
+          for (int t = 0; t < 4; ++t) {
+            const int a = ph >> 1;
+            ok = ok && s.tap_dy[ph][t] >= a - 1 && s.tap_dy[ph][t] <= a && s.tap_dx[ph][t] >= -1 && s.tap_dx[ph][t] <= 1;
+          }
+        p.aRows = 3; p.rowsPG = 2; p.rowsNPG = 2; p.rowsDyMin[0] = -1; p.rowsDyMin[1] = 0;
+        bn = 64;
+      }
+      if (ok) {
+        p.rows = 1;
+        p.MT = 2;
+        p.nAcc = 2;
+        p.tilesPerItem = 2;
+        p.BN = bn;
+        p.numNTiles = s.Cout / bn;
+      }
+    }
   }
   if (const char* e = getenv("CFR_IGEMM_DBG")) p.dbg = atoi(e);
   p.stageBytes = p.MT * kBM * 128 + (p.CG == 2 ? bn / 2 : bn) * 128;
@@ -651,6 +823,17 @@ int conv_build(const ConvSpec& s, ConvOp* op) {
   const int budget = 227 * 1024 - 1024 - ctrlBytes;
   p.numStages = budget / p.stageBytes;
   if (p.numStages > 8) p.numStages = 8;
+  if (p.rows) {                                        // two input-row boxes + a ring of weight tiles
+    p.aBoxBytes = (p.aRows * 130 * 128 + 1023) / 1024 * 1024;
+    p.tapsPerStage = ((budget - 2 * p.aBoxBytes) / (s.ntaps * bn * 128) >= 3) ? s.ntaps : 1;
+    p.bStages = (budget - 2 * p.aBoxBytes) / (p.tapsPerStage * bn * 128);
+    if (p.bStages > 6) p.bStages = 6;
+    if (p.bStages < 3) p.rows = 0;                     // (cannot happen for BN <= 128; falls back to the tile-pair kernel)
+    else {
+      p.numStages = p.bStages + 2;
+      p.stageBytes = 0;
+    }
+  }
   if (p.numStages < 3 && p.MT == 2) {                   // not enough stages to pipeline: fall back to one tile per step
     p.MT = 1;
     p.tilesPerItem = 1;
@@ -660,7 +843,8 @@ int conv_build(const ConvSpec& s, ConvOp* op) {
     if (p.numStages > 8) p.numStages = 8;
   }
   if (p.numStages < 2) { set_error("conv: not enough shared memory for 2 stages"); return 2; }
-  op->smemBytes = p.numStages * p.stageBytes + (8 * (2 * 8 + 4) + 16 + (s.stat_sum != nullptr ? p.MT * 8 * s.Cout * 4 : 0)) + 1024;
+  p.ctrlOffset = p.rows ? 2 * p.aBoxBytes + p.bStages * p.tapsPerStage * bn * 128 : p.numStages * p.stageBytes;
+  op->smemBytes = p.ctrlOffset + (8 * (2 * 8 + 4) + 16 + (s.stat_sum != nullptr ? p.MT * 8 * s.Cout * 4 : 0)) + 1024;
   p.wRowsPerSample = s.wRowsPerSample;
   p.wRowsPerPhase = s.wRowsPerPhase;
   if (s.outIsF32) p.out32 = static_cast<float*>(s.out); else p.out = static_cast<__half*>(s.out);
@@ -685,6 +869,16 @@ int conv_build(const ConvSpec& s, ConvOp* op) {
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(A) failed: %d (C=%d W=%d H=%d N=%d box=%u,%u,%u,%u)", (int)r, s.Cin, s.Win, s.Hin, s.N, box[0], box[1], box[2], box[3]); return 3; }
   }
+  if (p.rows) {                                        // input rows: (C, W, H, N), box {64, 130, aRows, 1}
+    cuuint64_t dims[4] = {(cuuint64_t)s.Cin, (cuuint64_t)s.Win, (cuuint64_t)s.Hin, (cuuint64_t)s.N};
+    cuuint64_t strides[3] = {(cuuint64_t)s.Cin * 2, (cuuint64_t)s.Win * s.Cin * 2, (cuuint64_t)s.Hin * s.Win * s.Cin * 2};
+    cuuint32_t box[4] = {64, 130, (cuuint32_t)p.aRows, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = enc(&p.tmA2, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(s.in), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(A rows) failed: %d", (int)r); return 3; }
+  }
   // weights: (Kpad, rows), fp16
   {
     cuuint64_t dims[2] = {(cuuint64_t)s.Kpad, (cuuint64_t)s.wRows};
@@ -698,7 +892,8 @@ int conv_build(const ConvSpec& s, ConvOp* op) {
   }
   if (s.Kpad % 64 != 0 || s.Kpad < s.ntaps * s.Cin) { set_error("conv: Kpad=%d must be a multiple of 64 and >= taps*Cin", s.Kpad); return 2; }
 
-  const int total = ((p.tilesX * p.tilesY * p.tilesN + p.tilesPerItem - 1) / p.tilesPerItem) * p.numPhases * p.numNTiles;
+  const int total = p.rows ? s.N * (s.Hout / 2) * p.rowsNPG * p.numNTiles
+                           : ((p.tilesX * p.tilesY * p.tilesN + p.tilesPerItem - 1) / p.tilesPerItem) * p.numPhases * p.numNTiles;
   op->grid = total < num_sms() ? total : num_sms();
   if (p.CG == 2) op->grid = 2 * (total < num_sms() / 2 ? total : num_sms() / 2);      // whole CTA pairs
   if (const char* e = getenv("CFR_MAX_CTAS")) {      // tests: few CTAs => many work items per CTA (ring wrap, phase flips)
@@ -778,6 +973,8 @@ int conv_launch(const ConvOp& op, cudaStream_t stream) {
       attr_err = cudaFuncSetAttribute(conv_igemm_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (attr_err == cudaSuccess)
       attr_err = cudaFuncSetAttribute(conv_igemm_kernel<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (attr_err == cudaSuccess)
+      attr_err = cudaFuncSetAttribute(conv_igemm_kernel<2, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   });
   if (attr_err != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(attr_err)); return 4; }
   cudaEvent_t e1 = nullptr;
@@ -806,7 +1003,8 @@ int conv_launch(const ConvOp& op, cudaStream_t stream) {
   cfg.stream = stream;
   cfg.attrs = attr;
   cfg.numAttrs = na;
-  if (op.p.CG == 2) cudaLaunchKernelEx(&cfg, conv_igemm_kernel<1, 2>, op.p);
+  if (op.p.rows) cudaLaunchKernelEx(&cfg, conv_igemm_kernel<2, 1, true>, op.p);
+  else if (op.p.CG == 2) cudaLaunchKernelEx(&cfg, conv_igemm_kernel<1, 2>, op.p);
   else if (op.p.MT == 2) cudaLaunchKernelEx(&cfg, conv_igemm_kernel<2>, op.p);
   else cudaLaunchKernelEx(&cfg, conv_igemm_kernel<1>, op.p);
   if (profile_on()) {

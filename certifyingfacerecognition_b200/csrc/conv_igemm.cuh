@@ -59,6 +59,19 @@ struct ConvParams {
   int CG;                        // 1, or 2: a CTA PAIR (2-CTA cluster, tcgen05 cta_group::2) works on two adjacent M tiles
                                  // (one per CTA) against a 256-wide N tile of which each CTA stages half the weight rows
   int tilesPerItem;              // M tiles per work item: MT, or 2 for a CTA pair
+  int ctrlOffset;                // bytes from the (1024-aligned) shared-memory base to the barrier block
+  // ROWS mode (128-pixel-wide layers: an M tile is one image row): per 64-channel K chunk ONE box of `aRows` input rows
+  // x 130 pixels serves every tap of two output rows -- taps are row / pixel shifts of the A descriptor, as in the halo
+  // kernel -- and, for up-convs, both column phases of a row phase; weights stream through their own ring
+  int rows;                      // 0 / 1
+  int aRows;                     // input rows per box: 4 (3x3) or 3 (nearest-x2 up-conv row phase)
+  int aBoxBytes;                 // aRows * 130 * 128 rounded up to 1024
+  int bStages;                   // weight ring depth
+  int tapsPerStage;              // weight tiles behind one barrier: all taps of a phase when the ring still holds >= 3 such
+                                 // stages (fewer, longer pipeline round trips), else 1
+  int rowsPG, rowsNPG;           // phases per work item (1 or 2: same row phase), work-item phase groups
+  int8_t rowsDyMin[2];           // first input row of the box relative to the item's first output row, per phase group
+  CUtensorMap tmA2;              // activations (C, W, H, N), box {64, 130, aRows, 1}
   int wRowsPerSample;            // 0: weights shared by all samples
   int wRowsPerPhase;
   // output

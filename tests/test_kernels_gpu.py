@@ -64,8 +64,8 @@ CONV_CASES = [
     (75, 256, 256, 14, 1, 3),    # CTA pairs, 115 M tiles (odd): the peer CTA's last tile is a dummy; tiles span images
     (40, 256, 512, 16, 1, 3),    # CTA pairs, two 256-wide N tiles
     (64, 256, 256, 28, 2, 3),    # CTA pairs, stride 2
-    (3, 128, 128, 128, 1, 3),    # 128-wide grid (one image row per M tile), two K chunks
-    (2, 64, 256, 128, 1, 3),     # ... two N tiles
+    (3, 128, 128, 128, 1, 3),    # 128-wide grid: ROWS kernel (row-shared A operand), 3x3, two K chunks
+    (2, 64, 256, 128, 1, 3),     # ROWS kernel, two N tiles
 ]
 
 
@@ -116,8 +116,8 @@ def test_conv_epilogue_noise_lrelu_stats(E):
 
 
 def test_conv_128_wide_epilogue_noise_lrelu_stats(E, monkeypatch):
-    """StyleGAN layer 11's shape (128-pixel-wide grid, one image row per M tile) with the StyleGAN epilogue and fused
-    statistics, on 3 CTAs so that every CTA walks many tile pairs / ring wraps; replayed for bit identity."""
+    """StyleGAN layer 11's shape (128-pixel-wide grid: the ROWS kernel) with the StyleGAN epilogue and fused statistics, on
+    3 CTAs so that every CTA walks many row pairs / ring wraps; replayed for bit identity."""
     monkeypatch.setenv("CFR_MAX_CTAS", "3")
     n, cin, c, res = 2, 128, 128, 128
     g = torch.Generator().manual_seed(56)
@@ -214,7 +214,8 @@ def test_conv_prelu_residual_classbias(E):
 
 @pytest.mark.parametrize("cin,cout,lo,fused", [(512, 512, 4, False), (64, 32, 16, True), (32, 16, 32, True),
                                                  (128, 64, 8, False),
-                                                 # 128-wide grids (StyleGAN layer 12's shape): one image row per M tile
+                                                 # 128-wide grids (StyleGAN layer 12's shape): the ROWS kernel -- one box of
+                                                 # input rows per K chunk serves all taps of two rows and both column phases
                                                  (128, 64, 128, False), (64, 128, 128, False)])
 def test_upconv_phases_match_upsample_conv(E, cin, cout, lo, fused):
     n = 2
