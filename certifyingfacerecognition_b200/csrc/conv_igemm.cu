@@ -823,6 +823,10 @@ int conv_build(const ConvSpec& s, ConvOp* op) {
   const int budget = 227 * 1024 - 1024 - ctrlBytes;
   p.numStages = budget / p.stageBytes;
   if (p.numStages > 8) p.numStages = 8;
+  if (const char* e = getenv("CFR_IGEMM_STAGES_MAX")) {          // experiment: pipeline depth vs throughput (Little's law)
+    const int m = atoi(e);
+    if (m >= 2 && p.numStages > m) p.numStages = m;
+  }
   if (p.rows) {                                        // two input-row boxes + a ring of weight tiles
     p.aBoxBytes = (p.aRows * 130 * 128 + 1023) / 1024 * 1024;
     p.tapsPerStage = ((budget - 2 * p.aBoxBytes) / (s.ntaps * bn * 128) >= 3) ? s.ntaps : 1;
