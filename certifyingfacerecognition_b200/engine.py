@@ -364,8 +364,8 @@ class SynthesisProgram(Program):
             off += 2 * layer_channels(l)
         self.style_rows = off
         rows_trunc = self.style_off[TRUNC_LAYERS]
-        w_style = self.hold(_f32(torch.cat(ws), dev))
-        b_style = self.hold(_f32(torch.cat(bs), dev))
+        w_style = self.w_style = self.hold(_f32(torch.cat(ws), dev))      # (kept: StyleGANGenerator's WP path fills `styles` itself)
+        b_style = self.b_style = self.hold(_f32(torch.cat(bs), dev))
         self.styles = self.hold(torch.zeros(chunk, off, device=dev))
         L.check(lib.cfr_program_add_styles(h, L.ptr(self.wp2), L.ptr(w_style), L.ptr(b_style), off, rows_trunc,
                                            chunk, L.ptr(self.styles)))

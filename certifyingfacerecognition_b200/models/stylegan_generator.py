@@ -3,8 +3,9 @@
 
 Z -> MappingModule (cfr_mapping) -> W -> truncation -> 18-layer synthesis (the same tcgen05 programs as the
 certification path) -> toRGB + postprocess at the full 1024^2 resolution.  Method names, argument meaning, returned
-dictionary keys ('z', 'w', 'wp', 'styleNN', 'image') and error behaviour follow the reference; 'WP' inputs whose 18
-rows differ arbitrarily are not supported (the engine feeds the truncated / un-truncated pair of one W), and say so."""
+dictionary keys ('z', 'w', 'wp', 'styleNN', 'image') and error behaviour follow the reference.  'WP' inputs (18 arbitrary
+per-layer latents, no truncation) evaluate the 18 style dense layers on the host side of the API and replay the recorded
+program from its second op (the engine's own styles kernel feeds the truncated / un-truncated pair of one W)."""
 from __future__ import annotations
 
 import math
@@ -116,8 +117,12 @@ class StyleGANGenerator:
                 ws = _f32(lc, self.device)
                 results["w"] = latent_codes
         elif t == "WP":
-            raise NotImplementedError("arbitrary per-layer WP latents are outside the built path (SURVEY.md section 8f); "
-                                      "pass Z or W codes")
+            # per-layer latents go straight to the synthesis network, no truncation (mod_stylegan_generator.py:257-279)
+            if not (lc.dim() == 3 and lc.shape[0] <= self.batch_size and lc.shape[1] == NUM_LAYERS and lc.shape[2] == LATENT_DIM):
+                raise ValueError("Latent_codes should be with shape [batch_size, num_layers, latent_space_dim], where "
+                                 f"`batch_size` no larger than {self.batch_size}, `num_layers` equal to {NUM_LAYERS}, and "
+                                 f"`latent_space_dim` equal to {LATENT_DIM}!\nBut {tuple(lc.shape)} received!")
+            return self._synthesize_wp(_f32(lc, self.device), latent_codes, generate_style, generate_image)
         else:
             raise ValueError(f"Latent space type `{latent_space_type}` is invalid!")
         b = ws.shape[0]
@@ -137,6 +142,29 @@ class StyleGANGenerator:
                 results[f"style{i:02d}"] = st[:, off:off + 2 * c].cpu().numpy()
         if generate_image:
             results["image"] = self.synth.img_planar[:b].clone()          # already postprocess()'d (see easy_synthesize)
+        return results
+
+    def _synthesize_wp(self, wps: torch.Tensor, latent_codes, generate_style: bool, generate_image: bool) -> Dict[str, object]:
+        """'WP' inputs: every layer has its own latent, so the 18 style dense layers (stylegan_generator_model.py:503) are
+        evaluated here -- styles[:, layer l] = wp[:, l] @ W_l^T / sqrt(512) + b_l, a host-side API path -- written into the
+        program's style buffer, and the recorded program is replayed from its second op (op 0 is the W-path styles kernel)."""
+        results: Dict[str, object] = {"wp": latent_codes}
+        b = wps.shape[0]
+        syn = self.synth
+        if generate_style or generate_image:
+            st = syn.styles
+            for l in range(NUM_LAYERS):
+                off, c = syn.style_off[l], layer_channels(l)
+                st[:b, off:off + 2 * c] = (wps[:, l] @ syn.w_style[off:off + 2 * c].T) * (1.0 / math.sqrt(LATENT_DIM)) \
+                    + syn.b_style[off:off + 2 * c]
+            syn.out_slot.zero_()
+            syn.run_range(1, syn.num_launches)
+        if generate_style:
+            for i in range(NUM_LAYERS):
+                off, c = syn.style_off[i], layer_channels(i)
+                results[f"style{i:02d}"] = syn.styles[:b, off:off + 2 * c].cpu().numpy()
+        if generate_image:
+            results["image"] = syn.img_planar[:b].clone()
         return results
 
     def easy_synthesize(self, latent_codes, **kwargs) -> Dict[str, object]:

@@ -75,6 +75,31 @@ def test_z_path_equals_w_path(gen):
         g.synthesize(v["z"][:2], latent_space_type="Q")
 
 
+def test_wp_latents_go_straight_to_synthesis(gen):
+    """latent_space_type='WP' (mod_stylegan_generator.py:257-279): [b,18,512] per-layer latents, no truncation.  Fed with
+    the 'wp' a W run returned, it must reproduce that run's styles and image; with layer-wise DIFFERENT latents only the
+    layers that changed move (style mixing), checked against the oracle's synthesis on the same wp."""
+    from oracle import mc_path as M
+    g, sd = gen
+    w = torch.from_numpy(np.load(os.path.join(ROOT, "tests", "golden", "mapping_vectors.npz"))["w"][:2])
+    out_w = g.easy_synthesize(w, latent_space_type="W", generate_style=True, generate_image=True)
+    out_wp = g.easy_synthesize(out_w["wp"], latent_space_type="WP", generate_style=True, generate_image=True)
+    for i in (0, 7, 8, 17):
+        assert np.allclose(out_wp[f"style{i:02d}"], out_w[f"style{i:02d}"], atol=1e-4)
+    assert (out_wp["image"] - out_w["image"]).abs().mean().item() < 1e-3
+    mixed = torch.from_numpy(out_w["wp"]).clone()
+    mixed[0, 8:] = mixed[1, 8:]                              # coarse layers of sample 0, fine layers of sample 1
+    out_m = g.easy_synthesize(mixed.numpy(), latent_space_type="WP", generate_style=True, generate_image=True)
+    assert np.allclose(out_m["style03"][0], out_w["style03"][0], atol=1e-4)
+    assert np.allclose(out_m["style12"][0], out_w["style12"][1], atol=1e-4)
+    with torch.no_grad():
+        ref = M.postprocess(M.synthesis(mixed, sd, literal=False))
+    d = (out_m["image"].cpu() - ref).abs()
+    assert d.mean().item() < 4e-3, d.mean().item()
+    with pytest.raises(ValueError):
+        g.synthesize(mixed[:, :17].numpy(), latent_space_type="WP")
+
+
 def test_generate_data_cli_writes_reference_layout(tmp_path):
     out = tmp_path / "gen"
     r = subprocess.run([sys.executable, os.path.join(ROOT, "generate_data.py"), "-m", "stylegan_ffhq", "-o", str(out),
