@@ -14,10 +14,18 @@ namespace cfr {
 // --------------------------------------------------------------------------------------------
 // device
 // --------------------------------------------------------------------------------------------
-// Warp roles.  The single MMA-issuing thread lives in the HIGHEST warp: the SM sub-partition arbiter favours
-// higher warp ids, and a starved issuer stalls the whole pipeline (profiles/ncu_r01_notes.md).
-constexpr int kProducerWarp = 4;
-constexpr int kMmaWarp = 5;
+// Warp roles: epilogue warps first (groups of four, warp id & 3 == TMEM lane quarter), then the TMA producer, and the
+// single MMA-issuing thread in the HIGHEST warp (round 1: the SM sub-partition arbiter favours higher warp ids and a starved
+// issuer stalls the whole pipeline; re-measured with 16 epilogue warps -- issuer in warp 5 of 18 vs warp 17: no difference,
+// CFR_IGEMM_MMA_WARP_LAST=0 builds the old layout).
+#ifndef CFR_IGEMM_MMA_WARP_LAST
+#define CFR_IGEMM_MMA_WARP_LAST 1
+#endif
+template <int MT> struct Roles {
+  static constexpr int kEpi = 8 * MT;                                         // epilogue warps
+  static constexpr int kProducer = CFR_IGEMM_MMA_WARP_LAST ? kEpi : 4;
+  static constexpr int kMma = CFR_IGEMM_MMA_WARP_LAST ? kEpi + 1 : 5;
+};
 
 struct TileCoord {
   int n0, y0, x0, phase, ntile;
@@ -141,7 +149,7 @@ conv_igemm_kernel(const __grid_constant__ ConvParams p) {
   uint32_t tmemCols = 32;
   while (tmemCols < static_cast<uint32_t>(p.nAcc * MT * accW)) tmemCols <<= 1;
 
-  if (warp == kProducerWarp && lane == 0) {
+  if (warp == Roles<MT>::kProducer && lane == 0) {
     tma_prefetch_desc(ROWS ? &p.tmA2 : &p.tmA);
     tma_prefetch_desc(&p.tmB);
   }
@@ -155,7 +163,7 @@ conv_igemm_kernel(const __grid_constant__ ConvParams p) {
     y0 = 2 * (r % hp);
     n = r / hp;
   };
-  if (warp == kMmaWarp) {
+  if (warp == Roles<MT>::kMma) {
     if (lane == 0) {
       for (int i = 0; i < S; ++i) {
         mbar_init(&full_bar[i], 1);
@@ -187,7 +195,7 @@ conv_igemm_kernel(const __grid_constant__ ConvParams p) {
   pdl_trigger();
   pdl_wait();
 
-  if (warp == kProducerWarp) {
+  if (warp == Roles<MT>::kProducer) {
     // ===================================================================== TMA producer
     // (whole warp runs the loop so coordinates / descriptors stay in uniform registers; one elected lane issues)
     const bool leader = elect_one();
@@ -286,7 +294,7 @@ conv_igemm_kernel(const __grid_constant__ ConvParams p) {
         }
       }
     }
-  } else if (warp == kMmaWarp) {
+  } else if (warp == Roles<MT>::kMma) {
     // ===================================================================== MMA issuer (CTA pair: the even CTA's only)
     const bool leader = elect_one() && crank == 0;
     const uint32_t idesc = make_idesc_f16(CG == 2 ? 2 * kBM : kBM, p.BN);
@@ -430,7 +438,7 @@ conv_igemm_kernel(const __grid_constant__ ConvParams p) {
     }
   } else {
     // ===================================================================== epilogue (warps 0..3 and 6..)
-    const int egrp = warp < 4 ? 0 : (warp - 2) >> 2;             // epilogue group 0 .. 2 * MT - 1
+    const int egrp = CFR_IGEMM_MMA_WARP_LAST ? (warp >> 2) : (warp < 4 ? 0 : (warp - 2) >> 2);   // group 0 .. 2 * MT - 1
     const int slice = MT == 2 ? (egrp & 1) : 0;  // which tile of this CTA's (MT) tiles this group drains
     const int sub = CG == 2 ? static_cast<int>(crank) : slice;     // ... = which tile of the work item
     const int half = MT == 2 ? (egrp >> 1) : egrp;               // which half of the tile's BN columns
@@ -652,7 +660,7 @@ conv_igemm_kernel(const __grid_constant__ ConvParams p) {
   tc_fence_before();
   __syncthreads();
   if constexpr (CG == 2) cluster_sync_all();      // no CTA leaves while its peer may still read its shared memory / TMEM
-  if (warp == kMmaWarp) {
+  if (warp == Roles<MT>::kMma) {
     tc_fence_after();
     if constexpr (CG == 2) tmem_dealloc_pair(tmem_base, tmemCols); else tmem_dealloc(tmem_base, tmemCols);
   }

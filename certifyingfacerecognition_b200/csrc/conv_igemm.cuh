@@ -22,8 +22,8 @@
 
 namespace cfr {
 
-// warps 0-3: epilogue, warp 4: TMA producer, warp 5: MMA issuer + TMEM owner, warps 6..: more epilogue groups of four
-// warps (one per TMEM lane quarter).  Every M tile is drained by TWO groups, each taking half of the tile's BN columns:
+// warps 0 .. 8*MT-1: epilogue groups of four warps (one per TMEM lane quarter), then the TMA producer warp, then the MMA
+// issuer + TMEM owner.  Every M tile is drained by TWO groups, each taking half of the tile's BN columns:
 // the epilogue is latency-bound (tcgen05.ld, __ldg of the per-channel vectors, shuffle reduces: ncu shows its warps
 // issuing 12 % of the time and never waiting on the fused-statistics layers), so twice the warps is twice its rate.
 // MT == 1: groups {0: half 0, 1: half 1};  MT == 2: groups {0: tile 0 half 0, 1: tile 1 half 0, 2: tile 0 half 1, 3: tile 1 half 1}
