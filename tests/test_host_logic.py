@@ -316,3 +316,36 @@ def test_reference_collection_recipe_lists_only_path_modules():
         assert os.path.isfile(os.path.join(dst, "smoothing", "smooth.py"))
         assert open(os.path.join(dst, "smoothing", "smooth.py")).read() == \
             open(os.path.join(build_ref.SRC, "smoothing", "smooth.py")).read()
+
+
+def test_committed_bench_lines_follow_the_contract():
+    """The bench lines committed under profiles/ (what the round's numbers are quoted from) carry every key of the bench
+    contract, and their derived numbers are consistent with each other."""
+    import json
+    with open(os.path.join(ROOT, "profiles", "bench_r02_final_1gpu.json")) as fh:
+        d = json.loads(fh.read().strip().splitlines()[-1])
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "e2e", "gpu_launches", "roofline", "cpu_baseline", "clocks"):
+        assert k in d, k
+    assert d["n_gpus"] == 1 and d["higher_is_better"] is True and d["vs_baseline"] is None and d["warmup"] >= 3
+    assert "workload" in d["config"] and "model" not in d["config"]
+    assert d["value"] == pytest.approx(250 / (d["ms_per_step"] * 1e-3), rel=1e-6)            # 250 samples per step
+    e = d["e2e"]
+    assert e["h2d_bytes_per_step"] > 0 and e["d2h_bytes_per_step"] > 0 and e["value"] != d["value"]
+    for r in (d["roofline"], d["roofline_second_kernel"]):
+        assert r["bound"] in ("hbm", "tensor") and r["frac"] == pytest.approx(r["achieved"] / r["peak"], rel=1e-9)
+        assert 0 < r["share_of_step"] < 1 and r["launches_timed"] > 0
+    assert d["roofline_second_kernel"]["traffic"] is not None and "traffic_r02_halo" in d["roofline_second_kernel"]["traffic_source"]
+    c = d["cpu_baseline"]
+    assert c["kind"] == "reference" and c["cores"] >= 1 and 0 < c["value"] < 100
+    assert not set(d["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+    with open(os.path.join(ROOT, "profiles", "bench_r02_reference_arm.json")) as fh:
+        r = json.loads(fh.read().strip().splitlines()[-1])
+    assert r["impl"] == "reference" and r["metric"] == d["metric"] and r["unit"] == d["unit"]
+    assert r["e2e"]["h2d_bytes_per_step"] == 0 and r["cpu_baseline"]["kind"] == "reference"
+    # N > 1: the headline is config 3 (samples sharded + NCCL sum), scaling "strong", identities-sharded beside it
+    for n in (2, 4, 8):
+        with open(os.path.join(ROOT, "profiles", f"cfg_r02_N{n}_bench.json")) as fh:
+            m = json.loads(fh.read().strip().splitlines()[-1])
+        assert m["n_gpus"] == n and m["scaling"] == "strong" and m["config"]["shard"] == "samples"
+        assert m["value"] > 0.9 * n * 7000 and m["identities_sharded"]["value"] > m["value"] * 0.9
