@@ -407,7 +407,12 @@ __global__ void __launch_bounds__(256) k_blur_act_stats(const T* __restrict__ ra
 // Separable [1,2,1]/4 x [1,2,1]/4 blur with a 3-row sliding window in registers: every thread owns 8 channels of one
 // pixel column and walks down a band of kBlurRows rows, so each raw element is loaded ~3x from L1 and ~1x from
 // HBM (the 9-tap form above loads it 9x).  Then +noise*w +bias, LeakyReLU(0.2), fp16 store, per-(n,c) sums.
-constexpr int kBlurRows = 32;
+// Strip height: 128 rows (2 halo rows re-read per 128 instead of per 32: L12 3.42 -> 3.1 us, L14 7.2 -> 6.5 us per sample;
+// 256 / 512 are within the run-to-run noise of 128 and leave fewer blocks for the small layers).
+#ifndef CFR_BLUR_ROWS
+#define CFR_BLUR_ROWS 128
+#endif
+constexpr int kBlurRows = CFR_BLUR_ROWS;
 
 struct Raw3 {
   uint4 l, c, r;
