@@ -78,41 +78,6 @@ struct cfr_sampler {
   }
 };
 
-// ---- the FRM side of one group: serial on `stream`, or on the sampler's second stream behind an image copy ----------
-static cudaStream_t frm_stream_begin(cfr_sampler* s, cudaStream_t stream, int chunks) {
-  if (!s->active) {
-    if (s->d.img_frm != nullptr)        // programs are recorded on img_frm: serial mode still needs the copy
-      cudaMemcpyAsync(s->d.img_frm, s->d.img_src, s->d.img_chunk_bytes * chunks, cudaMemcpyDeviceToDevice, stream);
-    return stream;
-  }
-  cudaEventRecord(s->ev_synth, stream);
-  cudaStreamWaitEvent(s->s2, s->ev_synth, 0);
-  cudaMemcpyAsync(s->d.img_frm, s->d.img_src, s->d.img_chunk_bytes * chunks, cudaMemcpyDeviceToDevice, s->s2);
-  cudaEventRecord(s->ev_copied, s->s2);
-  s->copied_pending = true;
-  return s->s2;
-}
-// before the caller's stream overwrites img_src again
-static void synth_may_overwrite(cfr_sampler* s, cudaStream_t stream) {
-  if (s->active && s->copied_pending) {
-    cudaStreamWaitEvent(stream, s->ev_copied, 0);
-    s->copied_pending = false;
-  }
-}
-static void overlap_begin(cfr_sampler* s, cudaStream_t stream, bool several_groups) {
-  s->active = s->overlap && several_groups;
-  if (!s->active) return;
-  cudaEventRecord(s->ev_start, stream);          // e.g. the caller's zeroing of `counts` precedes the votes
-  cudaStreamWaitEvent(s->s2, s->ev_start, 0);
-}
-static void overlap_join(cfr_sampler* s, cudaStream_t stream) {
-  if (!s->active) return;
-  cudaEventRecord(s->ev_done, s->s2);
-  cudaStreamWaitEvent(stream, s->ev_done, 0);
-  s->copied_pending = false;
-  s->active = false;
-}
-
 static inline cudaStream_t S(cfr_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 
 #define CFR_CUDA(call)                                                        \
@@ -123,6 +88,48 @@ static inline cudaStream_t S(cfr_stream_t s) { return reinterpret_cast<cudaStrea
       return 5;                                                               \
     }                                                                         \
   } while (0)
+
+// ---- the FRM side of one group: serial on `stream`, or on the sampler's second stream behind an image copy ----------
+static int frm_stream_begin(cfr_sampler* s, cudaStream_t stream, int chunks, cudaStream_t* out) {
+  const size_t bytes = static_cast<size_t>(s->d.img_chunk_bytes) * chunks;
+  if (!s->active) {
+    if (s->d.img_frm != nullptr)        // programs are recorded on img_frm: serial mode still needs the copy
+      CFR_CUDA(cudaMemcpyAsync(s->d.img_frm, s->d.img_src, bytes, cudaMemcpyDeviceToDevice, stream));
+    *out = stream;
+    return 0;
+  }
+  CFR_CUDA(cudaEventRecord(s->ev_synth, stream));
+  CFR_CUDA(cudaStreamWaitEvent(s->s2, s->ev_synth, 0));
+  CFR_CUDA(cudaMemcpyAsync(s->d.img_frm, s->d.img_src, bytes, cudaMemcpyDeviceToDevice, s->s2));
+  CFR_CUDA(cudaEventRecord(s->ev_copied, s->s2));
+  s->copied_pending = true;
+  *out = s->s2;
+  return 0;
+}
+// before the caller's stream overwrites img_src again
+static int synth_may_overwrite(cfr_sampler* s, cudaStream_t stream) {
+  if (s->active && s->copied_pending) {
+    CFR_CUDA(cudaStreamWaitEvent(stream, s->ev_copied, 0));
+    s->copied_pending = false;
+  }
+  return 0;
+}
+static int overlap_begin(cfr_sampler* s, cudaStream_t stream, bool several_groups) {
+  s->active = s->overlap && several_groups;
+  s->copied_pending = false;            // a call that failed half-way may have left it set
+  if (!s->active) return 0;
+  CFR_CUDA(cudaEventRecord(s->ev_start, stream));          // e.g. the caller's zeroing of `counts` precedes the votes
+  CFR_CUDA(cudaStreamWaitEvent(s->s2, s->ev_start, 0));
+  return 0;
+}
+static int overlap_join(cfr_sampler* s, cudaStream_t stream) {
+  if (!s->active) return 0;
+  s->active = false;
+  s->copied_pending = false;
+  CFR_CUDA(cudaEventRecord(s->ev_done, s->s2));
+  CFR_CUDA(cudaStreamWaitEvent(stream, s->ev_done, 0));
+  return 0;
+}
 
 extern "C" {
 
@@ -541,7 +548,7 @@ CFR_API int cfr_sample_votes(cfr_sampler* s, const float* z, const float* x, con
   if (sigma_len != 1 && sigma_len != 5) { set_error("sigma_len must be 1 or 5"); return 2; }
   const int K = (d.frm_group > 1 && d.frm_big != nullptr && d.out_slot != nullptr) ? d.frm_group : 1;
   int64_t done = 0;
-  overlap_begin(s, S(stream), num > static_cast<int64_t>(K) * d.chunk);
+  if (int r0 = overlap_begin(s, S(stream), num > static_cast<int64_t>(K) * d.chunk)) return r0;
   while (done < num) {
     const int64_t rem = num - done;
     if (rem < d.chunk && d.tail != nullptr) {
@@ -550,7 +557,7 @@ CFR_API int cfr_sample_votes(cfr_sampler* s, const float* z, const float* x, con
       for (cfr_sampler* t = d.tail; t != nullptr; t = t->d.tail)
         if (t->d.chunk >= rem && (best == nullptr || t->d.chunk < best->d.chunk)) best = t;
       if (best != nullptr) {
-        overlap_join(s, S(stream));
+        if (int rj = overlap_join(s, S(stream))) return rj;
         return cfr_sample_votes(best, z, x, sigma, sigma_len, noise_in ? noise_in + done * 5 : nullptr, rem, seed,
                                 sample_offset + done, counts, pred_out ? pred_out + done : nullptr,
                                 emb_out ? emb_out + done * 512 : nullptr, noise_out ? noise_out + done * 5 : nullptr, stream);
@@ -559,7 +566,7 @@ CFR_API int cfr_sample_votes(cfr_sampler* s, const float* z, const float* x, con
     // a full group of K chunks goes through the big ArcFace program (better SM fill); the tail chunk by chunk
     const int g = (num - done >= static_cast<int64_t>(K) * d.chunk) ? K : 1;
     const int b = static_cast<int>(num - done < static_cast<int64_t>(g) * d.chunk ? num - done : static_cast<int64_t>(g) * d.chunk);
-    synth_may_overwrite(s, S(stream));
+    if (int rw = synth_may_overwrite(s, S(stream))) return rw;
     for (int k = 0; k < g; ++k) {
       const int64_t off = done + static_cast<int64_t>(k) * d.chunk;
       const int bk = static_cast<int>(num - off < d.chunk ? num - off : d.chunk);
@@ -570,9 +577,11 @@ CFR_API int cfr_sample_votes(cfr_sampler* s, const float* z, const float* x, con
       if (r) return r;
       if ((r = cfr_program_run(d.synth, stream)) != 0) return r;
     }
-    cudaStream_t fs = frm_stream_begin(s, S(stream), g);
+    cudaStream_t fs = nullptr;
+    int r = frm_stream_begin(s, S(stream), g, &fs);
+    if (r) return r;
     cfr_stream_t fst = reinterpret_cast<cfr_stream_t>(fs);
-    int r = cfr_program_run(g == K && K > 1 ? d.frm_big : d.frm, fst);
+    r = cfr_program_run(g == K && K > 1 ? d.frm_big : d.frm, fst);
     if (r) return r;
     const float* emb = (g == K && K > 1) ? d.emb_big : d.emb;
     if (emb_out) {
@@ -587,8 +596,7 @@ CFR_API int cfr_sample_votes(cfr_sampler* s, const float* z, const float* x, con
     if (r) return r;
     done += b;
   }
-  overlap_join(s, S(stream));
-  return 0;
+  return overlap_join(s, S(stream));
 }
 
 CFR_API int cfr_sample_votes_multi(cfr_sampler* s, int n_ids, const float* z, const float* x, const float* sigma,
@@ -620,11 +628,11 @@ CFR_API int cfr_sample_votes_multi(cfr_sampler* s, int n_ids, const float* z, co
     int np = 0, slot = 0;
     int r = 0;
     if (cur != last) {
-      if (last != nullptr) overlap_join(last, S(stream));
-      overlap_begin(cur, S(stream), left > cur->d.chunk);
+      if (last != nullptr && (r = overlap_join(last, S(stream))) != 0) return r;
+      if ((r = overlap_begin(cur, S(stream), left > cur->d.chunk)) != 0) return r;
       last = cur;
     }
-    synth_may_overwrite(cur, S(stream));
+    if ((r = synth_may_overwrite(cur, S(stream))) != 0) return r;
     if (d.out_slot != nullptr && (r = launch_set_int(d.out_slot, 0, S(stream))) != 0) return r;
     while (slot < cap && g < n_ids) {
       const int64_t rem = num_host[g] - g_done;
@@ -640,7 +648,8 @@ CFR_API int cfr_sample_votes_multi(cfr_sampler* s, int n_ids, const float* z, co
       g_done += b;
     }
     if ((r = cfr_program_run(d.synth, stream)) != 0) return r;
-    cudaStream_t fs = frm_stream_begin(cur, S(stream), 1);
+    cudaStream_t fs = nullptr;
+    if ((r = frm_stream_begin(cur, S(stream), 1, &fs)) != 0) return r;
     cfr_stream_t fst = reinterpret_cast<cfr_stream_t>(fs);
     if ((r = cfr_program_run(d.frm, fst)) != 0) return r;
     for (int i = 0; i < np; ++i) {
@@ -653,8 +662,7 @@ CFR_API int cfr_sample_votes_multi(cfr_sampler* s, int n_ids, const float* z, co
     }
     left -= slot;
   }
-  if (last != nullptr) overlap_join(last, S(stream));
-  return 0;
+  return last != nullptr ? overlap_join(last, S(stream)) : 0;
 }
 
 CFR_API int cfr_sample_votes_host(cfr_sampler* s, const float* z_host, const float* x_host, const float* sigma_host,
