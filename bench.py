@@ -359,7 +359,7 @@ def main():
 
     headline_certify = world > 1 and ident_mode and not args.headline_batches
     # at least 10 untimed steps (~0.35 s): the SM clock is still settling under the power cap during the first few, and the
-    # timed region would otherwise read 3-4 % low (the number actually used is what the JSON line reports as "warmup")
+    # timed region would otherwise read 3-4 % low ("warmup" echoes the W asked for, "warmup_steps_run" the number run)
     warm = max(10, args.warmup)
     sampler = ClockSampler(local_rank) if rank == 0 else None
     results, snap = {}, {}
@@ -468,7 +468,8 @@ def main():
     second = results["batches" if headline_certify else "certify"]
     line = {
         "metric": "MC samples/sec (StyleGAN1024->ArcFace vote)", "value": value, "unit": "samples/s", "n_gpus": world,
-        "steps": args.steps, "warmup": warm, "ms_per_step": ms / args.steps, "higher_is_better": True,
+        "steps": args.steps, "warmup": args.warmup, "warmup_steps_run": warm, "ms_per_step": ms / args.steps,
+        "higher_is_better": True,
         "scaling": "strong" if (headline_certify or not ident_mode) else "weak", "vs_baseline": None,
         "dtype": "fp16 operands / fp32 accumulate (StyleGAN layers 1-%d: fp16 hi/lo split operands, fp32 activations)"
                  % eng.hp_layers,
