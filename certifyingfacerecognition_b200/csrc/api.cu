@@ -217,7 +217,7 @@ CFR_API int cfr_program_add_conv(cfr_program* p, const cfr_conv_desc* d) {
   char lab[160];
   snprintf(lab, sizeof(lab), "conv %dx%d s%d taps%dx%d Cin%d%s Cout%d grid%dx%d n%d BN%d%s", d->Hout, d->Wout, d->stride,
            d->numPhases, d->ntaps, d->kSplit == 3 ? d->Cin / 3 : d->Cin, d->kSplit == 3 ? "(x3 hi/lo)" : "", d->Cout,
-           d->Hout, d->Wout, d->N, raw->p.BN, raw->p.rows ? " rows" : (raw->p.CG == 2 ? " cta-pair" : ""));
+           d->Hout, d->Wout, d->N, raw->p.BN, raw->p.rows ? (raw->p.rowsMerge ? " rows-merged" : " rows") : (raw->p.CG == 2 ? " cta-pair" : ""));
   p->add([raw](cudaStream_t st) { return conv_launch(*raw, st); }, lab, raw->flops);
   return 0;
 }

@@ -223,6 +223,38 @@ conv_igemm_kernel(const __grid_constant__ ConvParams p) {
             ab = 0;
             abphase ^= 1;
           }
+          if (p.rowsMerge == 2) {
+            // one tile per stage, column by column of the 3x3, rows bottom-up: the tiles of (dy, dy - 1) are consecutive
+            for (int u = 0; u < 9; ++u) {
+              mbar_wait(&empty_bar[stage], phase ^ 1);
+              if (leader) {
+                mbar_expect_tx(&full_bar[stage], bBytes);
+                tma_load_2d(bring + stage * bBytes, &p.tmB, &full_bar[stage], (p.rowsTap[u] * p.nCB + cb) * 64, ntile * p.BN);
+              }
+              __syncwarp();
+              if (++stage == SB) {
+                stage = 0;
+                phase ^= 1;
+              }
+            }
+          } else if (p.rowsMerge) {
+            // one stage per input row i: [ph0 (i, left) | ph0 (i, centre) | ph1 (i, centre) | ph1 (i, right)] -- the two
+            // centre tiles are adjacent, so they form the 2*BN-row B operand of the shared MMA
+            for (int i = 0; i < 2; ++i) {
+              mbar_wait(&empty_bar[stage], phase ^ 1);
+              if (leader) {
+                mbar_expect_tx(&full_bar[stage], bBytes * 4);
+                for (int u = 0; u < 4; ++u)
+                  tma_load_2d(bring + (stage * 4 + u) * bBytes, &p.tmB, &full_bar[stage],
+                              ((2 * i + (u & 1)) * p.nCB + cb) * 64, (pg * 2 + (u >> 1)) * p.wRowsPerPhase + ntile * p.BN);
+              }
+              __syncwarp();
+              if (++stage == SB) {
+                stage = 0;
+                phase ^= 1;
+              }
+            }
+          } else
           for (int j = 0; j < p.rowsPG; ++j) {
             const int ph = pg * p.rowsPG + j;
             const int wrow = ph * p.wRowsPerPhase + ntile * p.BN;
@@ -325,6 +357,86 @@ conv_igemm_kernel(const __grid_constant__ ConvParams p) {
           mbar_wait(&full_bar[SB + ab], abphase);
           tc_fence_after();
           const uint32_t a_base = smem_lo + ab * abox16;
+          if (p.rowsMerge == 2) {
+            // 3x3, output rows y0 and y0 + 1: input row q (relative to y0) feeds row 0 with W(dy = q) and row 1 with
+            // W(dy = q - 1).  For q = 0, 1 both exist and their tiles are consecutive ring slots: ONE N = 256 MMA writes both
+            // rows' accumulators (columns [0,128) | [128,256)) unless the pair straddles the ring's wrap-around.
+            const uint32_t idesc2 = make_idesc_f16(kBM, 256);
+            for (int g = 0; g < 3; ++g) {
+              int st[3];
+              for (int v = 0; v < 3; ++v) {
+                st[v] = stage;
+                mbar_wait(&full_bar[stage], phase);
+                if (++stage == SB) {
+                  stage = 0;
+                  phase ^= 1;
+                }
+              }
+              tc_fence_after();
+              if (leader && !(p.dbg & 2)) {
+                const uint32_t aq = a_base + static_cast<uint32_t>(g) * 8u;       // box row 0 (q = -1), pixel offset dx + 1 = g
+                constexpr uint32_t row = 130u * 8u;
+                const uint32_t b0 = bring16 + st[0] * b16, b1 = bring16 + st[1] * b16, b2 = bring16 + st[2] * b16;
+                const uint32_t d0 = d_base, d1 = d_base + 128;
+#pragma unroll
+                for (uint32_t k = 0; k < 8; k += 2) {
+                  const uint32_t acc = (cb == 0 && g == 0 && k == 0) ? 0u : 1u;   // the first (q = 1) MMAs initialise both rows
+                  if (st[1] == st[0] + 1) {
+                    umma_f16_lohi(d0, aq + 2 * row + k, a_hi, b0 + k, b_hi, idesc2, acc);
+                  } else {
+                    umma_f16_lohi(d0, aq + 2 * row + k, a_hi, b0 + k, b_hi, idesc, acc);
+                    umma_f16_lohi(d1, aq + 2 * row + k, a_hi, b1 + k, b_hi, idesc, acc);
+                  }
+                  if (st[2] == st[1] + 1) {
+                    umma_f16_lohi(d0, aq + row + k, a_hi, b1 + k, b_hi, idesc2, 1u);
+                  } else {
+                    umma_f16_lohi(d0, aq + row + k, a_hi, b1 + k, b_hi, idesc, 1u);
+                    umma_f16_lohi(d1, aq + row + k, a_hi, b2 + k, b_hi, idesc, 1u);
+                  }
+                  umma_f16_lohi(d1, aq + 3 * row + k, a_hi, b0 + k, b_hi, idesc, 1u);     // q = 2: row 1 only, W(dy = +1)
+                  umma_f16_lohi(d0, aq + k, a_hi, b2 + k, b_hi, idesc, 1u);               // q = -1: row 0 only, W(dy = -1)
+                }
+              }
+              if (leader) {
+                umma_commit(&empty_bar[st[0]]);
+                umma_commit(&empty_bar[st[1]]);
+                umma_commit(&empty_bar[st[2]]);
+              }
+              __syncwarp();
+            }
+          } else if (p.rowsMerge) {
+            const uint32_t idesc2 = make_idesc_f16(kBM, 2 * p.BN);
+            const int ph0 = pg * 2, ph1 = ph0 + 1;
+            for (int i = 0; i < 2; ++i) {
+              mbar_wait(&full_bar[stage], phase);
+              tc_fence_after();
+              if (leader && !(p.dbg & 2)) {
+                const int r0 = p.tap_dy[ph0][2 * i] - p.rowsDyMin[pg];
+                const uint32_t arow = a_base + static_cast<uint32_t>(r0 * 130 + 1) * 8u;
+                const uint32_t aL = arow + p.tap_dx[ph0][2 * i] * 8, aC = arow + p.tap_dx[ph0][2 * i + 1] * 8,
+                               aR = arow + p.tap_dx[ph1][2 * i + 1] * 8;
+                const uint32_t bL = bring16 + (stage * 4) * b16, bC = bL + b16, bR = bL + 3 * b16;
+                const uint32_t dL = d_base, dR = d_base + p.BN;
+                constexpr uint32_t row2 = 130u * 8u;                          // second output row
+#pragma unroll
+                for (uint32_t k = 0; k < 8; k += 2) {
+                  const uint32_t acc = (cb == 0 && i == 0 && k == 0) ? 0u : 1u;    // the wide MMA initialises both phases
+                  umma_f16_lohi(dL, aC + k, a_hi, bC + k, b_hi, idesc2, acc);
+                  umma_f16_lohi(dL + 128, aC + row2 + k, a_hi, bC + k, b_hi, idesc2, acc);
+                  umma_f16_lohi(dL, aL + k, a_hi, bL + k, b_hi, idesc, 1u);
+                  umma_f16_lohi(dL + 128, aL + row2 + k, a_hi, bL + k, b_hi, idesc, 1u);
+                  umma_f16_lohi(dR, aR + k, a_hi, bR + k, b_hi, idesc, 1u);
+                  umma_f16_lohi(dR + 128, aR + row2 + k, a_hi, bR + k, b_hi, idesc, 1u);
+                }
+              }
+              if (leader) umma_commit(&empty_bar[stage]);
+              __syncwarp();
+              if (++stage == SB) {
+                stage = 0;
+                phase ^= 1;
+              }
+            }
+          } else
           for (int j = 0; j < p.rowsPG; ++j) {
             const int ph = pg * p.rowsPG + j;
             for (int t0 = 0; t0 < p.ntaps; t0 += p.tapsPerStage) {
@@ -796,13 +908,18 @@ int conv_build(const ConvSpec& s, ConvOp* op) {
     p.rows = 0;
     if (rows_env != 0 && p.CG == 1 && s.Wout == 128 && s.Win == 128 && s.Hin == s.Hout && s.stride == 1 && s.TW == 128 &&
         s.TH == 1 && s.TN == 1 && s.Hout % 2 == 0 && s.Cin % 64 == 0 && s.kSplit != 3 && s.wRowsPerSample == 0) {
-      bool ok = false;
+      bool ok = false, merge = false, merge3 = false;
       if (s.numPhases == 1 && s.ntaps == 9 && s.Cout % 128 == 0) {          // 3x3: rows y-1 .. y+2 serve two output rows
         ok = true;
         for (int t = 0; t < 9; ++t)
           ok = ok && s.tap_dy[0][t] >= -1 && s.tap_dy[0][t] <= 1 && s.tap_dx[0][t] >= -1 && s.tap_dx[0][t] <= 1;
         p.aRows = 4; p.rowsPG = 1; p.rowsNPG = 1; p.rowsDyMin[0] = -1; p.rowsDyMin[1] = -1;
         bn = 128;
+        static const int merge3_env = getenv("CFR_IGEMM_ROWS_MERGE") != nullptr ? atoi(getenv("CFR_IGEMM_ROWS_MERGE")) : 1;
+        for (int u = 0; u < 9; ++u) p.rowsTap[u] = -1;
+        for (int t = 0; ok && t < 9; ++t) p.rowsTap[(s.tap_dx[0][t] + 1) * 3 + (1 - s.tap_dy[0][t])] = t;
+        merge3 = ok && merge3_env != 0;
+        for (int u = 0; u < 9; ++u) merge3 = merge3 && p.rowsTap[u] >= 0;
       } else if (s.numPhases == 4 && s.ntaps == 4 && s.Cout % 64 == 0 && s.wRowsPerPhase == s.Cout) {
         // nearest-x2 up-conv: phases (a, b) = 2a + b; both column phases of row phase a read input rows {a-1, a}
         ok = true;
@@ -813,6 +930,15 @@ int conv_build(const ConvSpec& s, ConvOp* op) {
           }
         p.aRows = 3; p.rowsPG = 2; p.rowsNPG = 2; p.rowsDyMin[0] = -1; p.rowsDyMin[1] = 0;
         bn = 64;
+        // taps of a phase ordered (row, column) and the two column phases of a row phase sharing their middle input column
+        static const int merge_env = getenv("CFR_IGEMM_ROWS_MERGE") != nullptr ? atoi(getenv("CFR_IGEMM_ROWS_MERGE")) : 1;
+        merge = merge_env != 0;
+        for (int a = 0; a < 2; ++a)
+          for (int i = 0; i < 2; ++i) {
+            const int p0 = 2 * a, p1 = p0 + 1, dy = s.tap_dy[p0][2 * i];
+            merge = merge && s.tap_dy[p0][2 * i + 1] == dy && s.tap_dy[p1][2 * i] == dy && s.tap_dy[p1][2 * i + 1] == dy &&
+                    s.tap_dx[p0][2 * i + 1] == s.tap_dx[p1][2 * i];
+          }
       }
       if (ok) {
         p.rows = 1;
@@ -821,6 +947,7 @@ int conv_build(const ConvSpec& s, ConvOp* op) {
         p.tilesPerItem = 2;
         p.BN = bn;
         p.numNTiles = s.Cout / bn;
+        p.rowsMerge = merge ? 1 : (merge3 ? 2 : 0);
       }
     }
   }
@@ -840,6 +967,8 @@ int conv_build(const ConvSpec& s, ConvOp* op) {
     p.tapsPerStage = ((budget - 2 * p.aBoxBytes) / (s.ntaps * bn * 128) >= 3) ? s.ntaps : 1;
     p.bStages = (budget - 2 * p.aBoxBytes) / (p.tapsPerStage * bn * 128);
     if (p.bStages > 6) p.bStages = 6;
+    if (p.rowsMerge == 1 && p.tapsPerStage != s.ntaps) p.rowsMerge = 0;   // stages four tiles (one input row of both phases)
+    if (p.rowsMerge == 2 && p.tapsPerStage != 1) p.rowsMerge = 0;         // streams single tiles
     if (p.bStages < 3) p.rows = 0;                     // (cannot happen for BN <= 128; falls back to the tile-pair kernel)
     else {
       p.numStages = p.bStages + 2;

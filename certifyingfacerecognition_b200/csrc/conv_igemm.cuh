@@ -70,6 +70,9 @@ struct ConvParams {
   int tapsPerStage;              // weight tiles behind one barrier: all taps of a phase when the ring still holds >= 3 such
                                  // stages (fewer, longer pipeline round trips), else 1
   int rowsPG, rowsNPG;           // phases per work item (1 or 2: same row phase), work-item phase groups
+  int rowsMerge;                 // 1 (up-conv): the input column both column phases read feeds ONE N = 2*BN MMA (3 instead of 4
+                                 // per row); 2 (3x3): an input row both output rows read feeds ONE N = 256 MMA (12 instead of 18)
+  int rowsTap[9];                // rowsMerge == 2: tap index of (dx, dy) in the order dx = -1, 0, 1; dy = +1, 0, -1
   int8_t rowsDyMin[2];           // first input row of the box relative to the item's first output row, per phase group
   CUtensorMap tmA2;              // activations (C, W, H, N), box {64, 130, aRows, 1}
   int wRowsPerSample;            // 0: weights shared by all samples
