@@ -478,7 +478,7 @@ CFR_API int cfr_matcher_run(cfr_matcher* m, const float* emb, int b, int32_t* pr
   if (r) return r;
   if ((r = conv_launch(m->op, S(stream))) != 0) return r;
   // rows >= b are zero queries: their keys are reset below without being counted
-  r = launch_vote_argmax(m->keys, b, pred, reinterpret_cast<long long*>(counts), S(stream));
+  r = launch_vote_argmax(m->keys, b, m->n_gallery, pred, reinterpret_cast<long long*>(counts), S(stream));
   if (r) return r;
   if (b < m->max_b) CFR_CUDA(cudaMemsetAsync(m->keys + b, 0, sizeof(unsigned long long) * (m->max_b - b), S(stream)));
   return 0;

@@ -930,14 +930,15 @@ __global__ void __launch_bounds__(256) k_match(const float* __restrict__ emb, in
       if (e0 + e < b && best[e] != ~0ull) atomicMin(&keys[e0 + e], best[e]);
   }
 }
-__global__ void k_vote(unsigned long long* __restrict__ keys, int b, int* __restrict__ pred,
+__global__ void k_vote(unsigned long long* __restrict__ keys, int b, int n, int* __restrict__ pred,
                        unsigned long long* __restrict__ counts) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= b) return;
   const int pr = static_cast<int>(keys[i] & 0xffffffffull);
   keys[i] = ~0ull;                 // re-arm for the next batch
   if (pred != nullptr) pred[i] = pr;
-  if (counts != nullptr) atomicAdd(&counts[pr], 1ull);
+  // (a key nobody wrote decodes to row 0xffffffff: never index the tally with it)
+  if (counts != nullptr && static_cast<unsigned>(pr) < static_cast<unsigned>(n)) atomicAdd(&counts[pr], 1ull);
 }
 // ------------------------------------------------------------------------------------------
 // Tensor-core gallery match (large galleries): fp32 rows are split into fp16 hi + lo parts so that
@@ -973,18 +974,18 @@ int launch_split_hilo(const float* src, int rows, int rows_pad, int mode, __half
   CFR_LAUNCH_CHECK("split_hilo");
   return 0;
 }
-__global__ void k_vote_argmax(unsigned long long* __restrict__ keys, int b, int* __restrict__ pred,
+__global__ void k_vote_argmax(unsigned long long* __restrict__ keys, int b, int n, int* __restrict__ pred,
                               unsigned long long* __restrict__ counts) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= b) return;
   const int pr = static_cast<int>(0xFFFFFFFFu - static_cast<uint32_t>(keys[i] & 0xffffffffull));
   keys[i] = 0ull;                  // re-arm (atomicMax identity)
   if (pred != nullptr) pred[i] = pr;
-  if (counts != nullptr) atomicAdd(&counts[pr], 1ull);
+  if (counts != nullptr && static_cast<unsigned>(pr) < static_cast<unsigned>(n)) atomicAdd(&counts[pr], 1ull);
 }
-int launch_vote_argmax(unsigned long long* keys, int b, int* pred, long long* counts, cudaStream_t st) {
+int launch_vote_argmax(unsigned long long* keys, int b, int n, int* pred, long long* counts, cudaStream_t st) {
   if (b <= 0) return 0;
-  k_vote_argmax<<<(b + 127) / 128, 128, 0, st>>>(keys, b, pred, reinterpret_cast<unsigned long long*>(counts));
+  k_vote_argmax<<<(b + 127) / 128, 128, 0, st>>>(keys, b, n, pred, reinterpret_cast<unsigned long long*>(counts));
   CFR_LAUNCH_CHECK("vote_argmax");
   return 0;
 }
@@ -1002,7 +1003,7 @@ int launch_match_vote(const float* emb, int b, const float* gallery, int n, unsi
   dim3 grid((n + kMatchRows - 1) / kMatchRows, (b + kMatchEmb - 1) / kMatchEmb);
   k_match<<<grid, 256, 0, st>>>(emb, b, gallery, n, keys, 0u);
   CFR_LAUNCH_CHECK("match");
-  k_vote<<<(b + 127) / 128, 128, 0, st>>>(keys, b, pred, reinterpret_cast<unsigned long long*>(counts));
+  k_vote<<<(b + 127) / 128, 128, 0, st>>>(keys, b, n, pred, reinterpret_cast<unsigned long long*>(counts));
   CFR_LAUNCH_CHECK("vote");
   return 0;
 }

@@ -52,7 +52,7 @@ int launch_torgb_resize(const __half* x, const float* A, const float* B, int n, 
 int launch_set_int(int* p, int v, cudaStream_t st);
 // tensor-core gallery match helpers (see kernels.cu)
 int launch_split_hilo(const float* src, int rows, int rows_pad, int mode, __half* dst, float* bias, cudaStream_t st);
-int launch_vote_argmax(unsigned long long* keys, int b, int* pred, long long* counts, cudaStream_t st);
+int launch_vote_argmax(unsigned long long* keys, int b, int n, int* pred, long long* counts, cudaStream_t st);
 
 // smoothing_model.py:56-61 + smooth.py:135,140-146: argmin_j ||e - g_j||_2 (exact differences, fp32), votes
 int launch_match_vote(const float* emb, int b, const float* gallery, int n, unsigned long long* keys, int* pred,
