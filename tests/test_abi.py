@@ -24,6 +24,22 @@ def test_library_exports_every_declared_symbol():
     assert set(_lib.SIGNATURES) == set(names)
 
 
+def test_integration_doc_names_every_entry_point():
+    """INTEGRATION.md maps every exported entry point to the reference interface it replaces; a symbol added to the header
+    without a row there fails here.  Rows abbreviate families as `cfr_program_add_blur_act_stats`, `_finalize_stats`, ... or
+    `cfr_matcher_create / _run / _destroy`, so a name counts as documented when the text after its family prefix appears."""
+    text = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    missing = []
+    for n in _declared_symbols():
+        if n in text:
+            continue
+        stem = next((pre for pre in ("cfr_program_add", "cfr_program", "cfr_matcher", "cfr_sampler", "cfr_profile")
+                     if n.startswith(pre + "_")), None)
+        if stem is None or stem not in text or not re.search(r"[`/ ]" + re.escape(n[len(stem):]) + r"\b", text):
+            missing.append(n)
+    assert not missing, missing
+
+
 def test_version_and_error_string_without_gpu():
     from certifyingfacerecognition_b200 import _lib
     lib = _lib.load()
