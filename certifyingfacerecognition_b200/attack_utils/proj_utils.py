@@ -5,7 +5,6 @@ from __future__ import annotations
 
 import os.path as osp
 from collections import OrderedDict
-from glob import glob
 
 import numpy as np
 import scipy.linalg
@@ -73,27 +72,31 @@ def get_ellipse_mat(dirs):
     return ellipse_mat
 
 
+def selected_attrs(attrs2drop=()):
+    """The (name, budget) pairs that stay after dropping `attrs2drop`, in ATTRS order.  The module-level table is NOT
+    edited (the reference pops the dropped names out of its global dict, proj_utils.py:670-675, which is harmless there
+    because it builds its matrices once; here main_attack.py asks for the reduced AND the full direction set)."""
+    unknown = [a for a in attrs2drop if a not in ATTRS]
+    assert not unknown, f"Attribute {unknown[0]} is NOT valid"
+    return [(name, eps) for name, eps in ATTRS.items() if name not in set(attrs2drop)]
+
+
 def get_projection_matrices(dataset=DATASETS[0], gan_name=GAN_NAMES[0], attrs2drop=(), scale_factor=1.0):
-    """-> (proj_mat[512,512], ellipse_mat[512,512], dirs[512,n_dirs], red_ellipse_mat[n_dirs], files)."""
-    template = osp.join(BOUNDARIES_DIR, f"{gan_name}_{dataset}_%s_w_boundary.npy")
-    all_bounds = glob(osp.join(BOUNDARIES_DIR, "*.npy"))
-    for attr in attrs2drop:
-        assert attr in ATTRS.keys(), f"Attribute {attr} is NOT valid"
-        ATTRS.pop(attr)
-    dirs, files, magns = [], [], []
-    for att_name, magn in ATTRS.items():
-        this_file = template % att_name
-        assert this_file in all_bounds, f'Boundary for attr "{att_name}" not found!'
-        dirs.append(np.load(this_file))
-        magns.append(magn)
-        files.append(this_file)
-    dirs = np.concatenate(dirs, axis=0).T
-    assert dirs.shape[1] == len(ATTRS)
-    proj_mat = get_proj_mat(dirs)
+    """proj_utils.py:661-718 -> (proj_mat[512,512], ellipse_mat[512,512], dirs[512,n_dirs], red_ellipse_mat[n_dirs], files):
+    the projector onto the span of the kept InterFaceGAN boundaries, the minimum-volume ellipsoid through +-eps_k d_k
+    (completed with the null space) and its n_dirs-dimensional diagonal counterpart 1 / eps_k^2, both times scale_factor."""
+    keep = selected_attrs(attrs2drop)
+    files = [osp.join(BOUNDARIES_DIR, f"{gan_name}_{dataset}_{name}_w_boundary.npy") for name, _ in keep]
+    for (name, _), path in zip(keep, files):
+        assert osp.isfile(path), f'Boundary for attr "{name}" not found!'
+    dirs = np.concatenate([np.load(path) for path in files], axis=0).T          # one [1,512] row per file -> [512,n_dirs]
+    assert dirs.shape[1] == len(keep)
+    budgets = np.diag(np.array([eps for _, eps in keep]))
     ellipse_mat = scale_factor * get_ellipse_mat(dirs)
-    red_ellipse_mat = scale_factor * get_ellipse_mat(np.diag(np.array(magns)))
-    assert np.all(red_ellipse_mat == np.diag(np.diagonal(red_ellipse_mat))), "Matrix should be diagonal"
-    return proj_mat, ellipse_mat, dirs, np.diagonal(red_ellipse_mat), files
+    reduced = scale_factor * get_ellipse_mat(budgets)
+    red_diag = np.diagonal(reduced)
+    assert np.all(reduced == np.diag(red_diag)), "Matrix should be diagonal"
+    return get_proj_mat(dirs), ellipse_mat, dirs, red_diag, files
 
 
 # ------------------------------------------------------------------------------------------------------------------

@@ -149,6 +149,16 @@ def test_geometry_setup(tmp_path, monkeypatch):
     mats = gen_utils.get_all_matrices(device=torch.device("cpu"))
     assert len(mats) == 7 and mats[3].shape == (512, 5)
     assert torch.allclose(mats[6], torch.tensor([0.25, 0.25, 0.04, 0.25, 0.64]), rtol=2e-3)
+    # dropping attributes gives the reduced set and leaves the module's table alone: main_attack.py --attrs2drop asks
+    # for the reduced matrices (the attack's search space) and then for all five directions (the engine's)
+    red4 = gen_utils.get_all_matrices(["pose"], device=torch.device("cpu"))
+    assert red4[3].shape == (512, 4) and red4[5].shape == (4,)
+    assert torch.allclose(red4[6], torch.tensor([0.25, 0.25, 0.04, 0.64]), rtol=2e-3)
+    assert torch.equal(red4[3], mats[3][:, [0, 1, 2, 4]])
+    assert list(proj_utils.ATTRS) == ["age", "eyeglasses", "gender", "pose", "smile"]
+    assert gen_utils.get_all_matrices(device=torch.device("cpu"))[3].shape == (512, 5)
+    with pytest.raises(AssertionError):
+        proj_utils.get_projection_matrices("ffhq", "stylegan", attrs2drop=["beard"])
 
 
 def test_cli_surface_matches_reference():
