@@ -108,7 +108,10 @@ __device__ __forceinline__ void flush_stats(const ConvParams& p, float* s_sum, f
 // absolute shared-memory address, so shifted starts stay consistent with what TMA wrote, as in conv_halo.cu).  Weight
 // tiles stream through their own ring, one per (phase, tap, K chunk).  A bytes per K chunk: 66 KB instead of 18 x 16 KB
 // (3x3) and 50 KB instead of 16 x 16 KB for both column phases of an up-conv row phase: these layers sit on the
-// chip-wide L2 -> SM cap (profiles/ncu_r02_notes.md sections 4, 10).
+// chip-wide L2 -> SM cap (profiles/ncu_r02_notes.md sections 4, 10).  rowsMerge (section 15): operands that two accumulators
+// share are issued as ONE wider MMA -- up-conv: the input column both column phases read, B = the two phases' tiles side by
+// side (N = 2 * BN); 3x3: the input rows both output rows read, B = the tiles of (dy, dy - 1) in consecutive ring slots
+// (N = 256 across both rows' accumulators; two N = 128 MMAs when the pair straddles the ring's wrap-around).
 template <int MT, int CG = 1, bool ROWS = false>
 __global__ void __launch_bounds__(MT == 2 ? kConvThreadsMT2 : kConvThreads, 1)
 conv_igemm_kernel(const __grid_constant__ ConvParams p) {
